@@ -1,0 +1,410 @@
+/* TEST INFRASTRUCTURE ONLY -- not part of the product.
+ *
+ * Plain-C restatement of the reference's (feltor-dev/feltor v8.2.2) algorithms on the hot path:
+ * blas1 functors, exblas superaccumulator dot, Ell/Coo sparse block symv, CSR spmv, Elliptic2d apply,
+ * PCG and the nested-iteration multigrid.  Every function cites the reference file:line it follows
+ * (paths relative to /root/reference/).  Compiled by oracle/Makefile into oracle/libdgoracle.so with
+ * `gcc -O2 -mfma -ffp-contract=off` so that every fma() below is a real fused multiply-add and nothing
+ * else is contracted -- exactly the arithmetic the reference performs when DG_FMA is active
+ * (inc/dg/backend/config.h:21-26).
+ *
+ * Parity pin: tests/test_oracle.py checks this file against the reference's own golden vectors
+ * (inc/dg/blas1_t.cpp:102-184, inc/dg/topology/evaluation_t.cpp:56-175,
+ * inc/dg/topology/derivatives_t.cpp:54-133), against the committed fixtures in tests/golden/ that were
+ * produced by the unmodified reference (oracle/_ref, script tests/golden/make_golden.py), and -- when
+ * oracle/_ref/libdgref.so is present -- live against the reference on random inputs.
+ *
+ * Only tests/, __graft_entry__.smoke() and bench.py's cpu_baseline / --impl reference legs may load this.
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_API __attribute__((visibility("default")))
+
+/* ------------------------------------------------------------------------------------------------
+ * blas1 functors: inc/dg/subroutines.h:231-384 (explicit DG_FMA order), dispatch shortcuts of
+ * inc/dg/blas1.h:243-566 are applied by the caller (tests/host layer), not here.
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API void orc_copy(int n, const double* x, double* y) { for (int i = 0; i < n; i++) y[i] = x[i]; }
+/* Scal subroutines.h:233-244 */
+ORC_API void orc_scal(int n, double* x, double a) { for (int i = 0; i < n; i++) x[i] *= a; }
+/* Plus subroutines.h:247-258 */
+ORC_API void orc_plus(int n, double* x, double a) { for (int i = 0; i < n; i++) x[i] += a; }
+/* Axpby subroutines.h:260-274 */
+ORC_API void orc_axpby(int n, double a, const double* x, double b, double* y) {
+    for (int i = 0; i < n; i++) { double t = y[i] * b; y[i] = fma(a, x[i], t); }
+}
+/* z = a x + b y via Evaluate<equals,PairSum> blas1.h:382-385, subroutines.h:124-143: fma(a,x, b*y) */
+ORC_API void orc_axpbyz(int n, double a, const double* x, double b, const double* y, double* z) {
+    for (int i = 0; i < n; i++) z[i] = fma(a, x[i], b * y[i]);
+}
+/* Axpbypgz subroutines.h:294-310 */
+ORC_API void orc_axpbypgz(int n, double a, const double* x, double b, const double* y, double g, double* z) {
+    for (int i = 0; i < n; i++) { double t = z[i] * g; t = fma(a, x[i], t); z[i] = fma(b, y[i], t); }
+}
+/* PointwiseDot 3-arg subroutines.h:313-323 */
+ORC_API void orc_pointwiseDot(int n, double a, const double* x, const double* y, double b, double* z) {
+    for (int i = 0; i < n; i++) { double t = z[i] * b; z[i] = fma(a * x[i], y[i], t); }
+}
+/* AxyPby subroutines.h:276-292 (pointwiseDot with y aliasing an input, blas1.h:413-421) */
+ORC_API void orc_axypby(int n, double a, const double* x, double b, double* y) {
+    for (int i = 0; i < n; i++) { double tmp = y[i]; double t = tmp * b; y[i] = fma(a * x[i], tmp, t); }
+}
+/* z = x*y via Evaluate<equals,PairSum>(x,y) blas1.h:441-444: PairSum::sum(alpha=x, x=y) = x*y */
+ORC_API void orc_pointwiseDot_xy(int n, const double* x, const double* y, double* z) {
+    for (int i = 0; i < n; i++) z[i] = x[i] * y[i];
+}
+/* PointwiseDot 4-arg subroutines.h:325-330 */
+ORC_API void orc_pointwiseDot3(int n, double a, const double* x1, const double* x2, const double* x3, double b, double* y) {
+    for (int i = 0; i < n; i++) { double t = y[i] * b; y[i] = fma(a * x1[i], x2[i] * x3[i], t); }
+}
+/* PointwiseDot2 subroutines.h:336-352 */
+ORC_API void orc_pointwiseDot2(int n, double a, const double* x1, const double* y1, double b, const double* x2,
+                               const double* y2, double g, double* z) {
+    for (int i = 0; i < n; i++) {
+        double t = z[i] * g;
+        t = fma(a * x1[i], y1[i], t);
+        z[i] = fma(b * x2[i], y2[i], t);
+    }
+}
+/* PointwiseDivide subroutines.h:365-384 */
+ORC_API void orc_pointwiseDivide(int n, double a, const double* x, const double* y, double b, double* z) {
+    for (int i = 0; i < n; i++) { double t = z[i] * b; z[i] = fma(a, x[i] / y[i], t); }
+}
+ORC_API void orc_pointwiseDivide_alias(int n, double a, const double* y, double b, double* z) {
+    for (int i = 0; i < n; i++) { double tmp = z[i]; double t = tmp * b; z[i] = fma(a, tmp / y[i], t); }
+}
+ORC_API void orc_pointwiseDivide_xy(int n, const double* x, const double* y, double* z) {
+    for (int i = 0; i < n; i++) z[i] = x[i] / y[i];
+}
+/* TensorMultiply2d inc/dg/topology/multiply.h:18-32; NULL tensor component pointers mean the constant
+ * value the SparseTensor supplies for them (1 on the diagonal, 0 off-diagonal, tensor.h) */
+ORC_API void orc_tensor_multiply2d(int n, const double* lambda, double lambda_s, const double* t00, const double* t01,
+                                   const double* t10, const double* t11, const double* in0, const double* in1,
+                                   double mu, double* out0, double* out1) {
+    for (int i = 0; i < n; i++) {
+        double l = lambda ? lambda[i] : lambda_s;
+        double a = t00 ? t00[i] : 1., b = t01 ? t01[i] : 0., c = t10 ? t10[i] : 0., d = t11 ? t11[i] : 1.;
+        double i0 = in0[i], i1 = in1[i];
+        double tmp0 = fma(a, i0, b * i1);
+        double tmp1 = fma(c, i0, d * i1);
+        double temp = out1[i] * mu;
+        out1[i] = fma(l, tmp1, temp);
+        temp = out0[i] * mu;
+        out0[i] = fma(l, tmp0, temp);
+    }
+}
+/* EmbeddedPairSum subroutines.h:179-204: y = b0*y + sum b_i k_i ; yt likewise.  k = array of pointers */
+ORC_API void orc_embedded_pair_sum(int n, double* y, double* yt, double b0, double bt0, int nk, const double* b,
+                                   const double* bt, const double* const* k) {
+    for (int i = 0; i < n; i++) {
+        double a = b0 * y[i], at = bt0 * yt[i];
+        for (int s = 0; s < nk; s++) { a = fma(b[s], k[s][i], a); at = fma(bt[s], k[s][i], at); }
+        y[i] = a; yt[i] = at;
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * exblas superaccumulator: inc/dg/backend/exblas/config.h:86-92, accumulate.h:171-349, mylibm.hpp
+ * ---------------------------------------------------------------------------------------------- */
+#define KRX 8
+#define DIGITS 56
+#define F_WORDS 20
+#define E_WORDS 19
+#define BIN_COUNT 39
+static const double DELTASCALE = 72057594037927936.0; /* 2^56 */
+
+/* mylibm.hpp:168-183 (portable branch): returns old word, sets signed-overflow flag */
+static int64_t xadd(int64_t* mem, int64_t x, unsigned char* of) {
+    int64_t y = *mem;
+    uint64_t r = (uint64_t)y + (uint64_t)x;
+    *mem = (int64_t)r;
+    int64_t x63 = (x >> 63) & 1, y63 = (y >> 63) & 1, r63 = ((int64_t)r >> 63) & 1;
+    int64_t c62 = r63 ^ x63 ^ y63;
+    int64_t c63 = (x63 & y63) | (c62 & (x63 | y63));
+    *of = (unsigned char)(c63 ^ c62);
+    return y;
+}
+/* accumulate.h:171-208 */
+static void AccumulateWord(int64_t* acc, int i, int64_t x) {
+    unsigned char overflow;
+    int64_t carry = x, carrybit;
+    int64_t oldword = xadd(&acc[i], x, &overflow);
+    while (overflow) {
+        carry = (oldword + carry) >> DIGITS;
+        int s = oldword > 0;
+        carrybit = (s ? (int64_t)(1ll << KRX) : (int64_t)((unsigned long long)(-1ll) << KRX));
+        xadd(&acc[i], (int64_t)(-(uint64_t)((uint64_t)carry << DIGITS)), &overflow);
+        carry += carrybit;
+        ++i;
+        if (i >= BIN_COUNT) return;
+        oldword = xadd(&acc[i], carry, &overflow);
+    }
+}
+/* mylibm.hpp:72-81 exponent, :95-107 myldexp */
+static int exponent_of(double x) {
+    union { double d; uint64_t i; } c; c.d = x;
+    uint64_t e = ((c.i >> 52) & 0x7ff) - 0x3ff;
+    return (int)e;
+}
+static double myldexp(double x, int e) {
+    union { double d; uint64_t i; } c; c.d = x;
+    c.i += (uint64_t)e << 52;
+    return c.d;
+}
+/* accumulate.h:217-236 */
+ORC_API void orc_accumulate(int64_t* acc, double x) {
+    if (x == 0) return;
+    int e = exponent_of(x);
+    int exp_word = e / DIGITS;
+    int iup = exp_word + F_WORDS;
+    double xscaled = myldexp(x, -DIGITS * exp_word);
+    for (int i = iup; i >= 0 && xscaled != 0; --i) {
+        double xrounded = rint(xscaled);
+        int64_t xint = llrint(xscaled);
+        AccumulateWord(acc, i, xint);
+        xscaled -= xrounded;
+        xscaled *= DELTASCALE;
+    }
+}
+/* accumulate.h:267-285; returns sign */
+ORC_API int orc_normalize(int64_t* acc) {
+    int imin = 0;
+    int64_t carry_in = acc[imin] >> DIGITS;
+    acc[imin] -= (int64_t)((uint64_t)carry_in << DIGITS);
+    int i;
+    for (i = imin + 1; i < BIN_COUNT; ++i) {
+        acc[i] += carry_in;
+        int64_t carry_out = acc[i] >> DIGITS;
+        acc[i] -= (int64_t)((uint64_t)carry_out << DIGITS);
+        carry_in = carry_out;
+    }
+    int imax = i - 1;
+    acc[imax] += (int64_t)((uint64_t)carry_in << DIGITS);
+    return carry_in < 0;
+}
+/* mylibm.hpp:118-134 */
+static double OddRoundSumNonnegative(double th, double tl) {
+    union { double d; int64_t l; } thdb;
+    thdb.d = th + tl;
+    thdb.l |= (tl != 0.0);
+    return thdb.d;
+}
+/* accumulate.h:297-349 (modifies acc: it is normalised in place) */
+ORC_API double orc_round(int64_t* acc) {
+    int imin = 0, imax = BIN_COUNT - 1;
+    int negative = orc_normalize(acc);
+    int i;
+    for (i = imax; i >= imin && acc[i] == 0; --i) {}
+    if (negative) {
+        for (; i >= imin && (acc[i] & ((1ll << DIGITS) - 1)) == ((1ll << DIGITS) - 1); --i) {}
+    }
+    if (i < 0) return 0.0;
+    int64_t hiword = negative ? ((1ll << DIGITS) - 1) - acc[i] : acc[i];
+    double rounded = (double)hiword;
+    double hi = ldexp(rounded, (i - F_WORDS) * DIGITS);
+    if (i == 0) return negative ? -hi : hi;
+    hiword -= llrint(rounded);
+    double mid = ldexp((double)hiword, (i - F_WORDS) * DIGITS);
+    int64_t sticky = 0;
+    for (int j = imin; j != i - 1; ++j) sticky |= negative ? ((1ll << DIGITS) - acc[j]) : acc[j];
+    int64_t loword = negative ? ((1ll << DIGITS) - acc[i - 1]) : acc[i - 1];
+    loword |= !!sticky;
+    double lo = ldexp((double)loword, (i - 1 - F_WORDS) * DIGITS);
+    if (mid != 0) lo = OddRoundSumNonnegative(mid, lo);
+    hi = hi + lo;
+    return negative ? -hi : hi;
+}
+/* exdot: exdot_serial.h:62-135 / exdot_omp.h:95-245.  The FPE cache in front of the superaccumulator is an
+ * optimisation only (ExSUM.FPE.hpp:100-116): the accumulated VALUE is the exact sum of the individually
+ * rounded products, so accumulating each product directly gives the same normalised accumulator.
+ * Returns status (1 if a product is non-finite, blas1.h:161).  acc is returned NORMALISED. */
+ORC_API int orc_exdot2(int n, const double* x, const double* y, int64_t* acc) {
+    int status = 0;
+    memset(acc, 0, BIN_COUNT * sizeof(int64_t));
+    for (int i = 0; i < n; i++) {
+        double p = x[i] * y[i];
+        if (!isfinite(p)) status = 1;
+        else orc_accumulate(acc, p);
+    }
+    orc_normalize(acc);
+    return status;
+}
+/* 3 operands: round(round(x*w)*y), exdot_serial.h:126-128 */
+ORC_API int orc_exdot3(int n, const double* x, const double* w, const double* y, int64_t* acc) {
+    int status = 0;
+    memset(acc, 0, BIN_COUNT * sizeof(int64_t));
+    for (int i = 0; i < n; i++) {
+        double p1 = x[i] * w[i];
+        double p = p1 * y[i];
+        if (!isfinite(p)) status = 1;
+        else orc_accumulate(acc, p);
+    }
+    orc_normalize(acc);
+    return status;
+}
+/* blas1::dot / blas2::dot value (blas1.h:152-170, blas2.h:94-115); *status as above */
+ORC_API double orc_dot2(int n, const double* x, const double* y, int* status) {
+    int64_t acc[BIN_COUNT];
+    *status = orc_exdot2(n, x, y, acc);
+    return orc_round(acc);
+}
+ORC_API double orc_dot3(int n, const double* x, const double* w, const double* y, int* status) {
+    int64_t acc[BIN_COUNT];
+    *status = orc_exdot3(n, x, w, y, acc);
+    return orc_round(acc);
+}
+/* word-wise sum of two NORMALISED accumulators followed by Normalize: the cross-rank combine of
+ * inc/dg/backend/exblas/mpi_accumulate.h:94-125 */
+ORC_API void orc_superacc_add(int64_t* acc, const int64_t* other) {
+    for (int i = 0; i < BIN_COUNT; i++) acc[i] += other[i];
+    orc_normalize(acc);
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * EllSparseBlockMat symv: generic kernel inc/dg/backend/sparseblockmat_omp_kernels.h:10-55
+ * (the specialised kernels :57-290 perform the same arithmetic per output element; the only difference
+ * is that for right_size==1 an invalid column contributes fma(alpha, 0, y) instead of being skipped,
+ * which changes nothing but the sign of a zero).
+ * meta = {num_rows, num_cols, blocks_per_line, n, left_size, right_size, nblocks, rr0, rr1}
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API void orc_ell_symv(const int* meta, const double* data, const int* cols_idx, const int* data_idx, double alpha,
+                          const double* x, double beta, double* y) {
+    const int num_rows = meta[0], num_cols = meta[1], bpl = meta[2], n = meta[3], left = meta[4], right = meta[5];
+    const int rr0 = meta[7], rr1 = meta[8];
+    for (int s = 0; s < left; s++)
+        for (int i = 0; i < num_rows; i++)
+            for (int k = 0; k < n; k++)
+                for (int j = rr0; j < rr1; j++) {
+                    size_t I = ((size_t)(s * num_rows + i) * n + k) * right + j;
+                    double yy = beta == 0 ? 0. : y[I] * beta;
+                    for (int d = 0; d < bpl; d++) {
+                        int C = cols_idx[i * bpl + d];
+                        if (C == -1) continue;
+                        size_t J = (size_t)(s * num_cols + C) * n;
+                        int B = (data_idx[i * bpl + d] * n + k) * n;
+                        double temp = 0;
+                        for (int q = 0; q < n; q++) temp = fma(data[B + q], x[(J + q) * right + j], temp);
+                        yy = fma(alpha, temp, yy);
+                    }
+                    y[I] = yy;
+                }
+}
+/* CooSparseBlockMat symv: sparseblockmat_omp_kernels.h:356-377; x = array of chunk pointers, each chunk laid
+ * out [q][s][j]; beta == 1 implied.  meta = {num_rows, num_cols, num_entries, n, left_size, right_size} */
+ORC_API void orc_coo_symv(const int* meta, const double* data, const int* rows_idx, const int* cols_idx,
+                          const int* data_idx, double alpha, const double* const* x, double* y) {
+    const int num_rows = meta[0], num_entries = meta[2], n = meta[3], left = meta[4], right = meta[5];
+    for (int s = 0; s < left; s++)
+        for (int k = 0; k < n; k++)
+            for (int j = 0; j < right; j++)
+                for (int i = 0; i < num_entries; i++) {
+                    size_t I = ((size_t)(s * num_rows + rows_idx[i]) * n + k) * right + j;
+                    double temp = 0;
+                    for (int q = 0; q < n; q++)
+                        temp = fma(data[(data_idx[i] * n + k) * n + q], x[cols_idx[i]][((size_t)q * left + s) * right + j], temp);
+                    y[I] = fma(alpha, temp, y[I]);
+                }
+}
+/* CSR spmv: inc/dg/backend/sparsematrix_omp.h:17-52 */
+ORC_API void orc_csr_spmv(int nrows, const int* pos, const int* idx, const double* val, double alpha, const double* x,
+                          double beta, double* y) {
+    if (beta == 1.) {
+        for (int i = 0; i < nrows; i++)
+            for (int jj = pos[i]; jj < pos[i + 1]; jj++) y[i] = fma(alpha * val[jj], x[idx[jj]], y[i]);
+    } else {
+        for (int i = 0; i < nrows; i++) {
+            double temp = 0;
+            for (int jj = pos[i]; jj < pos[i + 1]; jj++) temp = fma(alpha * val[jj], x[idx[jj]], temp);
+            /* reference: y = fma(beta, y, temp); the CUDA backend (cuSPARSE) does not read y for beta==0 and
+             * the product follows that (NaN in y is overwritten) */
+            y[i] = beta == 0. ? temp : fma(beta, y[i], temp);
+        }
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * Elliptic2d::symv inc/dg/elliptic.h:428-458 as a composition of the kernels above.
+ * ---------------------------------------------------------------------------------------------- */
+typedef struct {
+    const int* meta; const double* data; const int* cols; const int* didx;
+} orc_ell;
+typedef struct {
+    orc_ell leftx, lefty, rightx, righty, jumpx, jumpy;
+    const double* sigma;                        /* m_sigma = chi_scalar * vol (elliptic.h:324-333) */
+    const double* vol;                          /* m_vol, NULL = all ones (Cartesian) */
+    const double* chi_xx; const double* chi_xy; const double* chi_yx; const double* chi_yy; /* NULL = identity */
+    double jfactor; int chi_weight_jump; int size;
+} orc_elliptic2d;
+
+static void ell(const orc_ell* m, double alpha, const double* x, double beta, double* y) {
+    orc_ell_symv(m->meta, m->data, m->cols, m->didx, alpha, x, beta, y);
+}
+/* work = 3*size doubles */
+ORC_API void orc_elliptic2d_symv(const orc_elliptic2d* e, double alpha, const double* x, double beta, double* y,
+                                 double* work) {
+    int n = e->size;
+    double *tempx = work, *tempy = work + n, *temp = work + 2 * n;
+    ell(&e->rightx, 1., x, 0., tempx);                                   /* elliptic.h:431 */
+    ell(&e->righty, 1., x, 0., tempy);                                   /* :432 */
+    orc_tensor_multiply2d(n, e->sigma, 1., e->chi_xx, e->chi_xy, e->chi_yx, e->chi_yy, tempx, tempy, 0., tempx,
+                          tempy);                                        /* :435 */
+    ell(&e->lefty, 1., tempy, 0., temp);                                 /* :438 */
+    ell(&e->leftx, -1., tempx, -1., temp);                               /* :439 */
+    if (0.0 != e->jfactor) {                                             /* :442 */
+        if (e->chi_weight_jump) {
+            ell(&e->jumpx, e->jfactor, x, 0., tempx);
+            ell(&e->jumpy, e->jfactor, x, 0., tempy);
+            orc_tensor_multiply2d(n, e->sigma, 1., e->chi_xx, e->chi_xy, e->chi_yx, e->chi_yy, tempx, tempy, 0.,
+                                  tempx, tempy);
+            orc_axpbypgz(n, 1.0, tempx, 1.0, tempy, 1.0, temp);
+        } else {
+            ell(&e->jumpx, e->jfactor, x, 1., temp);                     /* :454 */
+            ell(&e->jumpy, e->jfactor, x, 1., temp);                     /* :455 */
+        }
+    }
+    /* :458 pointwiseDivide(alpha, temp, vol, beta, y): z*=b; z = fma(a, x/y, z) */
+    for (int i = 0; i < n; i++) {
+        double v = e->vol ? e->vol[i] : 1.;
+        double t = beta == 0 ? 0. : y[i] * beta; /* product does not read y for beta==0 */
+        y[i] = fma(alpha, temp[i] / v, t);
+    }
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * PCG::solve inc/dg/pcg.h:136-195 with vector preconditioner P: symv(P,r,z) ==
+ * blas1::pointwiseDot(P,r,z) == P*r (blas2_dispatch_shared.h:126-134, blas1.h:441-444).
+ * A is the Elliptic2d above.  work = 6*size.  Returns iterations; max_iter if not converged.
+ * ---------------------------------------------------------------------------------------------- */
+ORC_API int orc_pcg_solve_elliptic2d(const orc_elliptic2d* A, double* x, const double* b, const double* P,
+                                     const double* W, double eps, double nrmb_correction, int test_frequency,
+                                     int max_iter, double* work, double* residuals /* optional, max_iter */) {
+    int n = A->size, st;
+    double *r = work, *p = work + n, *ap = work + 2 * n, *awork = work + 3 * n;
+    double nrmb = sqrt(orc_dot3(n, b, W, b, &st));                          /* pcg.h:140 */
+    double tol = eps * (nrmb + nrmb_correction);
+    if (nrmb == 0) { for (int i = 0; i < n; i++) x[i] = 0; return 0; }    /* :150-154 */
+    orc_elliptic2d_symv(A, 1., x, 0., r, awork);                            /* :155 */
+    orc_axpby(n, 1., b, -1., r);                                            /* :156 */
+    if (sqrt(orc_dot3(n, r, W, r, &st)) < tol) return 0;                    /* :157 */
+    for (int i = 0; i < n; i++) p[i] = P[i] * r[i];                      /* :159 symv(P,r,p) == pointwiseDot(P,r,p) = P*r */
+    double nrmzr_old = orc_dot3(n, p, W, r, &st);                           /* :160 */
+    for (int it = 1; it < max_iter; it++) {
+        orc_elliptic2d_symv(A, 1., p, 0., ap, awork);                       /* :165 */
+        double alpha = nrmzr_old / orc_dot3(n, p, W, ap, &st);              /* :166 */
+        orc_axpby(n, alpha, p, 1., x);                                      /* :167 */
+        orc_axpby(n, -alpha, ap, 1., r);                                    /* :168 */
+        if (0 == it % test_frequency) {                                     /* :169 */
+            double res = sqrt(orc_dot3(n, r, W, r, &st));
+            if (residuals) residuals[it] = res;
+            if (res < tol) return it;                                       /* :177 */
+        }
+        for (int i = 0; i < n; i++) ap[i] = P[i] * r[i];                  /* :180 */
+        double nrmzr_new = orc_dot3(n, ap, W, r, &st);                      /* :181 */
+        orc_axpby(n, 1., ap, nrmzr_new / nrmzr_old, p);                     /* :182 */
+        nrmzr_old = nrmzr_new;
+    }
+    return max_iter;
+}
