@@ -1,0 +1,265 @@
+// Bit-reproducible dot products: dgb_exdot2 / dgb_exdot3 and friends.
+// Replaces exdot_gpu (inc/dg/backend/exblas/exdot_cuda.cuh:319-357: fixed 64x512 threads, three launches, a
+// blocking D2H of 39 words and a host-side Round) by ONE persistent kernel sized to the SM count whose last block
+// normalises, rounds and publishes {acc[39], value, status} in device memory.
+#include "superacc.cuh"
+#include <cmath>
+#include <cstring>
+
+namespace dgb {
+
+struct DotWs {
+    sa::DotSlot slot;      // partials / status / ticket / (result unused here)
+    dgb_dot_result* result;  // default device result record
+    dgb_dot_result* host_result;  // pinned
+    int max_blocks;
+    int nslots;
+};
+
+constexpr int DOT_THREADS = 256;
+constexpr int DOT_WARPS = DOT_THREADS / 32;
+
+// products follow the reference exactly: 2 operands round(x*y); 3 operands round(round(x*w)*y)
+// (exdot_cuda.cuh:54,147-148); non-finite products raise status and are not accumulated.
+template <int NOPS, bool VEC>
+__global__ void __launch_bounds__(DOT_THREADS)
+exdot_kernel(const double* __restrict__ x, double xs, const double* __restrict__ w, double wsc,
+             const double* __restrict__ y, double ys, size_t n, sa::DotSlot slot) {
+    __shared__ long long smem[DOT_WARPS * sa::BINS];
+    sa::block_init<DOT_WARPS>(smem);
+    long long* my = smem + (threadIdx.x >> 5) * sa::BINS;
+    sa::Fpe fpe;
+    fpe.clear();
+    int bad = 0;
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (VEC) {
+        constexpr int U = 4;
+        const size_t nvec = n / 2;
+        for (size_t base = tid; base < nvec; base += U * T) {
+            double2 a[U], b[U], c[U];
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                size_t idx = base + u * T;
+                if (idx < nvec) {
+                    a[u] = x ? ld2(x + 2 * idx) : make_double2(xs, xs);
+                    if (NOPS == 3) b[u] = w ? ld2(w + 2 * idx) : make_double2(wsc, wsc);
+                    c[u] = y ? ld2(y + 2 * idx) : make_double2(ys, ys);
+                } else {
+                    a[u] = make_double2(0., 0.);
+                    b[u] = make_double2(0., 0.);
+                    c[u] = make_double2(0., 0.);
+                }
+            }
+#pragma unroll
+            for (int u = 0; u < U; u++) {
+                double p0, p1;
+                if (NOPS == 3) {
+                    p0 = __dmul_rn(__dmul_rn(a[u].x, b[u].x), c[u].x);
+                    p1 = __dmul_rn(__dmul_rn(a[u].y, b[u].y), c[u].y);
+                } else {
+                    p0 = __dmul_rn(a[u].x, c[u].x);
+                    p1 = __dmul_rn(a[u].y, c[u].y);
+                }
+                if (!isfinite(p0)) { bad = 1; p0 = 0.; }
+                if (!isfinite(p1)) { bad = 1; p1 = 0.; }
+                fpe.add(p0, my);
+                fpe.add(p1, my);
+            }
+        }
+        if ((n & 1) && tid == 0) {
+            double a = x ? x[n - 1] : xs, c = y ? y[n - 1] : ys;
+            double p = NOPS == 3 ? __dmul_rn(__dmul_rn(a, w ? w[n - 1] : wsc), c) : __dmul_rn(a, c);
+            if (!isfinite(p)) { bad = 1; p = 0.; }
+            fpe.add(p, my);
+        }
+    } else {
+        for (size_t i = tid; i < n; i += T) {
+            double a = x ? x[i] : xs, c = y ? y[i] : ys;
+            double p = NOPS == 3 ? __dmul_rn(__dmul_rn(a, w ? w[i] : wsc), c) : __dmul_rn(a, c);
+            if (!isfinite(p)) { bad = 1; p = 0.; }
+            fpe.add(p, my);
+        }
+    }
+    fpe.flush(my);
+    sa::block_finish<DOT_WARPS>(smem, bad, slot);
+}
+
+// combine `nparts` normalised accumulators (multi-GPU / recursive vectors)
+__global__ void __launch_bounds__(64) superacc_combine_kernel(const long long* parts, int nparts, const int* status,
+                                                              dgb_dot_result* result) {
+    __shared__ long long acc[sa::BINS + 1];
+    if (threadIdx.x < sa::BINS) acc[threadIdx.x] = 0;
+    __syncthreads();
+    for (int b0 = 0; b0 < nparts; b0 += 128) {
+        int b1 = min(b0 + 128, nparts);
+        if (threadIdx.x < sa::BINS) {
+            long long sum = acc[threadIdx.x];
+            for (int b = b0; b < b1; b++) sum += parts[(size_t)b * sa::BINS + threadIdx.x];
+            acc[threadIdx.x] = sum;
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) acc[sa::BINS] = sa::normalize(acc, 1);
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) {
+        int bad = 0;
+        if (status)
+            for (int b = 0; b < nparts; b++) bad |= status[b];
+        for (int i = 0; i < sa::BINS; i++) result->acc[i] = acc[i];
+        result->value = sa::round_normalized(acc, (int)acc[sa::BINS]);
+        result->status = bad;
+        result->pad = 0;
+    }
+}
+
+static int dot_grid(size_t n) {
+    size_t per_block = (size_t)DOT_THREADS * 8;  // 4 double2 per thread per trip
+    size_t want = (n + per_block - 1) / per_block;
+    if (want == 0) want = 1;
+    size_t cap = (size_t)sm_count() * 6;
+    return (int)(want < cap ? want : cap);
+}
+
+int exdot_launch(DotWs* ws, int nops, size_t n, const double* x, double xs, const double* w, double wsc,
+                 const double* y, double ys, dgb_dot_result* result, dgb_stream_t s) {
+    if (!ws) { set_error("dgb_exdot: workspace is NULL"); return DGB_ERR_INVALID; }
+    sa::DotSlot slot = ws->slot;
+    slot.result = result ? result : ws->result;
+    int grid = dot_grid(n);
+    if (grid > ws->max_blocks) grid = ws->max_blocks;
+    bool vec = (!x || aligned16(x)) && (!w || aligned16(w)) && (!y || aligned16(y));
+    cudaStream_t st = as_stream(s);
+    if (nops == 3) {
+        if (vec) exdot_kernel<3, true><<<grid, DOT_THREADS, 0, st>>>(x, xs, w, wsc, y, ys, n, slot);
+        else exdot_kernel<3, false><<<grid, DOT_THREADS, 0, st>>>(x, xs, w, wsc, y, ys, n, slot);
+    } else {
+        if (vec) exdot_kernel<2, true><<<grid, DOT_THREADS, 0, st>>>(x, xs, nullptr, 0., y, ys, n, slot);
+        else exdot_kernel<2, false><<<grid, DOT_THREADS, 0, st>>>(x, xs, nullptr, 0., y, ys, n, slot);
+    }
+    DGB_LAUNCHED();
+    return 0;
+}
+
+// host restatement of accumulate.h:267-349 for the convenience helpers (operates on host memory only)
+static int normalize_host(int64_t* acc) {
+    int64_t carry_in = acc[0] >> 56;
+    acc[0] -= (int64_t)((uint64_t)carry_in << 56);
+    for (int i = 1; i < 39; ++i) {
+        int64_t v = acc[i] + carry_in;
+        int64_t carry_out = v >> 56;
+        acc[i] = v - (int64_t)((uint64_t)carry_out << 56);
+        carry_in = carry_out;
+    }
+    acc[38] += (int64_t)((uint64_t)carry_in << 56);
+    return carry_in < 0;
+}
+static double round_host(const int64_t* in) {
+    int64_t acc[39];
+    memcpy(acc, in, sizeof(acc));
+    int negative = normalize_host(acc);
+    const int64_t MASK = (1ll << 56) - 1;
+    int i;
+    for (i = 38; i >= 0 && acc[i] == 0; --i) {}
+    if (negative)
+        for (; i >= 0 && (acc[i] & MASK) == MASK; --i) {}
+    if (i < 0) return 0.0;
+    int64_t hiword = negative ? MASK - acc[i] : acc[i];
+    double rounded = (double)hiword;
+    double hi = std::ldexp(rounded, (i - 20) * 56);
+    if (i == 0) return negative ? -hi : hi;
+    hiword -= std::llrint(rounded);
+    double mid = std::ldexp((double)hiword, (i - 20) * 56);
+    int64_t sticky = 0;
+    for (int j = 0; j != i - 1; ++j) sticky |= negative ? ((1ll << 56) - acc[j]) : acc[j];
+    int64_t loword = negative ? ((1ll << 56) - acc[i - 1]) : acc[i - 1];
+    loword |= !!sticky;
+    double lo = std::ldexp((double)loword, (i - 1 - 20) * 56);
+    if (mid != 0) {
+        union { double d; int64_t l; } u;
+        u.d = mid + lo;
+        u.l |= (lo != 0.0);
+        lo = u.d;
+    }
+    hi = hi + lo;
+    return negative ? -hi : hi;
+}
+
+}  // namespace dgb
+
+using namespace dgb;
+
+extern "C" {
+
+int dgb_dot_ws_create(dgb_dot_ws** out) {
+    DotWs* ws = new DotWs();
+    ws->max_blocks = 2048;
+    ws->nslots = 4;  // fused kernels may carry up to 4 simultaneous dots
+    size_t nb = (size_t)ws->max_blocks * ws->nslots;
+    DGB_CUDA(cudaMalloc(&ws->slot.partials, nb * sa::BINS * sizeof(long long)));
+    DGB_CUDA(cudaMalloc(&ws->slot.block_status, nb * sizeof(int)));
+    DGB_CUDA(cudaMalloc(&ws->slot.ticket, ws->nslots * sizeof(unsigned int)));
+    DGB_CUDA(cudaMemset(ws->slot.ticket, 0, ws->nslots * sizeof(unsigned int)));
+    DGB_CUDA(cudaMalloc(&ws->result, ws->nslots * sizeof(dgb_dot_result)));
+    DGB_CUDA(cudaMemset(ws->result, 0, ws->nslots * sizeof(dgb_dot_result)));
+    DGB_CUDA(cudaMallocHost(&ws->host_result, ws->nslots * sizeof(dgb_dot_result)));
+    ws->slot.result = ws->result;
+    *out = reinterpret_cast<dgb_dot_ws*>(ws);
+    return 0;
+}
+int dgb_dot_ws_destroy(dgb_dot_ws* p) {
+    DotWs* ws = reinterpret_cast<DotWs*>(p);
+    if (!ws) return 0;
+    cudaFree(ws->slot.partials);
+    cudaFree(ws->slot.block_status);
+    cudaFree(ws->slot.ticket);
+    cudaFree(ws->result);
+    cudaFreeHost(ws->host_result);
+    delete ws;
+    return 0;
+}
+int dgb_exdot2(dgb_dot_ws* ws, size_t n, const double* x, double xs, const double* y, double ys,
+               dgb_dot_result* result, dgb_stream_t s) {
+    return exdot_launch(reinterpret_cast<DotWs*>(ws), 2, n, x, xs, nullptr, 0., y, ys, result, s);
+}
+int dgb_exdot3(dgb_dot_ws* ws, size_t n, const double* x, double xs, const double* w, double wsc, const double* y,
+               double ys, dgb_dot_result* result, dgb_stream_t s) {
+    return exdot_launch(reinterpret_cast<DotWs*>(ws), 3, n, x, xs, w, wsc, y, ys, result, s);
+}
+static int dot_sync(DotWs* ws, int64_t* acc_host, double* value, int* status, dgb_stream_t s) {
+    DGB_CUDA(cudaMemcpyAsync(ws->host_result, ws->result, sizeof(dgb_dot_result), cudaMemcpyDeviceToHost, as_stream(s)));
+    DGB_CUDA(cudaStreamSynchronize(as_stream(s)));
+    if (acc_host) memcpy(acc_host, ws->host_result->acc, sizeof(int64_t) * DGB_BIN_COUNT);
+    if (value) *value = ws->host_result->value;
+    if (status) *status = ws->host_result->status;
+    if (ws->host_result->status != 0) {
+        set_error("dot product failed since one of the inputs contains NaN or Inf");
+        return DGB_ERR_NOTFINITE;
+    }
+    return 0;
+}
+int dgb_dot2(dgb_dot_ws* p, size_t n, const double* x, const double* y, int64_t* acc_host, double* value, int* status,
+             dgb_stream_t s) {
+    DotWs* ws = reinterpret_cast<DotWs*>(p);
+    int e = exdot_launch(ws, 2, n, x, 0., nullptr, 0., y, 0., nullptr, s);
+    if (e) return e;
+    return dot_sync(ws, acc_host, value, status, s);
+}
+int dgb_dot3(dgb_dot_ws* p, size_t n, const double* x, const double* w, const double* y, int64_t* acc_host,
+             double* value, int* status, dgb_stream_t s) {
+    DotWs* ws = reinterpret_cast<DotWs*>(p);
+    int e = exdot_launch(ws, 3, n, x, 0., w, 0., y, 0., nullptr, s);
+    if (e) return e;
+    return dot_sync(ws, acc_host, value, status, s);
+}
+int dgb_superacc_normalize_host(int64_t* acc) { return normalize_host(acc); }
+double dgb_superacc_round_host(const int64_t* acc) { return round_host(acc); }
+int dgb_superacc_combine(const int64_t* parts, int nparts, const int32_t* status_parts, dgb_dot_result* result,
+                         dgb_stream_t s) {
+    if (nparts < 1) { set_error("dgb_superacc_combine: nparts < 1"); return DGB_ERR_INVALID; }
+    superacc_combine_kernel<<<1, 64, 0, as_stream(s)>>>(reinterpret_cast<const long long*>(parts), nparts,
+                                                        status_parts, result);
+    DGB_LAUNCHED();
+    return 0;
+}
+}

@@ -1,0 +1,242 @@
+/* dgb200.h -- C ABI of libdgb200.so: the B200-native (sm_100a) data-parallel core of the Feltor `dg` library.
+ *
+ * This is the drop-in boundary.  Each entry point replaces one overload the reference resolves on
+ * `dg::CudaTag`; the citation next to each declaration names the reference
+ * interface it stands in for (paths relative to the feltor source tree, v8.2.2).
+ *
+ * Conventions
+ *  - All vector/matrix pointers are DEVICE pointers unless the name ends in `_host` / the comment says host.
+ *  - Every call enqueues on `stream` (a cudaStream_t passed as void*; NULL = legacy default stream, which
+ *    is what the reference uses everywhere) and returns asynchronously, except the functions documented
+ *    as synchronous (they return host data, like the reference's dot).
+ *  - Return value: 0 = success, otherwise a DGB_ERR_* code or a cudaError_t value (>0);
+ *    dgb_last_error() returns a thread-local message.  Nothing throws across the boundary; the C++ shim
+ *    (include/dg/backend/b200_dispatch.h) converts non-zero codes into dg::Error like blas1_cuda.cuh:39-41.
+ *  - Like the reference (static scratch buffers in blas1_cuda.cuh:18,33,50) the library is host-thread-affine:
+ *    one host thread per device context.  Workspaces are explicit handles so several may coexist.
+ *  - There is NO CPU fallback: every compute entry point fails with a CUDA error when no sm_100 device is present.
+ */
+#ifndef DGB200_H
+#define DGB200_H
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DGB_API __attribute__((visibility("default")))
+
+#define DGB_BIN_COUNT 39 /* exblas::BIN_COUNT, inc/dg/backend/exblas/config.h:90 */
+
+enum {
+    DGB_OK = 0,
+    DGB_ERR_INVALID = -1,     /* invalid argument (size mismatch, aliasing that the reference forbids, ...) */
+    DGB_ERR_UNSUPPORTED = -2, /* shape outside what the kernels were written for (n > DGB_MAX_N ...) */
+    DGB_ERR_NOTFINITE = -3,   /* dot product met NaN/Inf: maps to dg::Error in blas1.h:161 */
+    DGB_ERR_NOCONVERGE = -4   /* solver hit max_iter: maps to dg::Fail in pcg.h:189 */
+};
+#define DGB_MAX_N 8 /* polynomial coefficients per cell and dimension supported by the block kernels */
+
+/* boundary conditions and directions, same numeric values as inc/dg/enums.h:15-21,97-101 */
+enum { DGB_PER = 0, DGB_DIR = 1, DGB_DIR_NEU = 2, DGB_NEU_DIR = 3, DGB_NEU = 4 };
+enum { DGB_FORWARD = 0, DGB_BACKWARD = 1, DGB_CENTERED = 2 };
+
+typedef void* dgb_stream_t;
+
+/* ---------------------------------------------------------------------------------------------------
+ * runtime (replaces thrust::device_vector allocation/copies used by dg::assign/construct,
+ * inc/dg/backend/blas1_dispatch_shared.h:26-45)
+ * ------------------------------------------------------------------------------------------------- */
+DGB_API int dgb_version(void);
+DGB_API const char* dgb_last_error(void);
+DGB_API int dgb_device_count(int* count);
+DGB_API int dgb_set_device(int device);
+DGB_API int dgb_sm_count(int* count);
+DGB_API int dgb_malloc(void** ptr, size_t bytes);
+DGB_API int dgb_free(void* ptr);
+DGB_API int dgb_malloc_host(void** ptr, size_t bytes); /* pinned */
+DGB_API int dgb_free_host(void* ptr);
+DGB_API int dgb_memcpy_h2d(void* dst, const void* src_host, size_t bytes, dgb_stream_t stream);
+DGB_API int dgb_memcpy_d2h(void* dst_host, const void* src, size_t bytes, dgb_stream_t stream);
+DGB_API int dgb_memcpy_d2d(void* dst, const void* src, size_t bytes, dgb_stream_t stream);
+DGB_API int dgb_memset(void* dst, int value, size_t bytes, dgb_stream_t stream);
+DGB_API int dgb_stream_synchronize(dgb_stream_t stream);
+DGB_API int dgb_device_synchronize(void);
+/* number of kernels this library has launched so far in this process (bench.py's gpu_launches claim) */
+DGB_API long long dgb_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------------
+ * blas1: replaces doSubroutine_dispatch(CudaTag, size, functor, pointers...) inc/dg/backend/blas1_cuda.cuh:88
+ * for the closed set of library functors in inc/dg/subroutines.h:231-384 and inc/dg/topology/multiply.h:18-52.
+ * The arithmetic (order of roundings, explicit FMAs) is the functor's; aliasing between arguments is legal.
+ * The call-site shortcuts of inc/dg/blas1.h (alpha == 0, &x == &y ...) are applied by the host layer above.
+ * ------------------------------------------------------------------------------------------------- */
+DGB_API int dgb_copy(size_t n, const double* x, double* y, dgb_stream_t s);                      /* blas1.h:243  equals */
+DGB_API int dgb_fill(size_t n, double value, double* y, dgb_stream_t s);                         /* blas1.h:243  copy(scalar, y) */
+DGB_API int dgb_scal(size_t n, double* x, double alpha, dgb_stream_t s);                         /* subroutines.h:233 Scal */
+DGB_API int dgb_plus(size_t n, double* x, double alpha, dgb_stream_t s);                         /* subroutines.h:247 Plus */
+DGB_API int dgb_axpby(size_t n, double alpha, const double* x, double beta, double* y, dgb_stream_t s); /* :260 Axpby */
+DGB_API int dgb_axpbyz(size_t n, double alpha, const double* x, double beta, const double* y, double* z,
+                       dgb_stream_t s);                                                          /* blas1.h:382 PairSum */
+DGB_API int dgb_axpbypgz(size_t n, double alpha, const double* x, double beta, const double* y, double gamma,
+                         double* z, dgb_stream_t s);                                             /* :294 Axpbypgz */
+DGB_API int dgb_pointwise_dot(size_t n, double alpha, const double* x1, const double* x2, double beta, double* y,
+                              dgb_stream_t s); /* :313 PointwiseDot; x1==y or x2==y -> :276 AxyPby (blas1.h:413-421) */
+DGB_API int dgb_pointwise_dot_xy(size_t n, const double* x1, const double* x2, double* y, dgb_stream_t s); /* blas1.h:441 */
+DGB_API int dgb_pointwise_dot3(size_t n, double alpha, const double* x1, const double* x2, const double* x3,
+                               double beta, double* y, dgb_stream_t s);                          /* :325 */
+DGB_API int dgb_pointwise_dot2(size_t n, double alpha, const double* x1, const double* y1, double beta,
+                               const double* x2, const double* y2, double gamma, double* z, dgb_stream_t s); /* :336 */
+DGB_API int dgb_pointwise_divide(size_t n, double alpha, const double* x1, const double* x2, double beta, double* y,
+                                 dgb_stream_t s); /* :365 PointwiseDivide; x1==y -> 2-argument overload (blas1.h:501) */
+DGB_API int dgb_pointwise_divide_xy(size_t n, const double* x1, const double* x2, double* y, dgb_stream_t s); /* blas1.h:525 */
+/* TensorMultiply2d (multiply.h:18-32): out_i = lambda * T_ij in_j + mu*out_i.  lambda: vector or NULL (then the
+ * scalar lambda_s); t00..t11: vectors or NULL = the SparseTensor's implicit 1 (diagonal) / 0 (off-diagonal). */
+DGB_API int dgb_tensor_multiply2d(size_t n, const double* lambda, double lambda_s, const double* t00,
+                                  const double* t01, const double* t10, const double* t11, const double* in0,
+                                  const double* in1, double mu, double* out0, double* out1, dgb_stream_t s);
+/* EmbeddedPairSum (subroutines.h:179-204, used by ERKStep runge_kutta.h:35-62):
+ * y = b0*y + sum_s b[s]*k[s], yt = bt0*yt + sum_s bt[s]*k[s];  b, bt, k are HOST arrays (k of device pointers), nk <= 16 */
+DGB_API int dgb_embedded_pair_sum(size_t n, double* y, double* yt, double b0, double bt0, int nk, const double* b_host,
+                                  const double* bt_host, const double* const* k_host, dgb_stream_t s);
+/* blas1::transform with a unary functor of inc/dg/functors.h (y = op(x)); op codes below */
+enum { DGB_OP_EXP = 0, DGB_OP_LN = 1, DGB_OP_SQRT = 2, DGB_OP_INVERT = 3, DGB_OP_ABS = 4, DGB_OP_SQUARE = 5,
+       DGB_OP_INVSQRT = 6 };
+DGB_API int dgb_transform(size_t n, int op, const double* x, double* y, dgb_stream_t s);          /* blas1.h:585 */
+
+/* ---------------------------------------------------------------------------------------------------
+ * exblas dot: replaces doDot_dispatch(CudaTag, status, size, x, y[, z]) inc/dg/backend/blas1_cuda.cuh:30-64
+ * (exdot_gpu, inc/dg/backend/exblas/exdot_cuda.cuh:319-357).
+ * Contract: the exact sum of the individually rounded products  round(x*y)  resp.  round(round(x*w)*y)
+ * accumulated in a 39 x int64 superaccumulator (word i has weight 2^(56*(i-20))), returned NORMALISED
+ * (accumulate.h:267-285) so exblas::cpu::Round / Normalize accept it unchanged, plus the correctly rounded double
+ * (accumulate.h:297-349) computed on the device.  Bit-reproducible for any launch geometry / GPU count.
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct dgb_dot_result {
+    int64_t acc[DGB_BIN_COUNT]; /* normalised superaccumulator */
+    double value;               /* Round(acc) */
+    int32_t status;             /* 0 ok, 1 a product was NaN/Inf (blas1.h:161) */
+    int32_t pad;
+} dgb_dot_result;
+typedef struct dgb_dot_ws dgb_dot_ws; /* device scratch: per-block partial superaccumulators + ticket */
+DGB_API int dgb_dot_ws_create(dgb_dot_ws** ws);
+DGB_API int dgb_dot_ws_destroy(dgb_dot_ws* ws);
+/* asynchronous: result (a DEVICE pointer to dgb_dot_result) is complete when the stream reaches this point.
+ * A NULL operand pointer means the scalar given next to it (dot(1., v)). */
+DGB_API int dgb_exdot2(dgb_dot_ws* ws, size_t n, const double* x, double xs, const double* y, double ys,
+                       dgb_dot_result* result_dev, dgb_stream_t s);
+DGB_API int dgb_exdot3(dgb_dot_ws* ws, size_t n, const double* x, double xs, const double* w, double ws_,
+                       const double* y, double ys, dgb_dot_result* result_dev, dgb_stream_t s);
+/* synchronous convenience = the reference seam: superaccumulator on the host (acc_host[39], may be NULL),
+ * rounded value (may be NULL), *status as the reference sets it.  Returns DGB_ERR_NOTFINITE if status != 0. */
+DGB_API int dgb_dot2(dgb_dot_ws* ws, size_t n, const double* x, const double* y, int64_t* acc_host, double* value,
+                     int* status, dgb_stream_t s);
+DGB_API int dgb_dot3(dgb_dot_ws* ws, size_t n, const double* x, const double* w, const double* y, int64_t* acc_host,
+                     double* value, int* status, dgb_stream_t s);
+/* host-side helpers with the reference's arithmetic (accumulate.h:267-349), for callers that combine
+ * accumulators of std::vector<DVec> / ranks (blas1_dispatch_vector.h:153-176, mpi_accumulate.h:94-125) */
+DGB_API int dgb_superacc_normalize_host(int64_t* acc);
+DGB_API double dgb_superacc_round_host(const int64_t* acc);
+/* device-side combine for multi-GPU: acc[i] = Normalize(sum_r parts[r][i]) then Round; parts = nparts normalised
+ * accumulators (<= 256, mpi_accumulate.h:75-77) contiguous in device memory; result_dev filled like dgb_exdot */
+DGB_API int dgb_superacc_combine(const int64_t* parts_dev, int nparts, const int32_t* status_parts_dev,
+                                 dgb_dot_result* result_dev, dgb_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------------
+ * EllSparseBlockMat / CooSparseBlockMat symv: replaces launch_multiply_kernel(CudaTag, alpha, x, beta, y)
+ * inc/dg/backend/sparseblockmat.h:180-186,349-357 (kernels sparseblockmat_gpu_kernels.cuh:8-354).
+ * y = alpha (1_left (x) M (x) 1_right) x + beta y, fields exactly as sparseblockmat.h:168-177.
+ * Per output element: temp_d = fma-chain over q for block d; y = beta==0 ? 0 : y*beta; y = fma(alpha,temp_d,y)
+ * for d ascending (sparseblockmat_omp_kernels.h:36-50) -- bit-identical to the reference's OpenMP backend.
+ * x must not alias y.  beta == 0 does not read y (NaN is overwritten).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct dgb_ell_host { /* HOST description, fields as sparseblockmat.h:168-177 */
+    int num_rows, num_cols, blocks_per_line, n, left_size, right_size;
+    int num_blocks;      /* data holds num_blocks * n * n doubles */
+    int right_range[2];  /* sparseblockmat.h:175 */
+    const double* data;  /* host */
+    const int* cols_idx; /* host, num_rows*blocks_per_line, -1 = padding (sparseblockmat.h:49) */
+    const int* data_idx; /* host */
+} dgb_ell_host;
+typedef struct dgb_ell dgb_ell; /* device-resident matrix + launch plan (row classification, constant blocks) */
+DGB_API int dgb_ell_create(dgb_ell** m, const dgb_ell_host* host);
+DGB_API int dgb_ell_destroy(dgb_ell* m);
+/* the reference lets applications re-purpose a matrix for another dimension (sparseblockmat.h:139-166) */
+DGB_API int dgb_ell_set_left_size(dgb_ell* m, int left_size);
+DGB_API int dgb_ell_set_right_size(dgb_ell* m, int right_size); /* resets right_range to [0,right_size) */
+DGB_API int dgb_ell_set_right_range(dgb_ell* m, int begin, int end);
+DGB_API int dgb_ell_total_num_rows(const dgb_ell* m, size_t* rows);
+DGB_API int dgb_ell_total_num_cols(const dgb_ell* m, size_t* cols);
+DGB_API int dgb_ell_symv(const dgb_ell* m, double alpha, const double* x, double beta, double* y, dgb_stream_t s);
+/* same arithmetic through the fully general one-thread-per-element kernel (any n, any pattern); A/B testing */
+DGB_API int dgb_ell_symv_generic(const dgb_ell* m, double alpha, const double* x, double beta, double* y,
+                                 dgb_stream_t s);
+
+typedef struct dgb_coo {
+    int num_rows, num_cols, num_entries, n, left_size, right_size;
+    const double* data;  /* device */
+    const int* rows_idx; /* device, num_entries */
+    const int* cols_idx; /* device: index into the pointer table x */
+    const int* data_idx; /* device */
+} dgb_coo;
+/* x = DEVICE array of device pointers, chunk c laid out [q][s][j] (sparseblockmat_omp_kernels.h:370); beta must be 1 */
+DGB_API int dgb_coo_symv(const dgb_coo* m, double alpha, const double* const* x_ptrs_dev, double beta, double* y,
+                         dgb_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------------
+ * CSR spmv: replaces detail::spmv_gpu_kernel (cuSPARSE) inc/dg/backend/sparsematrix_gpu.cuh:190-214 with the
+ * reference OpenMP order (sparsematrix_omp.h:17-52): beta==1: y = fma(alpha*v, x[j], y) sequentially over the
+ * row, else t = sum fma(alpha*v, x[j], t); y = fma(beta, y, t) (beta == 0 does not read y).  Bit-reproducible.
+ * dgb_csr_spmv_planes applies the same 2-D matrix to nplanes planes in ONE launch (Fieldaligned::ePlus/eMinus,
+ * inc/geometries/fieldaligned.h:850-912): y[p] = alpha A x[(p + shift) mod nplanes] + beta y[p].
+ * ------------------------------------------------------------------------------------------------- */
+DGB_API int dgb_csr_spmv(int num_rows, int num_cols, const int* row_offsets, const int* cols, const double* vals,
+                         double alpha, const double* x, double beta, double* y, dgb_stream_t s);
+DGB_API int dgb_csr_spmv_planes(int num_rows, int num_cols, const int* row_offsets, const int* cols,
+                                const double* vals, double alpha, const double* x, double beta, double* y,
+                                int nplanes, int shift, dgb_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------------
+ * Fused Elliptic2d: replaces the 8-kernel composition of Elliptic2d::symv inc/dg/elliptic.h:428-458
+ *   y = alpha/vol * [ -Lx sigma (chi_xx Rx + chi_xy Ry) x - Ly sigma (chi_yx Rx + chi_yy Ry) x
+ *                     + jfactor (Jx + Jy) x ] + beta y
+ * by ONE kernel that replays the reference's rounding sequence in registers (bit-identical result).
+ * The six matrices are the ones Elliptic2d builds (elliptic.h:285-290); they must have the near-diagonal
+ * block structure dx.h produces (checked at creation; other matrices -> DGB_ERR_UNSUPPORTED, use dgb_ell_symv).
+ * Vector pointers set with the setters are BORROWED (the host layer owns them, like m_sigma/m_vol/m_chi).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct dgb_elliptic2d dgb_elliptic2d;
+/* matrices are given on the HOST (the plan uploads what it needs) */
+DGB_API int dgb_elliptic2d_create(dgb_elliptic2d** plan, const dgb_ell_host* leftx, const dgb_ell_host* lefty,
+                                  const dgb_ell_host* rightx, const dgb_ell_host* righty, const dgb_ell_host* jumpx,
+                                  const dgb_ell_host* jumpy, double jfactor, int chi_weight_jump);
+DGB_API int dgb_elliptic2d_destroy(dgb_elliptic2d* plan);
+DGB_API int dgb_elliptic2d_set_sigma(dgb_elliptic2d* plan, const double* sigma);  /* m_sigma (elliptic.h:327) */
+DGB_API int dgb_elliptic2d_set_vol(dgb_elliptic2d* plan, const double* vol);      /* m_vol; NULL = 1 (Cartesian) */
+DGB_API int dgb_elliptic2d_set_chi(dgb_elliptic2d* plan, const double* xx, const double* xy, const double* yx,
+                                   const double* yy);                             /* m_chi; NULL = identity entry */
+DGB_API int dgb_elliptic2d_set_jfactor(dgb_elliptic2d* plan, double jfactor);
+DGB_API int dgb_elliptic2d_symv(dgb_elliptic2d* plan, double alpha, const double* x, double beta, double* y,
+                                dgb_stream_t s);
+/* the unfused composition on the same plan (6 Ell symv + 2 blas1), kept for A/B tests and as the general path */
+DGB_API int dgb_elliptic2d_symv_unfused(dgb_elliptic2d* plan, double alpha, const double* x, double beta, double* y,
+                                        dgb_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------------
+ * PCG: replaces PCG<DVec>::solve inc/dg/pcg.h:136-195 for A = Elliptic2d plan, vector preconditioner P and
+ * weights W.  Same recurrences, same exact dots, alpha/beta from the rounded doubles; all scalars stay on the
+ * device, the host only polls a convergence flag every `check_every` iterations.  *iterations receives what the
+ * reference returns (max_iter when not converged -> also returns DGB_ERR_NOCONVERGE).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct dgb_pcg dgb_pcg;
+DGB_API int dgb_pcg_create(dgb_pcg** pcg, size_t n);
+DGB_API int dgb_pcg_destroy(dgb_pcg* pcg);
+DGB_API int dgb_pcg_solve_elliptic2d(dgb_pcg* pcg, dgb_elliptic2d* A, double* x, const double* b, const double* P,
+                                     const double* W, double eps, double nrmb_correction, int test_frequency,
+                                     int max_iter, int* iterations, dgb_stream_t s);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DGB200_H */
