@@ -185,6 +185,32 @@ DGB_API int dgb_coo_symv(const dgb_coo* m, double alpha, const double* const* x_
                          dgb_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------------
+ * Topology (HOST-side setup, no device work): what the applications obtain from inc/dg/topology of the reference.
+ * The coefficients are bit-identical to the reference's (tests/test_topology.py).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct dgb_grid { /* aRealTopology<double,Nd>, inc/dg/topology/grid.h:92; x is the fastest dimension */
+    int ndim;
+    double x0[3], x1[3];
+    int n[3], N[3], bc[3];
+} dgb_grid;
+typedef struct dgb_ellh dgb_ellh; /* host EllSparseBlockMat owning its arrays */
+DGB_API int dgb_topo_dlt(int which, int n, double* out_host); /* dlt.h: 0 abscissas, 1 weights, 2 backward, 3 forward */
+DGB_API int dgb_topo_size(const dgb_grid* g, size_t* size);
+DGB_API int dgb_topo_abscissas(const dgb_grid* g, int axis, double* out_host); /* grid.h:128 */
+DGB_API int dgb_topo_weights1d(const dgb_grid* g, int axis, double* out_host); /* grid.h:155 */
+DGB_API int dgb_topo_weights(const dgb_grid* g, double* out_host);             /* weights.h:60 create::weights */
+DGB_API int dgb_topo_dx(dgb_ellh** m, int n, int N, double h, int bc, int dir); /* dx.h:389 dx_normed */
+DGB_API int dgb_topo_jump(dgb_ellh** m, int n, int N, double h, int bc);        /* dx.h:301 jump */
+DGB_API int dgb_topo_derivative(dgb_ellh** m, const dgb_grid* g, int coord, int bc, int dir); /* derivatives.h:47 */
+DGB_API int dgb_topo_jump_nd(dgb_ellh** m, const dgb_grid* g, int coord, int bc);            /* derivatives.h:68 */
+DGB_API int dgb_topo_fast_projection(dgb_ellh** m, const dgb_grid* g, int coord, int dividen, int divideN);
+                                                                                /* fast_interpolation.h:326 */
+DGB_API int dgb_topo_fast_interpolation(dgb_ellh** m, const dgb_grid* g, int coord, int multiplyn, int multiplyN);
+                                                                                /* fast_interpolation.h:315 */
+DGB_API int dgb_ellh_view(const dgb_ellh* m, dgb_ell_host* view); /* pointers stay owned by m */
+DGB_API int dgb_ellh_destroy(dgb_ellh* m);
+
+/* ---------------------------------------------------------------------------------------------------
  * CSR spmv: replaces detail::spmv_gpu_kernel (cuSPARSE) inc/dg/backend/sparsematrix_gpu.cuh:190-214 with the
  * reference OpenMP order (sparsematrix_omp.h:17-52): beta==1: y = fma(alpha*v, x[j], y) sequentially over the
  * row, else t = sum fma(alpha*v, x[j], t); y = fma(beta, y, t) (beta == 0 does not read y).  Bit-reproducible.

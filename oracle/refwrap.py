@@ -60,6 +60,8 @@ def grid(x0, x1, n, N, bc):
     g.ndim = len(N)
     for u in range(g.ndim):
         g.x0[u], g.x1[u], g.n[u], g.N[u], g.bc[u] = x0[u], x1[u], n, N[u], bc[u]
+    if g.ndim == 3:
+        g.n[2] = 1  # dg::CartesianGrid3d has one coefficient per cell in z (inc/dg/topology/grid.h:738)
     return g
 
 
