@@ -1,0 +1,192 @@
+// dg::Elliptic2d: y = alpha/vol [ -Lx sigma (chi_xx Rx + chi_xy Ry) - Ly sigma (chi_yx Rx + chi_yy Ry) + jfactor (Jx + Jy) ] x + beta y
+// Replaces the 8-launch composition of Elliptic2d::symv (inc/dg/elliptic.h:428-458).
+//  * elliptic2d_symv_unfused: the same composition on our kernels (6 Ell symv + tensor multiply + divide) --
+//    the general path (any chi tensor, chi-weighted jumps, any matrix structure).
+//  * elliptic2d_fused_kernel: ONE pass.  A CTA owns a tile of TX x TY cells; it stages x and sigma (with a halo) in
+//    shared memory, computes the fluxes tx = sigma Rx x, ty = sigma Ry x for the tile plus the one-cell ring the
+//    adjoint derivative reaches into, and then one thread per cell replays the reference's rounding sequence for
+//    its n x n outputs in registers.  HBM traffic: read x, read sigma, write y (24 B/dof, +8 if beta != 0, +8 vol).
+//    The n x n blocks of interior rows are kernel parameters (constant-bank DFMA operands); boundary cells look
+//    their blocks up in global memory.
+#include "elliptic.cuh"
+#include <cstdlib>
+
+namespace dgb {
+
+// ------------------------------------------------------------------------------------------------ unfused
+extern "C" int dgb_tensor_multiply2d(size_t, const double*, double, const double*, const double*, const double*,
+                                     const double*, const double*, const double*, double, double*, double*, dgb_stream_t);
+extern "C" int dgb_axpbypgz(size_t, double, const double*, double, const double*, double, double*, dgb_stream_t);
+
+__global__ void __launch_bounds__(256)
+elliptic_finish_kernel(size_t n, double alpha, const double* __restrict__ temp, const double* __restrict__ vol,
+                       double beta, double* __restrict__ y) {
+    // pointwiseDivide(alpha, temp, vol, beta, y) (elliptic.h:458, functor subroutines.h:376); beta == 0 does not
+    // read y (the only deliberate deviation -- NaN in y is overwritten instead of propagated)
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double q = vol ? __ddiv_rn(temp[i], vol[i]) : temp[i];
+        double t = beta == 0. ? 0. : __dmul_rn(y[i], beta);
+        y[i] = __fma_rn(alpha, q, t);
+    }
+}
+
+static int ensure_temps(Elliptic2dPlan& p) {
+    if (p.tx) return 0;
+    DGB_CUDA(cudaMalloc(&p.tx, p.size * sizeof(double)));
+    DGB_CUDA(cudaMalloc(&p.ty, p.size * sizeof(double)));
+    DGB_CUDA(cudaMalloc(&p.t, p.size * sizeof(double)));
+    return 0;
+}
+
+static int elliptic2d_unfused(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st) {
+    int e = ensure_temps(p);
+    if (e) return e;
+    dgb_stream_t s = reinterpret_cast<dgb_stream_t>(st);
+    const size_t n = p.size;
+    if ((e = ell_symv(p.rightx, 1., x, 0., p.tx, st, false))) return e;                    // elliptic.h:431
+    if ((e = ell_symv(p.righty, 1., x, 0., p.ty, st, false))) return e;                    // :432
+    if ((e = dgb_tensor_multiply2d(n, p.sigma, 1., p.chi[0], p.chi[1], p.chi[2], p.chi[3], p.tx, p.ty, 0., p.tx, p.ty, s))) return e;  // :435
+    if ((e = ell_symv(p.lefty, 1., p.ty, 0., p.t, st, false))) return e;                   // :438
+    if ((e = ell_symv(p.leftx, -1., p.tx, -1., p.t, st, false))) return e;                 // :439
+    if (p.jfactor != 0.) {                                                                 // :442
+        if (p.chi_weight_jump) {
+            if ((e = ell_symv(p.jumpx, p.jfactor, x, 0., p.tx, st, false))) return e;
+            if ((e = ell_symv(p.jumpy, p.jfactor, x, 0., p.ty, st, false))) return e;
+            if ((e = dgb_tensor_multiply2d(n, p.sigma, 1., p.chi[0], p.chi[1], p.chi[2], p.chi[3], p.tx, p.ty, 0., p.tx, p.ty, s))) return e;
+            if ((e = dgb_axpbypgz(n, 1., p.tx, 1., p.ty, 1., p.t, s))) return e;
+        } else {
+            if ((e = ell_symv(p.jumpx, p.jfactor, x, 1., p.t, st, false))) return e;       // :454
+            if ((e = ell_symv(p.jumpy, p.jfactor, x, 1., p.t, st, false))) return e;       // :455
+        }
+    }
+    size_t want = (n + 255) / 256, cap = (size_t)sm_count() * 8;
+    elliptic_finish_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, st>>>(n, alpha, p.t, p.vol, beta, y);  // :458
+    DGB_LAUNCHED();
+    return 0;
+}
+
+int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
+                    bool force_unfused) {
+    if (!p.sigma) { set_error("dgb_elliptic2d_symv: sigma has not been set"); return DGB_ERR_INVALID; }
+    if (x == y) { set_error("dgb_elliptic2d_symv: x must not alias y"); return DGB_ERR_INVALID; }
+    static int env_unfused = -1;
+    if (env_unfused < 0) { const char* e = getenv("DGB_ELLIPTIC_UNFUSED"); env_unfused = (e && atoi(e)) ? 1 : 0; }
+    bool identity_chi = !p.chi[0] && !p.chi[1] && !p.chi[2] && !p.chi[3];
+    if (!force_unfused && !env_unfused && p.fusable && identity_chi && !p.chi_weight_jump)
+        return elliptic2d_fused_launch(p, alpha, x, beta, y, st);
+    return elliptic2d_unfused(p, alpha, x, beta, y, st);
+}
+
+// structure check for the fused kernel: near-diagonal pattern with |offset| <= 1, boundary slots either padding or
+// the (periodically wrapped) neighbour
+static bool dx_like(const EllDev& m, int expect_bpl, bool& wrap) {
+    if (!m.has_pattern || m.bpl != expect_bpl) return false;
+    wrap = false;
+    for (int d = 0; d < m.bpl; d++)
+        if (m.off[d] < -1 || m.off[d] > 1) return false;
+    if (m.num_rows != m.num_cols) return false;
+    for (int i = 0; i < m.num_rows; i++) {
+        if (i >= m.i_lo && i < m.i_hi) continue;
+        for (int d = 0; d < m.bpl; d++) {
+            int c = m.h_cols[(size_t)i * m.bpl + d];
+            if (c == -1) continue;
+            int want = i + m.off[d];
+            if (want < 0 || want >= m.num_rows) { want = (want + m.num_rows) % m.num_rows; wrap = true; }
+            if (c != want) return false;
+        }
+    }
+    return true;
+}
+
+static void analyse(Elliptic2dPlan& p) {
+    p.fusable = false;
+    const int n = p.rightx.n;
+    if (n < 2 || n > 4) return;
+    EllDev* xm[3] = {&p.rightx, &p.leftx, &p.jumpx};
+    EllDev* ym[3] = {&p.righty, &p.lefty, &p.jumpy};
+    int bder = p.rightx.bpl;
+    if (bder != 2 && bder != 3) return;
+    bool wx[3], wy[3];
+    for (int k = 0; k < 3; k++) {
+        int eb = k == 2 ? 3 : bder;
+        if (!dx_like(*xm[k], eb, wx[k]) || !dx_like(*ym[k], eb, wy[k])) return;
+        if (xm[k]->n != n || ym[k]->n != n) return;
+        if (xm[k]->right != 1 || ym[k]->left != 1) return;
+        if (xm[k]->rr0 != 0 || xm[k]->rr1 != 1 || ym[k]->rr0 != 0 || ym[k]->rr1 != ym[k]->right) return;
+    }
+    const int Nx = p.rightx.num_rows, Ny = p.righty.num_rows;
+    for (int k = 0; k < 3; k++) {
+        if (xm[k]->num_rows != Nx || ym[k]->num_rows != Ny) return;
+        if (xm[k]->left != Ny * n || ym[k]->right != Nx * n) return;
+    }
+    if (Nx < 5 || Ny < 5) return;
+    // a periodic family wraps in all three matrices; a non-periodic one in none.  (A matrix whose stencil never
+    // leaves the domain at a boundary row -- e.g. forward dx at row 0 -- reports no wrap there, so compare on the
+    // jump matrix, which reaches both sides.)
+    p.wrapx = wx[2]; p.wrapy = wy[2];
+    for (int k = 0; k < 2; k++) {
+        if (wx[k] && !p.wrapx) return;
+        if (wy[k] && !p.wrapy) return;
+    }
+    p.n = n; p.Nx = Nx; p.Ny = Ny; p.bder = bder;
+    p.fusable = true;
+}
+
+}  // namespace dgb
+
+using namespace dgb;
+
+extern "C" {
+int dgb_elliptic2d_create(dgb_elliptic2d** out, const dgb_ell_host* leftx, const dgb_ell_host* lefty,
+                          const dgb_ell_host* rightx, const dgb_ell_host* righty, const dgb_ell_host* jumpx,
+                          const dgb_ell_host* jumpy, double jfactor, int chi_weight_jump) {
+    Elliptic2dPlan* p = new Elliptic2dPlan();
+    const dgb_ell_host* hs[6] = {leftx, lefty, rightx, righty, jumpx, jumpy};
+    EllDev* ds[6] = {&p->leftx, &p->lefty, &p->rightx, &p->righty, &p->jumpx, &p->jumpy};
+    int e = 0;
+    for (int k = 0; k < 6 && !e; k++) e = ell_upload(*ds[k], hs[k]);
+    if (!e) {
+        p->size = p->rightx.total_cols();
+        for (int k = 0; k < 6; k++)
+            if (ds[k]->total_rows() != p->size || ds[k]->total_cols() != p->size) {
+                set_error("dgb_elliptic2d_create: matrix %d is not square of size %zu", k, p->size);
+                e = DGB_ERR_INVALID;
+            }
+    }
+    if (e) { for (int k = 0; k < 6; k++) ell_release(*ds[k]); delete p; return e; }
+    p->jfactor = jfactor;
+    p->chi_weight_jump = chi_weight_jump != 0;
+    analyse(*p);
+    *out = reinterpret_cast<dgb_elliptic2d*>(p);
+    return 0;
+}
+int dgb_elliptic2d_destroy(dgb_elliptic2d* h) {
+    Elliptic2dPlan* p = reinterpret_cast<Elliptic2dPlan*>(h);
+    if (!p) return 0;
+    EllDev* ds[6] = {&p->leftx, &p->lefty, &p->rightx, &p->righty, &p->jumpx, &p->jumpy};
+    for (int k = 0; k < 6; k++) ell_release(*ds[k]);
+    cudaFree(p->tx); cudaFree(p->ty); cudaFree(p->t);
+    delete p;
+    return 0;
+}
+int dgb_elliptic2d_set_sigma(dgb_elliptic2d* h, const double* sigma) { reinterpret_cast<Elliptic2dPlan*>(h)->sigma = sigma; return 0; }
+int dgb_elliptic2d_set_vol(dgb_elliptic2d* h, const double* vol) { reinterpret_cast<Elliptic2dPlan*>(h)->vol = vol; return 0; }
+int dgb_elliptic2d_set_chi(dgb_elliptic2d* h, const double* xx, const double* xy, const double* yx, const double* yy) {
+    Elliptic2dPlan* p = reinterpret_cast<Elliptic2dPlan*>(h);
+    p->chi[0] = xx; p->chi[1] = xy; p->chi[2] = yx; p->chi[3] = yy;
+    return 0;
+}
+int dgb_elliptic2d_set_jfactor(dgb_elliptic2d* h, double jfactor) { reinterpret_cast<Elliptic2dPlan*>(h)->jfactor = jfactor; return 0; }
+int dgb_elliptic2d_size(const dgb_elliptic2d* h, size_t* size, int* fused) {
+    const Elliptic2dPlan* p = reinterpret_cast<const Elliptic2dPlan*>(h);
+    if (size) *size = p->size;
+    if (fused) *fused = p->fusable ? 1 : 0;
+    return 0;
+}
+int dgb_elliptic2d_symv(dgb_elliptic2d* h, double alpha, const double* x, double beta, double* y, dgb_stream_t s) {
+    return elliptic2d_symv(*reinterpret_cast<Elliptic2dPlan*>(h), alpha, x, beta, y, as_stream(s), false);
+}
+int dgb_elliptic2d_symv_unfused(dgb_elliptic2d* h, double alpha, const double* x, double beta, double* y, dgb_stream_t s) {
+    return elliptic2d_symv(*reinterpret_cast<Elliptic2dPlan*>(h), alpha, x, beta, y, as_stream(s), true);
+}
+}

@@ -1,0 +1,26 @@
+// Internal: Elliptic2d plan shared by elliptic.cu, pcg.cu and multigrid.cu.
+#pragma once
+#include "ell.cuh"
+
+namespace dgb {
+
+struct Elliptic2dPlan {
+    EllDev leftx, lefty, rightx, righty, jumpx, jumpy;
+    double jfactor = 1.;
+    bool chi_weight_jump = false;
+    const double* sigma = nullptr;  // borrowed
+    const double* vol = nullptr;    // borrowed, nullptr = 1
+    const double* chi[4] = {nullptr, nullptr, nullptr, nullptr};  // xx, xy, yx, yy; nullptr = identity entry
+    double *tx = nullptr, *ty = nullptr, *t = nullptr;  // owned temporaries of the unfused path
+    size_t size = 0;
+    int n = 0, Nx = 0, Ny = 0;
+    bool fusable = false;  // matrices have the dx.h structure the fused kernel was written for
+    int bder = 0;          // blocks per line of the four derivative matrices (2 or 3)
+    bool wrapx = false, wrapy = false;
+};
+
+int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
+                    bool force_unfused);
+int elliptic2d_fused_launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st);
+
+}  // namespace dgb

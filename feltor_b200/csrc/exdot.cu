@@ -5,11 +5,12 @@
 #include "superacc.cuh"
 #include <cmath>
 #include <cstring>
+#include <cstdlib>
 
 namespace dgb {
 
 struct DotWs {
-    sa::DotSlot slot;      // partials / status / ticket / (result unused here)
+    sa::DotSlot slot;      // global accumulators / status / ticket / (result unused here)
     dgb_dot_result* result;  // default device result record
     dgb_dot_result* host_result;  // pinned
     int max_blocks;
@@ -91,8 +92,8 @@ __global__ void __launch_bounds__(64) superacc_combine_kernel(const long long* p
     __shared__ long long acc[sa::BINS + 1];
     if (threadIdx.x < sa::BINS) acc[threadIdx.x] = 0;
     __syncthreads();
-    for (int b0 = 0; b0 < nparts; b0 += 128) {
-        int b1 = min(b0 + 128, nparts);
+    for (int b0 = 0; b0 < nparts; b0 += 64) {  // 65 normalised words (< 2^56 each) cannot overflow int64
+        int b1 = min(b0 + 64, nparts);
         if (threadIdx.x < sa::BINS) {
             long long sum = acc[threadIdx.x];
             for (int b = b0; b < b1; b++) sum += parts[(size_t)b * sa::BINS + threadIdx.x];
@@ -117,7 +118,13 @@ static int dot_grid(size_t n) {
     size_t per_block = (size_t)DOT_THREADS * 8;  // 4 double2 per thread per trip
     size_t want = (n + per_block - 1) / per_block;
     if (want == 0) want = 1;
-    size_t cap = (size_t)sm_count() * 6;
+    static int per_sm = 0;
+    if (per_sm == 0) {
+        const char* e = getenv("DGB_DOT_BLOCKS_PER_SM");  // tuning knob for experiments
+        per_sm = e ? atoi(e) : 4;
+        if (per_sm < 1) per_sm = 1;
+    }
+    size_t cap = (size_t)sm_count() * per_sm;
     return (int)(want < cap ? want : cap);
 }
 
@@ -195,9 +202,10 @@ int dgb_dot_ws_create(dgb_dot_ws** out) {
     DotWs* ws = new DotWs();
     ws->max_blocks = 2048;
     ws->nslots = 4;  // fused kernels may carry up to 4 simultaneous dots
-    size_t nb = (size_t)ws->max_blocks * ws->nslots;
-    DGB_CUDA(cudaMalloc(&ws->slot.partials, nb * sa::BINS * sizeof(long long)));
-    DGB_CUDA(cudaMalloc(&ws->slot.block_status, nb * sizeof(int)));
+    DGB_CUDA(cudaMalloc(&ws->slot.gacc, ws->nslots * sa::BINS * sizeof(long long)));
+    DGB_CUDA(cudaMemset(ws->slot.gacc, 0, ws->nslots * sa::BINS * sizeof(long long)));
+    DGB_CUDA(cudaMalloc(&ws->slot.gstatus, ws->nslots * sizeof(int)));
+    DGB_CUDA(cudaMemset(ws->slot.gstatus, 0, ws->nslots * sizeof(int)));
     DGB_CUDA(cudaMalloc(&ws->slot.ticket, ws->nslots * sizeof(unsigned int)));
     DGB_CUDA(cudaMemset(ws->slot.ticket, 0, ws->nslots * sizeof(unsigned int)));
     DGB_CUDA(cudaMalloc(&ws->result, ws->nslots * sizeof(dgb_dot_result)));
@@ -210,8 +218,8 @@ int dgb_dot_ws_create(dgb_dot_ws** out) {
 int dgb_dot_ws_destroy(dgb_dot_ws* p) {
     DotWs* ws = reinterpret_cast<DotWs*>(p);
     if (!ws) return 0;
-    cudaFree(ws->slot.partials);
-    cudaFree(ws->slot.block_status);
+    cudaFree(ws->slot.gacc);
+    cudaFree(ws->slot.gstatus);
     cudaFree(ws->slot.ticket);
     cudaFree(ws->result);
     cudaFreeHost(ws->host_result);

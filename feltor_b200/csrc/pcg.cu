@@ -1,0 +1,306 @@
+// dg::PCG<DVec>::solve (inc/dg/pcg.h:136-195) for A = Elliptic2d plan, vector preconditioner P, weights W.
+// Same recurrences and the same exact (superaccumulator) dots as the reference, restructured so that one iteration
+// is three launches and 128 B/dof of HBM traffic instead of ~46 vector passes:
+//   K1  ap = A p  fused with dot(p,W,ap);   its last block computes alpha = nrmzr_old / pAp        (pcg.h:165-166)
+//   K2  x += alpha p; r -= alpha ap; z = P r -> ap; dot(r,W,r) and dot(z,W,r) in the same pass;
+//       its last blocks test ||r||_W < tol and compute beta = nrmzr_new / nrmzr_old               (pcg.h:167-181)
+//   K3  p = z + beta p                                                                             (pcg.h:182)
+// All scalars live in a PcgState record on the device.  The host enqueues batches of iterations and reads the
+// record once per batch; after convergence the remaining launches of a batch exit at their first instruction, so
+// x, r and the iteration count are exactly those of the reference's loop exit.
+#include "elliptic.cuh"
+#include "pcg.cuh"
+#include <cmath>
+#include <cstdlib>
+
+namespace dgb {
+
+constexpr int PCG_THREADS = 256;
+constexpr int PCG_WARPS = PCG_THREADS / 32;
+
+struct Pcg {
+    size_t n = 0;
+    double *r = nullptr, *p = nullptr, *ap = nullptr;
+    PcgState* st = nullptr;       // device
+    PcgState* st_host = nullptr;  // pinned
+    sa::DotSlot slot;             // 4 slots: 0 pAp, 1 rWr, 2 zWr, 3 setup dots
+    dgb_dot_result* results = nullptr;
+    dgb_dot_result* results_host = nullptr;
+    int check_every = 8;
+};
+
+// -------------------------------------------------------------------------------------------- setup kernels
+// generic 3-operand exact dot into slot `si`; finisher hook selected by MODE
+//   MODE 0: none (host reads results[si])
+//   MODE 1: nrmzr_old = value                       (pcg.h:160)
+//   MODE 2: pAp/alpha                               (generic-operator path of K1)
+template <int MODE>
+__global__ void __launch_bounds__(PCG_THREADS)
+pcg_dot3_kernel(size_t n, const double* __restrict__ x, const double* __restrict__ w, const double* __restrict__ y,
+                sa::DotSlot slot, int si, PcgState* st) {
+    __shared__ long long smem[PCG_WARPS * sa::BINS];
+    if (MODE == 2 && st->done) return;
+    sa::block_init<PCG_WARPS>(smem);
+    long long* my = smem + (threadIdx.x >> 5) * sa::BINS;
+    sa::Fpe fpe;
+    fpe.clear();
+    int bad = 0;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double pr = __dmul_rn(__dmul_rn(x[i], w[i]), y[i]);
+        if (!isfinite(pr)) { bad = 1; pr = 0.; }
+        fpe.add(pr, my);
+    }
+    fpe.flush(my);
+    if (sa::block_finish<PCG_WARPS>(smem, bad, slot, si) && threadIdx.x == 0) {
+        const dgb_dot_result* r = slot.result + si;
+        if (MODE == 1) { st->nrmzr_old = r->value; if (r->status) { st->status = 1; st->done = 1; } }
+        if (MODE == 2) pcg_after_pAp(st, r);
+    }
+}
+
+// K2 (pcg.h:167-181)
+template <bool CHECK>
+__global__ void __launch_bounds__(PCG_THREADS)
+pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ ap, double* __restrict__ x,
+                  double* __restrict__ r, const double* __restrict__ P, const double* __restrict__ W, PcgState* st,
+                  sa::DotSlot slot, int iter) {
+    __shared__ long long smem[2 * PCG_WARPS * sa::BINS];
+    if (st->done) return;
+    const double alpha = st->alpha, malpha = -alpha;
+    sa::block_init<2 * PCG_WARPS>(smem);
+    long long* my_rr = smem + (threadIdx.x >> 5) * sa::BINS;
+    long long* my_zr = smem + (PCG_WARPS + (threadIdx.x >> 5)) * sa::BINS;
+    sa::Fpe frr, fzr;
+    frr.clear();
+    fzr.clear();
+    int bad = 0;
+    const size_t T = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nvec = n / 2;
+    for (size_t i = tid; i < nvec; i += T) {
+        double2 pv = ld2(p + 2 * i), av = ld2(ap + 2 * i), xv = ld2(x + 2 * i), rv = ld2(r + 2 * i), Pv = ld2(P + 2 * i),
+                Wv = ld2(W + 2 * i);
+        // Axpby(alpha,1): y = y*1; y = fma(alpha, x, y)   (subroutines.h:260-274)
+        xv.x = __fma_rn(alpha, pv.x, __dmul_rn(xv.x, 1.));
+        xv.y = __fma_rn(alpha, pv.y, __dmul_rn(xv.y, 1.));
+        rv.x = __fma_rn(malpha, av.x, __dmul_rn(rv.x, 1.));
+        rv.y = __fma_rn(malpha, av.y, __dmul_rn(rv.y, 1.));
+        double2 z = make_double2(__dmul_rn(Pv.x, rv.x), __dmul_rn(Pv.y, rv.y));  // symv(P, r, ap) == P*r
+        st2(x + 2 * i, xv);
+        st2(r + 2 * i, rv);
+        st2(ap + 2 * i, z);
+        if (CHECK) {
+            double a0 = __dmul_rn(__dmul_rn(rv.x, Wv.x), rv.x), a1 = __dmul_rn(__dmul_rn(rv.y, Wv.y), rv.y);
+            if (!isfinite(a0)) { bad = 1; a0 = 0.; }
+            if (!isfinite(a1)) { bad = 1; a1 = 0.; }
+            frr.add(a0, my_rr);
+            frr.add(a1, my_rr);
+        }
+        double b0 = __dmul_rn(__dmul_rn(z.x, Wv.x), rv.x), b1 = __dmul_rn(__dmul_rn(z.y, Wv.y), rv.y);
+        if (!isfinite(b0)) { bad = 1; b0 = 0.; }
+        if (!isfinite(b1)) { bad = 1; b1 = 0.; }
+        fzr.add(b0, my_zr);
+        fzr.add(b1, my_zr);
+    }
+    if ((n & 1) && tid == 0) {
+        size_t i = n - 1;
+        double xs = __fma_rn(alpha, p[i], __dmul_rn(x[i], 1.));
+        double rs = __fma_rn(malpha, ap[i], __dmul_rn(r[i], 1.));
+        double z = __dmul_rn(P[i], rs);
+        x[i] = xs; r[i] = rs; ap[i] = z;
+        if (CHECK) {
+            double a0 = __dmul_rn(__dmul_rn(rs, W[i]), rs);
+            if (!isfinite(a0)) { bad = 1; a0 = 0.; }
+            frr.add(a0, my_rr);
+        }
+        double b0 = __dmul_rn(__dmul_rn(z, W[i]), rs);
+        if (!isfinite(b0)) { bad = 1; b0 = 0.; }
+        fzr.add(b0, my_zr);
+    }
+    if (CHECK) {
+        frr.flush(my_rr);
+        if (sa::block_finish<PCG_WARPS>(smem, bad, slot, 1) && threadIdx.x == 0) {
+            const dgb_dot_result* rr = slot.result + 1;
+            double res = __dsqrt_rn(rr->value);  // pcg.h:171
+            st->res = res;
+            if (rr->status) { st->status = 1; st->done = 1; st->iter = iter; }
+            else if (res < st->tol) { st->done = 1; st->iter = iter; }  // pcg.h:177
+        }
+        __syncthreads();
+    }
+    fzr.flush(my_zr);
+    if (sa::block_finish<PCG_WARPS>(smem + PCG_WARPS * sa::BINS, bad, slot, 2) && threadIdx.x == 0) {
+        const dgb_dot_result* zr = slot.result + 2;
+        double nw = zr->value;                         // pcg.h:181
+        st->beta = __ddiv_rn(nw, st->nrmzr_old);       // pcg.h:182
+        st->nrmzr_old = nw;                            // pcg.h:183
+        st->cur = iter;
+        if (zr->status) { st->status = 1; st->done = 1; st->iter = iter; }
+    }
+}
+
+// K3 (pcg.h:182): axpby(1, ap, beta, p): p = p*beta; p = fma(1, ap, p)
+__global__ void __launch_bounds__(PCG_THREADS)
+pcg_direction_kernel(size_t n, const double* __restrict__ z, double* __restrict__ p, const PcgState* st) {
+    if (st->done) return;
+    const double beta = st->beta;
+    const size_t T = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nvec = n / 2;
+    for (size_t i = tid; i < nvec; i += T) {
+        double2 zv = ld2(z + 2 * i), pv = ld2(p + 2 * i);
+        pv.x = __fma_rn(1., zv.x, __dmul_rn(pv.x, beta));
+        pv.y = __fma_rn(1., zv.y, __dmul_rn(pv.y, beta));
+        st2(p + 2 * i, pv);
+    }
+    if ((n & 1) && tid == 0) p[n - 1] = __fma_rn(1., z[n - 1], __dmul_rn(p[n - 1], beta));
+}
+
+// r = b - r (axpby(1, b, -1, r), pcg.h:156) ; p = P*r (pcg.h:159)
+__global__ void __launch_bounds__(PCG_THREADS)
+pcg_residual_kernel(size_t n, const double* __restrict__ b, double* __restrict__ r) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        r[i] = __fma_rn(1., b[i], __dmul_rn(r[i], -1.));
+}
+__global__ void __launch_bounds__(PCG_THREADS)
+pcg_precond_kernel(size_t n, const double* __restrict__ P, const double* __restrict__ r, double* __restrict__ p) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x)
+        p[i] = __dmul_rn(P[i], r[i]);
+}
+
+static unsigned grid_for(size_t n, int per_thread) {
+    size_t want = (n + (size_t)PCG_THREADS * per_thread - 1) / ((size_t)PCG_THREADS * per_thread);
+    if (want == 0) want = 1;
+    size_t cap = (size_t)sm_count() * 4;
+    return (unsigned)(want < cap ? want : cap);
+}
+
+static int fetch_state(Pcg& s, cudaStream_t st) {
+    DGB_CUDA(cudaMemcpyAsync(s.st_host, s.st, sizeof(PcgState), cudaMemcpyDeviceToHost, st));
+    DGB_CUDA(cudaStreamSynchronize(st));
+    return 0;
+}
+static int fetch_result(Pcg& s, int si, cudaStream_t st) {
+    DGB_CUDA(cudaMemcpyAsync(s.results_host + si, s.results + si, sizeof(dgb_dot_result), cudaMemcpyDeviceToHost, st));
+    DGB_CUDA(cudaStreamSynchronize(st));
+    if (s.results_host[si].status) {
+        set_error("dot product failed since one of the inputs contains NaN or Inf");
+        return DGB_ERR_NOTFINITE;
+    }
+    return 0;
+}
+
+int pcg_solve(Pcg& s, Elliptic2dPlan& A, double* x, const double* b, const double* P, const double* W, double eps,
+              double nrmb_correction, int test_frequency, int max_iter, int* iterations, cudaStream_t st) {
+    const size_t n = s.n;
+    if (A.size != n) { set_error("dgb_pcg_solve: operator size %zu != workspace size %zu", A.size, n); return DGB_ERR_INVALID; }
+    if (test_frequency < 1) { set_error("dgb_pcg_solve: test_frequency must be >= 1"); return DGB_ERR_INVALID; }
+    int e;
+    const unsigned g1 = grid_for(n, 4);
+    // pcg.h:140  nrmb = sqrt(dot(b, W, b))
+    pcg_dot3_kernel<0><<<g1, PCG_THREADS, 0, st>>>(n, b, W, b, s.slot, 3, s.st);
+    DGB_LAUNCHED();
+    if ((e = fetch_result(s, 3, st))) return e;
+    const double nrmb = std::sqrt(s.results_host[3].value);
+    const double tol = eps * (nrmb + nrmb_correction);
+    if (nrmb == 0) {  // pcg.h:150-154
+        DGB_CUDA(cudaMemsetAsync(x, 0, n * sizeof(double), st));
+        *iterations = 0;
+        return 0;
+    }
+    PcgState init{};
+    init.tol = tol;
+    DGB_CUDA(cudaMemcpyAsync(s.st, &init, sizeof(PcgState), cudaMemcpyHostToDevice, st));
+    if ((e = elliptic2d_symv(A, 1., x, 0., s.r, st, false))) return e;      // pcg.h:155
+    pcg_residual_kernel<<<grid_for(n, 1), PCG_THREADS, 0, st>>>(n, b, s.r);  // pcg.h:156
+    DGB_LAUNCHED();
+    pcg_dot3_kernel<0><<<g1, PCG_THREADS, 0, st>>>(n, s.r, W, s.r, s.slot, 3, s.st);
+    DGB_LAUNCHED();
+    pcg_precond_kernel<<<grid_for(n, 1), PCG_THREADS, 0, st>>>(n, P, s.r, s.p);  // pcg.h:159
+    DGB_LAUNCHED();
+    pcg_dot3_kernel<1><<<g1, PCG_THREADS, 0, st>>>(n, s.p, W, s.r, s.slot, 0, s.st);  // pcg.h:160
+    DGB_LAUNCHED();
+    if ((e = fetch_result(s, 3, st))) return e;
+    if (std::sqrt(s.results_host[3].value) < tol) { *iterations = 0; return 0; }  // pcg.h:157
+    const bool identity_chi = !A.chi[0] && !A.chi[1] && !A.chi[2] && !A.chi[3];
+    const bool fused = A.fusable && identity_chi && !A.chi_weight_jump && !getenv("DGB_ELLIPTIC_UNFUSED");
+    FusedDot fd{W, s.slot, s.st};
+    const unsigned g2 = grid_for(n, 2);
+    int i = 1;
+    while (i < max_iter) {
+        int stop = i + s.check_every < max_iter ? i + s.check_every : max_iter;
+        for (; i < stop; i++) {
+            if (fused) {
+                if ((e = elliptic2d_fused_launch_dot(A, s.p, s.ap, st, fd))) return e;
+            } else {
+                if ((e = elliptic2d_symv(A, 1., s.p, 0., s.ap, st, false))) return e;
+                pcg_dot3_kernel<2><<<g1, PCG_THREADS, 0, st>>>(n, s.p, W, s.ap, s.slot, 0, s.st);
+                DGB_LAUNCHED();
+            }
+            if (i % test_frequency == 0)
+                pcg_update_kernel<true><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+            else
+                pcg_update_kernel<false><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+            DGB_LAUNCHED();
+            pcg_direction_kernel<<<g2, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st);
+            DGB_LAUNCHED();
+        }
+        if ((e = fetch_state(s, st))) return e;
+        if (s.st_host->status) {
+            set_error("dot product failed since one of the inputs contains NaN or Inf");
+            return DGB_ERR_NOTFINITE;
+        }
+        if (s.st_host->done) { *iterations = s.st_host->iter; return 0; }
+    }
+    *iterations = max_iter;
+    set_error("PCG failed to converge within max_iter = %d iterations (residual %g, tolerance %g)", max_iter,
+              s.st_host->res, tol);
+    return DGB_ERR_NOCONVERGE;
+}
+
+}  // namespace dgb
+
+using namespace dgb;
+
+extern "C" {
+int dgb_pcg_create(dgb_pcg** out, size_t n) {
+    Pcg* s = new Pcg();
+    s->n = n;
+    size_t bytes = (n ? n : 1) * sizeof(double);
+    DGB_CUDA(cudaMalloc(&s->r, bytes));
+    DGB_CUDA(cudaMalloc(&s->p, bytes));
+    DGB_CUDA(cudaMalloc(&s->ap, bytes));
+    DGB_CUDA(cudaMalloc(&s->st, sizeof(PcgState)));
+    DGB_CUDA(cudaMemset(s->st, 0, sizeof(PcgState)));
+    DGB_CUDA(cudaMallocHost(&s->st_host, sizeof(PcgState)));
+    const int ns = 4;
+    DGB_CUDA(cudaMalloc(&s->slot.gacc, ns * sa::BINS * sizeof(long long)));
+    DGB_CUDA(cudaMemset(s->slot.gacc, 0, ns * sa::BINS * sizeof(long long)));
+    DGB_CUDA(cudaMalloc(&s->slot.gstatus, ns * sizeof(int)));
+    DGB_CUDA(cudaMemset(s->slot.gstatus, 0, ns * sizeof(int)));
+    DGB_CUDA(cudaMalloc(&s->slot.ticket, ns * sizeof(unsigned int)));
+    DGB_CUDA(cudaMemset(s->slot.ticket, 0, ns * sizeof(unsigned int)));
+    DGB_CUDA(cudaMalloc(&s->results, ns * sizeof(dgb_dot_result)));
+    DGB_CUDA(cudaMemset(s->results, 0, ns * sizeof(dgb_dot_result)));
+    DGB_CUDA(cudaMallocHost(&s->results_host, ns * sizeof(dgb_dot_result)));
+    s->slot.result = s->results;
+    const char* ce = getenv("DGB_PCG_CHECK_EVERY");
+    if (ce && atoi(ce) > 0) s->check_every = atoi(ce);
+    *out = reinterpret_cast<dgb_pcg*>(s);
+    return 0;
+}
+int dgb_pcg_destroy(dgb_pcg* h) {
+    Pcg* s = reinterpret_cast<Pcg*>(h);
+    if (!s) return 0;
+    cudaFree(s->r); cudaFree(s->p); cudaFree(s->ap); cudaFree(s->st); cudaFreeHost(s->st_host);
+    cudaFree(s->slot.gacc); cudaFree(s->slot.gstatus); cudaFree(s->slot.ticket);
+    cudaFree(s->results); cudaFreeHost(s->results_host);
+    delete s;
+    return 0;
+}
+int dgb_pcg_solve_elliptic2d(dgb_pcg* h, dgb_elliptic2d* A, double* x, const double* b, const double* P,
+                             const double* W, double eps, double nrmb_correction, int test_frequency, int max_iter,
+                             int* iterations, dgb_stream_t s) {
+    if (!h || !A) { set_error("dgb_pcg_solve_elliptic2d: NULL handle"); return DGB_ERR_INVALID; }
+    return pcg_solve(*reinterpret_cast<Pcg*>(h), *reinterpret_cast<Elliptic2dPlan*>(A), x, b, P, W, eps,
+                     nrmb_correction, test_frequency, max_iter, iterations, as_stream(s));
+}
+}

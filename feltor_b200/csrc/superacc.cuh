@@ -11,9 +11,10 @@
 //  * the shared accumulators (one per warp) are updated with native 64-bit shared atomics; signed wrap-around of
 //    a word is detected from the value the atomic returns and compensated in the next word, so the update is
 //    value-preserving under any interleaving;
-//  * the per-block result is normalised and written to global memory; the last block to finish (atomic ticket)
-//    combines all blocks (integer addition is associative => any grid size gives the same normalised words),
-//    normalises, rounds (accumulate.h:297-349, replicated operation by operation) and writes the result record.
+//  * the per-block result is normalised and added word by word into one global accumulator with the same wrap-safe
+//    atomics (integer addition is associative => any grid size and arrival order gives the same normalised words);
+//    the last block to finish (atomic ticket) normalises, rounds (accumulate.h:297-349, replicated operation by
+//    operation) and writes the result record.
 #pragma once
 #include "common.cuh"
 
@@ -72,7 +73,7 @@ __device__ inline void add_word(long long* acc, int i, long long x, int stride) 
 }
 
 // add the double x exactly to the accumulator (decomposition into 56-bit digits, cf. accumulate.h:217-236)
-__device__ __noinline__ void accumulate(long long* acc, double x, int stride) {
+static __device__ __noinline__ void accumulate(long long* acc, double x, int stride) {
     if (x == 0.0) return;
     int e = ((int)((unsigned long long)__double_as_longlong(x) >> 52) & 0x7ff) - 0x3ff;
     int exp_word = e / DIGITS;  // truncation toward zero, as the reference
@@ -171,9 +172,9 @@ struct Fpe {
 // Shared memory: NWARPS accumulators of BINS words (stride 1, accumulator w at smem + w*BINS).
 // Global scratch ("slot"): partials[gridDim.x * BINS], status flags, a ticket; result record.
 struct DotSlot {
-    long long* partials;      // [max_blocks][BINS]
-    int* block_status;        // [max_blocks]
-    unsigned int* ticket;     // zero-initialised, reset by the finishing block
+    long long* gacc;          // [nslots][BINS] global accumulators, zero between launches
+    int* gstatus;             // [nslots] OR of the per-block status flags, zero between launches
+    unsigned int* ticket;     // [nslots] zero-initialised, reset by the finishing block
     dgb_dot_result* result;   // device
 };
 
@@ -183,10 +184,11 @@ __device__ inline void block_init(long long* smem) {
     __syncthreads();
 }
 
-// combines the per-warp accumulators of this block, publishes the block partial, and lets the last block
-// produce the final normalised accumulator + rounded value.  `status` = 1 if this thread saw a non-finite product.
-// All threads of the block must call.  Returns true in ALL threads of the finishing block after the result is
-// written (so callers can chain scalar post-processing).
+// combines the per-warp accumulators of this block, adds the block partial into the global accumulator of the slot
+// (wrap-safe 64-bit atomics: integer addition is associative => any grid size / arrival order gives the same VALUE)
+// and lets the last block to arrive normalise, round and publish {acc, value, status}.
+// `status` = 1 if this thread saw a non-finite product.  All threads of the block must call.  Returns true in ALL
+// threads of the finishing block after the result is written (so callers can chain scalar post-processing).
 template <int NWARPS>
 __device__ inline bool block_finish(long long* smem, int status, const DotSlot& slot, int slot_idx = 0) {
     __shared__ int s_last;
@@ -194,52 +196,40 @@ __device__ inline bool block_finish(long long* smem, int status, const DotSlot& 
     // 1. normalise each warp accumulator (one thread each), then sum word-wise (NWARPS <= 32 -> no overflow)
     if (threadIdx.x < NWARPS) normalize(smem + threadIdx.x * BINS, 1);
     __syncthreads();
-    long long* part = slot.partials + ((size_t)slot_idx * gridDim.x + blockIdx.x) * BINS;
+    long long sum = 0;
     if (threadIdx.x < BINS) {
-        long long sum = 0;
 #pragma unroll
         for (int w = 0; w < NWARPS; w++) sum += smem[w * BINS + threadIdx.x];
-        smem[threadIdx.x] = sum;  // reuse accumulator 0 (each thread overwrites only the word it has just read last)
     }
     __syncthreads();
+    long long* gacc = slot.gacc + (size_t)slot_idx * BINS;
+    // 2. word-parallel atomic accumulation into the global accumulator
+    if (threadIdx.x < BINS && sum != 0) add_word(gacc, threadIdx.x, sum, 1);
+    if (threadIdx.x == 0 && any_bad) atomicOr(slot.gstatus + slot_idx, 1);
+    __threadfence();
+    __syncthreads();
     if (threadIdx.x == 0) {
-        normalize(smem, 1);
-        for (int i = 0; i < BINS; i++) part[i] = smem[i];
-        slot.block_status[(size_t)slot_idx * gridDim.x + blockIdx.x] = any_bad;
-        __threadfence();
         unsigned int t = atomicAdd(slot.ticket + slot_idx, 1u);
         s_last = (t == gridDim.x - 1);
     }
     __syncthreads();
     if (!s_last) return false;
-    // 2. last block: combine all partials.  Each is normalised (< 2^56 per word), so up to 128 can be summed
-    //    in int64 before renormalising (exblas allows 256, mpi_accumulate.h:75-77).
+    // 3. last block: fetch, reset, normalise, round
     __threadfence();
-    const long long* all = slot.partials + (size_t)slot_idx * gridDim.x * BINS;
-    const int* st = slot.block_status + (size_t)slot_idx * gridDim.x;
-    if (threadIdx.x < BINS) smem[threadIdx.x] = 0;
-    int bad = 0;
-    for (int b = threadIdx.x; b < (int)gridDim.x; b += blockDim.x) bad |= st[b];
-    bad = __syncthreads_or(bad);
-    for (int b0 = 0; b0 < (int)gridDim.x; b0 += 128) {
-        int b1 = min(b0 + 128, (int)gridDim.x);
-        if (threadIdx.x < BINS) {
-            long long sum = smem[threadIdx.x];
-            for (int b = b0; b < b1; b++) sum += __ldcg(all + (size_t)b * BINS + threadIdx.x);
-            smem[threadIdx.x] = sum;
-        }
-        __syncthreads();
-        if (threadIdx.x == 0) smem[BINS] = normalize(smem, 1);  // smem[BINS] = sign flag (NWARPS >= 2 assumed)
-        __syncthreads();
+    if (threadIdx.x < BINS) {
+        smem[threadIdx.x] = __ldcg(gacc + threadIdx.x);
+        gacc[threadIdx.x] = 0;  // ready for the next launch on the same stream
     }
+    __syncthreads();
     if (threadIdx.x == 0) {
-        int negative = (int)smem[BINS];
+        int negative = normalize(smem, 1);
         dgb_dot_result* r = slot.result + slot_idx;
         for (int i = 0; i < BINS; i++) r->acc[i] = smem[i];
         r->value = round_normalized(smem, negative);
-        r->status = bad;
+        r->status = __ldcg(slot.gstatus + slot_idx);
         r->pad = 0;
-        slot.ticket[slot_idx] = 0;  // ready for the next launch on the same stream
+        slot.gstatus[slot_idx] = 0;
+        slot.ticket[slot_idx] = 0;
         __threadfence();
     }
     __syncthreads();

@@ -1,0 +1,107 @@
+"""dg::Elliptic2d / dg::PCG on device tensors (inc/dg/elliptic.h:233-516, inc/dg/pcg.h:25-199) through the C ABI."""
+import ctypes as C
+import numpy as np
+import torch
+from ._lib import lib, DgbError
+from ._dev import ptr, stream, dvec
+from . import blas1, topology as T
+
+d = C.c_double
+
+
+class Elliptic2d:
+    """-div( chi grad ) on a Cartesian 2d grid; same constructor arguments as elliptic.h:281-283"""
+
+    def __init__(self, g, bcx=None, bcy=None, direction=T.FORWARD, jfactor=1.0, chi_weight_jump=False):
+        bcx = g.bc[0] if bcx is None else bcx
+        bcy = g.bc[1] if bcy is None else bcy
+        self.grid = g
+        self.mats = dict(
+            leftx=T.derivative(0, g, T.inverse_bc(bcx), T.inverse_dir(direction)),
+            lefty=T.derivative(1, g, T.inverse_bc(bcy), T.inverse_dir(direction)),
+            rightx=T.derivative(0, g, bcx, direction), righty=T.derivative(1, g, bcy, direction),
+            jumpx=T.jump(0, g, bcx), jumpy=T.jump(1, g, bcy))
+        hs = {k: m.host_struct() for k, m in self.mats.items()}
+        self.h = C.c_void_p()
+        lib().elliptic2d_create(C.byref(self.h), *[C.byref(hs[k]) for k in ("leftx", "lefty", "rightx", "righty",
+                                                                           "jumpx", "jumpy")], d(jfactor),
+                                int(chi_weight_jump))
+        self.size = g.size
+        self.jfactor = jfactor
+        self._weights = dvec(g.weights())                      # create::volume == weights on a Cartesian grid
+        self._precond = torch.ones(self.size, dtype=torch.float64, device="cuda")
+        self._vol = None                                       # Cartesian: tensor::volume == 1 (not stored)
+        self._sigma = torch.ones(self.size, dtype=torch.float64, device="cuda")
+        lib().elliptic2d_set_sigma(self.h, ptr(self._sigma))
+
+    @property
+    def fused(self):
+        f = C.c_int()
+        lib().elliptic2d_size(self.h, None, C.byref(f))
+        return bool(f.value)
+
+    def weights(self):
+        return self._weights
+
+    def precond(self):
+        return self._precond
+
+    def set_chi(self, sigma):
+        """elliptic.h:324-333: m_sigma = sigma*vol, precond = 1/sigma"""
+        if self._vol is None:
+            blas1.copy(sigma, self._sigma)  # sigma * 1. is exact
+        else:
+            blas1.pointwiseDot(sigma, self._vol, self._sigma)
+        one = torch.ones_like(sigma)
+        blas1.pointwiseDivide(one, sigma, self._precond)
+
+    def set_jfactor(self, jf):
+        self.jfactor = jf
+        lib().elliptic2d_set_jfactor(self.h, d(jf))
+
+    def symv(self, *a, unfused=False):
+        """symv(x, y) | symv(alpha, x, beta, y)  (elliptic.h:402-458)"""
+        alpha, x, beta, y = (1., a[0], 0., a[1]) if len(a) == 2 else a
+        if x.numel() != self.size or y.numel() != self.size:
+            raise ValueError("dg::Error: vector size does not match the operator")
+        fn = lib().elliptic2d_symv_unfused if unfused else lib().elliptic2d_symv
+        fn(self.h, d(alpha), ptr(x), d(beta), ptr(y), stream())
+
+    def __del__(self):
+        try:
+            lib().elliptic2d_destroy(self.h)
+        except Exception:
+            pass
+
+
+class PCG:
+    """dg::PCG<DVec> (pcg.h:25-199): solve(A, x, b, P, W, eps, nrmb_correction, test_frequency) -> iterations"""
+
+    def __init__(self, size, max_iterations):
+        self.size, self.max_iter = size, max_iterations
+        self.throw_on_fail = True
+        self.h = C.c_void_p()
+        lib().pcg_create(C.byref(self.h), size)
+
+    def set_max(self, m):
+        self.max_iter = m
+
+    def set_throw_on_fail(self, v):
+        self.throw_on_fail = v
+
+    def solve(self, A, x, b, P, W, eps=1e-12, nrmb_correction=1.0, test_frequency=1):
+        it = C.c_int()
+        try:
+            lib().pcg_solve_elliptic2d(self.h, A.h, ptr(x), ptr(b), ptr(P), ptr(W), d(eps), d(nrmb_correction),
+                                       test_frequency, self.max_iter, C.byref(it), stream())
+        except DgbError as e:
+            if e.code == -4 and not self.throw_on_fail:   # dg::Fail, pcg.h:189-193
+                return it.value
+            raise
+        return it.value
+
+    def __del__(self):
+        try:
+            lib().pcg_destroy(self.h)
+        except Exception:
+            pass

@@ -243,6 +243,8 @@ DGB_API int dgb_elliptic2d_set_vol(dgb_elliptic2d* plan, const double* vol);    
 DGB_API int dgb_elliptic2d_set_chi(dgb_elliptic2d* plan, const double* xx, const double* xy, const double* yx,
                                    const double* yy);                             /* m_chi; NULL = identity entry */
 DGB_API int dgb_elliptic2d_set_jfactor(dgb_elliptic2d* plan, double jfactor);
+/* size of the operator; *fused = 1 if the one-pass kernel applies to these matrices (else the composition runs) */
+DGB_API int dgb_elliptic2d_size(const dgb_elliptic2d* plan, size_t* size, int* fused);
 DGB_API int dgb_elliptic2d_symv(dgb_elliptic2d* plan, double alpha, const double* x, double beta, double* y,
                                 dgb_stream_t s);
 /* the unfused composition on the same plan (6 Ell symv + 2 blas1), kept for A/B tests and as the general path */

@@ -1,0 +1,54 @@
+"""CPU: the C-ABI library loads without a GPU and exports every symbol include/dgb200.h declares; host-only entry
+points (topology, superaccumulator helpers, error reporting) work; compute entry points fail loudly without a device."""
+import ctypes as C
+import numpy as np
+import pytest
+import feltor_b200 as fb
+from feltor_b200._lib import parse_header
+from oracle import orc
+from util import rng, wide
+
+
+def test_exports_every_declared_symbol():
+    L = fb.lib()
+    protos = parse_header()
+    assert len(protos) > 70
+    assert L.missing == []
+    for name in protos:
+        assert hasattr(L.cdll, name), name
+
+
+def test_version_and_error_string():
+    L = fb.lib()
+    assert L.raw["dgb_version"]() >= 100
+    with pytest.raises(fb.DgbError) as e:
+        L.topo_dlt(0, 99, None)
+    assert "dgb_topo_dlt" in str(e.value)
+
+
+def test_host_superacc_helpers_match_oracle():
+    """dgb_superacc_normalize_host / round_host == accumulate.h:267-349 as restated (and pinned) in the oracle"""
+    L = fb.lib()
+    r = rng(1)
+    for n in (1, 10, 1000):
+        x, y = wide(r, n, -200, 200), wide(r, n, -50, 50)
+        acc, _ = orc.exdot2(x, y)
+        raw = acc.copy()
+        raw[3] += 5 << 56  # de-normalise: push carries into a word
+        raw[4] -= 5
+        a = raw.copy()
+        L.raw["dgb_superacc_normalize_host"](a.ctypes.data)
+        assert np.array_equal(a, acc)
+        assert L.raw["dgb_superacc_round_host"](raw.ctypes.data) == orc.round_acc(acc)
+
+
+def test_compute_fails_loudly_without_device():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a device is present")
+    ws = C.c_void_p()
+    with pytest.raises(fb.DgbError):
+        fb.lib().dot_ws_create(C.byref(ws))
+    p = C.c_void_p()
+    with pytest.raises(fb.DgbError):
+        fb.lib().malloc(C.byref(p), 1024)

@@ -1,0 +1,213 @@
+"""GPU parity of the Elliptic2d apply (fused and unfused) and PCG against the oracle and the reference fixtures."""
+import numpy as np
+import pytest
+from oracle import orc
+from util import same_bits, rng
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_backend
+    gpu_backend.require_library_loaded()
+    return gpu_backend
+
+
+def oracle_elliptic(T, g, bcx, bcy, d, jf, chi):
+    mats = dict(leftx=T.derivative(0, g, T.inverse_bc(bcx), T.inverse_dir(d)),
+                lefty=T.derivative(1, g, T.inverse_bc(bcy), T.inverse_dir(d)),
+                rightx=T.derivative(0, g, bcx, d), righty=T.derivative(1, g, bcy, d),
+                jumpx=T.jump(0, g, bcx), jumpy=T.jump(1, g, bcy))
+    return orc.Elliptic2d(mats, sigma=chi.copy(), jfactor=jf)
+
+
+@pytest.mark.parametrize("tag,bcx,bcy,d,jf", [("dirper_fwd", 1, 0, 0, 1.0), ("neu_cen", 4, 0, 2, 0.1),
+                                              ("dirneu_bwd", 2, 1, 1, 1.0)])
+def test_elliptic_fixtures(G, golden, tag, bcx, bcy, d, jf):
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic2d
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, [10, 8], [bcx, bcy])
+    E = Elliptic2d(g, bcx, bcy, d, jf)
+    assert E.fused
+    E.set_chi(G.make(golden[f"elliptic/{tag}/chi"]))
+    assert same_bits(G.get(E.weights()), golden[f"elliptic/{tag}/weights"])
+    assert same_bits(G.get(E.precond()), golden[f"elliptic/{tag}/precond"])
+    x, y0 = golden[f"elliptic/{tag}/x"], golden[f"elliptic/{tag}/y0"]
+    for al, be in ((1., 0.), (-0.5, 2.)):
+        for unfused in (True, False):
+            y = G.make(y0)
+            E.symv(al, G.make(x), be, y, unfused=unfused)
+            assert same_bits(G.get(y), golden[f"elliptic/{tag}/a{al}b{be}"]), (tag, al, be, unfused)
+
+
+CASES = []
+for n in (2, 3, 4):
+    for (bcx, bcy) in ((0, 0), (1, 0), (4, 1), (2, 3), (3, 2)):
+        for d in (0, 1, 2):
+            CASES.append((n, bcx, bcy, d))
+
+
+@pytest.mark.parametrize("n,bcx,bcy,d", CASES)
+def test_elliptic_vs_oracle(G, n, bcx, bcy, d):
+    """ragged sizes (not multiples of the 32 x 8 cell tile), every boundary family and direction; bit-exact"""
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic2d
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], n, [37, 19], [bcx, bcy])
+    r = rng(n * 100 + bcx * 10 + d)
+    chi = 1. + 0.9 * r.uniform(0, 1, g.size)
+    x, y0 = r.uniform(-1, 1, g.size), r.uniform(-1, 1, g.size)
+    O = oracle_elliptic(T, g, bcx, bcy, d, 0.7, chi)
+    E = Elliptic2d(g, bcx, bcy, d, 0.7)
+    assert E.fused
+    E.set_chi(G.make(chi))
+    for al, be in ((1., 0.), (-0.5, 2.)):
+        yo = y0.copy()
+        O.symv(al, x, be, yo)
+        for unfused in (True, False):
+            y = G.make(y0)
+            E.symv(al, G.make(x), be, y, unfused=unfused)
+            assert same_bits(G.get(y), yo), (n, bcx, bcy, d, al, be, unfused)
+
+
+def test_elliptic_small_and_n5_fall_back(G):
+    """grids the fused kernel does not cover run through the composition and still match the oracle"""
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic2d
+    for n, N in ((5, [9, 7]), (3, [4, 3]), (1, [12, 9])):
+        g = T.Grid([0, 0], [1, 1], n, N, [T.DIR, T.PER])
+        r = rng(n)
+        chi = 1. + r.uniform(0, 1, g.size)
+        x = r.uniform(-1, 1, g.size)
+        O = oracle_elliptic(T, g, T.DIR, T.PER, T.FORWARD, 1.0, chi)
+        E = Elliptic2d(g, T.DIR, T.PER, T.FORWARD, 1.0)
+        assert not E.fused
+        E.set_chi(G.make(chi))
+        yo = np.zeros(g.size)
+        O.symv(1., x, 0., yo)
+        y = G.make(np.full(g.size, np.nan))
+        E.symv(G.make(x), y)
+        assert same_bits(G.get(y), yo)
+
+
+def test_elliptic_full_size_fused_equals_unfused(G):
+    """benchmark size n=3 1024^2: fused kernel == composition bit for bit; symmetry <x, W A y> == <y, W A x> to 1e-12"""
+    import torch
+    from feltor_b200 import topology as T, blas2
+    from feltor_b200.elliptic import Elliptic2d
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, [1024, 1024], [T.DIR, T.PER])
+    E = Elliptic2d(g, T.DIR, T.PER, T.FORWARD, 1.0)
+    gen = torch.Generator(device="cuda").manual_seed(5)
+    chi = 1. + torch.rand(g.size, dtype=torch.float64, device="cuda", generator=gen)
+    E.set_chi(chi)
+    x = torch.rand(g.size, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    z = torch.rand(g.size, dtype=torch.float64, device="cuda", generator=gen) - 0.5
+    y1, y2 = torch.full_like(x, float("nan")), torch.full_like(x, float("nan"))
+    E.symv(x, y1)
+    E.symv(x, y2, unfused=True)
+    assert torch.equal(y1.view(torch.int64), y2.view(torch.int64))
+    az = torch.empty_like(x)
+    E.symv(z, az)
+    a, b = blas2.dot(z, E.weights(), y1), blas2.dot(x, E.weights(), az)
+    assert abs(a - b) <= 1e-12 * abs(a)
+
+
+# ------------------------------------------------------------------------------------------------ PCG
+def test_pcg_fixture(G, golden):
+    """elliptic2d_b.cpp-style problem at 10 x 8 cells: iteration count and solution identical to the reference"""
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic2d, PCG
+    tag = "dirper_fwd"
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, [10, 8], [T.DIR, T.PER])
+    E = Elliptic2d(g, T.DIR, T.PER, T.FORWARD, 1.0)
+    E.set_chi(G.make(golden[f"elliptic/{tag}/chi"]))
+    b = G.make(golden[f"elliptic/{tag}/pcg_b"])
+    x = G.make(np.zeros(g.size))
+    pcg = PCG(g.size, g.size)
+    it = pcg.solve(E, x, b, E.precond(), E.weights(), 1e-8, 1.0, 1)
+    assert it == int(golden[f"elliptic/{tag}/pcg_it"][0])
+    assert same_bits(G.get(x), golden[f"elliptic/{tag}/pcg_x"])
+
+
+@pytest.mark.parametrize("n,N,bcx,bcy,d,tf,unfused", [
+    (3, [40, 24], 1, 0, 0, 1, False), (3, [40, 24], 1, 0, 0, 1, True), (3, [33, 17], 4, 1, 2, 1, False),
+    (2, [24, 40], 1, 1, 1, 3, False), (4, [12, 16], 1, 0, 0, 10, False), (5, [8, 8], 1, 0, 0, 1, False)])
+def test_pcg_vs_oracle(G, monkeypatch, n, N, bcx, bcy, d, tf, unfused):
+    """same iteration count, bit-identical solution; test_frequency > 1; the generic (unfused operator) path"""
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic2d, PCG
+    if unfused:
+        monkeypatch.setenv("DGB_ELLIPTIC_UNFUSED", "1")
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], n, N, [bcx, bcy])
+    chi = g.evaluate(lambda x, y: 1. + 0.9 * np.sin(x) * np.sin(y))
+    b = g.evaluate(lambda x, y: np.sin(x) * np.sin(y) * (1 + np.cos(3 * y)))
+    w = g.weights()
+    O = oracle_elliptic(T, g, bcx, bcy, d, 1.0, chi)
+    xo = np.zeros(g.size)
+    res = np.zeros(g.size)
+    ito = O.pcg_solve(xo, b, 1. / chi, w, 1e-9, 1.0, tf, max_iter=g.size, residuals=res)
+    E = Elliptic2d(g, bcx, bcy, d, 1.0)
+    E.set_chi(G.make(chi))
+    x = G.make(np.zeros(g.size))
+    pcg = PCG(g.size, g.size)
+    it = pcg.solve(E, x, G.make(b), E.precond(), E.weights(), 1e-9, 1.0, tf)
+    assert it == ito
+    assert same_bits(G.get(x), xo)
+
+
+def test_pcg_edge_cases(G):
+    """zero right hand side (pcg.h:150), converged initial guess (pcg.h:157), max_iter hit -> dg::Fail / no-throw"""
+    import feltor_b200 as fb
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic2d, PCG
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, [12, 12], [T.DIR, T.PER])
+    E = Elliptic2d(g, T.DIR, T.PER, T.FORWARD, 1.0)
+    pcg = PCG(g.size, g.size)
+    x = G.make(np.ones(g.size))
+    assert pcg.solve(E, x, G.make(np.zeros(g.size)), E.precond(), E.weights(), 1e-8) == 0
+    assert float(x.abs().max()) == 0.0
+    b = G.make(g.evaluate(lambda x, y: np.sin(x) * np.sin(y)))
+    x = G.make(np.zeros(g.size))
+    it = pcg.solve(E, x, b, E.precond(), E.weights(), 1e-10)
+    assert it > 0
+    assert pcg.solve(E, x, b, E.precond(), E.weights(), 1e-6) == 0
+    x = G.make(np.zeros(g.size))
+    pcg.set_max(5)
+    with pytest.raises(fb.DgbError):
+        pcg.solve(E, x, b, E.precond(), E.weights(), 1e-14)
+    pcg.set_throw_on_fail(False)
+    x = G.make(np.zeros(g.size))
+    assert pcg.solve(E, x, b, E.precond(), E.weights(), 1e-14) == 5
+    bad = G.make(np.full(g.size, np.nan))
+    with pytest.raises(fb.DgbError):
+        pcg.solve(E, x, bad, E.precond(), E.weights(), 1e-8)
+
+
+def test_pcg_full_size_residual(G):
+    """config 2 (n=3, 1024^2, eps=1e-8, DIR x PER): the returned x satisfies the stopping criterion recomputed
+    independently, and a second solve from that x returns 0 iterations"""
+    import torch
+    from feltor_b200 import topology as T, blas1, blas2
+    from feltor_b200.elliptic import Elliptic2d, PCG
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, [1024, 1024], [T.DIR, T.PER])
+    E = Elliptic2d(g, T.DIR, T.PER, T.FORWARD, 1.0)
+    chi = G.make(g.evaluate(lambda x, y: 1. + 0.9 * np.sin(x) * np.sin(y)))
+    E.set_chi(chi)
+    amp = 0.9
+    b = G.make(g.evaluate(lambda x, y: 2. * np.sin(x) * np.sin(y) * (amp * np.sin(x) * np.sin(y) + 1)
+                          - amp * np.sin(x) ** 2 * np.cos(y) ** 2 - amp * np.cos(x) ** 2 * np.sin(y) ** 2))
+    x = torch.zeros(g.size, dtype=torch.float64, device="cuda")
+    pcg = PCG(g.size, 5000)
+    it = pcg.solve(E, x, b, E.precond(), E.weights(), 1e-8, 1.0, 1)
+    assert 0 < it < 5000
+    r = torch.empty_like(x)
+    E.symv(x, r)
+    blas1.axpby(1., b, -1., r)
+    res = np.sqrt(blas2.dot(r, E.weights(), r))
+    nrmb = np.sqrt(blas2.dot(b, E.weights(), b))
+    assert res < 1e-8 * (nrmb + 1.0) * 1.01
+    assert pcg.solve(E, x, b, E.precond(), E.weights(), 1e-8, 1.0, 1) == 0
+    sol = G.make(g.evaluate(lambda x, y: np.sin(x) * np.sin(y)))
+    blas1.axpby(1., sol, -1., x)
+    err = np.sqrt(blas2.dot(x, E.weights(), x) / blas2.dot(sol, E.weights(), sol))
+    assert err < 1e-6
