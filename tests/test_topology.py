@@ -60,8 +60,8 @@ def test_live_reference(ref):
                 for d in range(3):
                     assert eq(ref.ell_create(rg, "derivative", 0, bc, d), T.derivative(0, g, bc, d)), (n, N, bc, d)
                 assert eq(ref.ell_create(rg, "jump", 0, bc), T.jump(0, g, bc)), (n, N, bc)
-    rg = ref.grid([0, 0, -1], [1, 2 * np.pi, 3], 3, [6, 8, 4], [0, 1, 4])
-    g = T.Grid([0, 0, -1], [1, 2 * np.pi, 3], [3, 3, 1], [6, 8, 4], [0, 1, 4])
+    rg = ref.grid([0, 0, -1], [1, 2 * np.pi, 3], 3, [12, 8, 4], [0, 1, 4])
+    g = T.Grid([0, 0, -1], [1, 2 * np.pi, 3], [3, 3, 1], [12, 8, 4], [0, 1, 4])
     assert same_bits(ref.weights(rg), g.weights())
     for u in range(3):
         assert same_bits(ref.abscissas(rg, u), g.abscissas(u))
