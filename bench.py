@@ -1,0 +1,308 @@
+#!/usr/bin/env python
+"""bench.py -- the headline benchmark of BASELINE.json on the B200-native dg core.
+
+Workload (config 2 of BASELINE.json): 2-D dg::Elliptic + dg::PCG Poisson problem, n=3, Nx=Ny=1024
+(9 437 184 dof), Dirichlet x periodic, chi = 1 + 0.9 sin x sin y, forward discretisation, jfactor 1, P = 1/chi,
+W = weights, eps = 1e-8, x0 = 0 (inc/dg/elliptic2d_b.cpp:22-38).  One STEP = one call of PCG::solve limited to a
+fixed number of iterations (set_max(k), set_throw_on_fail(false); the full solve needs ~16 000 iterations at this
+size).  metric = PCG iterations per second (whole job).
+
+  value   device-resident inputs, timed with CUDA events on the launching stream
+  e2e     the same solve through the C-ABI entry point with HOST buffers: b and x0 copied host->device from
+          pinned memory and x copied back inside the timed region, every step
+  roofline  dominant kernel = the fused Elliptic apply + dot(p,W,Ap) kernel (K1): algorithmic 32 B/dof
+          (read p, sigma, W; write Ap) / its live CUDA-event duration, against MEASURED_PEAKS.json
+  cpu_baseline  the reference's own OpenMP implementation (oracle/_ref/libdgref.so) on the host cores, bounded sample
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--iters M] [--cells 1024] [--impl reference]
+N > 1 (torchrun): every rank solves its own 1024^2 problem (weak scaling, replicas; the halo-exchanged
+decomposition of one global problem is not wired into bench.py yet) -- value = sum of iterations / max time.
+"""
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+import numpy as np  # noqa: E402
+
+AMP = 0.9
+
+
+def problem_functions():
+    chi = lambda x, y: 1. + AMP * np.sin(x) * np.sin(y)  # noqa: E731  elliptic2d_b.cpp:33
+    rhs = lambda x, y: (2. * np.sin(x) * np.sin(y) * (AMP * np.sin(x) * np.sin(y) + 1)  # noqa: E731  :38
+                        - AMP * np.sin(x) ** 2 * np.cos(y) ** 2 - AMP * np.cos(x) ** 2 * np.sin(y) ** 2)
+    return chi, rhs
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)"""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.rows, self.proc = index, [], None
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([c.strip() for c in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm, mx, reasons = [], None, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0]))
+                mx = float(r[1])
+                for k, nm in enumerate(names):
+                    if r[3 + k].lower().startswith("active"):
+                        reasons.add(nm)
+            except Exception:
+                pass
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def peaks():
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))["hbm_gbs"], "measured"
+    except Exception:
+        return 6650.0, "fallback"
+
+
+def reference_arm(args, rank, world):
+    """the reference's own CPU implementation of the path (oracle/_ref) on the host cores; rank 0 only"""
+    if rank != 0:
+        return
+    from oracle import refwrap as R
+    cells = args.cells
+    kind = "reference"
+    m = args.ref_iters
+    if R.available():
+        g = R.grid([0, 0], [np.pi, 2 * np.pi], 3, [cells, cells], [R.DIR, R.PER])
+        E = R.Elliptic2d(g, R.DIR, R.PER, R.FORWARD, 1.0)
+        chi = R.evaluate(g, "pol")
+        E.set_chi(chi)
+        b = R.evaluate(g, "rhs")
+        P, W = E.precond(), E.weights()
+        cores = R.lib().ref_get_max_threads()
+
+        def step():
+            x = np.zeros(E.size)
+            it, sec = E.pcg_solve(x, b, P, W, 1e-8, 1.0, 1, max_iter=m + 1)
+            return min(it, m), sec
+    else:  # the oracle port (single thread)
+        from oracle import orc
+        from feltor_b200 import topology as T
+        kind, cores = "port", 1
+        g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, [cells, cells], [T.DIR, T.PER])
+        fchi, frhs = problem_functions()
+        chi, b, W = g.evaluate(fchi), g.evaluate(frhs), g.weights()
+        mats = dict(leftx=T.derivative(0, g, T.NEU, T.BACKWARD), lefty=T.derivative(1, g, T.PER, T.BACKWARD),
+                    rightx=T.derivative(0, g, T.DIR, T.FORWARD), righty=T.derivative(1, g, T.PER, T.FORWARD),
+                    jumpx=T.jump(0, g, T.DIR), jumpy=T.jump(1, g, T.PER))
+        E = orc.Elliptic2d(mats, sigma=chi.copy(), jfactor=1.0)
+        P = 1. / chi
+
+        def step():
+            x = np.zeros(g.size)
+            t0 = time.time()
+            it = E.pcg_solve(x, b, P, W, 1e-8, 1.0, 1, max_iter=m + 1)
+            return min(it, m), time.time() - t0
+    for _ in range(args.warmup if args.warmup < 2 else 1):
+        step()
+    its, secs = 0, 0.
+    for _ in range(args.steps):
+        i, s = step()
+        its += i
+        secs += s
+    v = its / secs
+    sample = "%d PCG iterations per step of the n=3 %dx%d problem, %d steps" % (m, cells, cells, args.steps)
+    out = {"metric": "pcg_iterations_per_second", "value": v, "unit": "iterations/s", "n_gpus": args.gpus,
+           "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+           "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
+           "config": {"workload": "2D dg::Elliptic+dg::PCG Poisson n=3 Nx=Ny=%d eps=1e-8 DIRxPER (config 2)" % cells,
+                      "iterations_per_step": m},
+           "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": cores, "kind": kind, "sample": sample},
+           "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+           "gpu_launches": 0}
+    print(json.dumps(out), flush=True)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--iters", type=int, default=200, help="PCG iterations per step (our arm)")
+    ap.add_argument("--ref-iters", type=int, default=10, help="PCG iterations per step of the CPU reference arm")
+    ap.add_argument("--cells", type=int, default=1024)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        return reference_arm(args, rank, world)
+
+    import torch
+    import torch.distributed as dist
+    import feltor_b200 as fb
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic2d, PCG
+    from feltor_b200._dev import ptr, stream
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    L = fb.lib()
+    cells, M = args.cells, args.iters
+    g = T.Grid([0., 0.], [np.pi, 2 * np.pi], 3, [cells, cells], [T.DIR, T.PER])
+    fchi, frhs = problem_functions()
+    E = Elliptic2d(g, T.DIR, T.PER, T.FORWARD, 1.0)
+    E.set_chi(torch.from_numpy(g.evaluate(fchi)).cuda())
+    b_host = torch.from_numpy(g.evaluate(frhs)).pin_memory()
+    x0_host = torch.zeros(g.size, dtype=torch.float64).pin_memory()
+    xout_host = torch.empty(g.size, dtype=torch.float64).pin_memory()
+    b = b_host.cuda()
+    x = torch.zeros(g.size, dtype=torch.float64, device="cuda")
+    pcg = PCG(g.size, M + 1)
+    pcg.set_throw_on_fail(False)
+    P, W = E.precond(), E.weights()
+
+    def solve_device():
+        x.zero_()
+        return min(pcg.solve(E, x, b, P, W, 1e-8, 1.0, 1), M)
+
+    def solve_e2e():
+        b.copy_(b_host, non_blocking=True)
+        x.copy_(x0_host, non_blocking=True)
+        it = min(pcg.solve(E, x, b, P, W, 1e-8, 1.0, 1), M)
+        xout_host.copy_(x, non_blocking=True)
+        torch.cuda.current_stream().synchronize()
+        return it
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def timed(fn, steps):
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        its = 0
+        for _ in range(steps):
+            its += fn()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms, float(its)], dtype=torch.float64, device="cuda")
+            tmax = t.clone()
+            dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+            dist.all_reduce(t, op=dist.ReduceOp.SUM)
+            return tmax[0].item(), int(t[1].item())
+        return ms, its
+
+    for _ in range(max(args.warmup, 3)):
+        solve_device()
+    L.pcg_set_profile(pcg.h, 1)
+    sampler = ClockSampler(local)
+    if rank == 0:
+        sampler.start()
+    launches0 = L.raw["dgb_launch_count"]()
+    ms, its = timed(solve_device, args.steps)
+    launches = L.raw["dgb_launch_count"]() - launches0
+    clocks = sampler.stop() if rank == 0 else None
+    prof = [C.c_double(), C.c_double(), C.c_double()]
+    pn = C.c_longlong()
+    L.pcg_get_profile(pcg.h, C.byref(prof[0]), C.byref(prof[1]), C.byref(prof[2]), C.byref(pn))
+    L.pcg_set_profile(pcg.h, 0)
+    solve_e2e()
+    ms_e2e, its_e2e = timed(solve_e2e, args.steps)
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+    peak, peak_kind = peaks()
+    ndof = g.size
+    k1_ms = prof[0].value / max(pn.value, 1)
+    k1_bytes = 32 * ndof  # read p, sigma, W; write Ap  (24 B/dof apply + 8 B/dof weights of the fused dot)
+    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["elliptic2d_fused_dot_bytes_per_launch"]
+    except Exception:
+        pass
+    value = its / (ms * 1e-3)
+    out = {
+        "metric": "pcg_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": world,
+        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "2D dg::Elliptic+dg::PCG Poisson n=3 Nx=Ny=%d eps=1e-8 DIRxPER (config 2)" % cells,
+                   "dof_per_gpu": ndof, "iterations_per_step": M, "l2": "working set 8 vectors x %.0f MB > 126 MB L2"
+                   % (ndof * 8 / 1e6), "parallelism": "replicas" if world > 1 else "single"},
+        "e2e": {"value": its_e2e / (ms_e2e * 1e-3), "unit": "iterations/s", "h2d_bytes_per_step": 2 * ndof * 8,
+                "d2h_bytes_per_step": ndof * 8},
+        "gpu_launches": int(launches),
+        "clocks": clocks,
+        "roofline": {"bound": "hbm", "kernel": "elliptic2d_fused_kernel<3,2,dot> (Elliptic apply + dot(p,W,Ap))",
+                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
+                     "frac": achieved / peak if achieved else None, "traffic": traffic,
+                     "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms},
+        "kernels_ms_per_iteration": {"apply_dot": k1_ms, "update_dots": prof[1].value / max(pn.value, 1),
+                                     "direction": prof[2].value / max(pn.value, 1)},
+        "pcg_gbs_at_128B_per_dof": 128 * ndof * value / world / 1e9,
+    }
+    if not args.no_cpu_baseline and world == 1:
+        try:
+            from oracle import refwrap as R
+            if R.available():
+                m = args.ref_iters * 4
+                gr = R.grid([0, 0], [np.pi, 2 * np.pi], 3, [cells, cells], [R.DIR, R.PER])
+                Er = R.Elliptic2d(gr, R.DIR, R.PER, R.FORWARD, 1.0)
+                Er.set_chi(R.evaluate(gr, "pol"))
+                br = R.evaluate(gr, "rhs")
+                xr = np.zeros(Er.size)
+                it, sec = Er.pcg_solve(xr, br, Er.precond(), Er.weights(), 1e-8, 1.0, 1, max_iter=m + 1)
+                out["cpu_baseline"] = {"value": min(it, m) / sec, "unit": "iterations/s",
+                                       "cores": R.lib().ref_get_max_threads(), "kind": "reference",
+                                       "sample": "%d PCG iterations of the same n=3 %dx%d problem (reference OpenMP "
+                                       "backend, oracle/_ref)" % (m, cells, cells)}
+            else:
+                out["cpu_baseline"] = {"value": None, "unit": "iterations/s", "cores": 0, "kind": "reference",
+                                       "sample": "oracle/_ref/libdgref.so not present"}
+        except Exception as e:  # never lose the GPU number over the baseline leg
+            out["cpu_baseline"] = {"value": None, "unit": "iterations/s", "cores": 0, "kind": "reference",
+                                   "sample": "failed: %r" % (e,)}
+    print(json.dumps(out), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

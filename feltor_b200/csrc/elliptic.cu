@@ -90,9 +90,10 @@ static bool dx_like(const EllDev& m, int expect_bpl, bool& wrap) {
         for (int d = 0; d < m.bpl; d++) {
             int c = m.h_cols[(size_t)i * m.bpl + d];
             if (c == -1) continue;
-            int want = i + m.off[d];
-            if (want < 0 || want >= m.num_rows) { want = (want + m.num_rows) % m.num_rows; wrap = true; }
-            if (c != want) return false;
+            int o = c - i;  // boundary rows may assign slots to neighbours differently from interior rows
+            if (o > 1) { o -= m.num_rows; wrap = true; }
+            else if (o < -1) { o += m.num_rows; wrap = true; }
+            if (o < -1 || o > 1) return false;
         }
     }
     return true;

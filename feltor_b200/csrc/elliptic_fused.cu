@@ -1,6 +1,13 @@
-// Fused Elliptic2d apply (see elliptic.cu for the overview).  One CTA = TX x TY cells, 256 threads.
+// Fused Elliptic2d apply (see elliptic.cu for the overview).
+// Persistent kernel: min(#tiles, 2 x #SM) CTAs of 256 threads walk over tiles of TX x TY cells.  Per tile
+//   phase 0  x (halo H cells) and sigma (halo 1 cell) arrive in shared memory by TMA (cp.async.bulk.tensor.2d,
+//            out-of-bounds elements are zero-filled by the hardware = non-periodic boundary); tiles that touch a
+//            periodic seam, or operands TMA cannot describe, use an LDGSTS (cp.async) loader instead;
+//   phase 1  fluxes tx = sigma Rx x, ty = sigma Ry x on the tile plus the ring the adjoint derivative reaches;
+//   phase 2  one thread per cell replays the reference's rounding sequence for its n x n outputs in registers;
+//   phase 3  coalesced epilogue y = alpha t / vol + beta y, optionally fused with the exact dot(x, w, y).
 //
-// Rounding sequence replayed per output element (inc/dg/elliptic.h:431-458 on top of
+// Rounding sequence per output element (inc/dg/elliptic.h:431-458 on top of
 // inc/dg/backend/sparseblockmat_omp_kernels.h:36-50 and inc/dg/topology/multiply.h:18-32), with
 // blk(M,d) = fma-chain over q of M's block in slot d:
 //   gx = 0; for d: gx = fma(1, blk(Rx,d), gx)            tx = fma(sigma, gx, gx*0)      (identity chi tensor)
@@ -12,6 +19,9 @@
 #include "superacc.cuh"
 #include "pcg.cuh"
 #include <algorithm>
+#include <cstring>
+#include <cstdlib>
+#include <cuda.h>
 
 namespace dgb {
 
@@ -34,6 +44,7 @@ struct FusedArgs {
     MatView rx, ry, lx, ly, jx, jy;
     int Nx, Ny, wrapx, wrapy;
     int txlo, txhi, tylo, tyhi;  // range of flux cells (relative to the tile) the adjoint derivatives reach
+    int ntx, ntiles, use_tma;
     const double* sigma;
     const double* vol;
     const double* x;
@@ -44,6 +55,42 @@ struct FusedArgs {
     sa::DotSlot slot;
     PcgState* pcg;
 };
+
+// ------------------------------------------------------------------------------------------------ TMA / LDGSTS
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    } while (!ok);
+}
+// 2-d tile load global -> shared through the tensor map; completion is signalled on the mbarrier in bytes
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// 8-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination without touching memory
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, bool valid) {
+    int bytes = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
 
 // out[k] = fma(a, sum_q C[d][k][q] * s[(off_d*N + q)*stride], out[k]) for the slots d of block-row `cell` of M
 template <int N, int BPL>
@@ -65,11 +112,17 @@ __device__ __forceinline__ void apply_row(const MatView& M, const double (&C)[BP
             }
         }
     } else {
-#pragma unroll
+#pragma unroll 1
         for (int d = 0; d < BPL; d++) {
-            if (M.cols[cell * BPL + d] < 0) continue;
+            const int col = M.cols[cell * BPL + d];
+            if (col < 0) continue;
+            // boundary rows keep their own slot -> neighbour assignment (dx.h:85-97): take the offset from the
+            // column index, undoing the periodic wrap
+            int o = col - cell;
+            if (o > 1) o -= M.num;
+            else if (o < -1) o += M.num;
             const double* blk = M.data + (size_t)M.didx[cell * BPL + d] * N * N;
-            const double* p = s + (M.off[d] * N) * stride;
+            const double* p = s + (o * N) * stride;
             double xv[N];
 #pragma unroll
             for (int q = 0; q < N; q++) xv[q] = p[q * stride];
@@ -91,11 +144,55 @@ __device__ __forceinline__ int gcell(int c, int num, int wrap) {
     return c < 0 ? c + num : c - num;
 }
 
+// LDGSTS loader of a (rows x cols) tile whose first cell is (cy, cx): one smem row at a time, columns by thread
+template <int N, int ROWS, int COLS, int PITCH>
+__device__ __forceinline__ void load_tile_ldgsts(double* dst, const double* src, int cy, int cx, const FusedArgs& A, int tid) {
+    const int LDG = A.Nx * N;
+    for (int c = tid % 128; c < COLS; c += 128) {
+        const int gx = gcell(cx + c / N, A.Nx, A.wrapx);
+        const int gcol = gx * N + c % N;
+        for (int r = tid / 128; r < ROWS; r += FUSED_THREADS / 128) {
+            const int gy = gcell(cy + r / N, A.Ny, A.wrapy);
+            const bool ok = gx >= 0 && gy >= 0;
+            cp_async8(dst + r * PITCH + c, ok ? src + (size_t)(gy * N + r % N) * LDG + gcol : src, ok);
+        }
+    }
+}
+
+template <int N, int B>
+struct Tile {
+    static constexpr int H = (B == 2) ? 1 : 2;                          // halo of the x tile in cells
+    static constexpr int XR = (TY + 2 * H) * N, XC = (TX + 2 * H) * N;  // x tile
+    static constexpr int SR = (TY + 2) * N, SC = (TX + 2) * N;          // sigma tile (one-cell ring)
+    // TMA needs a 16-byte aligned start in the contiguous dimension: the first tile column (cx0 - halo)*N has the
+    // parity of halo*N for every tile (TX*N is even), so odd cases load one extra column on each side
+    static constexpr int XSH = (H * N) & 1, SSH = N & 1;
+    static constexpr int XP = XC + 2 * XSH, SP = SC + 2 * SSH;          // row pitches of the x / sigma tiles
+    static constexpr int TXR = TY * N, TXC = (TX + 2) * N;              // tx: tile rows, one-cell ring in x
+    static constexpr int TYR = (TY + 2) * N, TYC = TX * N;              // ty: one-cell ring in y, tile columns
+    static constexpr int OR = TY * N, OC = TX * N;                      // output staging tile (aliases tx)
+    static constexpr size_t pad(size_t doubles) { return (doubles + 15) / 16 * 16; }  // keep every buffer 128-B aligned
+    static constexpr size_t XS = 0, SS = pad(XR * XP), TXS = SS + pad(SR * SP), TYS = TXS + pad(TXR * TXC),
+                            END = TYS + pad(TYR * TYC);
+    static constexpr size_t BYTES = END * sizeof(double) + 16;  // + mbarrier
+};
+
 template <int N, int B, bool DOT>
 __global__ void __launch_bounds__(FUSED_THREADS, 2)
-elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_constant__ EllipticCoef<N, B> C) {
+elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_constant__ EllipticCoef<N, B> C,
+                        const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_s) {
+    using TL = Tile<N, B>;
+    constexpr int H = TL::H, XC = TL::XP, SC = TL::SP, TXC = TL::TXC, TYC = TL::TYC, OC = TL::OC;  // XC, SC: row pitches
     constexpr int NW = FUSED_THREADS / 32;
     __shared__ long long dsm[DOT ? NW * sa::BINS : 1];
+    extern __shared__ __align__(128) double smem[];
+    double* xs = smem + TL::XS + TL::XSH;  // element (r, c) of the x tile is xs[r * XC + c]
+    double* ss = smem + TL::SS + TL::SSH;
+    double* txs = smem + TL::TXS;
+    double* tys = smem + TL::TYS;
+    unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + TL::END);
+    const int tid = threadIdx.x;
+    const int LDG = A.Nx * N;  // global row length
     sa::Fpe fpe;
     int bad = 0;
     if (DOT) {
@@ -103,155 +200,206 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
         sa::block_init<NW>(dsm);
         fpe.clear();
     }
-    constexpr int H = (B == 2) ? 1 : 2;          // halo of the x tile in cells
-    constexpr int XR = (TY + 2 * H) * N, XC = (TX + 2 * H) * N;  // x tile
-    constexpr int SR = (TY + 2) * N, SC = (TX + 2) * N;          // sigma tile (one-cell ring)
-    constexpr int TXR = TY * N, TXC = (TX + 2) * N;              // tx: tile rows, one-cell ring in x
-    constexpr int TYR = (TY + 2) * N, TYC = TX * N;              // ty: one-cell ring in y, tile columns
-    extern __shared__ double smem[];
-    double* xs = smem;
-    double* ss = xs + XR * XC;
-    double* txs = ss + SR * SC;
-    double* tys = txs + TXR * TXC;
-    const int cx0 = blockIdx.x * TX, cy0 = blockIdx.y * TY;
-    const int LDG = A.Nx * N;  // global row length
-    const int tid = threadIdx.x;
-
-    // ---- phase 0: stage x (halo H) and sigma (halo 1)
-    for (int e = tid; e < XR * XC; e += FUSED_THREADS) {
-        int r = e / XC, c = e - r * XC;
-        int gy = gcell(cy0 - H + r / N, A.Ny, A.wrapy), gx = gcell(cx0 - H + c / N, A.Nx, A.wrapx);
-        double v = 0.;
-        if (gy >= 0 && gx >= 0) v = __ldg(A.x + (size_t)(gy * N + r % N) * LDG + gx * N + c % N);
-        xs[e] = v;
-    }
-    for (int e = tid; e < SR * SC; e += FUSED_THREADS) {
-        int r = e / SC, c = e - r * SC;
-        int gy = gcell(cy0 - 1 + r / N, A.Ny, A.wrapy), gx = gcell(cx0 - 1 + c / N, A.Nx, A.wrapx);
-        double v = 0.;
-        if (gy >= 0 && gx >= 0) v = __ldg(A.sigma + (size_t)(gy * N + r % N) * LDG + gx * N + c % N);
-        ss[e] = v;
-    }
+    if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
+    unsigned phase = 0;
 
-    // ---- phase 1a: tx = sigma * (Rx x) on tile rows x (tile + ring) cells; item = (row r, cell c)
-    for (int it = tid; it < TXR * (TX + 2); it += FUSED_THREADS) {
-        int r = it / (TX + 2), c = it - r * (TX + 2);  // c = 0 is the cell left of the tile
-        int gx = gcell(cx0 - 1 + c, A.Nx, A.wrapx);
-        int gyc = cy0 + r / N;
-        double g[N];
-#pragma unroll
-        for (int k = 0; k < N; k++) g[k] = 0.;
-        if (gx >= 0 && gyc < A.Ny && c - 1 >= A.txlo && c - 1 <= TX - 1 + A.txhi) {
-            apply_row<N, B>(A.rx, C.rx, gx, xs + (H * N + r) * XC + (H - 1 + c) * N, 1, 1., g);
-            const double* sg = ss + (N + r) * SC + c * N;
-#pragma unroll
-            for (int k = 0; k < N; k++) g[k] = __fma_rn(sg[k], g[k], __dmul_rn(g[k], 0.));
-        }
-#pragma unroll
-        for (int k = 0; k < N; k++) txs[r * TXC + c * N + k] = g[k];
-    }
-    // ---- phase 1b: ty = sigma * (Ry x) on (tile + ring) cells x tile columns; item = (cell r, column c)
-    for (int it = tid; it < (TY + 2) * TYC; it += FUSED_THREADS) {
-        int r = it / TYC, c = it - r * TYC;  // r = 0 is the cell below the tile
-        int gy = gcell(cy0 - 1 + r, A.Ny, A.wrapy);
-        int gxc = cx0 + c / N;
-        double g[N];
-#pragma unroll
-        for (int k = 0; k < N; k++) g[k] = 0.;
-        if (gy >= 0 && gxc < A.Nx && r - 1 >= A.tylo && r - 1 <= TY - 1 + A.tyhi) {
-            apply_row<N, B>(A.ry, C.ry, gy, xs + ((H - 1 + r) * N) * XC + H * N + c, XC, 1., g);
-            const double* sg = ss + (r * N) * SC + N + c;
-#pragma unroll
-            for (int k = 0; k < N; k++) g[k] = __fma_rn(sg[k * SC], g[k], __dmul_rn(g[k], 0.));
-        }
-#pragma unroll
-        for (int k = 0; k < N; k++) tys[(r * N + k) * TYC + c] = g[k];
-    }
-    __syncthreads();
-
-    // ---- phase 2: one thread per cell
+    constexpr int ITER = (TL::OR * OC) / FUSED_THREADS;
+    static_assert(ITER * FUSED_THREADS == TL::OR * OC, "tile must be a multiple of the CTA size");
     const int cx = tid % TX, cy = tid / TX;
-    const int ix = cx0 + cx, iy = cy0 + cy;
-    double acc[N][N];  // [ky][kx]
-#pragma unroll
-    for (int a = 0; a < N; a++)
-#pragma unroll
-        for (int b = 0; b < N; b++) acc[a][b] = 0.;
-    const bool active = ix < A.Nx && iy < A.Ny;
-    if (active) {
-        // Ly ty (alpha = 1, beta = 0)
-#pragma unroll
-        for (int kx = 0; kx < N; kx++) {
-            double col[N];
-#pragma unroll
-            for (int k = 0; k < N; k++) col[k] = 0.;
-            apply_row<N, B>(A.ly, C.ly, iy, tys + ((cy + 1) * N) * TYC + cx * N + kx, TYC, 1., col);
-#pragma unroll
-            for (int k = 0; k < N; k++) acc[k][kx] = col[k];
-        }
-        // - Lx tx - t   (alpha = -1, beta = -1)
-#pragma unroll
-        for (int ky = 0; ky < N; ky++) {
-            double row[N];
-#pragma unroll
-            for (int k = 0; k < N; k++) row[k] = __dmul_rn(acc[ky][k], -1.);
-            apply_row<N, B>(A.lx, C.lx, ix, txs + (cy * N + ky) * TXC + (cx + 1) * N, 1, -1., row);
-#pragma unroll
-            for (int k = 0; k < N; k++) acc[ky][k] = row[k];
-        }
-        if (A.jfactor != 0.) {
-#pragma unroll
-            for (int ky = 0; ky < N; ky++) {
-                double row[N];
-#pragma unroll
-                for (int k = 0; k < N; k++) row[k] = acc[ky][k];
-                apply_row<N, 3>(A.jx, C.jx, ix, xs + ((cy + H) * N + ky) * XC + (cx + H) * N, 1, A.jfactor, row);
-#pragma unroll
-                for (int k = 0; k < N; k++) acc[ky][k] = row[k];
+
+    for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+        const int tyi = tile / A.ntx, txi = tile - tyi * A.ntx;
+        const int cx0 = txi * TX, cy0 = tyi * TY;
+        // ---- phase 0
+        const bool seam = (A.wrapx && (cx0 - H < 0 || cx0 + TX + H > A.Nx)) || (A.wrapy && (cy0 - H < 0 || cy0 + TY + H > A.Ny));
+        if (A.use_tma && !seam) {
+            if (tid == 0) {
+                mbar_expect_tx(bar, (unsigned)((TL::XR * XC + TL::SR * SC) * sizeof(double)));
+                tma_load_2d(smem + TL::XS, &map_x, bar, (cx0 - H) * N - TL::XSH, (cy0 - H) * N);
+                tma_load_2d(smem + TL::SS, &map_s, bar, (cx0 - 1) * N - TL::SSH, (cy0 - 1) * N);
             }
+            mbar_wait(bar, phase);
+            phase ^= 1;
+        } else {
+            load_tile_ldgsts<N, TL::XR, TL::XC, XC>(xs, A.x, cy0 - H, cx0 - H, A, tid);
+            load_tile_ldgsts<N, TL::SR, TL::SC, SC>(ss, A.sigma, cy0 - 1, cx0 - 1, A, tid);
+            cp_async_wait_all();
+            __syncthreads();
+        }
+
+        // ---- phase 1a: tx = sigma * (Rx x) on tile rows x (tile + ring) cells; item = (row r, cell c)
+        {
+            int r = tid / (TX + 2), c = tid - r * (TX + 2);  // c = 0 is the cell left of the tile
+            constexpr int DR = FUSED_THREADS / (TX + 2), DC = FUSED_THREADS - DR * (TX + 2);
+            for (; r < TL::TXR; r += DR, c += DC) {
+                if (c >= TX + 2) { c -= TX + 2; if (++r >= TL::TXR) break; }
+                const int gx = gcell(cx0 - 1 + c, A.Nx, A.wrapx);
+                double g[N];
+#pragma unroll
+                for (int k = 0; k < N; k++) g[k] = 0.;
+                if (gx >= 0 && cy0 + r / N < A.Ny && c - 1 >= A.txlo && c - 1 <= TX - 1 + A.txhi) {
+                    apply_row<N, B>(A.rx, C.rx, gx, xs + (H * N + r) * XC + (H - 1 + c) * N, 1, 1., g);
+                    const double* sg = ss + (N + r) * SC + c * N;
+#pragma unroll
+                    for (int k = 0; k < N; k++) g[k] = __fma_rn(sg[k], g[k], __dmul_rn(g[k], 0.));
+                }
+#pragma unroll
+                for (int k = 0; k < N; k++) txs[r * TXC + c * N + k] = g[k];
+            }
+        }
+        // ---- phase 1b: ty = sigma * (Ry x) on (tile + ring) cells x tile columns; item = (cell r, column c)
+        {
+            int r = tid / TYC, c = tid - r * TYC;  // r = 0 is the cell below the tile
+            constexpr int DR = FUSED_THREADS / TYC, DC = FUSED_THREADS - DR * TYC;
+            for (; r < TY + 2; r += DR, c += DC) {
+                if (c >= TYC) { c -= TYC; if (++r >= TY + 2) break; }
+                const int gy = gcell(cy0 - 1 + r, A.Ny, A.wrapy);
+                double g[N];
+#pragma unroll
+                for (int k = 0; k < N; k++) g[k] = 0.;
+                if (gy >= 0 && cx0 + c / N < A.Nx && r - 1 >= A.tylo && r - 1 <= TY - 1 + A.tyhi) {
+                    apply_row<N, B>(A.ry, C.ry, gy, xs + ((H - 1 + r) * N) * XC + H * N + c, XC, 1., g);
+                    const double* sg = ss + (r * N) * SC + N + c;
+#pragma unroll
+                    for (int k = 0; k < N; k++) g[k] = __fma_rn(sg[k * SC], g[k], __dmul_rn(g[k], 0.));
+                }
+#pragma unroll
+                for (int k = 0; k < N; k++) tys[(r * N + k) * TYC + c] = g[k];
+            }
+        }
+        __syncthreads();
+
+        // ---- phase 2: one thread per cell
+        const int ix = cx0 + cx, iy = cy0 + cy;
+        double acc[N][N];  // [ky][kx]
+#pragma unroll
+        for (int a = 0; a < N; a++)
+#pragma unroll
+            for (int b = 0; b < N; b++) acc[a][b] = 0.;
+        if (ix < A.Nx && iy < A.Ny) {
+            // Ly ty (alpha = 1, beta = 0)
 #pragma unroll
             for (int kx = 0; kx < N; kx++) {
                 double col[N];
 #pragma unroll
-                for (int k = 0; k < N; k++) col[k] = acc[k][kx];
-                apply_row<N, 3>(A.jy, C.jy, iy, xs + ((cy + H) * N) * XC + (cx + H) * N + kx, XC, A.jfactor, col);
+                for (int k = 0; k < N; k++) col[k] = 0.;
+                apply_row<N, B>(A.ly, C.ly, iy, tys + ((cy + 1) * N) * TYC + cx * N + kx, TYC, 1., col);
 #pragma unroll
                 for (int k = 0; k < N; k++) acc[k][kx] = col[k];
             }
-        }
-    }
-    __syncthreads();  // every read of txs is done: reuse it as the output staging tile (TY*N x TX*N)
-    double* outs = txs;
-    constexpr int OC = TX * N;
+            // - Lx tx - t   (alpha = -1, beta = -1)
 #pragma unroll
-    for (int ky = 0; ky < N; ky++)
+            for (int ky = 0; ky < N; ky++) {
+                double row[N];
 #pragma unroll
-        for (int kx = 0; kx < N; kx++) outs[(cy * N + ky) * OC + cx * N + kx] = acc[ky][kx];
-    __syncthreads();
-    // ---- phase 3: coalesced epilogue  y = fma(alpha, t/vol, beta*y)
-    for (int e = tid; e < TY * N * OC; e += FUSED_THREADS) {
-        int r = e / OC, c = e - r * OC;
-        int gyc = cy0 + r / N, gxc = cx0 + c / N;
-        if (gyc >= A.Ny || gxc >= A.Nx) continue;
-        size_t g = (size_t)(cy0 * N + r) * LDG + cx0 * N + c;
-        double t = outs[e];
-        if (A.vol) t = __ddiv_rn(t, __ldg(A.vol + g));
-        double b = A.beta == 0. ? 0. : __dmul_rn(A.y[g], A.beta);
-        double v = __fma_rn(A.alpha, t, b);
-        A.y[g] = v;
-        if (DOT) {
-            constexpr int Hh = (B == 2) ? 1 : 2;
-            double xv = xs[(Hh * N + r) * ((TX + 2 * Hh) * N) + Hh * N + c];
-            double pr = __dmul_rn(__dmul_rn(xv, __ldg(A.dot_w + g)), v);
-            if (!isfinite(pr)) { bad = 1; pr = 0.; }
-            fpe.add(pr, dsm + (tid >> 5) * sa::BINS);
+                for (int k = 0; k < N; k++) row[k] = __dmul_rn(acc[ky][k], -1.);
+                apply_row<N, B>(A.lx, C.lx, ix, txs + (cy * N + ky) * TXC + (cx + 1) * N, 1, -1., row);
+#pragma unroll
+                for (int k = 0; k < N; k++) acc[ky][k] = row[k];
+            }
+            if (A.jfactor != 0.) {
+#pragma unroll
+                for (int ky = 0; ky < N; ky++) {
+                    double row[N];
+#pragma unroll
+                    for (int k = 0; k < N; k++) row[k] = acc[ky][k];
+                    apply_row<N, 3>(A.jx, C.jx, ix, xs + ((cy + H) * N + ky) * XC + (cx + H) * N, 1, A.jfactor, row);
+#pragma unroll
+                    for (int k = 0; k < N; k++) acc[ky][k] = row[k];
+                }
+#pragma unroll
+                for (int kx = 0; kx < N; kx++) {
+                    double col[N];
+#pragma unroll
+                    for (int k = 0; k < N; k++) col[k] = acc[k][kx];
+                    apply_row<N, 3>(A.jy, C.jy, iy, xs + ((cy + H) * N) * XC + (cx + H) * N + kx, XC, A.jfactor, col);
+#pragma unroll
+                    for (int k = 0; k < N; k++) acc[k][kx] = col[k];
+                }
+            }
         }
+        __syncthreads();  // every read of txs is done: reuse it as the output staging tile (OR x OC)
+        double* outs = txs;
+#pragma unroll
+        for (int ky = 0; ky < N; ky++)
+#pragma unroll
+            for (int kx = 0; kx < N; kx++) outs[(cy * N + ky) * OC + cx * N + kx] = acc[ky][kx];
+        __syncthreads();
+
+        // ---- phase 3: coalesced epilogue  y = fma(alpha, t/vol, beta*y); all global loads are issued before use
+        const size_t gbase = (size_t)(cy0 * N) * LDG + cx0 * N;
+        double yin[ITER], vin[ITER], win[ITER];
+        bool okv[ITER];
+#pragma unroll
+        for (int u = 0; u < ITER; u++) {
+            const int e = tid + u * FUSED_THREADS;
+            const int r = e / OC, c = e - r * OC;
+            okv[u] = (cy0 + r / N) < A.Ny && (cx0 + c / N) < A.Nx;
+            const size_t g = gbase + (size_t)r * LDG + c;
+            yin[u] = 0.; vin[u] = 1.; win[u] = 0.;
+            if (okv[u]) {
+                if (A.beta != 0.) yin[u] = A.y[g];
+                if (A.vol) vin[u] = __ldg(A.vol + g);
+                if (DOT) win[u] = __ldg(A.dot_w + g);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < ITER; u++) {
+            if (!okv[u]) continue;
+            const int e = tid + u * FUSED_THREADS;
+            const int r = e / OC, c = e - r * OC;
+            double t = outs[e];
+            if (A.vol) t = __ddiv_rn(t, vin[u]);
+            const double b = A.beta == 0. ? 0. : __dmul_rn(yin[u], A.beta);
+            const double v = __fma_rn(A.alpha, t, b);
+            A.y[gbase + (size_t)r * LDG + c] = v;
+            if (DOT) {
+                const double xv = xs[(H * N + r) * XC + H * N + c];
+                double pr = __dmul_rn(__dmul_rn(xv, win[u]), v);
+                if (!isfinite(pr)) { bad = 1; pr = 0.; }
+                fpe.add(pr, dsm + (tid >> 5) * sa::BINS);
+            }
+        }
+        __syncthreads();  // the tile buffers are free for the next TMA / LDGSTS round
     }
     if (DOT) {
         fpe.flush(dsm + (tid >> 5) * sa::BINS);
         if (sa::block_finish<NW>(dsm, bad, A.slot, 0) && tid == 0) pcg_after_pAp(A.pcg, A.slot.result);
     }
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// 2-d map over a row-major (rows x ld) array of doubles with a (box_r x box_c) box; false if TMA cannot describe it
+static bool make_map(CUtensorMap* m, const double* base, int rows, int ld, int box_r, int box_c) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((size_t)ld * sizeof(double)) % 16 || box_c > 256 || box_r > 256) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
 }
 
 static MatView view(const EllDev& m) {
@@ -271,14 +419,14 @@ static void fill(double (&dst)[BPL][N][N], const EllDev& m) {
 template <int N, int B, bool DOT>
 static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                   const FusedDot* fd) {
-    constexpr int H = (B == 2) ? 1 : 2;
-    constexpr size_t smem = sizeof(double) * ((size_t)(TY + 2 * H) * N * (TX + 2 * H) * N + (size_t)(TY + 2) * N * (TX + 2) * N +
-                                              (size_t)TY * N * (TX + 2) * N + (size_t)(TY + 2) * N * TX * N);
+    using TL = Tile<N, B>;
     static bool configured = false;
+    static int no_tma = -1;
     if (!configured) {
-        DGB_CUDA(cudaFuncSetAttribute(elliptic2d_fused_kernel<N, B, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        DGB_CUDA(cudaFuncSetAttribute(elliptic2d_fused_kernel<N, B, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::BYTES));
         configured = true;
     }
+    if (no_tma < 0) { const char* e = getenv("DGB_NO_TMA"); no_tma = (e && atoi(e)) ? 1 : 0; }
     FusedArgs A;
     A.rx = view(p.rightx); A.ry = view(p.righty); A.lx = view(p.leftx); A.ly = view(p.lefty);
     A.jx = view(p.jumpx); A.jy = view(p.jumpy);
@@ -288,15 +436,23 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
         A.txlo = std::min(A.txlo, p.leftx.off[d]); A.txhi = std::max(A.txhi, p.leftx.off[d]);
         A.tylo = std::min(A.tylo, p.lefty.off[d]); A.tyhi = std::max(A.tyhi, p.lefty.off[d]);
     }
+    A.ntx = (p.Nx + TX - 1) / TX;
+    A.ntiles = A.ntx * ((p.Ny + TY - 1) / TY);
     A.sigma = p.sigma; A.vol = p.vol; A.x = x; A.y = y;
     A.alpha = alpha; A.beta = beta; A.jfactor = p.jfactor;
     A.dot_w = nullptr; A.pcg = nullptr; A.slot = sa::DotSlot{nullptr, nullptr, nullptr, nullptr};
     if (DOT) { A.dot_w = fd->w; A.slot = fd->slot; A.pcg = fd->pcg; }
+    CUtensorMap mx, ms;
+    memset(&mx, 0, sizeof(mx));
+    memset(&ms, 0, sizeof(ms));
+    A.use_tma = !no_tma && make_map(&mx, x, p.Ny * N, p.Nx * N, TL::XR, TL::XP) &&
+                make_map(&ms, p.sigma, p.Ny * N, p.Nx * N, TL::SR, TL::SP);
     EllipticCoef<N, B> C;
     fill<N, B>(C.rx, p.rightx); fill<N, B>(C.ry, p.righty); fill<N, B>(C.lx, p.leftx); fill<N, B>(C.ly, p.lefty);
     fill<N, 3>(C.jx, p.jumpx); fill<N, 3>(C.jy, p.jumpy);
-    dim3 grid((p.Nx + TX - 1) / TX, (p.Ny + TY - 1) / TY);
-    elliptic2d_fused_kernel<N, B, DOT><<<grid, FUSED_THREADS, smem, st>>>(A, C);
+    int per_sm = TL::BYTES > 110 * 1024 ? 1 : 2;
+    int grid = std::min(A.ntiles, per_sm * sm_count());
+    elliptic2d_fused_kernel<N, B, DOT><<<grid, FUSED_THREADS, TL::BYTES, st>>>(A, C, mx, ms);
     DGB_LAUNCHED();
     return 0;
 }

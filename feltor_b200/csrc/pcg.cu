@@ -27,6 +27,14 @@ struct Pcg {
     dgb_dot_result* results = nullptr;
     dgb_dot_result* results_host = nullptr;
     int check_every = 8;
+    // optional per-kernel timing (bench.py roofline): CUDA events on the launching stream around K1/K2/K3
+    bool profile = false;
+    static constexpr int PROF_MAX = 64;
+    cudaEvent_t ev[PROF_MAX][4];
+    bool ev_ready = false;
+    int prof_n = 0;
+    double prof_ms[3] = {0., 0., 0.};
+    long long prof_count = 0;
 };
 
 // -------------------------------------------------------------------------------------------- setup kernels
@@ -228,6 +236,8 @@ int pcg_solve(Pcg& s, Elliptic2dPlan& A, double* x, const double* b, const doubl
     while (i < max_iter) {
         int stop = i + s.check_every < max_iter ? i + s.check_every : max_iter;
         for (; i < stop; i++) {
+            const bool prof = s.profile && s.prof_n < Pcg::PROF_MAX;
+            if (prof) cudaEventRecord(s.ev[s.prof_n][0], st);
             if (fused) {
                 if ((e = elliptic2d_fused_launch_dot(A, s.p, s.ap, st, fd))) return e;
             } else {
@@ -235,15 +245,27 @@ int pcg_solve(Pcg& s, Elliptic2dPlan& A, double* x, const double* b, const doubl
                 pcg_dot3_kernel<2><<<g1, PCG_THREADS, 0, st>>>(n, s.p, W, s.ap, s.slot, 0, s.st);
                 DGB_LAUNCHED();
             }
+            if (prof) cudaEventRecord(s.ev[s.prof_n][1], st);
             if (i % test_frequency == 0)
                 pcg_update_kernel<true><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
             else
                 pcg_update_kernel<false><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
             DGB_LAUNCHED();
+            if (prof) cudaEventRecord(s.ev[s.prof_n][2], st);
             pcg_direction_kernel<<<g2, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st);
             DGB_LAUNCHED();
+            if (prof) cudaEventRecord(s.ev[s.prof_n++][3], st);
         }
         if ((e = fetch_state(s, st))) return e;
+        if (s.profile) {  // the stream is idle here: harvest the event pairs
+            for (int k = 0; k < s.prof_n; k++)
+                for (int j = 0; j < 3; j++) {
+                    float ms = 0.f;
+                    if (cudaEventElapsedTime(&ms, s.ev[k][j], s.ev[k][j + 1]) == cudaSuccess) s.prof_ms[j] += ms;
+                }
+            s.prof_count += s.prof_n;
+            s.prof_n = 0;
+        }
         if (s.st_host->status) {
             set_error("dot product failed since one of the inputs contains NaN or Inf");
             return DGB_ERR_NOTFINITE;
@@ -287,9 +309,33 @@ int dgb_pcg_create(dgb_pcg** out, size_t n) {
     *out = reinterpret_cast<dgb_pcg*>(s);
     return 0;
 }
+int dgb_pcg_set_profile(dgb_pcg* h, int on) {
+    Pcg* s = reinterpret_cast<Pcg*>(h);
+    if (on && !s->ev_ready) {
+        for (int k = 0; k < Pcg::PROF_MAX; k++)
+            for (int j = 0; j < 4; j++) DGB_CUDA(cudaEventCreate(&s->ev[k][j]));
+        s->ev_ready = true;
+    }
+    s->profile = on != 0;
+    s->prof_n = 0;
+    s->prof_count = 0;
+    s->prof_ms[0] = s->prof_ms[1] = s->prof_ms[2] = 0.;
+    return 0;
+}
+int dgb_pcg_get_profile(dgb_pcg* h, double* ms_apply_dot, double* ms_update, double* ms_direction, long long* iterations) {
+    Pcg* s = reinterpret_cast<Pcg*>(h);
+    if (ms_apply_dot) *ms_apply_dot = s->prof_ms[0];
+    if (ms_update) *ms_update = s->prof_ms[1];
+    if (ms_direction) *ms_direction = s->prof_ms[2];
+    if (iterations) *iterations = s->prof_count;
+    return 0;
+}
 int dgb_pcg_destroy(dgb_pcg* h) {
     Pcg* s = reinterpret_cast<Pcg*>(h);
     if (!s) return 0;
+    if (s->ev_ready)
+        for (int k = 0; k < Pcg::PROF_MAX; k++)
+            for (int j = 0; j < 4; j++) cudaEventDestroy(s->ev[k][j]);
     cudaFree(s->r); cudaFree(s->p); cudaFree(s->ap); cudaFree(s->st); cudaFreeHost(s->st_host);
     cudaFree(s->slot.gacc); cudaFree(s->slot.gstatus); cudaFree(s->slot.ticket);
     cudaFree(s->results); cudaFreeHost(s->results_host);

@@ -48,26 +48,16 @@ __device__ __forceinline__ int atomic_add_wrap(long long* w, long long x, long l
     return o > 0 ? 1 : -1;
 }
 
-// add the integer x (|x| <= 2^63-1) to word i of a (possibly shared, concurrently updated) accumulator
-// with element stride `stride`; never loses a bit: a wrap of 2^64 equals 2^8 units of the next word.
+// add the integer x to word i of a (possibly shared or global, concurrently updated) accumulator with element
+// stride `stride`.  Never loses a bit: when the 64-bit word wraps, the lost +-2^64 equals +-2^8 units of the next
+// word (2^64 = 2^8 * 2^56) and is added there; the wrapped word itself stays a valid two's complement digit, so the
+// represented VALUE sum_i acc[i] 2^(56 (i-20)) is preserved under any interleaving of the atomics.
 __device__ inline void add_word(long long* acc, int i, long long x, int stride) {
     while (i < BINS) {
         long long stored;
         int wrap = atomic_add_wrap(&acc[i * stride], x, stored);
         if (wrap == 0) return;
-        // true word value = stored + wrap*2^64: move everything above bit 56 of `stored`, and the lost 2^64,
-        // upward.  Cancelling c*2^56 in this word can itself wrap when other threads interfere -> repeat.
-        long long c = stored >> DIGITS;  // arithmetic shift
-        long long carry_up = c + (long long)wrap * (1ll << KRX);
-        long long cancel = (long long)(0ull - ((unsigned long long)c << DIGITS));
-        while (cancel != 0) {
-            int wrap2 = atomic_add_wrap(&acc[i * stride], cancel, stored);
-            if (wrap2 == 0) break;
-            long long c2 = stored >> DIGITS;
-            carry_up += c2 + (long long)wrap2 * (1ll << KRX);
-            cancel = (long long)(0ull - ((unsigned long long)c2 << DIGITS));
-        }
-        x = carry_up;
+        x = (long long)wrap * (1ll << KRX);
         ++i;
     }
 }
@@ -210,7 +200,7 @@ __device__ inline bool block_finish(long long* smem, int status, const DotSlot& 
     __syncthreads();
     if (threadIdx.x == 0) {
         unsigned int t = atomicAdd(slot.ticket + slot_idx, 1u);
-        s_last = (t == gridDim.x - 1);
+        s_last = (t == gridDim.x * gridDim.y * gridDim.z - 1);
     }
     __syncthreads();
     if (!s_last) return false;

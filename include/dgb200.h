@@ -264,6 +264,12 @@ DGB_API int dgb_pcg_solve_elliptic2d(dgb_pcg* pcg, dgb_elliptic2d* A, double* x,
                                      const double* W, double eps, double nrmb_correction, int test_frequency,
                                      int max_iter, int* iterations, dgb_stream_t s);
 
+/* measurement aid: when on, CUDA events on the launching stream bracket the three kernels of every iteration
+ * (operator+dot, update+dots, direction); get returns the accumulated milliseconds and the iterations timed */
+DGB_API int dgb_pcg_set_profile(dgb_pcg* pcg, int on);
+DGB_API int dgb_pcg_get_profile(dgb_pcg* pcg, double* ms_apply_dot, double* ms_update, double* ms_direction,
+                                long long* iterations);
+
 #ifdef __cplusplus
 }
 #endif
