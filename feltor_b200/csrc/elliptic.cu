@@ -129,7 +129,22 @@ static void analyse(Elliptic2dPlan& p) {
         if (wx[k] && !p.wrapx) return;
         if (wy[k] && !p.wrapy) return;
     }
-    p.n = n; p.Nx = Nx; p.Ny = Ny; p.bder = bder;
+    // the fused kernel hard-wires the interior stencil offsets of dx.h: right {0,+1} / left {-1,0} (forward),
+    // right {-1,0} / left {0,+1} (backward), {-1,0,+1} for centered derivatives and for the jumps
+    auto offs = [](const EllDev& m, int first) {
+        for (int d = 0; d < m.bpl; d++)
+            if (m.off[d] != first + d) return false;
+        return true;
+    };
+    int dirk;
+    if (bder == 3) dirk = 2;
+    else if (offs(p.rightx, 0)) dirk = 0;
+    else dirk = 1;
+    const int rfirst = dirk == 0 ? 0 : -1, lfirst = dirk == 1 ? 0 : -1;
+    if (!offs(p.rightx, rfirst) || !offs(p.righty, rfirst) || !offs(p.leftx, lfirst) || !offs(p.lefty, lfirst) ||
+        !offs(p.jumpx, -1) || !offs(p.jumpy, -1))
+        return;
+    p.n = n; p.Nx = Nx; p.Ny = Ny; p.bder = bder; p.dirk = dirk;
     p.fusable = true;
 }
 

@@ -16,6 +16,7 @@ struct Elliptic2dPlan {
     int n = 0, Nx = 0, Ny = 0;
     bool fusable = false;  // matrices have the dx.h structure the fused kernel was written for
     int bder = 0;          // blocks per line of the four derivative matrices (2 or 3)
+    int dirk = 0;          // stencil kind of the right derivatives: 0 {0,+1} forward, 1 {-1,0} backward, 2 {-1,0,+1}
     bool wrapx = false, wrapy = false;
 };
 

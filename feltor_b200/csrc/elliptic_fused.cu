@@ -25,7 +25,11 @@
 
 namespace dgb {
 
-constexpr int TX = 32, TY = 8, FUSED_THREADS = TX * TY;
+#ifndef DGB_TY
+#define DGB_TY 8
+#endif
+constexpr int TX = 32, TY = DGB_TY, FUSED_THREADS = TX * TY;  // one thread per cell of the tile
+constexpr int FUSED_MIN_CTAS = 512 / FUSED_THREADS;           // 16 warps per SM
 
 struct MatView {
     const double* data;
@@ -43,7 +47,7 @@ struct EllipticCoef {
 struct FusedArgs {
     MatView rx, ry, lx, ly, jx, jy;
     int Nx, Ny, wrapx, wrapy;
-    int txlo, txhi, tylo, tyhi;  // range of flux cells (relative to the tile) the adjoint derivatives reach
+    int fx_lo, fx_hi, fy_lo, fy_hi;  // cells [lo, hi) that are interior rows of all three x- resp. y-matrices
     int ntx, ntiles, use_tma;
     const double* sigma;
     const double* vol;
@@ -137,6 +141,31 @@ __device__ __forceinline__ void apply_row(const MatView& M, const double (&C)[BP
     }
 }
 
+// interior rows with the stencil offsets known at compile time (DIRK: 0 forward, 1 backward, 2 centered; jumps are
+// always {-1,0,1}): out[k] = fma(a, sum_q C[d][k][q] * s[(OFF_d*N + q)*stride], out[k])
+template <int KIND>  // 0: {0,+1}   1: {-1,0}   2: {-1,0,+1}
+struct Offs {
+    static constexpr int BPL = KIND == 2 ? 3 : 2;
+    static constexpr int first = KIND == 0 ? 0 : -1;
+    __host__ __device__ static constexpr int at(int d) { return first + d; }
+};
+template <int N, int KIND, int STRIDE>
+__device__ __forceinline__ void apply_fast(const double (&C)[Offs<KIND>::BPL][N][N], const double* s, double a, double (&out)[N]) {
+#pragma unroll
+    for (int d = 0; d < Offs<KIND>::BPL; d++) {
+        double xv[N];
+#pragma unroll
+        for (int q = 0; q < N; q++) xv[q] = s[(Offs<KIND>::at(d) * N + q) * STRIDE];
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            double t = 0.;
+#pragma unroll
+            for (int q = 0; q < N; q++) t = __fma_rn(C[d][k][q], xv[q], t);
+            out[k] = __fma_rn(a, t, out[k]);
+        }
+    }
+}
+
 // global cell index of tile-relative cell c (may lie in the halo): wrapped if periodic, -1 if outside
 __device__ __forceinline__ int gcell(int c, int num, int wrap) {
     if (c >= 0 && c < num) return c;
@@ -177,12 +206,191 @@ struct Tile {
     static constexpr size_t BYTES = END * sizeof(double) + 16;  // + mbarrier
 };
 
-template <int N, int B, bool DOT>
-__global__ void __launch_bounds__(FUSED_THREADS, 2)
-elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_constant__ EllipticCoef<N, B> C,
-                        const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_s) {
+// phases 1-3 for one staged tile.  FAST = every cell of the tile and of its ring is an interior row of all six
+// matrices and the tile lies completely inside the domain: no per-item checks, stencil offsets are immediates.
+template <int N, int DIRK, bool DOT, bool FAST>
+__device__ __forceinline__ void compute_tile(const FusedArgs& A, const EllipticCoef<N, Offs<DIRK>::BPL>& C, double* xs, double* ss,
+                                             double* txs, double* tys, int cx0, int cy0, int tid, sa::Fpe& fpe, int& bad,
+                                             long long* dsm) {
+    constexpr int B = Offs<DIRK>::BPL;
+    constexpr int RK = DIRK, LK = DIRK == 0 ? 1 : (DIRK == 1 ? 0 : 2);  // stencil kinds of the right / left derivatives
     using TL = Tile<N, B>;
-    constexpr int H = TL::H, XC = TL::XP, SC = TL::SP, TXC = TL::TXC, TYC = TL::TYC, OC = TL::OC;  // XC, SC: row pitches
+    constexpr int H = TL::H, XC = TL::XP, SC = TL::SP, TXC = TL::TXC, TYC = TL::TYC, OC = TL::OC;
+    const int LDG = A.Nx * N;
+    // flux cells the adjoint derivative reaches (relative to the tile): [LO, TX-1+HI]
+    constexpr int LO = Offs<LK>::first, HI = Offs<LK>::first + Offs<LK>::BPL - 1;
+
+    // ---- phase 1a: tx = sigma * (Rx x); item = (row r, cell c), c = 0 is the cell left of the tile
+    {
+        int r = tid / (TX + 2), c = tid - r * (TX + 2);
+        constexpr int DR = FUSED_THREADS / (TX + 2), DC = FUSED_THREADS - DR * (TX + 2);
+        for (; r < TL::TXR; r += DR, c += DC) {
+            if (c >= TX + 2) { c -= TX + 2; if (++r >= TL::TXR) break; }
+            double g[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) g[k] = 0.;
+            if (c - 1 >= LO && c - 1 <= TX - 1 + HI) {
+                const double* sx = xs + (H * N + r) * XC + (H - 1 + c) * N;
+                bool on = true;
+                if (FAST) apply_fast<N, RK, 1>(C.rx, sx, 1., g);
+                else {
+                    const int gx = gcell(cx0 - 1 + c, A.Nx, A.wrapx);
+                    on = gx >= 0 && cy0 + r / N < A.Ny;
+                    if (on) apply_row<N, B>(A.rx, C.rx, gx, sx, 1, 1., g);
+                }
+                if (on) {
+                    const double* sg = ss + (N + r) * SC + c * N;
+#pragma unroll
+                    for (int k = 0; k < N; k++) g[k] = __fma_rn(sg[k], g[k], __dmul_rn(g[k], 0.));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < N; k++) txs[r * TXC + c * N + k] = g[k];
+        }
+    }
+    // ---- phase 1b: ty = sigma * (Ry x); item = (cell r, column c), r = 0 is the cell below the tile
+    {
+        int r = tid / TYC, c = tid - r * TYC;
+        constexpr int DR = FUSED_THREADS / TYC, DC = FUSED_THREADS - DR * TYC;
+        for (; r < TY + 2; r += DR, c += DC) {
+            if (c >= TYC) { c -= TYC; if (++r >= TY + 2) break; }
+            double g[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) g[k] = 0.;
+            if (r - 1 >= LO && r - 1 <= TY - 1 + HI) {
+                const double* sx = xs + ((H - 1 + r) * N) * XC + H * N + c;
+                bool on = true;
+                if (FAST) apply_fast<N, RK, XC>(C.ry, sx, 1., g);
+                else {
+                    const int gy = gcell(cy0 - 1 + r, A.Ny, A.wrapy);
+                    on = gy >= 0 && cx0 + c / N < A.Nx;
+                    if (on) apply_row<N, B>(A.ry, C.ry, gy, sx, XC, 1., g);
+                }
+                if (on) {
+                    const double* sg = ss + (r * N) * SC + N + c;
+#pragma unroll
+                    for (int k = 0; k < N; k++) g[k] = __fma_rn(sg[k * SC], g[k], __dmul_rn(g[k], 0.));
+                }
+            }
+#pragma unroll
+            for (int k = 0; k < N; k++) tys[(r * N + k) * TYC + c] = g[k];
+        }
+    }
+    __syncthreads();
+
+    // ---- phase 2: one thread per cell
+    const int cx = tid % TX, cy = tid / TX;
+    const int ix = cx0 + cx, iy = cy0 + cy;
+    double acc[N][N];  // [ky][kx]
+#pragma unroll
+    for (int a = 0; a < N; a++)
+#pragma unroll
+        for (int b = 0; b < N; b++) acc[a][b] = 0.;
+    if (FAST || (ix < A.Nx && iy < A.Ny)) {
+        // Ly ty (alpha = 1, beta = 0)
+#pragma unroll
+        for (int kx = 0; kx < N; kx++) {
+            double col[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) col[k] = 0.;
+            const double* sp = tys + ((cy + 1) * N) * TYC + cx * N + kx;
+            if (FAST) apply_fast<N, LK, TYC>(C.ly, sp, 1., col);
+            else apply_row<N, B>(A.ly, C.ly, iy, sp, TYC, 1., col);
+#pragma unroll
+            for (int k = 0; k < N; k++) acc[k][kx] = col[k];
+        }
+        // - Lx tx - t   (alpha = -1, beta = -1)
+#pragma unroll
+        for (int ky = 0; ky < N; ky++) {
+            double row[N];
+#pragma unroll
+            for (int k = 0; k < N; k++) row[k] = __dmul_rn(acc[ky][k], -1.);
+            const double* sp = txs + (cy * N + ky) * TXC + (cx + 1) * N;
+            if (FAST) apply_fast<N, LK, 1>(C.lx, sp, -1., row);
+            else apply_row<N, B>(A.lx, C.lx, ix, sp, 1, -1., row);
+#pragma unroll
+            for (int k = 0; k < N; k++) acc[ky][k] = row[k];
+        }
+        if (A.jfactor != 0.) {
+#pragma unroll
+            for (int ky = 0; ky < N; ky++) {
+                double row[N];
+#pragma unroll
+                for (int k = 0; k < N; k++) row[k] = acc[ky][k];
+                const double* sp = xs + ((cy + H) * N + ky) * XC + (cx + H) * N;
+                if (FAST) apply_fast<N, 2, 1>(C.jx, sp, A.jfactor, row);
+                else apply_row<N, 3>(A.jx, C.jx, ix, sp, 1, A.jfactor, row);
+#pragma unroll
+                for (int k = 0; k < N; k++) acc[ky][k] = row[k];
+            }
+#pragma unroll
+            for (int kx = 0; kx < N; kx++) {
+                double col[N];
+#pragma unroll
+                for (int k = 0; k < N; k++) col[k] = acc[k][kx];
+                const double* sp = xs + ((cy + H) * N) * XC + (cx + H) * N + kx;
+                if (FAST) apply_fast<N, 2, XC>(C.jy, sp, A.jfactor, col);
+                else apply_row<N, 3>(A.jy, C.jy, iy, sp, XC, A.jfactor, col);
+#pragma unroll
+                for (int k = 0; k < N; k++) acc[k][kx] = col[k];
+            }
+        }
+    }
+    __syncthreads();  // every read of txs is done: reuse it as the output staging tile (OR x OC)
+    double* outs = txs;
+#pragma unroll
+    for (int ky = 0; ky < N; ky++)
+#pragma unroll
+        for (int kx = 0; kx < N; kx++) outs[(cy * N + ky) * OC + cx * N + kx] = acc[ky][kx];
+    __syncthreads();
+
+    // ---- phase 3: coalesced epilogue  y = fma(alpha, t/vol, beta*y).  Warp w owns rows w*N .. w*N+N-1 of the tile,
+    //      its lanes the columns lane + 32 j: every access of a warp is one contiguous 256-byte segment.
+    const int warp = tid >> 5, lane = tid & 31;
+    const size_t gbase = (size_t)(cy0 * N + warp * N) * LDG + cx0 * N + lane;
+    const double* so = outs + (warp * N) * OC + lane;
+    const double* sxr = xs + (H * N + warp * N) * XC + H * N + lane;
+    double yin[N][N], vin[N][N], win[N][N];
+    bool okv[N][N];
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            const size_t g = gbase + (size_t)i * LDG + 32 * j;
+            okv[i][j] = FAST || ((cy0 + warp) < A.Ny && (cx0 + (lane + 32 * j) / N) < A.Nx);
+            yin[i][j] = 0.; vin[i][j] = 1.; win[i][j] = 0.;
+            if (okv[i][j]) {
+                if (A.beta != 0.) yin[i][j] = A.y[g];
+                if (A.vol) vin[i][j] = __ldg(A.vol + g);
+                if (DOT) win[i][j] = __ldg(A.dot_w + g);
+            }
+        }
+#pragma unroll
+    for (int i = 0; i < N; i++)
+#pragma unroll
+        for (int j = 0; j < N; j++) {
+            if (!okv[i][j]) continue;
+            double t = so[i * OC + 32 * j];
+            if (A.vol) t = __ddiv_rn(t, vin[i][j]);
+            const double b = A.beta == 0. ? 0. : __dmul_rn(yin[i][j], A.beta);
+            const double v = __fma_rn(A.alpha, t, b);
+            A.y[gbase + (size_t)i * LDG + 32 * j] = v;
+            if (DOT) {
+                double pr = __dmul_rn(__dmul_rn(sxr[i * XC + 32 * j], win[i][j]), v);
+                if (!isfinite(pr)) { bad = 1; pr = 0.; }
+                fpe.add(pr, dsm + warp * sa::BINS);
+            }
+        }
+    __syncthreads();  // the tile buffers are free for the next TMA / LDGSTS round
+}
+
+template <int N, int DIRK, bool DOT>
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
+elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_constant__ EllipticCoef<N, Offs<DIRK>::BPL> C,
+                        const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_s) {
+    constexpr int B = Offs<DIRK>::BPL;
+    using TL = Tile<N, B>;
+    constexpr int H = TL::H, XC = TL::XP, SC = TL::SP;  // XC, SC: row pitches
     constexpr int NW = FUSED_THREADS / 32;
     __shared__ long long dsm[DOT ? NW * sa::BINS : 1];
     extern __shared__ __align__(128) double smem[];
@@ -192,7 +400,6 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
     double* tys = smem + TL::TYS;
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(smem + TL::END);
     const int tid = threadIdx.x;
-    const int LDG = A.Nx * N;  // global row length
     sa::Fpe fpe;
     int bad = 0;
     if (DOT) {
@@ -203,11 +410,7 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
     unsigned phase = 0;
-
-    constexpr int ITER = (TL::OR * OC) / FUSED_THREADS;
-    static_assert(ITER * FUSED_THREADS == TL::OR * OC, "tile must be a multiple of the CTA size");
-    const int cx = tid % TX, cy = tid / TX;
-
+    // rows/columns of cells that are interior rows of every matrix (host-computed intersection)
     for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
         const int tyi = tile / A.ntx, txi = tile - tyi * A.ntx;
         const int cx0 = txi * TX, cy0 = tyi * TY;
@@ -218,150 +421,19 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
                 mbar_expect_tx(bar, (unsigned)((TL::XR * XC + TL::SR * SC) * sizeof(double)));
                 tma_load_2d(smem + TL::XS, &map_x, bar, (cx0 - H) * N - TL::XSH, (cy0 - H) * N);
                 tma_load_2d(smem + TL::SS, &map_s, bar, (cx0 - 1) * N - TL::SSH, (cy0 - 1) * N);
+                mbar_wait(bar, phase);  // one thread polls, the CTA sleeps on the barrier below
             }
-            mbar_wait(bar, phase);
             phase ^= 1;
+            __syncthreads();
         } else {
             load_tile_ldgsts<N, TL::XR, TL::XC, XC>(xs, A.x, cy0 - H, cx0 - H, A, tid);
             load_tile_ldgsts<N, TL::SR, TL::SC, SC>(ss, A.sigma, cy0 - 1, cx0 - 1, A, tid);
             cp_async_wait_all();
             __syncthreads();
         }
-
-        // ---- phase 1a: tx = sigma * (Rx x) on tile rows x (tile + ring) cells; item = (row r, cell c)
-        {
-            int r = tid / (TX + 2), c = tid - r * (TX + 2);  // c = 0 is the cell left of the tile
-            constexpr int DR = FUSED_THREADS / (TX + 2), DC = FUSED_THREADS - DR * (TX + 2);
-            for (; r < TL::TXR; r += DR, c += DC) {
-                if (c >= TX + 2) { c -= TX + 2; if (++r >= TL::TXR) break; }
-                const int gx = gcell(cx0 - 1 + c, A.Nx, A.wrapx);
-                double g[N];
-#pragma unroll
-                for (int k = 0; k < N; k++) g[k] = 0.;
-                if (gx >= 0 && cy0 + r / N < A.Ny && c - 1 >= A.txlo && c - 1 <= TX - 1 + A.txhi) {
-                    apply_row<N, B>(A.rx, C.rx, gx, xs + (H * N + r) * XC + (H - 1 + c) * N, 1, 1., g);
-                    const double* sg = ss + (N + r) * SC + c * N;
-#pragma unroll
-                    for (int k = 0; k < N; k++) g[k] = __fma_rn(sg[k], g[k], __dmul_rn(g[k], 0.));
-                }
-#pragma unroll
-                for (int k = 0; k < N; k++) txs[r * TXC + c * N + k] = g[k];
-            }
-        }
-        // ---- phase 1b: ty = sigma * (Ry x) on (tile + ring) cells x tile columns; item = (cell r, column c)
-        {
-            int r = tid / TYC, c = tid - r * TYC;  // r = 0 is the cell below the tile
-            constexpr int DR = FUSED_THREADS / TYC, DC = FUSED_THREADS - DR * TYC;
-            for (; r < TY + 2; r += DR, c += DC) {
-                if (c >= TYC) { c -= TYC; if (++r >= TY + 2) break; }
-                const int gy = gcell(cy0 - 1 + r, A.Ny, A.wrapy);
-                double g[N];
-#pragma unroll
-                for (int k = 0; k < N; k++) g[k] = 0.;
-                if (gy >= 0 && cx0 + c / N < A.Nx && r - 1 >= A.tylo && r - 1 <= TY - 1 + A.tyhi) {
-                    apply_row<N, B>(A.ry, C.ry, gy, xs + ((H - 1 + r) * N) * XC + H * N + c, XC, 1., g);
-                    const double* sg = ss + (r * N) * SC + N + c;
-#pragma unroll
-                    for (int k = 0; k < N; k++) g[k] = __fma_rn(sg[k * SC], g[k], __dmul_rn(g[k], 0.));
-                }
-#pragma unroll
-                for (int k = 0; k < N; k++) tys[(r * N + k) * TYC + c] = g[k];
-            }
-        }
-        __syncthreads();
-
-        // ---- phase 2: one thread per cell
-        const int ix = cx0 + cx, iy = cy0 + cy;
-        double acc[N][N];  // [ky][kx]
-#pragma unroll
-        for (int a = 0; a < N; a++)
-#pragma unroll
-            for (int b = 0; b < N; b++) acc[a][b] = 0.;
-        if (ix < A.Nx && iy < A.Ny) {
-            // Ly ty (alpha = 1, beta = 0)
-#pragma unroll
-            for (int kx = 0; kx < N; kx++) {
-                double col[N];
-#pragma unroll
-                for (int k = 0; k < N; k++) col[k] = 0.;
-                apply_row<N, B>(A.ly, C.ly, iy, tys + ((cy + 1) * N) * TYC + cx * N + kx, TYC, 1., col);
-#pragma unroll
-                for (int k = 0; k < N; k++) acc[k][kx] = col[k];
-            }
-            // - Lx tx - t   (alpha = -1, beta = -1)
-#pragma unroll
-            for (int ky = 0; ky < N; ky++) {
-                double row[N];
-#pragma unroll
-                for (int k = 0; k < N; k++) row[k] = __dmul_rn(acc[ky][k], -1.);
-                apply_row<N, B>(A.lx, C.lx, ix, txs + (cy * N + ky) * TXC + (cx + 1) * N, 1, -1., row);
-#pragma unroll
-                for (int k = 0; k < N; k++) acc[ky][k] = row[k];
-            }
-            if (A.jfactor != 0.) {
-#pragma unroll
-                for (int ky = 0; ky < N; ky++) {
-                    double row[N];
-#pragma unroll
-                    for (int k = 0; k < N; k++) row[k] = acc[ky][k];
-                    apply_row<N, 3>(A.jx, C.jx, ix, xs + ((cy + H) * N + ky) * XC + (cx + H) * N, 1, A.jfactor, row);
-#pragma unroll
-                    for (int k = 0; k < N; k++) acc[ky][k] = row[k];
-                }
-#pragma unroll
-                for (int kx = 0; kx < N; kx++) {
-                    double col[N];
-#pragma unroll
-                    for (int k = 0; k < N; k++) col[k] = acc[k][kx];
-                    apply_row<N, 3>(A.jy, C.jy, iy, xs + ((cy + H) * N) * XC + (cx + H) * N + kx, XC, A.jfactor, col);
-#pragma unroll
-                    for (int k = 0; k < N; k++) acc[k][kx] = col[k];
-                }
-            }
-        }
-        __syncthreads();  // every read of txs is done: reuse it as the output staging tile (OR x OC)
-        double* outs = txs;
-#pragma unroll
-        for (int ky = 0; ky < N; ky++)
-#pragma unroll
-            for (int kx = 0; kx < N; kx++) outs[(cy * N + ky) * OC + cx * N + kx] = acc[ky][kx];
-        __syncthreads();
-
-        // ---- phase 3: coalesced epilogue  y = fma(alpha, t/vol, beta*y); all global loads are issued before use
-        const size_t gbase = (size_t)(cy0 * N) * LDG + cx0 * N;
-        double yin[ITER], vin[ITER], win[ITER];
-        bool okv[ITER];
-#pragma unroll
-        for (int u = 0; u < ITER; u++) {
-            const int e = tid + u * FUSED_THREADS;
-            const int r = e / OC, c = e - r * OC;
-            okv[u] = (cy0 + r / N) < A.Ny && (cx0 + c / N) < A.Nx;
-            const size_t g = gbase + (size_t)r * LDG + c;
-            yin[u] = 0.; vin[u] = 1.; win[u] = 0.;
-            if (okv[u]) {
-                if (A.beta != 0.) yin[u] = A.y[g];
-                if (A.vol) vin[u] = __ldg(A.vol + g);
-                if (DOT) win[u] = __ldg(A.dot_w + g);
-            }
-        }
-#pragma unroll
-        for (int u = 0; u < ITER; u++) {
-            if (!okv[u]) continue;
-            const int e = tid + u * FUSED_THREADS;
-            const int r = e / OC, c = e - r * OC;
-            double t = outs[e];
-            if (A.vol) t = __ddiv_rn(t, vin[u]);
-            const double b = A.beta == 0. ? 0. : __dmul_rn(yin[u], A.beta);
-            const double v = __fma_rn(A.alpha, t, b);
-            A.y[gbase + (size_t)r * LDG + c] = v;
-            if (DOT) {
-                const double xv = xs[(H * N + r) * XC + H * N + c];
-                double pr = __dmul_rn(__dmul_rn(xv, win[u]), v);
-                if (!isfinite(pr)) { bad = 1; pr = 0.; }
-                fpe.add(pr, dsm + (tid >> 5) * sa::BINS);
-            }
-        }
-        __syncthreads();  // the tile buffers are free for the next TMA / LDGSTS round
+        const bool fast = cx0 - 1 >= A.fx_lo && cx0 + TX + 1 <= A.fx_hi && cy0 - 1 >= A.fy_lo && cy0 + TY + 1 <= A.fy_hi;
+        if (fast) compute_tile<N, DIRK, DOT, true>(A, C, xs, ss, txs, tys, cx0, cy0, tid, fpe, bad, dsm);
+        else compute_tile<N, DIRK, DOT, false>(A, C, xs, ss, txs, tys, cx0, cy0, tid, fpe, bad, dsm);
     }
     if (DOT) {
         fpe.flush(dsm + (tid >> 5) * sa::BINS);
@@ -416,14 +488,15 @@ static void fill(double (&dst)[BPL][N][N], const EllDev& m) {
             for (int q = 0; q < N; q++) dst[d][k][q] = m.h_data[((size_t)m.did[d] * N + k) * N + q];
 }
 
-template <int N, int B, bool DOT>
+template <int N, int DIRK, bool DOT>
 static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                   const FusedDot* fd) {
+    constexpr int B = Offs<DIRK>::BPL;
     using TL = Tile<N, B>;
     static bool configured = false;
     static int no_tma = -1;
     if (!configured) {
-        DGB_CUDA(cudaFuncSetAttribute(elliptic2d_fused_kernel<N, B, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::BYTES));
+        DGB_CUDA(cudaFuncSetAttribute(elliptic2d_fused_kernel<N, DIRK, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL::BYTES));
         configured = true;
     }
     if (no_tma < 0) { const char* e = getenv("DGB_NO_TMA"); no_tma = (e && atoi(e)) ? 1 : 0; }
@@ -431,11 +504,10 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
     A.rx = view(p.rightx); A.ry = view(p.righty); A.lx = view(p.leftx); A.ly = view(p.lefty);
     A.jx = view(p.jumpx); A.jy = view(p.jumpy);
     A.Nx = p.Nx; A.Ny = p.Ny; A.wrapx = p.wrapx; A.wrapy = p.wrapy;
-    A.txlo = A.txhi = A.tylo = A.tyhi = 0;
-    for (int d = 0; d < B; d++) {
-        A.txlo = std::min(A.txlo, p.leftx.off[d]); A.txhi = std::max(A.txhi, p.leftx.off[d]);
-        A.tylo = std::min(A.tylo, p.lefty.off[d]); A.tyhi = std::max(A.tyhi, p.lefty.off[d]);
-    }
+    A.fx_lo = std::max({p.rightx.i_lo, p.leftx.i_lo, p.jumpx.i_lo});
+    A.fx_hi = std::min({p.rightx.i_hi, p.leftx.i_hi, p.jumpx.i_hi});
+    A.fy_lo = std::max({p.righty.i_lo, p.lefty.i_lo, p.jumpy.i_lo});
+    A.fy_hi = std::min({p.righty.i_hi, p.lefty.i_hi, p.jumpy.i_hi});
     A.ntx = (p.Nx + TX - 1) / TX;
     A.ntiles = A.ntx * ((p.Ny + TY - 1) / TY);
     A.sigma = p.sigma; A.vol = p.vol; A.x = x; A.y = y;
@@ -450,9 +522,9 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
     EllipticCoef<N, B> C;
     fill<N, B>(C.rx, p.rightx); fill<N, B>(C.ry, p.righty); fill<N, B>(C.lx, p.leftx); fill<N, B>(C.ly, p.lefty);
     fill<N, 3>(C.jx, p.jumpx); fill<N, 3>(C.jy, p.jumpy);
-    int per_sm = TL::BYTES > 110 * 1024 ? 1 : 2;
+    int per_sm = std::max(1, std::min(FUSED_MIN_CTAS, (int)(220 * 1024 / (TL::BYTES + 1024))));
     int grid = std::min(A.ntiles, per_sm * sm_count());
-    elliptic2d_fused_kernel<N, B, DOT><<<grid, FUSED_THREADS, TL::BYTES, st>>>(A, C, mx, ms);
+    elliptic2d_fused_kernel<N, DIRK, DOT><<<grid, FUSED_THREADS, TL::BYTES, st>>>(A, C, mx, ms);
     DGB_LAUNCHED();
     return 0;
 }
@@ -460,15 +532,18 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
 template <bool DOT>
 static int dispatch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                     const FusedDot* fd) {
-    switch (p.n * 10 + p.bder) {
+    switch (p.n * 10 + p.dirk) {
+        case 20: return launch<2, 0, DOT>(p, alpha, x, beta, y, st, fd);
+        case 21: return launch<2, 1, DOT>(p, alpha, x, beta, y, st, fd);
         case 22: return launch<2, 2, DOT>(p, alpha, x, beta, y, st, fd);
-        case 23: return launch<2, 3, DOT>(p, alpha, x, beta, y, st, fd);
+        case 30: return launch<3, 0, DOT>(p, alpha, x, beta, y, st, fd);
+        case 31: return launch<3, 1, DOT>(p, alpha, x, beta, y, st, fd);
         case 32: return launch<3, 2, DOT>(p, alpha, x, beta, y, st, fd);
-        case 33: return launch<3, 3, DOT>(p, alpha, x, beta, y, st, fd);
+        case 40: return launch<4, 0, DOT>(p, alpha, x, beta, y, st, fd);
+        case 41: return launch<4, 1, DOT>(p, alpha, x, beta, y, st, fd);
         case 42: return launch<4, 2, DOT>(p, alpha, x, beta, y, st, fd);
-        case 43: return launch<4, 3, DOT>(p, alpha, x, beta, y, st, fd);
     }
-    set_error("elliptic2d fused kernel: unsupported n=%d bpl=%d", p.n, p.bder);
+    set_error("elliptic2d fused kernel: unsupported n=%d direction kind=%d", p.n, p.dirk);
     return DGB_ERR_UNSUPPORTED;
 }
 int elliptic2d_fused_launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st) {

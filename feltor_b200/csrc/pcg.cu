@@ -10,6 +10,7 @@
 // x, r and the iteration count are exactly those of the reference's loop exit.
 #include "elliptic.cuh"
 #include "pcg.cuh"
+#include "pcg_internal.cuh"
 #include <cmath>
 #include <cstdlib>
 
@@ -84,9 +85,14 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
     int bad = 0;
     const size_t T = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nvec = n / 2;
-    for (size_t i = tid; i < nvec; i += T) {
-        double2 pv = ld2(p + 2 * i), av = ld2(ap + 2 * i), xv = ld2(x + 2 * i), rv = ld2(r + 2 * i), Pv = ld2(P + 2 * i),
-                Wv = ld2(W + 2 * i);
+    // software pipeline: the six 128-bit loads of the next trip are in flight while this trip is reduced
+    size_t i = tid;
+    double2 pv, av, xv, rv, Pv, Wv;
+    if (i < nvec) { pv = ld2(p + 2 * i); av = ld2(ap + 2 * i); xv = ld2(x + 2 * i); rv = ld2(r + 2 * i); Pv = ld2(P + 2 * i); Wv = ld2(W + 2 * i); }
+    while (i < nvec) {
+        const size_t inext = i + T;
+        double2 pn, an, xn, rn, Pn, Wn;
+        if (inext < nvec) { pn = ld2(p + 2 * inext); an = ld2(ap + 2 * inext); xn = ld2(x + 2 * inext); rn = ld2(r + 2 * inext); Pn = ld2(P + 2 * inext); Wn = ld2(W + 2 * inext); }
         // Axpby(alpha,1): y = y*1; y = fma(alpha, x, y)   (subroutines.h:260-274)
         xv.x = __fma_rn(alpha, pv.x, __dmul_rn(xv.x, 1.));
         xv.y = __fma_rn(alpha, pv.y, __dmul_rn(xv.y, 1.));
@@ -108,6 +114,8 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
         if (!isfinite(b1)) { bad = 1; b1 = 0.; }
         fzr.add(b0, my_zr);
         fzr.add(b1, my_zr);
+        pv = pn; av = an; xv = xn; rv = rn; Pv = Pn; Wv = Wn;
+        i = inext;
     }
     if ((n & 1) && tid == 0) {
         size_t i = n - 1;
@@ -177,7 +185,7 @@ pcg_precond_kernel(size_t n, const double* __restrict__ P, const double* __restr
 static unsigned grid_for(size_t n, int per_thread) {
     size_t want = (n + (size_t)PCG_THREADS * per_thread - 1) / ((size_t)PCG_THREADS * per_thread);
     if (want == 0) want = 1;
-    size_t cap = (size_t)sm_count() * 4;
+    size_t cap = (size_t)sm_count() * 2;  // the reduction kernels hold ~100 registers: two resident CTAs per SM, one wave
     return (unsigned)(want < cap ? want : cap);
 }
 
@@ -278,13 +286,7 @@ int pcg_solve(Pcg& s, Elliptic2dPlan& A, double* x, const double* b, const doubl
     return DGB_ERR_NOCONVERGE;
 }
 
-}  // namespace dgb
-
-using namespace dgb;
-
-extern "C" {
-int dgb_pcg_create(dgb_pcg** out, size_t n) {
-    Pcg* s = new Pcg();
+static int pcg_alloc(Pcg* s, size_t n) {
     s->n = n;
     size_t bytes = (n ? n : 1) * sizeof(double);
     DGB_CUDA(cudaMalloc(&s->r, bytes));
@@ -306,6 +308,34 @@ int dgb_pcg_create(dgb_pcg** out, size_t n) {
     s->slot.result = s->results;
     const char* ce = getenv("DGB_PCG_CHECK_EVERY");
     if (ce && atoi(ce) > 0) s->check_every = atoi(ce);
+    return 0;
+}
+Pcg* pcg_new(size_t n, int* err) {
+    Pcg* s = new Pcg();
+    int e = pcg_alloc(s, n);
+    if (e) { if (err) *err = e; pcg_delete(s); return nullptr; }
+    return s;
+}
+void pcg_delete(Pcg* s) {
+    if (!s) return;
+    if (s->ev_ready)
+        for (int k = 0; k < Pcg::PROF_MAX; k++)
+            for (int j = 0; j < 4; j++) cudaEventDestroy(s->ev[k][j]);
+    cudaFree(s->r); cudaFree(s->p); cudaFree(s->ap); cudaFree(s->st); cudaFreeHost(s->st_host);
+    cudaFree(s->slot.gacc); cudaFree(s->slot.gstatus); cudaFree(s->slot.ticket);
+    cudaFree(s->results); cudaFreeHost(s->results_host);
+    delete s;
+}
+
+}  // namespace dgb
+
+using namespace dgb;
+
+extern "C" {
+int dgb_pcg_create(dgb_pcg** out, size_t n) {
+    int e = 0;
+    Pcg* s = pcg_new(n, &e);
+    if (!s) return e;
     *out = reinterpret_cast<dgb_pcg*>(s);
     return 0;
 }
@@ -331,15 +361,7 @@ int dgb_pcg_get_profile(dgb_pcg* h, double* ms_apply_dot, double* ms_update, dou
     return 0;
 }
 int dgb_pcg_destroy(dgb_pcg* h) {
-    Pcg* s = reinterpret_cast<Pcg*>(h);
-    if (!s) return 0;
-    if (s->ev_ready)
-        for (int k = 0; k < Pcg::PROF_MAX; k++)
-            for (int j = 0; j < 4; j++) cudaEventDestroy(s->ev[k][j]);
-    cudaFree(s->r); cudaFree(s->p); cudaFree(s->ap); cudaFree(s->st); cudaFreeHost(s->st_host);
-    cudaFree(s->slot.gacc); cudaFree(s->slot.gstatus); cudaFree(s->slot.ticket);
-    cudaFree(s->results); cudaFreeHost(s->results_host);
-    delete s;
+    pcg_delete(reinterpret_cast<Pcg*>(h));
     return 0;
 }
 int dgb_pcg_solve_elliptic2d(dgb_pcg* h, dgb_elliptic2d* A, double* x, const double* b, const double* P,

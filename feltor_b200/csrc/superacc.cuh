@@ -131,7 +131,8 @@ struct Fpe {
 #pragma unroll
         for (int i = 0; i < NF; i++) a[i] = 0.0;
     }
-    // add x; a non-representable residue and the whole expansion are spilled to `acc` (shared, stride 1)
+    // add x; a residue the expansion cannot hold is spilled (exactly) to `acc` (shared, stride 1).  The expansion
+    // itself stays valid: after the cascade a[] + residue equals the old a[] + x exactly.
     __device__ __forceinline__ void add(double x, long long* acc) {
 #pragma unroll
         for (int i = 0; i < NF; i++) {
@@ -139,14 +140,7 @@ struct Fpe {
             a[i] = two_sum(a[i], x, s);
             x = s;
         }
-        if (x != 0.0) {
-            accumulate(acc, x, 1);
-#pragma unroll
-            for (int i = 0; i < NF; i++) {
-                accumulate(acc, a[i], 1);
-                a[i] = 0.0;
-            }
-        }
+        if (x != 0.0) accumulate(acc, x, 1);
     }
     __device__ __forceinline__ void flush(long long* acc) {
 #pragma unroll

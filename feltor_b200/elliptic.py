@@ -105,3 +105,46 @@ class PCG:
             lib().pcg_destroy(self.h)
         except Exception:
             pass
+
+
+class MultigridCG2d:
+    """dg::MultigridCG2d (inc/dg/multigrid.h:500-668): nested grids, projection and the nested-iteration solve"""
+
+    def __init__(self, g, stages):
+        self.h = C.c_void_p()
+        lib().multigrid2d_create(C.byref(self.h), g.ref(), stages)
+        self.stages = stages
+        self.grids, self.sizes = [], []
+        for u in range(stages):
+            cg, sz = T.CGrid(), C.c_size_t()
+            lib().multigrid2d_grid(self.h, u, C.byref(cg), C.byref(sz))
+            self.grids.append(T.Grid([cg.x0[0], cg.x0[1]], [cg.x1[0], cg.x1[1]], [cg.n[0], cg.n[1]], [cg.N[0], cg.N[1]],
+                                     [cg.bc[0], cg.bc[1]]))
+            self.sizes.append(sz.value)
+
+    def grid(self, u):
+        return self.grids[u]
+
+    def project(self, src):
+        """multigrid.h:94-110: returns the list of the projections of src onto every stage"""
+        out = [torch.empty(s, dtype=torch.float64, device="cuda") for s in self.sizes]
+        arr = (C.c_void_p * self.stages)(*[o.data_ptr() for o in out])
+        lib().multigrid2d_project(self.h, ptr(src), arr, stream())
+        return out
+
+    def solve(self, ops, x, b, eps):
+        """multigrid.h:617-658: ops = list of Elliptic2d (one per stage); eps scalar or list; returns iteration numbers"""
+        eps = [eps] * self.stages if np.isscalar(eps) else list(eps)
+        A = (C.c_void_p * self.stages)(*[o.h.value for o in ops])
+        P = (C.c_void_p * self.stages)(*[o.precond().data_ptr() for o in ops])
+        W = (C.c_void_p * self.stages)(*[o.weights().data_ptr() for o in ops])
+        E = (C.c_double * self.stages)(*eps)
+        num = (C.c_int * self.stages)()
+        lib().multigrid2d_solve(self.h, A, P, W, ptr(x), ptr(b), E, num, stream())
+        return [int(v) for v in num]
+
+    def __del__(self):
+        try:
+            lib().multigrid2d_destroy(self.h)
+        except Exception:
+            pass

@@ -264,6 +264,27 @@ DGB_API int dgb_pcg_solve_elliptic2d(dgb_pcg* pcg, dgb_elliptic2d* A, double* x,
                                      const double* W, double eps, double nrmb_correction, int test_frequency,
                                      int max_iter, int* iterations, dgb_stream_t s);
 
+/* ---------------------------------------------------------------------------------------------------
+ * MultigridCG2d: replaces NestedGrids + nested_iterations + MultigridCG2d::solve inc/dg/multigrid.h:28-171,197-245,
+ * 500-668.  The caller owns one Elliptic2d plan per stage (as multi_pol[u].construct(multigrid.grid(u), ...) does in
+ * src/toefl/toefl.h) and passes each stage's preconditioner / weights vectors (pol.precond(), pol.weights()).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct dgb_multigrid2d dgb_multigrid2d;
+DGB_API int dgb_multigrid2d_create(dgb_multigrid2d** mg, const dgb_grid* grid, int stages);
+DGB_API int dgb_multigrid2d_destroy(dgb_multigrid2d* mg);
+DGB_API int dgb_multigrid2d_stages(const dgb_multigrid2d* mg);
+DGB_API int dgb_multigrid2d_grid(const dgb_multigrid2d* mg, int stage, dgb_grid* grid, size_t* size); /* multigrid.h:128 */
+/* project(src, out): out = HOST array of `stages` device vectors (multigrid.h:94-99) */
+DGB_API int dgb_multigrid2d_project(dgb_multigrid2d* mg, const double* src, double* const* out, dgb_stream_t s);
+/* xf = alpha * interpolation(coarse_stage-1) xc + beta xf (multigrid.h:232) */
+DGB_API int dgb_multigrid2d_interpolate(dgb_multigrid2d* mg, int coarse_stage, double alpha, const double* xc, double beta,
+                                        double* xf, dgb_stream_t s);
+/* solve(ops, x, b, eps[stages]) -> numbers[stages] = PCG iterations per stage (multigrid.h:627-658); ops, precond,
+ * weights are HOST arrays of length `stages` */
+DGB_API int dgb_multigrid2d_solve(dgb_multigrid2d* mg, dgb_elliptic2d* const* ops, const double* const* precond,
+                                  const double* const* weights, double* x, const double* b, const double* eps,
+                                  int* numbers, dgb_stream_t s);
+
 /* measurement aid: when on, CUDA events on the launching stream bracket the three kernels of every iteration
  * (operator+dot, update+dots, direction); get returns the accumulated milliseconds and the iterations timed */
 DGB_API int dgb_pcg_set_profile(dgb_pcg* pcg, int on);

