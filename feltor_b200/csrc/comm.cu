@@ -1,0 +1,168 @@
+// Multi-GPU plumbing: one process per GPU, NCCL over NVLink/NVSwitch.  Replaces the MPI layer of the reference on
+// this path: MPIKroneckerGather / MPIContiguousGather halo exchange (inc/dg/backend/mpi_gather_kron.h:143-291,
+// mpi_gather.h:255-440: MPI_Isend/Irecv + cudaDeviceSynchronize per exchange) by one grouped ncclSend/ncclRecv
+// enqueued on the compute stream (no host synchronisation), and exblas::reduce_mpi_cpu
+// (inc/dg/backend/exblas/mpi_accumulate.h:42-125: D2H, MPI_Reduce on 39 longs, MPI_Bcast) by an in-place
+// ncclAllReduce(int64, sum) of the normalised superaccumulator words on the device -- integer sums are associative,
+// so the global dot is bit-reproducible for any number of GPUs.
+// NCCL is bound at run time (dlopen) so that single-GPU users do not need it.
+#include "comm.cuh"
+#include "superacc.cuh"
+#include <dlfcn.h>
+#include <cstring>
+
+namespace dgb {
+
+typedef struct ncclComm* ncclComm_t;
+typedef struct { char internal[128]; } ncclUniqueId;
+typedef int ncclResult_t;
+enum { ncclInt64 = 4, ncclFloat64 = 8 };  // nccl.h ncclDataType_t
+enum { ncclSum = 0 };
+
+struct NcclApi {
+    void* lib = nullptr;
+    ncclResult_t (*GetUniqueId)(ncclUniqueId*) = nullptr;
+    ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
+    ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
+    ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*GroupStart)() = nullptr;
+    ncclResult_t (*GroupEnd)() = nullptr;
+    const char* (*GetErrorString)(ncclResult_t) = nullptr;
+};
+static NcclApi* nccl() {
+    static NcclApi api;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        api.lib = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+        if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+        if (api.lib) {
+#define BIND(name) *(void**)(&api.name) = dlsym(api.lib, "nccl" #name)
+            BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(AllReduce); BIND(Send); BIND(Recv);
+            BIND(GroupStart); BIND(GroupEnd); BIND(GetErrorString);
+#undef BIND
+        }
+    }
+    if (!api.lib || !api.GetUniqueId || !api.CommInitRank || !api.AllReduce || !api.Send || !api.Recv || !api.GroupStart ||
+        !api.GroupEnd)
+        return nullptr;
+    return &api;
+}
+#define DGB_NCCL(call)                                                                          \
+    do {                                                                                        \
+        ncclResult_t _r = (call);                                                               \
+        if (_r != 0) {                                                                          \
+            set_error("NCCL error %d (%s) in %s", _r, nccl()->GetErrorString ? nccl()->GetErrorString(_r) : "?", #call); \
+            return DGB_ERR_INVALID;                                                             \
+        }                                                                                       \
+    } while (0)
+
+struct Comm {
+    ncclComm_t comm = nullptr;
+    int rank = 0, size = 1;
+};
+int comm_rank(const Comm* c) { return c ? c->rank : 0; }
+int comm_size(const Comm* c) { return c ? c->size : 1; }
+
+int comm_allreduce_i64(Comm* c, long long* buf, size_t count, cudaStream_t st) {
+    if (!c || c->size == 1) return 0;
+    DGB_NCCL(nccl()->AllReduce(buf, buf, count, ncclInt64, ncclSum, c->comm, st));
+    return 0;
+}
+
+int comm_halo_rows(Comm* c, double* interior, size_t row_len, size_t nrows, size_t ghost_rows, int periodic, cudaStream_t st) {
+    const int rank = comm_rank(c), size = comm_size(c);
+    const size_t cnt = ghost_rows * row_len;
+    if (cnt == 0) return 0;
+    if (nrows < ghost_rows) { set_error("halo exchange: slab has fewer rows than the halo"); return DGB_ERR_INVALID; }
+    double* lo_ghost = interior - cnt;
+    double* up_ghost = interior + nrows * row_len;
+    double* bottom = interior;
+    double* top = interior + (nrows - ghost_rows) * row_len;
+    int lower = rank - 1, upper = rank + 1;
+    if (lower < 0) lower = periodic ? size - 1 : -1;
+    if (upper >= size) upper = periodic ? 0 : -1;
+    if (size == 1) {  // the ring closes on this device
+        if (periodic) {
+            DGB_CUDA(cudaMemcpyAsync(up_ghost, bottom, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+            DGB_CUDA(cudaMemcpyAsync(lo_ghost, top, cnt * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        }
+        return 0;
+    }
+    NcclApi* n = nccl();
+    // posting order matters when lower == upper (two ranks): a peer's first send (its bottom rows) must meet our first
+    // receive from it (our upper ghost)
+    DGB_NCCL(n->GroupStart());
+    if (lower >= 0) DGB_NCCL(n->Send(bottom, cnt, ncclFloat64, lower, c->comm, st));
+    if (upper >= 0) DGB_NCCL(n->Send(top, cnt, ncclFloat64, upper, c->comm, st));
+    if (upper >= 0) DGB_NCCL(n->Recv(up_ghost, cnt, ncclFloat64, upper, c->comm, st));
+    if (lower >= 0) DGB_NCCL(n->Recv(lo_ghost, cnt, ncclFloat64, lower, c->comm, st));
+    DGB_NCCL(n->GroupEnd());
+    return 0;
+}
+
+// normalise + round a summed superaccumulator record in place (status = number of ranks that met NaN/Inf)
+__global__ void superacc_finalize_kernel(dgb_dot_result* r, int nrec) {
+    int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= nrec) return;
+    long long acc[sa::BINS];
+    for (int i = 0; i < sa::BINS; i++) acc[i] = r[k].acc[i];
+    int neg = sa::normalize(acc, 1);
+    for (int i = 0; i < sa::BINS; i++) r[k].acc[i] = acc[i];
+    r[k].value = sa::round_normalized(acc, neg);
+    r[k].status = r[k].status != 0 || r[k].pad != 0;
+    r[k].pad = 0;
+}
+
+}  // namespace dgb
+
+using namespace dgb;
+
+extern "C" {
+int dgb_comm_unique_id(char* id128) {
+    NcclApi* n = nccl();
+    if (!n) { set_error("dgb_comm: libnccl.so.2 could not be loaded"); return DGB_ERR_UNSUPPORTED; }
+    ncclUniqueId id;
+    DGB_NCCL(n->GetUniqueId(&id));
+    memcpy(id128, id.internal, 128);
+    return 0;
+}
+int dgb_comm_create(dgb_comm** out, const char* id128, int rank, int nranks) {
+    if (nranks < 1 || rank < 0 || rank >= nranks) { set_error("dgb_comm_create: invalid rank %d of %d", rank, nranks); return DGB_ERR_INVALID; }
+    Comm* c = new Comm();
+    c->rank = rank; c->size = nranks;
+    if (nranks > 1) {
+        NcclApi* n = nccl();
+        if (!n) { delete c; set_error("dgb_comm: libnccl.so.2 could not be loaded"); return DGB_ERR_UNSUPPORTED; }
+        ncclUniqueId id;
+        memcpy(id.internal, id128, 128);
+        ncclResult_t r = n->CommInitRank(&c->comm, nranks, id, rank);
+        if (r != 0) { delete c; set_error("ncclCommInitRank failed with %d", r); return DGB_ERR_INVALID; }
+    }
+    *out = reinterpret_cast<dgb_comm*>(c);
+    return 0;
+}
+int dgb_comm_destroy(dgb_comm* h) {
+    Comm* c = reinterpret_cast<Comm*>(h);
+    if (!c) return 0;
+    if (c->comm && nccl() && nccl()->CommDestroy) nccl()->CommDestroy(c->comm);
+    delete c;
+    return 0;
+}
+int dgb_comm_halo_rows(dgb_comm* h, double* interior, size_t row_len, size_t nrows, size_t ghost_rows, int periodic, dgb_stream_t s) {
+    return comm_halo_rows(reinterpret_cast<Comm*>(h), interior, row_len, nrows, ghost_rows, periodic, as_stream(s));
+}
+// global exact dot: every rank passes the record its local dgb_exdot2/3 produced; on return all ranks hold the
+// normalised global accumulator, the correctly rounded value and the OR of the status flags
+int dgb_comm_allreduce_dot(dgb_comm* h, dgb_dot_result* result_dev, int nrecords, dgb_stream_t s) {
+    Comm* c = reinterpret_cast<Comm*>(h);
+    if (nrecords < 1) return 0;
+    int e = comm_allreduce_i64(c, reinterpret_cast<long long*>(result_dev), (size_t)nrecords * sizeof(dgb_dot_result) / 8, as_stream(s));
+    if (e) return e;
+    superacc_finalize_kernel<<<1, 32, 0, as_stream(s)>>>(result_dev, nrecords);
+    DGB_LAUNCHED();
+    return 0;
+}
+}

@@ -72,6 +72,13 @@ int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double bet
     static int env_unfused = -1;
     if (env_unfused < 0) { const char* e = getenv("DGB_ELLIPTIC_UNFUSED"); env_unfused = (e && atoi(e)) ? 1 : 0; }
     bool identity_chi = !p.chi[0] && !p.chi[1] && !p.chi[2] && !p.chi[3];
+    if (p.slab) {
+        if (!p.fusable || !identity_chi || p.chi_weight_jump) {
+            set_error("dgb_elliptic2d_symv: a slab (multi-GPU) plan needs the fused kernel (dx.h matrices, identity chi tensor)");
+            return DGB_ERR_UNSUPPORTED;
+        }
+        return elliptic2d_fused_launch(p, alpha, x, beta, y, st);
+    }
     if (!force_unfused && !env_unfused && p.fusable && identity_chi && !p.chi_weight_jump)
         return elliptic2d_fused_launch(p, alpha, x, beta, y, st);
     return elliptic2d_unfused(p, alpha, x, beta, y, st);
@@ -193,9 +200,16 @@ int dgb_elliptic2d_set_chi(dgb_elliptic2d* h, const double* xx, const double* xy
     return 0;
 }
 int dgb_elliptic2d_set_jfactor(dgb_elliptic2d* h, double jfactor) { reinterpret_cast<Elliptic2dPlan*>(h)->jfactor = jfactor; return 0; }
+int dgb_elliptic2d_set_slab(dgb_elliptic2d* h, int yoff, int rows, int ghost) {
+    Elliptic2dPlan* p = reinterpret_cast<Elliptic2dPlan*>(h);
+    if (!p->fusable) { set_error("dgb_elliptic2d_set_slab: the plan's matrices are not supported by the fused kernel"); return DGB_ERR_UNSUPPORTED; }
+    if (yoff < 0 || rows < 1 || yoff + rows > p->Ny || ghost < 0) { set_error("dgb_elliptic2d_set_slab: invalid slab"); return DGB_ERR_INVALID; }
+    p->slab = true; p->slab_yoff = yoff; p->slab_rows = rows; p->slab_ghost = ghost;
+    return 0;
+}
 int dgb_elliptic2d_size(const dgb_elliptic2d* h, size_t* size, int* fused) {
     const Elliptic2dPlan* p = reinterpret_cast<const Elliptic2dPlan*>(h);
-    if (size) *size = p->size;
+    if (size) *size = p->slab ? (size_t)p->slab_rows * p->n * p->Nx * p->n : p->size;
     if (fused) *fused = p->fusable ? 1 : 0;
     return 0;
 }

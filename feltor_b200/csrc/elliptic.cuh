@@ -18,6 +18,10 @@ struct Elliptic2dPlan {
     int bder = 0;          // blocks per line of the four derivative matrices (2 or 3)
     int dirk = 0;          // stencil kind of the right derivatives: 0 {0,+1} forward, 1 {-1,0} backward, 2 {-1,0,+1}
     bool wrapx = false, wrapy = false;
+    // slab of a y-decomposed global operator: rows [slab_yoff, slab_yoff + slab_rows) of the Ny global cell rows; x and
+    // sigma operands carry slab_ghost ghost cell rows on either side (filled by the halo exchange)
+    bool slab = false;
+    int slab_yoff = 0, slab_rows = 0, slab_ghost = 0;
 };
 
 int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,

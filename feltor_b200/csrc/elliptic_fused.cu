@@ -49,6 +49,9 @@ struct FusedArgs {
     int Nx, Ny, wrapx, wrapy;
     int fx_lo, fx_hi, fy_lo, fy_hi;  // cells [lo, hi) that are interior rows of all three x- resp. y-matrices
     int ntx, ntiles, use_tma;
+    // slab mode (domain decomposition in y): the operands x and sigma carry `ghost` cell rows on either side, row 0
+    // of the slab is global cell row `yoff` of `Nyg`; the periodic wrap in y is done by the halo exchange
+    int slab, ghost, yoff, Nyg, pery;
     const double* sigma;
     const double* vol;
     const double* x;
@@ -173,6 +176,26 @@ __device__ __forceinline__ int gcell(int c, int num, int wrap) {
     return c < 0 ? c + num : c - num;
 }
 
+constexpr int NOROW = -(1 << 30);
+// local cell row c (may lie in the halo) -> row used for ADDRESSING the operand, NOROW if no data exists
+__device__ __forceinline__ int yaddr(int c, const FusedArgs& A) {
+    if (!A.slab) { int g = gcell(c, A.Ny, A.wrapy); return g < 0 ? NOROW : g; }
+    if (c < -A.ghost || c >= A.Ny + A.ghost) return NOROW;
+    const int g = c + A.yoff;
+    if (!A.pery && (g < 0 || g >= A.Nyg)) return NOROW;
+    return c;
+}
+// local cell row c -> block-row index of the (global) y-matrices, NOROW if the row does not exist
+__device__ __forceinline__ int ymat(int c, const FusedArgs& A) {
+    if (!A.slab) { int g = gcell(c, A.Ny, A.wrapy); return g < 0 ? NOROW : g; }
+    int g = c + A.yoff;
+    if (g < 0 || g >= A.Nyg) {
+        if (!A.pery) return NOROW;
+        g = g < 0 ? g + A.Nyg : g - A.Nyg;
+    }
+    return g;
+}
+
 // LDGSTS loader of a (rows x cols) tile whose first cell is (cy, cx): one smem row at a time, columns by thread
 template <int N, int ROWS, int COLS, int PITCH>
 __device__ __forceinline__ void load_tile_ldgsts(double* dst, const double* src, int cy, int cx, const FusedArgs& A, int tid) {
@@ -181,9 +204,9 @@ __device__ __forceinline__ void load_tile_ldgsts(double* dst, const double* src,
         const int gx = gcell(cx + c / N, A.Nx, A.wrapx);
         const int gcol = gx * N + c % N;
         for (int r = tid / 128; r < ROWS; r += FUSED_THREADS / 128) {
-            const int gy = gcell(cy + r / N, A.Ny, A.wrapy);
-            const bool ok = gx >= 0 && gy >= 0;
-            cp_async8(dst + r * PITCH + c, ok ? src + (size_t)(gy * N + r % N) * LDG + gcol : src, ok);
+            const int gy = yaddr(cy + r / N, A);
+            const bool ok = gx >= 0 && gy != NOROW;
+            cp_async8(dst + r * PITCH + c, ok ? src + ((long long)(gy * N + r % N) * LDG + gcol) : src, ok);
         }
     }
 }
@@ -236,7 +259,7 @@ __device__ __forceinline__ void compute_tile(const FusedArgs& A, const EllipticC
                 else {
                     const int gx = gcell(cx0 - 1 + c, A.Nx, A.wrapx);
                     on = gx >= 0 && cy0 + r / N < A.Ny;
-                    if (on) apply_row<N, B>(A.rx, C.rx, gx, sx, 1, 1., g);
+                    if (on) apply_row<N, B>(A.rx, C.rx, gx, sx, 1, 1., g);  // rows of the slab itself always exist
                 }
                 if (on) {
                     const double* sg = ss + (N + r) * SC + c * N;
@@ -262,8 +285,8 @@ __device__ __forceinline__ void compute_tile(const FusedArgs& A, const EllipticC
                 bool on = true;
                 if (FAST) apply_fast<N, RK, XC>(C.ry, sx, 1., g);
                 else {
-                    const int gy = gcell(cy0 - 1 + r, A.Ny, A.wrapy);
-                    on = gy >= 0 && cx0 + c / N < A.Nx;
+                    const int gy = ymat(cy0 - 1 + r, A);
+                    on = gy != NOROW && cx0 + c / N < A.Nx && cy0 - 1 + r < A.Ny + (A.slab ? A.ghost : 1);
                     if (on) apply_row<N, B>(A.ry, C.ry, gy, sx, XC, 1., g);
                 }
                 if (on) {
@@ -295,7 +318,7 @@ __device__ __forceinline__ void compute_tile(const FusedArgs& A, const EllipticC
             for (int k = 0; k < N; k++) col[k] = 0.;
             const double* sp = tys + ((cy + 1) * N) * TYC + cx * N + kx;
             if (FAST) apply_fast<N, LK, TYC>(C.ly, sp, 1., col);
-            else apply_row<N, B>(A.ly, C.ly, iy, sp, TYC, 1., col);
+            else apply_row<N, B>(A.ly, C.ly, iy + A.yoff, sp, TYC, 1., col);
 #pragma unroll
             for (int k = 0; k < N; k++) acc[k][kx] = col[k];
         }
@@ -330,7 +353,7 @@ __device__ __forceinline__ void compute_tile(const FusedArgs& A, const EllipticC
                 for (int k = 0; k < N; k++) col[k] = acc[k][kx];
                 const double* sp = xs + ((cy + H) * N) * XC + (cx + H) * N + kx;
                 if (FAST) apply_fast<N, 2, XC>(C.jy, sp, A.jfactor, col);
-                else apply_row<N, 3>(A.jy, C.jy, iy, sp, XC, A.jfactor, col);
+                else apply_row<N, 3>(A.jy, C.jy, iy + A.yoff, sp, XC, A.jfactor, col);
 #pragma unroll
                 for (int k = 0; k < N; k++) acc[k][kx] = col[k];
             }
@@ -415,12 +438,14 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
         const int tyi = tile / A.ntx, txi = tile - tyi * A.ntx;
         const int cx0 = txi * TX, cy0 = tyi * TY;
         // ---- phase 0
-        const bool seam = (A.wrapx && (cx0 - H < 0 || cx0 + TX + H > A.Nx)) || (A.wrapy && (cy0 - H < 0 || cy0 + TY + H > A.Ny));
+        const bool seam = (A.wrapx && (cx0 - H < 0 || cx0 + TX + H > A.Nx)) ||
+                          (!A.slab && A.wrapy && (cy0 - H < 0 || cy0 + TY + H > A.Ny));
         if (A.use_tma && !seam) {
             if (tid == 0) {
                 mbar_expect_tx(bar, (unsigned)((TL::XR * XC + TL::SR * SC) * sizeof(double)));
-                tma_load_2d(smem + TL::XS, &map_x, bar, (cx0 - H) * N - TL::XSH, (cy0 - H) * N);
-                tma_load_2d(smem + TL::SS, &map_s, bar, (cx0 - 1) * N - TL::SSH, (cy0 - 1) * N);
+                // in slab mode the maps start at the first ghost row
+                tma_load_2d(smem + TL::XS, &map_x, bar, (cx0 - H) * N - TL::XSH, (cy0 - H + A.ghost) * N);
+                tma_load_2d(smem + TL::SS, &map_s, bar, (cx0 - 1) * N - TL::SSH, (cy0 - 1 + A.ghost) * N);
                 mbar_wait(bar, phase);  // one thread polls, the CTA sleeps on the barrier below
             }
             phase ^= 1;
@@ -431,13 +456,14 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
             cp_async_wait_all();
             __syncthreads();
         }
-        const bool fast = cx0 - 1 >= A.fx_lo && cx0 + TX + 1 <= A.fx_hi && cy0 - 1 >= A.fy_lo && cy0 + TY + 1 <= A.fy_hi;
+        const bool fast = cx0 - 1 >= A.fx_lo && cx0 + TX + 1 <= A.fx_hi && cy0 + A.yoff - 1 >= A.fy_lo &&
+                          cy0 + A.yoff + TY + 1 <= A.fy_hi && cy0 + TY <= A.Ny;
         if (fast) compute_tile<N, DIRK, DOT, true>(A, C, xs, ss, txs, tys, cx0, cy0, tid, fpe, bad, dsm);
         else compute_tile<N, DIRK, DOT, false>(A, C, xs, ss, txs, tys, cx0, cy0, tid, fpe, bad, dsm);
     }
     if (DOT) {
         fpe.flush(dsm + (tid >> 5) * sa::BINS);
-        if (sa::block_finish<NW>(dsm, bad, A.slot, 0) && tid == 0) pcg_after_pAp(A.pcg, A.slot.result);
+        if (sa::block_finish<NW>(dsm, bad, A.slot, 0) && tid == 0 && !A.pcg->dist) pcg_after_pAp(A.pcg, A.slot.result);
     }
 }
 
@@ -503,13 +529,18 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
     FusedArgs A;
     A.rx = view(p.rightx); A.ry = view(p.righty); A.lx = view(p.leftx); A.ly = view(p.lefty);
     A.jx = view(p.jumpx); A.jy = view(p.jumpy);
-    A.Nx = p.Nx; A.Ny = p.Ny; A.wrapx = p.wrapx; A.wrapy = p.wrapy;
+    A.Nx = p.Nx; A.Ny = p.slab ? p.slab_rows : p.Ny; A.wrapx = p.wrapx; A.wrapy = p.slab ? 0 : p.wrapy;
+    A.slab = p.slab; A.ghost = p.slab ? p.slab_ghost : 0; A.yoff = p.slab ? p.slab_yoff : 0; A.Nyg = p.Ny; A.pery = p.wrapy;
+    if (p.slab && p.slab_ghost < TL::H) {
+        set_error("elliptic2d slab: %d ghost cell rows given, the stencil needs %d", p.slab_ghost, TL::H);
+        return DGB_ERR_INVALID;
+    }
     A.fx_lo = std::max({p.rightx.i_lo, p.leftx.i_lo, p.jumpx.i_lo});
     A.fx_hi = std::min({p.rightx.i_hi, p.leftx.i_hi, p.jumpx.i_hi});
     A.fy_lo = std::max({p.righty.i_lo, p.lefty.i_lo, p.jumpy.i_lo});
     A.fy_hi = std::min({p.righty.i_hi, p.lefty.i_hi, p.jumpy.i_hi});
     A.ntx = (p.Nx + TX - 1) / TX;
-    A.ntiles = A.ntx * ((p.Ny + TY - 1) / TY);
+    A.ntiles = A.ntx * ((A.Ny + TY - 1) / TY);
     A.sigma = p.sigma; A.vol = p.vol; A.x = x; A.y = y;
     A.alpha = alpha; A.beta = beta; A.jfactor = p.jfactor;
     A.dot_w = nullptr; A.pcg = nullptr; A.slot = sa::DotSlot{nullptr, nullptr, nullptr, nullptr};
@@ -517,8 +548,9 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
     CUtensorMap mx, ms;
     memset(&mx, 0, sizeof(mx));
     memset(&ms, 0, sizeof(ms));
-    A.use_tma = !no_tma && make_map(&mx, x, p.Ny * N, p.Nx * N, TL::XR, TL::XP) &&
-                make_map(&ms, p.sigma, p.Ny * N, p.Nx * N, TL::SR, TL::SP);
+    const long long gh = (long long)A.ghost * N * p.Nx * N;  // doubles in the ghost rows below the slab
+    A.use_tma = !no_tma && make_map(&mx, x - gh, (A.Ny + 2 * A.ghost) * N, p.Nx * N, TL::XR, TL::XP) &&
+                make_map(&ms, p.sigma - gh, (A.Ny + 2 * A.ghost) * N, p.Nx * N, TL::SR, TL::SP);
     EllipticCoef<N, B> C;
     fill<N, B>(C.rx, p.rightx); fill<N, B>(C.ry, p.righty); fill<N, B>(C.lx, p.leftx); fill<N, B>(C.ly, p.lefty);
     fill<N, 3>(C.jx, p.jumpx); fill<N, 3>(C.jy, p.jumpy);

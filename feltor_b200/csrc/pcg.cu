@@ -11,6 +11,7 @@
 #include "elliptic.cuh"
 #include "pcg.cuh"
 #include "pcg_internal.cuh"
+#include "comm.cuh"
 #include <cmath>
 #include <cstdlib>
 
@@ -22,6 +23,8 @@ constexpr int PCG_WARPS = PCG_THREADS / 32;
 struct Pcg {
     size_t n = 0;
     double *r = nullptr, *p = nullptr, *ap = nullptr;
+    double* p_base = nullptr;  // allocation behind p (p may be offset by the ghost rows of a slab)
+    size_t p_cap = 0;
     PcgState* st = nullptr;       // device
     PcgState* st_host = nullptr;  // pinned
     sa::DotSlot slot;             // 4 slots: 0 pAp, 1 rWr, 2 zWr, 3 setup dots
@@ -62,6 +65,7 @@ pcg_dot3_kernel(size_t n, const double* __restrict__ x, const double* __restrict
     fpe.flush(my);
     if (sa::block_finish<PCG_WARPS>(smem, bad, slot, si) && threadIdx.x == 0) {
         const dgb_dot_result* r = slot.result + si;
+        if (st->dist) return;  // completed by the allreduce + pcg_scalar_kernel
         if (MODE == 1) { st->nrmzr_old = r->value; if (r->status) { st->status = 1; st->done = 1; } }
         if (MODE == 2) pcg_after_pAp(st, r);
     }
@@ -134,23 +138,36 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
     }
     if (CHECK) {
         frr.flush(my_rr);
-        if (sa::block_finish<PCG_WARPS>(smem, bad, slot, 1) && threadIdx.x == 0) {
-            const dgb_dot_result* rr = slot.result + 1;
-            double res = __dsqrt_rn(rr->value);  // pcg.h:171
-            st->res = res;
-            if (rr->status) { st->status = 1; st->done = 1; st->iter = iter; }
-            else if (res < st->tol) { st->done = 1; st->iter = iter; }  // pcg.h:177
-        }
+        if (sa::block_finish<PCG_WARPS>(smem, bad, slot, 1) && threadIdx.x == 0 && !st->dist) pcg_after_rr(st, slot.result + 1, iter);
         __syncthreads();
     }
     fzr.flush(my_zr);
-    if (sa::block_finish<PCG_WARPS>(smem + PCG_WARPS * sa::BINS, bad, slot, 2) && threadIdx.x == 0) {
-        const dgb_dot_result* zr = slot.result + 2;
-        double nw = zr->value;                         // pcg.h:181
-        st->beta = __ddiv_rn(nw, st->nrmzr_old);       // pcg.h:182
-        st->nrmzr_old = nw;                            // pcg.h:183
-        st->cur = iter;
-        if (zr->status) { st->status = 1; st->done = 1; st->iter = iter; }
+    if (sa::block_finish<PCG_WARPS>(smem + PCG_WARPS * sa::BINS, bad, slot, 2) && threadIdx.x == 0 && !st->dist)
+        pcg_after_zr(st, slot.result + 2, iter);
+}
+
+// multi-GPU: after the integer allreduce of the local accumulators, one thread normalises, rounds and runs the hook
+//   MODE 0: res[3] only   MODE 1: nrmzr_old = dot (pcg.h:160)   MODE 2: alpha (pcg.h:166)   MODE 3: K2 hooks
+__device__ inline void finalize_record(dgb_dot_result* r) {
+    long long acc[sa::BINS];
+    for (int i = 0; i < sa::BINS; i++) acc[i] = r->acc[i];
+    int neg = sa::normalize(acc, 1);
+    for (int i = 0; i < sa::BINS; i++) r->acc[i] = acc[i];
+    r->value = sa::round_normalized(acc, neg);
+    r->status = r->status != 0 || r->pad != 0;
+    r->pad = 0;
+}
+template <int MODE>
+__global__ void pcg_scalar_kernel(PcgState* st, dgb_dot_result* res, int iter, int check) {
+    if (threadIdx.x != 0) return;
+    if (MODE >= 2 && st->done) return;
+    if (MODE == 0) finalize_record(res + 3);
+    if (MODE == 1) { finalize_record(res + 0); st->nrmzr_old = res[0].value; if (res[0].status) { st->status = 1; st->done = 1; } }
+    if (MODE == 2) { finalize_record(res + 0); pcg_after_pAp(st, res + 0); }
+    if (MODE == 3) {
+        if (check) { finalize_record(res + 1); pcg_after_rr(st, res + 1, iter); }
+        finalize_record(res + 2);
+        pcg_after_zr(st, res + 2, iter);
     }
 }
 
@@ -204,16 +221,48 @@ static int fetch_result(Pcg& s, int si, cudaStream_t st) {
     return 0;
 }
 
-int pcg_solve(Pcg& s, Elliptic2dPlan& A, double* x, const double* b, const double* P, const double* W, double eps,
-              double nrmb_correction, int test_frequency, int max_iter, int* iterations, cudaStream_t st) {
+// dist: complete the dot(s) in slots [first, first+count) across ranks, then run the scalar hook MODE
+template <int MODE>
+static int dist_finish(Pcg& s, Comm* comm, int first, int count, int iter, int check, cudaStream_t st) {
+    int e = comm_allreduce_i64(comm, reinterpret_cast<long long*>(s.results + first), (size_t)count * sizeof(dgb_dot_result) / 8, st);
+    if (e) return e;
+    pcg_scalar_kernel<MODE><<<1, 32, 0, st>>>(s.st, s.results, iter, check);
+    DGB_LAUNCHED();
+    return 0;
+}
+
+int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const double* b, const double* P, const double* W,
+                   double eps, double nrmb_correction, int test_frequency, int max_iter, int* iterations, cudaStream_t st) {
     const size_t n = s.n;
-    if (A.size != n) { set_error("dgb_pcg_solve: operator size %zu != workspace size %zu", A.size, n); return DGB_ERR_INVALID; }
+    const bool dist = comm != nullptr;
+    const size_t nA = A.slab ? (size_t)A.slab_rows * A.n * A.Nx * A.n : A.size;
+    if (nA != n) { set_error("dgb_pcg_solve: operator size %zu != workspace size %zu", nA, n); return DGB_ERR_INVALID; }
+    if (dist != A.slab) { set_error("dgb_pcg_solve: a slab plan needs the distributed solve and vice versa"); return DGB_ERR_INVALID; }
     if (test_frequency < 1) { set_error("dgb_pcg_solve: test_frequency must be >= 1"); return DGB_ERR_INVALID; }
     int e;
+    // search direction: in slab mode it carries ghost rows that the halo exchange fills
+    const size_t row_len = dist ? (size_t)A.Nx * A.n : 0;
+    const size_t ghost_rows = dist ? (size_t)A.slab_ghost * A.n : 0, gh = ghost_rows * row_len;
+    if (s.p_cap < n + 2 * gh) {
+        cudaFree(s.p_base);
+        s.p_base = nullptr;
+        DGB_CUDA(cudaMalloc(&s.p_base, (n + 2 * gh) * sizeof(double)));
+        DGB_CUDA(cudaMemsetAsync(s.p_base, 0, (n + 2 * gh) * sizeof(double), st));
+        s.p_cap = n + 2 * gh;
+    }
+    s.p = s.p_base + gh;
+    auto halo = [&](double* v) -> int {
+        if (!dist) return 0;
+        return comm_halo_rows(comm, v, row_len, (size_t)A.slab_rows * A.n, ghost_rows, A.wrapy, st);
+    };
+    PcgState init{};
+    init.dist = dist ? 1 : 0;
+    DGB_CUDA(cudaMemcpyAsync(s.st, &init, sizeof(PcgState), cudaMemcpyHostToDevice, st));
     const unsigned g1 = grid_for(n, 4);
     // pcg.h:140  nrmb = sqrt(dot(b, W, b))
     pcg_dot3_kernel<0><<<g1, PCG_THREADS, 0, st>>>(n, b, W, b, s.slot, 3, s.st);
     DGB_LAUNCHED();
+    if (dist && (e = dist_finish<0>(s, comm, 3, 1, 0, 0, st))) return e;
     if ((e = fetch_result(s, 3, st))) return e;
     const double nrmb = std::sqrt(s.results_host[3].value);
     const double tol = eps * (nrmb + nrmb_correction);
@@ -222,22 +271,30 @@ int pcg_solve(Pcg& s, Elliptic2dPlan& A, double* x, const double* b, const doubl
         *iterations = 0;
         return 0;
     }
-    PcgState init{};
     init.tol = tol;
     DGB_CUDA(cudaMemcpyAsync(s.st, &init, sizeof(PcgState), cudaMemcpyHostToDevice, st));
-    if ((e = elliptic2d_symv(A, 1., x, 0., s.r, st, false))) return e;      // pcg.h:155
+    if (dist) {  // the operator needs the ghost rows of its argument: stage x in the padded buffer
+        DGB_CUDA(cudaMemcpyAsync(s.p, x, n * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        if ((e = halo(s.p))) return e;
+        if ((e = elliptic2d_symv(A, 1., s.p, 0., s.r, st, false))) return e;
+    } else {
+        if ((e = elliptic2d_symv(A, 1., x, 0., s.r, st, false))) return e;  // pcg.h:155
+    }
     pcg_residual_kernel<<<grid_for(n, 1), PCG_THREADS, 0, st>>>(n, b, s.r);  // pcg.h:156
     DGB_LAUNCHED();
     pcg_dot3_kernel<0><<<g1, PCG_THREADS, 0, st>>>(n, s.r, W, s.r, s.slot, 3, s.st);
     DGB_LAUNCHED();
+    if (dist && (e = dist_finish<0>(s, comm, 3, 1, 0, 0, st))) return e;
     pcg_precond_kernel<<<grid_for(n, 1), PCG_THREADS, 0, st>>>(n, P, s.r, s.p);  // pcg.h:159
     DGB_LAUNCHED();
     pcg_dot3_kernel<1><<<g1, PCG_THREADS, 0, st>>>(n, s.p, W, s.r, s.slot, 0, s.st);  // pcg.h:160
     DGB_LAUNCHED();
+    if (dist && (e = dist_finish<1>(s, comm, 0, 1, 0, 0, st))) return e;
+    if ((e = halo(s.p))) return e;
     if ((e = fetch_result(s, 3, st))) return e;
     if (std::sqrt(s.results_host[3].value) < tol) { *iterations = 0; return 0; }  // pcg.h:157
     const bool identity_chi = !A.chi[0] && !A.chi[1] && !A.chi[2] && !A.chi[3];
-    const bool fused = A.fusable && identity_chi && !A.chi_weight_jump && !getenv("DGB_ELLIPTIC_UNFUSED");
+    const bool fused = A.fusable && identity_chi && !A.chi_weight_jump && (dist || !getenv("DGB_ELLIPTIC_UNFUSED"));
     FusedDot fd{W, s.slot, s.st};
     const unsigned g2 = grid_for(n, 2);
     int i = 1;
@@ -245,6 +302,7 @@ int pcg_solve(Pcg& s, Elliptic2dPlan& A, double* x, const double* b, const doubl
         int stop = i + s.check_every < max_iter ? i + s.check_every : max_iter;
         for (; i < stop; i++) {
             const bool prof = s.profile && s.prof_n < Pcg::PROF_MAX;
+            const int check = i % test_frequency == 0;
             if (prof) cudaEventRecord(s.ev[s.prof_n][0], st);
             if (fused) {
                 if ((e = elliptic2d_fused_launch_dot(A, s.p, s.ap, st, fd))) return e;
@@ -253,15 +311,18 @@ int pcg_solve(Pcg& s, Elliptic2dPlan& A, double* x, const double* b, const doubl
                 pcg_dot3_kernel<2><<<g1, PCG_THREADS, 0, st>>>(n, s.p, W, s.ap, s.slot, 0, s.st);
                 DGB_LAUNCHED();
             }
+            if (dist && (e = dist_finish<2>(s, comm, 0, 1, i, 0, st))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n][1], st);
-            if (i % test_frequency == 0)
+            if (check)
                 pcg_update_kernel<true><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
             else
                 pcg_update_kernel<false><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
             DGB_LAUNCHED();
+            if (dist && (e = dist_finish<3>(s, comm, check ? 1 : 2, check ? 2 : 1, i, check, st))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n][2], st);
             pcg_direction_kernel<<<g2, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st);
             DGB_LAUNCHED();
+            if ((e = halo(s.p))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n++][3], st);
         }
         if ((e = fetch_state(s, st))) return e;
@@ -286,11 +347,18 @@ int pcg_solve(Pcg& s, Elliptic2dPlan& A, double* x, const double* b, const doubl
     return DGB_ERR_NOCONVERGE;
 }
 
+int pcg_solve(Pcg& s, Elliptic2dPlan& A, double* x, const double* b, const double* P, const double* W, double eps,
+              double nrmb_correction, int test_frequency, int max_iter, int* iterations, cudaStream_t st) {
+    return pcg_solve_impl(s, nullptr, A, x, b, P, W, eps, nrmb_correction, test_frequency, max_iter, iterations, st);
+}
+
 static int pcg_alloc(Pcg* s, size_t n) {
     s->n = n;
     size_t bytes = (n ? n : 1) * sizeof(double);
     DGB_CUDA(cudaMalloc(&s->r, bytes));
-    DGB_CUDA(cudaMalloc(&s->p, bytes));
+    DGB_CUDA(cudaMalloc(&s->p_base, bytes));
+    s->p = s->p_base;
+    s->p_cap = n ? n : 1;
     DGB_CUDA(cudaMalloc(&s->ap, bytes));
     DGB_CUDA(cudaMalloc(&s->st, sizeof(PcgState)));
     DGB_CUDA(cudaMemset(s->st, 0, sizeof(PcgState)));
@@ -321,7 +389,7 @@ void pcg_delete(Pcg* s) {
     if (s->ev_ready)
         for (int k = 0; k < Pcg::PROF_MAX; k++)
             for (int j = 0; j < 4; j++) cudaEventDestroy(s->ev[k][j]);
-    cudaFree(s->r); cudaFree(s->p); cudaFree(s->ap); cudaFree(s->st); cudaFreeHost(s->st_host);
+    cudaFree(s->r); cudaFree(s->p_base); cudaFree(s->ap); cudaFree(s->st); cudaFreeHost(s->st_host);
     cudaFree(s->slot.gacc); cudaFree(s->slot.gstatus); cudaFree(s->slot.ticket);
     cudaFree(s->results); cudaFreeHost(s->results_host);
     delete s;
@@ -363,6 +431,13 @@ int dgb_pcg_get_profile(dgb_pcg* h, double* ms_apply_dot, double* ms_update, dou
 int dgb_pcg_destroy(dgb_pcg* h) {
     pcg_delete(reinterpret_cast<Pcg*>(h));
     return 0;
+}
+int dgb_pcg_solve_elliptic2d_dist(dgb_pcg* h, dgb_comm* comm, dgb_elliptic2d* A, double* x, const double* b, const double* P,
+                                  const double* W, double eps, double nrmb_correction, int test_frequency, int max_iter,
+                                  int* iterations, dgb_stream_t s) {
+    if (!h || !A || !comm) { set_error("dgb_pcg_solve_elliptic2d_dist: NULL handle"); return DGB_ERR_INVALID; }
+    return pcg_solve_impl(*reinterpret_cast<Pcg*>(h), reinterpret_cast<Comm*>(comm), *reinterpret_cast<Elliptic2dPlan*>(A), x,
+                          b, P, W, eps, nrmb_correction, test_frequency, max_iter, iterations, as_stream(s));
 }
 int dgb_pcg_solve_elliptic2d(dgb_pcg* h, dgb_elliptic2d* A, double* x, const double* b, const double* P,
                              const double* W, double eps, double nrmb_correction, int test_frequency, int max_iter,

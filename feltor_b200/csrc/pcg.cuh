@@ -10,6 +10,8 @@ struct PcgState {
     int iter;      // iteration at which `done` was raised
     int status;    // 1: a dot product met NaN/Inf (blas1.h:161)
     int cur;       // iteration the launches in flight belong to (written by the update kernel's finisher)
+    int dist;      // 1: dots are completed by an integer allreduce + pcg_scalar_kernel, the fused finishers only publish
+                   //    the local accumulator
 };
 
 struct FusedDot {
@@ -23,6 +25,22 @@ __device__ __forceinline__ void pcg_after_pAp(PcgState* st, const dgb_dot_result
     st->pAp = r->value;
     st->alpha = __ddiv_rn(st->nrmzr_old, r->value);
     if (r->status) { st->status = 1; st->done = 1; }
+}
+
+// pcg.h:171-177  res = sqrt(dot(r,W,r)); converged if res < tol
+__device__ __forceinline__ void pcg_after_rr(PcgState* st, const dgb_dot_result* rr, int iter) {
+    double res = __dsqrt_rn(rr->value);
+    st->res = res;
+    if (rr->status) { st->status = 1; st->done = 1; st->iter = iter; }
+    else if (res < st->tol) { st->done = 1; st->iter = iter; }
+}
+// pcg.h:181-183  beta = nrmzr_new / nrmzr_old; nrmzr_old = nrmzr_new
+__device__ __forceinline__ void pcg_after_zr(PcgState* st, const dgb_dot_result* zr, int iter) {
+    double nw = zr->value;
+    st->beta = __ddiv_rn(nw, st->nrmzr_old);
+    st->nrmzr_old = nw;
+    st->cur = iter;
+    if (zr->status) { st->status = 1; st->done = 1; st->iter = iter; }
 }
 
 struct Elliptic2dPlan;

@@ -285,6 +285,31 @@ DGB_API int dgb_multigrid2d_solve(dgb_multigrid2d* mg, dgb_elliptic2d* const* op
                                   const double* const* weights, double* x, const double* b, const double* eps,
                                   int* numbers, dgb_stream_t s);
 
+/* ---------------------------------------------------------------------------------------------------
+ * Multi-GPU (one process per GPU, NCCL over NVLink/NVSwitch): replaces MPI_Vector / MPISparseBlockMat /
+ * MPIKroneckerGather / reduce_mpi_cpu (inc/dg/backend/mpi_vector.h, mpi_matrix.h:183-217, mpi_gather_kron.h:143-291,
+ * exblas/mpi_accumulate.h:42-125) for a decomposition of the 2-d grid into slabs of cell rows (y direction).
+ * ------------------------------------------------------------------------------------------------- */
+typedef struct dgb_comm dgb_comm;
+DGB_API int dgb_comm_unique_id(char* id128);                 /* ncclGetUniqueId on rank 0; ship the 128 bytes to the others */
+DGB_API int dgb_comm_create(dgb_comm** comm, const char* id128, int rank, int nranks);
+DGB_API int dgb_comm_destroy(dgb_comm* comm);
+/* halo exchange of `ghost_rows` rows with the lower/upper neighbour; buffer layout [ghost | nrows | ghost], `interior`
+ * points to the first interior row; periodic closes the ring (mpi_gather_kron.h global_gather_init/wait) */
+DGB_API int dgb_comm_halo_rows(dgb_comm* comm, double* interior, size_t row_len, size_t nrows, size_t ghost_rows,
+                               int periodic, dgb_stream_t s);
+/* exact global dot: sums the normalised superaccumulators of `nrecords` device records over all ranks (integer
+ * allreduce), renormalises and rounds on the device (blas1_dispatch_mpi.h:91-109) */
+DGB_API int dgb_comm_allreduce_dot(dgb_comm* comm, dgb_dot_result* result_dev, int nrecords, dgb_stream_t s);
+/* declare the plan (built from the GLOBAL matrices) to act on the slab of cell rows [yoff, yoff+rows) whose x and
+ * sigma operands carry `ghost` cell rows on either side; vectors passed to symv/PCG then have rows*n*Nx*n elements */
+DGB_API int dgb_elliptic2d_set_slab(dgb_elliptic2d* plan, int yoff, int rows, int ghost);
+/* PCG on the decomposed problem: same arithmetic, halo exchange of the search direction and integer allreduce of the
+ * three dots per iteration; the result is bit-identical to the single-GPU solve for any number of ranks */
+DGB_API int dgb_pcg_solve_elliptic2d_dist(dgb_pcg* pcg, dgb_comm* comm, dgb_elliptic2d* A, double* x, const double* b,
+                                          const double* P, const double* W, double eps, double nrmb_correction,
+                                          int test_frequency, int max_iter, int* iterations, dgb_stream_t s);
+
 /* measurement aid: when on, CUDA events on the launching stream bracket the three kernels of every iteration
  * (operator+dot, update+dots, direction); get returns the accumulated milliseconds and the iterations timed */
 DGB_API int dgb_pcg_set_profile(dgb_pcg* pcg, int on);

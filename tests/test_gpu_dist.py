@@ -1,0 +1,56 @@
+"""Slab (multi-GPU) path on ONE device: a communicator of size 1 exercises the padded operands, the ring-closing halo
+copy, the slab tables of the fused kernel and the allreduce+scalar-kernel completion of the dots.  Results must be
+bit-identical to the plain single-GPU objects.  (tools/dist_check.py runs the same comparison on N GPUs under torchrun.)"""
+import numpy as np
+import pytest
+from util import same_bits, rng
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_backend
+    gpu_backend.require_library_loaded()
+    return gpu_backend
+
+
+@pytest.mark.parametrize("N,bcx,bcy,d", [([40, 24], 1, 0, 0), ([37, 19], 4, 0, 2), ([33, 40], 1, 1, 1), ([64, 16], 0, 0, 0)])
+def test_slab_symv_equals_global(G, N, bcx, bcy, d):
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic2d
+    from feltor_b200.dist import Comm, SlabElliptic2d
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, N, [bcx, bcy])
+    r = rng(5)
+    chi = 1. + r.uniform(0, 1, g.size)
+    x = r.uniform(-1, 1, g.size)
+    E = Elliptic2d(g, bcx, bcy, d, 0.7)
+    E.set_chi(G.make(chi))
+    y = G.make(np.zeros(g.size))
+    E.symv(G.make(x), y)
+    comm = Comm(0, 1)
+    S = SlabElliptic2d(comm, g, bcx, bcy, d, 0.7)
+    S.set_chi(G.make(S.local(chi)))
+    ys = G.make(np.full(g.size, np.nan))
+    S.symv(G.make(S.local(x)), ys)
+    assert same_bits(G.get(ys), G.get(y))
+
+
+def test_slab_pcg_equals_global(G):
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic2d, PCG
+    from feltor_b200.dist import Comm, SlabElliptic2d, DistPCG
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, [40, 24], [T.DIR, T.PER])
+    chi = g.evaluate(lambda x, y: 1. + 0.9 * np.sin(x) * np.sin(y))
+    b = g.evaluate(lambda x, y: np.sin(x) * np.sin(y) * (1 + np.cos(3 * y)))
+    E = Elliptic2d(g, T.DIR, T.PER, T.FORWARD, 1.0)
+    E.set_chi(G.make(chi))
+    x = G.make(np.zeros(g.size))
+    it = PCG(g.size, g.size).solve(E, x, G.make(b), E.precond(), E.weights(), 1e-9, 1.0, 1)
+    comm = Comm(0, 1)
+    S = SlabElliptic2d(comm, g, T.DIR, T.PER, T.FORWARD, 1.0)
+    S.set_chi(G.make(chi))
+    xs = G.make(np.zeros(g.size))
+    its = DistPCG(comm, g.size, g.size).solve(S, xs, G.make(b), S.precond(), S.weights(), 1e-9, 1.0, 1)
+    assert its == it
+    assert same_bits(G.get(xs), G.get(x))

@@ -1,0 +1,61 @@
+#!/usr/bin/env python
+"""N-GPU parity check (run under torchrun): the slab-decomposed Elliptic apply and PCG solve give, on every rank, exactly
+the rows of the single-GPU result (bitwise) and the same iteration count; the global dot is bit-reproducible.
+  python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port 29511 tools/dist_check.py"""
+import os
+import sys
+import numpy as np
+import torch
+import torch.distributed as dist
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+from feltor_b200 import topology as T, blas2  # noqa: E402
+from feltor_b200.elliptic import Elliptic2d, PCG  # noqa: E402
+from feltor_b200.dist import Comm, SlabElliptic2d, DistPCG  # noqa: E402
+from feltor_b200._dev import dvec, hvec, ptr, stream  # noqa: E402
+import feltor_b200 as fb  # noqa: E402
+import ctypes as C  # noqa: E402
+
+local = int(os.environ.get("LOCAL_RANK", "0"))
+torch.cuda.set_device(local)
+dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+comm = Comm.from_torch_distributed()
+rank, size = comm.rank, comm.size
+ok = True
+for N, bcx, bcy, d in (([40, 24], T.DIR, T.PER, T.FORWARD), ([37, 21], T.NEU, T.DIR, T.CENTERED), ([96, 64], T.DIR, T.PER, T.BACKWARD)):
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, N, [bcx, bcy])
+    r = np.random.default_rng(3)
+    chi = 1. + r.uniform(0, 1, g.size)
+    x = r.uniform(-1, 1, g.size)
+    b = g.evaluate(lambda xx, yy: np.sin(xx) * np.sin(yy) * (1 + np.cos(3 * yy)))
+    # single-GPU reference on every rank
+    E = Elliptic2d(g, bcx, bcy, d, 0.7)
+    E.set_chi(dvec(chi))
+    y = torch.zeros(g.size, dtype=torch.float64, device="cuda")
+    E.symv(dvec(x), y)
+    xs1 = torch.zeros(g.size, dtype=torch.float64, device="cuda")
+    it1 = PCG(g.size, g.size).solve(E, xs1, dvec(b), E.precond(), E.weights(), 1e-9, 1.0, 1)
+    # decomposed
+    S = SlabElliptic2d(comm, g, bcx, bcy, d, 0.7)
+    S.set_chi(dvec(S.local(chi)))
+    ys = torch.full((S.size,), float("nan"), dtype=torch.float64, device="cuda")
+    S.symv(dvec(S.local(x)), ys)
+    same_symv = np.array_equal(hvec(ys).view(np.int64), S.local(hvec(y)).view(np.int64))
+    xs = torch.zeros(S.size, dtype=torch.float64, device="cuda")
+    its = DistPCG(comm, S.size, g.size).solve(S, xs, dvec(S.local(b)), S.precond(), S.weights(), 1e-9, 1.0, 1)
+    same_pcg = its == it1 and np.array_equal(hvec(xs).view(np.int64), S.local(hvec(xs1)).view(np.int64))
+    # global exact dot through the integer allreduce
+    ws = blas2.DotWorkspace()
+    rec = torch.zeros(41, dtype=torch.int64, device="cuda")
+    xl, wl = dvec(S.local(x)), S.weights()
+    fb.lib().exdot3(ws.h, S.size, ptr(xl), C.c_double(0), ptr(wl), C.c_double(0), ptr(xl), C.c_double(0), ptr(rec), stream())
+    comm.allreduce_dot(rec)
+    val = rec[39:40].view(torch.float64).item()
+    same_dot = val == blas2.dot(dvec(x), E.weights(), dvec(x))
+    print(f"rank {rank}/{size} N={N} bc=({bcx},{bcy}) dir={d}: symv {same_symv} pcg {same_pcg} (it {its} vs {it1}) dot {same_dot}", flush=True)
+    ok = ok and same_symv and same_pcg and same_dot
+t = torch.tensor([1 if ok else 0], device="cuda")
+dist.all_reduce(t, op=dist.ReduceOp.MIN)
+if rank == 0:
+    print("DIST_CHECK", "PASS" if t.item() == 1 else "FAIL", flush=True)
+dist.destroy_process_group()
+sys.exit(0 if t.item() == 1 else 1)
