@@ -93,7 +93,8 @@ class SlabElliptic2d:
         self._sigma_pad = torch.ones((self.nrows + 2 * self.ghost_rows) * self.row_len, dtype=torch.float64, device="cuda")
         self._sigma = self._sigma_pad[self.ghost_rows * self.row_len:][:self.size]
         lib().elliptic2d_set_sigma(self.h, ptr(self._sigma))
-        self._weights = dvec(self.local(g.weights()))
+        wx, wy = g.weights1d(0), g.weights1d(1)[self.yoff * n:(self.yoff + self.rows) * n]
+        self._weights = dvec((wy[:, None] * wx[None, :]).reshape(-1))  # = rows of create::weights (w_x[i] * w_y[j])
         self._precond = torch.ones(self.size, dtype=torch.float64, device="cuda")
 
     def local(self, global_host_vector):
@@ -101,6 +102,13 @@ class SlabElliptic2d:
         a = np.asarray(global_host_vector).reshape(-1, self.row_len)
         n = self.grid.n[0]
         return np.ascontiguousarray(a[self.yoff * n:(self.yoff + self.rows) * n]).reshape(-1)
+
+    def evaluate(self, f):
+        """dg::evaluate restricted to this rank's rows (same abscissas as the global grid)"""
+        n = self.grid.n[0]
+        ax, ay = self.grid.abscissas(0), self.grid.abscissas(1)[self.yoff * n:(self.yoff + self.rows) * n]
+        Y, X = np.meshgrid(ay, ax, indexing="ij")
+        return np.ascontiguousarray(np.broadcast_to(f(X, Y), X.shape).reshape(-1), dtype=np.float64)
 
     def weights(self):
         return self._weights
