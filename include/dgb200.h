@@ -224,6 +224,27 @@ DGB_API int dgb_csr_spmv_planes(int num_rows, int num_cols, const int* row_offse
                                 int nplanes, int shift, dgb_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------------
+ * dg::geo::Fieldaligned / dg::geo::DS apply path (inc/geometries/fieldaligned.h:806-912, ds.h:170-330,744-852).  The
+ * 2-d interpolation matrices m_plus / m_minus are CSR arrays on the device (their construction by field-line tracing
+ * stays on the host, out of scope).
+ * ------------------------------------------------------------------------------------------------- */
+/* ePlus (plus=1: out[k] = M f[k+1]) / eMinus (plus=0: out[k] = M f[k-1]) on all planes in one launch + the ghost-cell
+ * fix-up of the last/first plane for bcz != DGB_PER (bnd = m_right/m_left, limiter = m_limiter, ghost = scratch) */
+DGB_API int dgb_fa_shift(int plus, int num_rows, int nplanes, const int* pos, const int* idx, const double* val,
+                         const double* f, double* out, int bcz, const double* bnd, const double* limiter, double* ghost,
+                         double delta_phi, dgb_stream_t s);
+/* ds_forward / ds_backward / ds_centered / ds_forward2 / ds_backward2 / dss_centered (ds.h:744-852): kind 0..5,
+ * operands (a, b, c) in the argument order of the reference functions, see feltor_b200/csrc/ds.cu */
+DGB_API int dgb_ds_apply(int kind, size_t n, double alpha, const double* a, const double* b, const double* c,
+                         const double* bphi_m, const double* bphi, const double* bphi_p, double delta_phi, double beta,
+                         double* g, dgb_stream_t s);
+/* DS::centered(alpha, f, beta, g) (ds.h:481-485) for periodic z fused into one kernel (gather f+, f-, formula) */
+DGB_API int dgb_ds_centered_fused(int num_rows, int nplanes, const int* plus_pos, const int* plus_idx,
+                                  const double* plus_val, const int* minus_pos, const int* minus_idx,
+                                  const double* minus_val, double alpha, const double* f, const double* bphi,
+                                  double delta_phi, double beta, double* g, dgb_stream_t s);
+
+/* ---------------------------------------------------------------------------------------------------
  * Fused Elliptic2d: replaces the 8-kernel composition of Elliptic2d::symv inc/dg/elliptic.h:428-458
  *   y = alpha/vol * [ -Lx sigma (chi_xx Rx + chi_xy Ry) x - Ly sigma (chi_yx Rx + chi_yy Ry) x
  *                     + jfactor (Jx + Jy) x ] + beta y

@@ -1,0 +1,114 @@
+"""GPU parity of the Fieldaligned shift (ePlus/eMinus incl. ghost-cell boundary fix-up) and the DS formulas against a
+numpy/oracle restatement of inc/geometries/fieldaligned.h:850-912 and ds.h:744-852 (the CSR part bitwise, the
+user-lambda formulas to 1e-14 relative), plus fused DS::centered == its composition bit for bit."""
+import ctypes as C
+import numpy as np
+import pytest
+from oracle import orc
+from util import same_bits, rng
+
+pytestmark = pytest.mark.gpu
+PER, DIR, DIR_NEU, NEU_DIR, NEU = 0, 1, 2, 3, 4
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_backend
+    gpu_backend.require_library_loaded()
+    return gpu_backend
+
+
+def stencil_csr(r, n, width, maxlen):
+    """interpolation-like matrix: each row couples to a few columns near its own index"""
+    counts = r.integers(1, maxlen + 1, n)
+    pos = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    idx = np.concatenate([np.clip(i + r.integers(-width, width + 1, c), 0, n - 1) for i, c in enumerate(counts)]).astype(np.int32)
+    val = r.uniform(-1, 1, pos[-1])
+    return pos, idx, val
+
+
+def oracle_shift(plus, pos, idx, val, f, nplanes, bcz, bnd, lim, dphi):
+    n = len(pos) - 1
+    out = np.zeros_like(f)
+    for k in range(nplanes):
+        src = (k + 1) % nplanes if plus else (k - 1) % nplanes
+        y = out[k * n:(k + 1) * n]
+        orc.csr_spmv(pos, idx, val, 1., np.ascontiguousarray(f[src * n:(src + 1) * n]), 0., y)
+    if bcz != PER:
+        i0 = nplanes - 1 if plus else 0
+        fi, ti = f[i0 * n:(i0 + 1) * n], out[i0 * n:(i0 + 1) * n]
+        ghost = np.empty(n)
+        dirichlet = bcz in ((DIR, NEU_DIR) if plus else (DIR, DIR_NEU))
+        if dirichlet:
+            orc.axpbyz(2., bnd, -1., np.ascontiguousarray(fi), ghost)
+        else:
+            orc.axpbyz(dphi if plus else -dphi, bnd, 1., np.ascontiguousarray(fi), ghost)
+        orc.axpbyz(1., ghost.copy(), -1., np.ascontiguousarray(ti), ghost)
+        orc.pointwiseDot(1., lim, ghost, 1., ti)
+    return out
+
+
+def dev_csr(G, pos, idx, val):
+    from feltor_b200._dev import dvec
+    return dvec(pos), dvec(idx), dvec(val)
+
+
+@pytest.mark.parametrize("bcz", [PER, DIR, NEU, DIR_NEU, NEU_DIR])
+def test_fieldaligned_shift(G, bcz):
+    from feltor_b200 import lib
+    from feltor_b200._dev import ptr, stream
+    r = rng(bcz)
+    n, nz = 700, 7
+    pos, idx, val = stencil_csr(r, n, 30, 35)
+    f = r.uniform(-1, 1, n * nz)
+    bnd, lim = r.uniform(-1, 1, n), r.integers(0, 2, n).astype(np.float64)
+    dphi = 2 * np.pi / nz
+    dpos, didx, dval = dev_csr(G, pos, idx, val)
+    for plus in (1, 0):
+        want = oracle_shift(plus, pos, idx, val, f, nz, bcz, bnd, lim, dphi)
+        out = G.make(np.full(n * nz, np.nan))
+        ghost = G.make(np.zeros(n))
+        lib().fa_shift(plus, n, nz, ptr(dpos), ptr(didx), ptr(dval), ptr(G.make(f)), ptr(out), bcz, ptr(G.make(bnd)),
+                       ptr(G.make(lim)), ptr(ghost), C.c_double(dphi), stream())
+        assert same_bits(G.get(out), want), (bcz, plus)
+
+
+def test_ds_formulas_and_fused_centered(G):
+    from feltor_b200 import lib
+    from feltor_b200._dev import ptr, stream
+    r = rng(9)
+    n, nz = 1000, 9
+    N = n * nz
+    ppos, pidx, pval = stencil_csr(r, n, 20, 40)
+    mpos, midx, mval = stencil_csr(r, n, 20, 40)
+    f, g0 = r.uniform(-1, 1, N), r.uniform(-1, 1, N)
+    bphi, bm, bp = r.uniform(0.5, 1.5, N), r.uniform(0.5, 1.5, N), r.uniform(0.5, 1.5, N)
+    dphi = 2 * np.pi / nz
+    fp = oracle_shift(1, ppos, pidx, pval, f, nz, PER, None, None, dphi)
+    fm = oracle_shift(0, mpos, midx, mval, f, nz, PER, None, None, dphi)
+    al, be = 0.7, -0.3
+    want = {0: al * bphi * (fp - f) / dphi + be * g0, 1: al * bphi * (f - fm) / dphi + be * g0,
+            2: al * bphi * (fp - fm) / 2. / dphi + be * g0,
+            3: al * bphi * (-3. * f + 4. * fp - fm) / 2. / dphi + be * g0,   # (fm stands in for fpp)
+            4: al * bphi * (3. * f - 4. * fm + fp) / 2. / dphi + be * g0,
+            5: al * bphi * (((bp + bphi) / 2.) * ((fp - f) / dphi) - ((bm + bphi) / 2.) * ((f - fm) / dphi)) / dphi + be * g0}
+    args = {0: (f, fp, None), 1: (f, fm, None), 2: (fm, fp, None), 3: (f, fp, fm), 4: (f, fm, fp), 5: (fm, f, fp)}
+    d = {k: G.make(v) for k, v in dict(f=f, fp=fp, fm=fm, bphi=bphi, bm=bm, bp=bp).items()}
+    name = {id(f): "f", id(fp): "fp", id(fm): "fm"}
+    for kind in range(6):
+        a, b, c = args[kind]
+        g = G.make(g0)
+        lib().ds_apply(kind, N, C.c_double(al), ptr(d[name[id(a)]]), ptr(d[name[id(b)]]), ptr(d[name[id(c)]]) if c is not None else None,
+                       ptr(d["bm"]), ptr(d["bphi"]), ptr(d["bp"]), C.c_double(dphi), C.c_double(be), ptr(g), stream())
+        got = G.get(g)
+        assert np.max(np.abs(got - want[kind]) / (np.abs(want[kind]) + 1e-300)) < 1e-13 or np.allclose(got, want[kind], rtol=1e-14, atol=1e-15), kind
+    # fused DS::centered == shift + shift + ds_centered, bit for bit; beta = 0 overwrites NaN
+    dp, dm = dev_csr(G, ppos, pidx, pval), dev_csr(G, mpos, midx, mval)
+    for beta in (be, 0.):
+        g1 = G.make(g0 if beta != 0. else np.full(N, np.nan))
+        lib().ds_centered_fused(n, nz, ptr(dp[0]), ptr(dp[1]), ptr(dp[2]), ptr(dm[0]), ptr(dm[1]), ptr(dm[2]), C.c_double(al),
+                                ptr(d["f"]), ptr(d["bphi"]), C.c_double(dphi), C.c_double(beta), ptr(g1), stream())
+        g2 = G.make(g0 if beta != 0. else np.full(N, np.nan))
+        lib().ds_apply(2, N, C.c_double(al), ptr(d["fm"]), ptr(d["fp"]), None, None, ptr(d["bphi"]), None, C.c_double(dphi),
+                       C.c_double(beta), ptr(g2), stream())
+        assert same_bits(G.get(g1), G.get(g2)), beta
