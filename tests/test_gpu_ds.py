@@ -64,12 +64,13 @@ def test_fieldaligned_shift(G, bcz):
     bnd, lim = r.uniform(-1, 1, n), r.integers(0, 2, n).astype(np.float64)
     dphi = 2 * np.pi / nz
     dpos, didx, dval = dev_csr(G, pos, idx, val)
+    df, dbnd, dlim = G.make(f), G.make(bnd), G.make(lim)  # keep the device operands alive across the call
     for plus in (1, 0):
         want = oracle_shift(plus, pos, idx, val, f, nz, bcz, bnd, lim, dphi)
         out = G.make(np.full(n * nz, np.nan))
         ghost = G.make(np.zeros(n))
-        lib().fa_shift(plus, n, nz, ptr(dpos), ptr(didx), ptr(dval), ptr(G.make(f)), ptr(out), bcz, ptr(G.make(bnd)),
-                       ptr(G.make(lim)), ptr(ghost), C.c_double(dphi), stream())
+        lib().fa_shift(plus, n, nz, ptr(dpos), ptr(didx), ptr(dval), ptr(df), ptr(out), bcz, ptr(dbnd), ptr(dlim),
+                       ptr(ghost), C.c_double(dphi), stream())
         assert same_bits(G.get(out), want), (bcz, plus)
 
 
