@@ -9,7 +9,7 @@ import os
 import re
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libdgb200.so")
+LIB_PATH = os.environ.get("DGB200_LIB") or os.path.join(_HERE, "libdgb200.so")  # override: kernel experiments only
 HEADER_PATH = os.path.join(_HERE, "..", "include", "dgb200.h")
 
 _SCALARS = {

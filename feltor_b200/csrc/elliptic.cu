@@ -189,6 +189,7 @@ int dgb_elliptic2d_destroy(dgb_elliptic2d* h) {
     EllDev* ds[6] = {&p->leftx, &p->lefty, &p->rightx, &p->righty, &p->jumpx, &p->jumpy};
     for (int k = 0; k < 6; k++) ell_release(*ds[k]);
     cudaFree(p->tx); cudaFree(p->ty); cudaFree(p->t);
+    elliptic2d_walker_release(*p);
     delete p;
     return 0;
 }

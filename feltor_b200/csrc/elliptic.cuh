@@ -22,7 +22,9 @@ struct Elliptic2dPlan {
     // sigma operands carry slab_ghost ghost cell rows on either side (filled by the halo exchange)
     bool slab = false;
     int slab_yoff = 0, slab_rows = 0, slab_ghost = 0;
+    void* walk_part[2] = {nullptr, nullptr};  // work partitions of the walker kernel (plain / fused-dot variant)
 };
+void elliptic2d_walker_release(Elliptic2dPlan& p);
 
 int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                     bool force_unfused);

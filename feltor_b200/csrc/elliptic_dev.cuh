@@ -1,0 +1,130 @@
+// Internal: device helpers shared by the two fused Elliptic2d kernels (elliptic_fused.cu: CTA tiles,
+// elliptic_walker.cu: warp-private sliding window).
+#pragma once
+#include "elliptic.cuh"
+#include "superacc.cuh"
+#include "pcg.cuh"
+#include <algorithm>
+#include <cstring>
+#include <cstdlib>
+#include <cuda.h>
+
+namespace dgb {
+
+struct MatView {
+    const double* data;
+    const int* cols;
+    const int* didx;
+    int i_lo, i_hi, num;
+    int off[3];
+};
+
+template <int N, int B>
+struct EllipticCoef {
+    double rx[B][N][N], ry[B][N][N], lx[B][N][N], ly[B][N][N], jx[3][N][N], jy[3][N][N];
+};
+
+// ------------------------------------------------------------------------------------------------ TMA / LDGSTS
+__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
+    unsigned ok;
+    do {
+        asm volatile(
+            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
+            : "=r"(ok)
+            : "r"(smem_u32(bar)), "r"(phase)
+            : "memory");
+    } while (!ok);
+}
+// 2-d tile load global -> shared through the tensor map; completion is signalled on the mbarrier in bytes
+__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
+            smem_u32(dst)),
+        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+        : "memory");
+}
+// 8-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination without touching memory
+__device__ __forceinline__ void cp_async8(double* dst, const double* src, bool valid) {
+    int bytes = valid ? 8 : 0;
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() {
+    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
+}
+
+// interior rows with the stencil offsets known at compile time (DIRK: 0 forward, 1 backward, 2 centered; jumps are
+// always {-1,0,1}): out[k] = fma(a, sum_q C[d][k][q] * s[(OFF_d*N + q)*stride], out[k])
+template <int KIND>  // 0: {0,+1}   1: {-1,0}   2: {-1,0,+1}
+struct Offs {
+    static constexpr int BPL = KIND == 2 ? 3 : 2;
+    static constexpr int first = KIND == 0 ? 0 : -1;
+    __host__ __device__ static constexpr int at(int d) { return first + d; }
+};
+// global cell index of tile-relative cell c (may lie in the halo): wrapped if periodic, -1 if outside
+__device__ __forceinline__ int gcell(int c, int num, int wrap) {
+    if (c >= 0 && c < num) return c;
+    if (!wrap) return -1;
+    return c < 0 ? c + num : c - num;
+}
+
+// ------------------------------------------------------------------------------------------------ host
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+inline EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = nullptr;
+    static bool tried = false;
+    if (!tried) {
+        tried = true;
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+        else
+            cudaGetLastError();
+    }
+    return fn;
+}
+// 2-d map over a row-major (rows x ld) array of doubles with a (box_r x box_c) box; false if TMA cannot describe it
+inline bool make_map(CUtensorMap* m, const double* base, int rows, int ld, int box_r, int box_c) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) return false;
+    if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((size_t)ld * sizeof(double)) % 16 || box_c > 256 || box_r > 256) return false;
+    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
+    cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
+    cuuint32_t estr[2] = {1, 1};
+    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
+              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
+}
+
+inline MatView view(const EllDev& m) {
+    MatView v;
+    v.data = m.data; v.cols = m.cols; v.didx = m.didx;
+    v.i_lo = m.i_lo; v.i_hi = m.i_hi; v.num = m.num_rows;
+    for (int d = 0; d < 3; d++) v.off[d] = m.off[d];
+    return v;
+}
+template <int N, int BPL>
+inline void fill(double (&dst)[BPL][N][N], const EllDev& m) {
+    for (int d = 0; d < BPL; d++)
+        for (int k = 0; k < N; k++)
+            for (int q = 0; q < N; q++) dst[d][k][q] = m.h_data[((size_t)m.did[d] * N + k) * N + q];
+}
+
+
+int elliptic2d_walker_launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
+                             const FusedDot* fd);
+bool elliptic2d_walker_supported(const Elliptic2dPlan& p);
+
+}  // namespace dgb

@@ -15,13 +15,7 @@
 //   t  = 0; for d: t = fma(1, blk(Ly,d)[ty], t);  t = t*(-1);  for d: t = fma(-1, blk(Lx,d)[tx], t)
 //   for d: t = fma(jfactor, blk(Jx,d)[x], t);  for d: t = fma(jfactor, blk(Jy,d)[x], t)
 //   y = fma(alpha, t/vol, beta*y)
-#include "elliptic.cuh"
-#include "superacc.cuh"
-#include "pcg.cuh"
-#include <algorithm>
-#include <cstring>
-#include <cstdlib>
-#include <cuda.h>
+#include "elliptic_dev.cuh"
 
 namespace dgb {
 
@@ -30,19 +24,6 @@ namespace dgb {
 #endif
 constexpr int TX = 32, TY = DGB_TY, FUSED_THREADS = TX * TY;  // one thread per cell of the tile
 constexpr int FUSED_MIN_CTAS = 512 / FUSED_THREADS;           // 16 warps per SM
-
-struct MatView {
-    const double* data;
-    const int* cols;
-    const int* didx;
-    int i_lo, i_hi, num;
-    int off[3];
-};
-
-template <int N, int B>
-struct EllipticCoef {
-    double rx[B][N][N], ry[B][N][N], lx[B][N][N], ly[B][N][N], jx[3][N][N], jy[3][N][N];
-};
 
 struct FusedArgs {
     MatView rx, ry, lx, ly, jx, jy;
@@ -62,42 +43,6 @@ struct FusedArgs {
     sa::DotSlot slot;
     PcgState* pcg;
 };
-
-// ------------------------------------------------------------------------------------------------ TMA / LDGSTS
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
-    unsigned ok;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(phase)
-            : "memory");
-    } while (!ok);
-}
-// 2-d tile load global -> shared through the tensor map; completion is signalled on the mbarrier in bytes
-__device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
-    asm volatile(
-        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];\n" ::"r"(
-            smem_u32(dst)),
-        "l"(map), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-        : "memory");
-}
-// 8-byte asynchronous global -> shared copy (LDGSTS); !valid zero-fills the destination without touching memory
-__device__ __forceinline__ void cp_async8(double* dst, const double* src, bool valid) {
-    int bytes = valid ? 8 : 0;
-    asm volatile("cp.async.ca.shared.global [%0], [%1], 8, %2;\n" ::"r"(smem_u32(dst)), "l"(src), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void cp_async_wait_all() {
-    asm volatile("cp.async.commit_group;\ncp.async.wait_group 0;\n" ::: "memory");
-}
 
 // out[k] = fma(a, sum_q C[d][k][q] * s[(off_d*N + q)*stride], out[k]) for the slots d of block-row `cell` of M
 template <int N, int BPL>
@@ -144,14 +89,6 @@ __device__ __forceinline__ void apply_row(const MatView& M, const double (&C)[BP
     }
 }
 
-// interior rows with the stencil offsets known at compile time (DIRK: 0 forward, 1 backward, 2 centered; jumps are
-// always {-1,0,1}): out[k] = fma(a, sum_q C[d][k][q] * s[(OFF_d*N + q)*stride], out[k])
-template <int KIND>  // 0: {0,+1}   1: {-1,0}   2: {-1,0,+1}
-struct Offs {
-    static constexpr int BPL = KIND == 2 ? 3 : 2;
-    static constexpr int first = KIND == 0 ? 0 : -1;
-    __host__ __device__ static constexpr int at(int d) { return first + d; }
-};
 template <int N, int KIND, int STRIDE>
 __device__ __forceinline__ void apply_fast(const double (&C)[Offs<KIND>::BPL][N][N], const double* s, double a, double (&out)[N]) {
 #pragma unroll
@@ -167,13 +104,6 @@ __device__ __forceinline__ void apply_fast(const double (&C)[Offs<KIND>::BPL][N]
             out[k] = __fma_rn(a, t, out[k]);
         }
     }
-}
-
-// global cell index of tile-relative cell c (may lie in the halo): wrapped if periodic, -1 if outside
-__device__ __forceinline__ int gcell(int c, int num, int wrap) {
-    if (c >= 0 && c < num) return c;
-    if (!wrap) return -1;
-    return c < 0 ? c + num : c - num;
 }
 
 constexpr int NOROW = -(1 << 30);
@@ -467,53 +397,6 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
     }
 }
 
-// ------------------------------------------------------------------------------------------------ host
-typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
-                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
-                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
-static EncodeTiledFn encode_fn() {
-    static EncodeTiledFn fn = nullptr;
-    static bool tried = false;
-    if (!tried) {
-        tried = true;
-        void* p = nullptr;
-        cudaDriverEntryPointQueryResult q;
-        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
-            q == cudaDriverEntryPointSuccess)
-            fn = reinterpret_cast<EncodeTiledFn>(p);
-        else
-            cudaGetLastError();
-    }
-    return fn;
-}
-// 2-d map over a row-major (rows x ld) array of doubles with a (box_r x box_c) box; false if TMA cannot describe it
-static bool make_map(CUtensorMap* m, const double* base, int rows, int ld, int box_r, int box_c) {
-    EncodeTiledFn fn = encode_fn();
-    if (!fn) return false;
-    if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((size_t)ld * sizeof(double)) % 16 || box_c > 256 || box_r > 256) return false;
-    cuuint64_t dims[2] = {(cuuint64_t)ld, (cuuint64_t)rows};
-    cuuint64_t strides[1] = {(cuuint64_t)ld * sizeof(double)};
-    cuuint32_t box[2] = {(cuuint32_t)box_c, (cuuint32_t)box_r};
-    cuuint32_t estr[2] = {1, 1};
-    return fn(m, CU_TENSOR_MAP_DATA_TYPE_FLOAT64, 2, const_cast<double*>(base), dims, strides, box, estr,
-              CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
-              CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE) == CUDA_SUCCESS;
-}
-
-static MatView view(const EllDev& m) {
-    MatView v;
-    v.data = m.data; v.cols = m.cols; v.didx = m.didx;
-    v.i_lo = m.i_lo; v.i_hi = m.i_hi; v.num = m.num_rows;
-    for (int d = 0; d < 3; d++) v.off[d] = m.off[d];
-    return v;
-}
-template <int N, int BPL>
-static void fill(double (&dst)[BPL][N][N], const EllDev& m) {
-    for (int d = 0; d < BPL; d++)
-        for (int k = 0; k < N; k++)
-            for (int q = 0; q < N; q++) dst[d][k][q] = m.h_data[((size_t)m.did[d] * N + k) * N + q];
-}
-
 template <int N, int DIRK, bool DOT>
 static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                   const FusedDot* fd) {
@@ -579,10 +462,12 @@ static int dispatch(Elliptic2dPlan& p, double alpha, const double* x, double bet
     return DGB_ERR_UNSUPPORTED;
 }
 int elliptic2d_fused_launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st) {
+    if (elliptic2d_walker_supported(p)) return elliptic2d_walker_launch(p, alpha, x, beta, y, st, nullptr);
     return dispatch<false>(p, alpha, x, beta, y, st, nullptr);
 }
 // y = A x fused with dot(x, w, y) and the PCG alpha update (pcg.h:165-166)
 int elliptic2d_fused_launch_dot(Elliptic2dPlan& p, const double* x, double* y, cudaStream_t st, const FusedDot& fd) {
+    if (elliptic2d_walker_supported(p)) return elliptic2d_walker_launch(p, 1., x, 0., y, st, &fd);
     return dispatch<true>(p, 1., x, 0., y, st, &fd);
 }
 
