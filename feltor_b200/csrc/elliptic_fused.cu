@@ -331,7 +331,7 @@ __device__ __forceinline__ void compute_tile(const FusedArgs& A, const EllipticC
             if (DOT) {
                 double pr = __dmul_rn(__dmul_rn(sxr[i * XC + 32 * j], win[i][j]), v);
                 if (!isfinite(pr)) { bad = 1; pr = 0.; }
-                fpe.add(pr, dsm + warp * sa::BINS);
+                fpe.add(pr, dsm);
             }
         }
     __syncthreads();  // the tile buffers are free for the next TMA / LDGSTS round
@@ -345,7 +345,7 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
     using TL = Tile<N, B>;
     constexpr int H = TL::H, XC = TL::XP, SC = TL::SP;  // XC, SC: row pitches
     constexpr int NW = FUSED_THREADS / 32;
-    __shared__ long long dsm[DOT ? NW * sa::BINS : 1];
+    __shared__ long long dsm[DOT ? sa::BINS : 1];  // one accumulator per block
     extern __shared__ __align__(128) double smem[];
     double* xs = smem + TL::XS + TL::XSH;  // element (r, c) of the x tile is xs[r * XC + c]
     double* ss = smem + TL::SS + TL::SSH;
@@ -357,7 +357,7 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
     int bad = 0;
     if (DOT) {
         if (A.pcg->done) return;  // solver already converged: the remaining launches of the batch are no-ops
-        sa::block_init<NW>(dsm);
+        sa::block_init<1>(dsm);
         fpe.clear();
     }
     if (tid == 0) mbar_init(bar, 1);
@@ -392,8 +392,8 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
         else compute_tile<N, DIRK, DOT, false>(A, C, xs, ss, txs, tys, cx0, cy0, tid, fpe, bad, dsm);
     }
     if (DOT) {
-        fpe.flush(dsm + (tid >> 5) * sa::BINS);
-        if (sa::block_finish<NW>(dsm, bad, A.slot, 0) && tid == 0 && !A.pcg->dist) pcg_after_pAp(A.pcg, A.slot.result);
+        fpe.flush_warp(dsm);
+        if (sa::block_finish<1>(dsm, bad, A.slot, 0) && tid == 0 && !A.pcg->dist) pcg_after_pAp(A.pcg, A.slot.result);
     }
 }
 

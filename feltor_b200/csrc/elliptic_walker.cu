@@ -77,7 +77,11 @@ struct WL {
     static constexpr int FIT = (227 * 1024 - 4096) / (WARP_DOUBLES * 8);  // warps whose rings fit into one SM
     // warps come in multiples of 4 (one per scheduler, the register file is per scheduler): 12 warps leave 168
     // registers per thread, enough for the one-sided stencils; the centered one needs ~250 -> 8 warps
-    static constexpr int WANT = (DIRK == 2 && N > 2 && WALK_MAX_WARPS > 8) ? 8 : WALK_MAX_WARPS;
+#ifndef DGB_WALK_DOT_WARPS
+#define DGB_WALK_DOT_WARPS 8  // the fused-dot variant needs ~210 registers: 2 warps per scheduler
+#endif
+    static constexpr int WANT0 = (DIRK == 2 && N > 2 && WALK_MAX_WARPS > 8) ? 8 : WALK_MAX_WARPS;
+    static constexpr int WANT = (DOT && WANT0 > DGB_WALK_DOT_WARPS) ? DGB_WALK_DOT_WARPS : WANT0;
     static constexpr int WARPS = FIT < WANT ? FIT : WANT, THREADS = 32 * WARPS;
     static constexpr size_t BYTES = (size_t)WARP_DOUBLES * 8 * WARPS;
     static_assert(SX <= 8, "mbarrier block / wait switch too small");
@@ -307,7 +311,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
     constexpr int RK = L::RK, LK = L::LK, HL = L::HL, UL = L::UL, WX = L::WX, LY = L::LY, LLO = L::LLO, NGY = L::NGY,
                   NP = L::NP, SX = L::SX, SS = L::SS, SW = L::SW, RP = L::RP, SLOT = L::SLOT, OP = L::OP, WALK_WARPS = L::WARPS;
     constexpr unsigned SLOT_BYTES = N * RP * 8;
-    __shared__ long long dsm[DOT ? WALK_WARPS * sa::BINS : 1];
+    __shared__ long long dsm[DOT ? sa::BINS : 1];  // one accumulator per block
     extern __shared__ __align__(128) double smem[];
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double* wb = smem + (size_t)warp * L::WARP_DOUBLES;
@@ -316,12 +320,15 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
     double* Wr = wb + L::WOFF;
     double* ob = wb + L::OOFF;
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(wb + L::BOFF);
-    sa::Fpe fpe;
+    // N independent two-term expansions per lane: the fused dot rides in the FP64 pipe this kernel is bound by, so it
+    // uses the short expansion and keeps the add cascades of one cell row independent of each other
+    sa::FpeT<2> fpe[N];
     int bad = 0;
     if (DOT) {
         if (A.pcg->done) return;  // solver already converged: the remaining launches of the batch are no-ops
-        sa::block_init<WALK_WARPS>(dsm);
-        fpe.clear();
+        sa::block_init<1>(dsm);
+#pragma unroll
+        for (int k = 0; k < N; k++) fpe[k].clear();
     }
     if (lane == 0) {
 #pragma unroll
@@ -544,14 +551,21 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                         double WV[N][N], XC[N][N];
                         ld_cell<N, RP>(wrow(iy), eo, WV);
                         ld_cell<N, RP>(x0, eo, XC);
+                        double res[N][N];
+                        bool spill = false;
 #pragma unroll
                         for (int ky = 0; ky < N; ky++)
 #pragma unroll
                             for (int kx = 0; kx < N; kx++) {
                                 double pr = __dmul_rn(__dmul_rn(XC[ky][kx], WV[ky][kx]), acc[ky][kx]);
                                 if (!isfinite(pr)) { bad = 1; pr = 0.; }
-                                fpe.add(pr, dsm + warp * sa::BINS);
+                                res[ky][kx] = fpe[kx].add_lazy(pr);
+                                spill = spill || res[ky][kx] != 0.;
                             }
+                        if (spill) {  // rare: residues the expansions cannot hold go to the shared accumulator (exact)
+#pragma unroll 1
+                            for (int k = 0; k < N * N; k++) sa::accumulate(dsm, res[k / N][k % N], 1);
+                        }
                     }
                 }
                 if (A.tma_store) {
@@ -584,8 +598,10 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
     cp_async_wait<0>();
     if (A.tma_store && lane == 0) bulk_wait<0>();
     if (DOT) {
-        fpe.flush(dsm + warp * sa::BINS);
-        if (sa::block_finish<WALK_WARPS>(dsm, bad, A.slot, 0) && threadIdx.x == 0 && !A.pcg->dist) pcg_after_pAp(A.pcg, A.slot.result);
+#pragma unroll
+        for (int k = 1; k < N; k++) fpe[0].merge(fpe[k], dsm);
+        fpe[0].flush_warp(dsm);
+        if (sa::block_finish<1>(dsm, bad, A.slot, 0) && threadIdx.x == 0 && !A.pcg->dist) pcg_after_pAp(A.pcg, A.slot.result);
     }
 }
 

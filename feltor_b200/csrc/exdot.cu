@@ -22,68 +22,88 @@ constexpr int DOT_WARPS = DOT_THREADS / 32;
 
 // products follow the reference exactly: 2 operands round(x*y); 3 operands round(round(x*w)*y)
 // (exdot_cuda.cuh:54,147-148); non-finite products raise status and are not accumulated.
-template <int NOPS, bool VEC>
-__global__ void __launch_bounds__(DOT_THREADS)
+template <int NOPS>
+__device__ __forceinline__ double dot_product(double a, double b, double c, int& bad) {
+    double p = NOPS == 3 ? __dmul_rn(__dmul_rn(a, b), c) : __dmul_rn(a, c);
+    if (!isfinite(p)) { bad = 1; p = 0.; }
+    return p;
+}
+
+// One pass, software pipelined: the U 128-bit loads per operand of the NEXT trip are in flight while the current trip
+// goes through the floating-point expansion, so with BPS resident CTAs every SM keeps
+// BPS * 256 * NOPS * U * 16 bytes outstanding all the time (the kernel is a pure HBM stream: 16 / 24 B per element).
+template <int NOPS, int U, int BPS, int NE>  // NE independent expansions per thread (NE divides 2 U)
+__global__ void __launch_bounds__(DOT_THREADS, BPS)
 exdot_kernel(const double* __restrict__ x, double xs, const double* __restrict__ w, double wsc,
              const double* __restrict__ y, double ys, size_t n, sa::DotSlot slot) {
-    __shared__ long long smem[DOT_WARPS * sa::BINS];
-    sa::block_init<DOT_WARPS>(smem);
-    long long* my = smem + (threadIdx.x >> 5) * sa::BINS;
+    __shared__ long long smem[sa::BINS];  // one accumulator per block
+    sa::block_init<1>(smem);
+    long long* my = smem;
+    sa::Fpe fpe[NE];  // independent expansions: their add cascades interleave in the FP64 pipe
+#pragma unroll
+    for (int u = 0; u < NE; u++) fpe[u].clear();
+    int bad = 0;
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const size_t nvec = n / 2;
+    const double2 z2 = make_double2(0., 0.);
+    double2 a[U], b[U], c[U];
+    auto load = [&](size_t base, double2 (&A)[U], double2 (&B)[U], double2 (&Cc)[U]) {
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t idx = base + (size_t)u * T;
+            const bool ok = idx < nvec;
+            A[u] = ok ? (x ? ld2(x + 2 * idx) : make_double2(xs, xs)) : z2;
+            if (NOPS == 3) B[u] = ok ? (w ? ld2(w + 2 * idx) : make_double2(wsc, wsc)) : z2;
+            Cc[u] = ok ? (y ? ld2(y + 2 * idx) : make_double2(ys, ys)) : z2;
+        }
+    };
+    size_t i = tid;
+    load(i, a, b, c);
+    while (i < nvec) {
+        const size_t inext = i + (size_t)U * T;
+        double2 an[U], bn[U], cn[U];
+        load(inext, an, bn, cn);  // everything beyond nvec loads as zero (adds +0 exactly)
+        double res[2 * U];
+        bool spill = false;
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            res[2 * u] = fpe[(2 * u) % NE].add_lazy(dot_product<NOPS>(a[u].x, b[u].x, c[u].x, bad));
+            res[2 * u + 1] = fpe[(2 * u + 1) % NE].add_lazy(dot_product<NOPS>(a[u].y, b[u].y, c[u].y, bad));
+            spill = spill || res[2 * u] != 0.0 || res[2 * u + 1] != 0.0;
+        }
+        if (spill) {  // rare: a residue the expansions cannot hold goes to the shared accumulator (exact)
+#pragma unroll 1
+            for (int u = 0; u < 2 * U; u++) sa::accumulate(my, res[u], 1);
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) { a[u] = an[u]; b[u] = bn[u]; c[u] = cn[u]; }
+        i = inext;
+    }
+    if ((n & 1) && tid == 0)
+        fpe[0].add(dot_product<NOPS>(x ? x[n - 1] : xs, NOPS == 3 ? (w ? w[n - 1] : wsc) : 0., y ? y[n - 1] : ys, bad), my);
+#pragma unroll
+    for (int u = 1; u < NE; u++) fpe[0].merge(fpe[u], my);
+    fpe[0].flush_warp(my);
+    sa::block_finish<1>(smem, bad, slot);
+}
+
+// operands that are not 16-byte aligned: scalar loads, same arithmetic
+template <int NOPS>
+__global__ void __launch_bounds__(DOT_THREADS)
+exdot_scalar_kernel(const double* __restrict__ x, double xs, const double* __restrict__ w, double wsc,
+                    const double* __restrict__ y, double ys, size_t n, sa::DotSlot slot) {
+    __shared__ long long smem[sa::BINS];  // one accumulator per block
+    sa::block_init<1>(smem);
+    long long* my = smem;
     sa::Fpe fpe;
     fpe.clear();
     int bad = 0;
     const size_t T = (size_t)gridDim.x * blockDim.x;
-    const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (VEC) {
-        constexpr int U = 4;
-        const size_t nvec = n / 2;
-        for (size_t base = tid; base < nvec; base += U * T) {
-            double2 a[U], b[U], c[U];
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                size_t idx = base + u * T;
-                if (idx < nvec) {
-                    a[u] = x ? ld2(x + 2 * idx) : make_double2(xs, xs);
-                    if (NOPS == 3) b[u] = w ? ld2(w + 2 * idx) : make_double2(wsc, wsc);
-                    c[u] = y ? ld2(y + 2 * idx) : make_double2(ys, ys);
-                } else {
-                    a[u] = make_double2(0., 0.);
-                    b[u] = make_double2(0., 0.);
-                    c[u] = make_double2(0., 0.);
-                }
-            }
-#pragma unroll
-            for (int u = 0; u < U; u++) {
-                double p0, p1;
-                if (NOPS == 3) {
-                    p0 = __dmul_rn(__dmul_rn(a[u].x, b[u].x), c[u].x);
-                    p1 = __dmul_rn(__dmul_rn(a[u].y, b[u].y), c[u].y);
-                } else {
-                    p0 = __dmul_rn(a[u].x, c[u].x);
-                    p1 = __dmul_rn(a[u].y, c[u].y);
-                }
-                if (!isfinite(p0)) { bad = 1; p0 = 0.; }
-                if (!isfinite(p1)) { bad = 1; p1 = 0.; }
-                fpe.add(p0, my);
-                fpe.add(p1, my);
-            }
-        }
-        if ((n & 1) && tid == 0) {
-            double a = x ? x[n - 1] : xs, c = y ? y[n - 1] : ys;
-            double p = NOPS == 3 ? __dmul_rn(__dmul_rn(a, w ? w[n - 1] : wsc), c) : __dmul_rn(a, c);
-            if (!isfinite(p)) { bad = 1; p = 0.; }
-            fpe.add(p, my);
-        }
-    } else {
-        for (size_t i = tid; i < n; i += T) {
-            double a = x ? x[i] : xs, c = y ? y[i] : ys;
-            double p = NOPS == 3 ? __dmul_rn(__dmul_rn(a, w ? w[i] : wsc), c) : __dmul_rn(a, c);
-            if (!isfinite(p)) { bad = 1; p = 0.; }
-            fpe.add(p, my);
-        }
-    }
-    fpe.flush(my);
-    sa::block_finish<DOT_WARPS>(smem, bad, slot);
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += T)
+        fpe.add(dot_product<NOPS>(x ? x[i] : xs, NOPS == 3 ? (w ? w[i] : wsc) : 0., y ? y[i] : ys, bad), my);
+    fpe.flush_warp(my);
+    sa::block_finish<1>(smem, bad, slot);
 }
 
 // combine `nparts` normalised accumulators (multi-GPU / recursive vectors)
@@ -114,18 +134,33 @@ __global__ void __launch_bounds__(64) superacc_combine_kernel(const long long* p
     }
 }
 
-static int dot_grid(size_t n) {
-    size_t per_block = (size_t)DOT_THREADS * 8;  // 4 double2 per thread per trip
+// tuning knob for experiments: DGB_DOT_VARIANT = 0 (U=2, 3 CTAs/SM, 2 FPE)  1 (U=4, 2 CTAs/SM, 4 FPE)  2 (U=2, 2 CTAs/SM, 4 FPE)  3 (U=2, 3 CTAs/SM, 4 FPE)
+static int dot_variant() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DGB_DOT_VARIANT"); v = e ? atoi(e) : 0; if (v < 0 || v > 3) v = 0; }
+    return v;
+}
+template <int NOPS, int U, int BPS, int NE>
+static void exdot_go(int max_blocks, size_t n, const double* x, double xs, const double* w, double wsc, const double* y, double ys,
+                     const sa::DotSlot& slot, cudaStream_t st) {
+    const size_t per_block = (size_t)DOT_THREADS * 2 * U;
     size_t want = (n + per_block - 1) / per_block;
     if (want == 0) want = 1;
-    static int per_sm = 0;
-    if (per_sm == 0) {
-        const char* e = getenv("DGB_DOT_BLOCKS_PER_SM");  // tuning knob for experiments
-        per_sm = e ? atoi(e) : 4;
-        if (per_sm < 1) per_sm = 1;
+    static int waves = 0;  // CTAs beyond one resident wave are balanced by the hardware block scheduler
+    if (waves == 0) { const char* e = getenv("DGB_DOT_WAVES"); waves = e ? atoi(e) : 1; if (waves < 1) waves = 1; }
+    size_t cap = (size_t)sm_count() * BPS * waves;
+    if (cap > (size_t)max_blocks) cap = max_blocks;
+    exdot_kernel<NOPS, U, BPS, NE><<<(unsigned)(want < cap ? want : cap), DOT_THREADS, 0, st>>>(x, xs, w, wsc, y, ys, n, slot);
+}
+template <int NOPS>
+static void exdot_pick(int max_blocks, size_t n, const double* x, double xs, const double* w, double wsc, const double* y, double ys,
+                       const sa::DotSlot& slot, cudaStream_t st) {
+    switch (dot_variant()) {
+        case 1: exdot_go<NOPS, 4, 2, 4>(max_blocks, n, x, xs, w, wsc, y, ys, slot, st); break;
+        case 2: exdot_go<NOPS, 2, 2, 4>(max_blocks, n, x, xs, w, wsc, y, ys, slot, st); break;
+        case 3: exdot_go<NOPS, 2, 3, 4>(max_blocks, n, x, xs, w, wsc, y, ys, slot, st); break;
+        default: exdot_go<NOPS, 2, 3, 2>(max_blocks, n, x, xs, w, wsc, y, ys, slot, st); break;
     }
-    size_t cap = (size_t)sm_count() * per_sm;
-    return (int)(want < cap ? want : cap);
 }
 
 int exdot_launch(DotWs* ws, int nops, size_t n, const double* x, double xs, const double* w, double wsc,
@@ -133,16 +168,18 @@ int exdot_launch(DotWs* ws, int nops, size_t n, const double* x, double xs, cons
     if (!ws) { set_error("dgb_exdot: workspace is NULL"); return DGB_ERR_INVALID; }
     sa::DotSlot slot = ws->slot;
     slot.result = result ? result : ws->result;
-    int grid = dot_grid(n);
-    if (grid > ws->max_blocks) grid = ws->max_blocks;
     bool vec = (!x || aligned16(x)) && (!w || aligned16(w)) && (!y || aligned16(y));
     cudaStream_t st = as_stream(s);
-    if (nops == 3) {
-        if (vec) exdot_kernel<3, true><<<grid, DOT_THREADS, 0, st>>>(x, xs, w, wsc, y, ys, n, slot);
-        else exdot_kernel<3, false><<<grid, DOT_THREADS, 0, st>>>(x, xs, w, wsc, y, ys, n, slot);
+    if (vec) {
+        if (nops == 3) exdot_pick<3>(ws->max_blocks, n, x, xs, w, wsc, y, ys, slot, st);
+        else exdot_pick<2>(ws->max_blocks, n, x, xs, nullptr, 0., y, ys, slot, st);
     } else {
-        if (vec) exdot_kernel<2, true><<<grid, DOT_THREADS, 0, st>>>(x, xs, nullptr, 0., y, ys, n, slot);
-        else exdot_kernel<2, false><<<grid, DOT_THREADS, 0, st>>>(x, xs, nullptr, 0., y, ys, n, slot);
+        size_t want = (n + DOT_THREADS - 1) / DOT_THREADS;
+        if (want == 0) want = 1;
+        size_t cap = (size_t)sm_count() * 4;
+        const unsigned grid = (unsigned)(want < cap ? want : cap);
+        if (nops == 3) exdot_scalar_kernel<3><<<grid, DOT_THREADS, 0, st>>>(x, xs, w, wsc, y, ys, n, slot);
+        else exdot_scalar_kernel<2><<<grid, DOT_THREADS, 0, st>>>(x, xs, nullptr, 0., y, ys, n, slot);
     }
     DGB_LAUNCHED();
     return 0;
@@ -200,10 +237,10 @@ extern "C" {
 
 int dgb_dot_ws_create(dgb_dot_ws** out) {
     DotWs* ws = new DotWs();
-    ws->max_blocks = 2048;
+    ws->max_blocks = 1 << 16;
     ws->nslots = 4;  // fused kernels may carry up to 4 simultaneous dots
-    DGB_CUDA(cudaMalloc(&ws->slot.gacc, ws->nslots * sa::BINS * sizeof(long long)));
-    DGB_CUDA(cudaMemset(ws->slot.gacc, 0, ws->nslots * sa::BINS * sizeof(long long)));
+    DGB_CUDA(cudaMalloc(&ws->slot.gacc, ws->nslots * sa::GACC_WORDS * sizeof(long long)));
+    DGB_CUDA(cudaMemset(ws->slot.gacc, 0, ws->nslots * sa::GACC_WORDS * sizeof(long long)));
     DGB_CUDA(cudaMalloc(&ws->slot.gstatus, ws->nslots * sizeof(int)));
     DGB_CUDA(cudaMemset(ws->slot.gstatus, 0, ws->nslots * sizeof(int)));
     DGB_CUDA(cudaMalloc(&ws->slot.ticket, ws->nslots * sizeof(unsigned int)));

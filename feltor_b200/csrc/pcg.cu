@@ -50,10 +50,10 @@ template <int MODE>
 __global__ void __launch_bounds__(PCG_THREADS)
 pcg_dot3_kernel(size_t n, const double* __restrict__ x, const double* __restrict__ w, const double* __restrict__ y,
                 sa::DotSlot slot, int si, PcgState* st) {
-    __shared__ long long smem[PCG_WARPS * sa::BINS];
+    __shared__ long long smem[sa::BINS];
     if (MODE == 2 && st->done) return;
-    sa::block_init<PCG_WARPS>(smem);
-    long long* my = smem + (threadIdx.x >> 5) * sa::BINS;
+    sa::block_init<1>(smem);
+    long long* my = smem;
     sa::Fpe fpe;
     fpe.clear();
     int bad = 0;
@@ -62,8 +62,8 @@ pcg_dot3_kernel(size_t n, const double* __restrict__ x, const double* __restrict
         if (!isfinite(pr)) { bad = 1; pr = 0.; }
         fpe.add(pr, my);
     }
-    fpe.flush(my);
-    if (sa::block_finish<PCG_WARPS>(smem, bad, slot, si) && threadIdx.x == 0) {
+    fpe.flush_warp(my);
+    if (sa::block_finish<1>(smem, bad, slot, si) && threadIdx.x == 0) {
         const dgb_dot_result* r = slot.result + si;
         if (st->dist) return;  // completed by the allreduce + pcg_scalar_kernel
         if (MODE == 1) { st->nrmzr_old = r->value; if (r->status) { st->status = 1; st->done = 1; } }
@@ -77,15 +77,17 @@ __global__ void __launch_bounds__(PCG_THREADS)
 pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ ap, double* __restrict__ x,
                   double* __restrict__ r, const double* __restrict__ P, const double* __restrict__ W, PcgState* st,
                   sa::DotSlot slot, int iter) {
-    __shared__ long long smem[2 * PCG_WARPS * sa::BINS];
+    __shared__ long long smem[2 * sa::BINS];  // one accumulator per dot and block
     if (st->done) return;
     const double alpha = st->alpha, malpha = -alpha;
-    sa::block_init<2 * PCG_WARPS>(smem);
-    long long* my_rr = smem + (threadIdx.x >> 5) * sa::BINS;
-    long long* my_zr = smem + (PCG_WARPS + (threadIdx.x >> 5)) * sa::BINS;
-    sa::Fpe frr, fzr;
+    sa::block_init<2>(smem);
+    long long* my_rr = smem;
+    long long* my_zr = smem + sa::BINS;
+    sa::Fpe frr, fzr, frr1, fzr1;  // two independent expansions per dot: the add cascades interleave in the FP64 pipe
     frr.clear();
     fzr.clear();
+    frr1.clear();
+    fzr1.clear();
     int bad = 0;
     const size_t T = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nvec = n / 2;
@@ -106,18 +108,22 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
         st2(x + 2 * i, xv);
         st2(r + 2 * i, rv);
         st2(ap + 2 * i, z);
+        double ra0 = 0., ra1 = 0.;
         if (CHECK) {
             double a0 = __dmul_rn(__dmul_rn(rv.x, Wv.x), rv.x), a1 = __dmul_rn(__dmul_rn(rv.y, Wv.y), rv.y);
             if (!isfinite(a0)) { bad = 1; a0 = 0.; }
             if (!isfinite(a1)) { bad = 1; a1 = 0.; }
-            frr.add(a0, my_rr);
-            frr.add(a1, my_rr);
+            ra0 = frr.add_lazy(a0);
+            ra1 = frr1.add_lazy(a1);
         }
         double b0 = __dmul_rn(__dmul_rn(z.x, Wv.x), rv.x), b1 = __dmul_rn(__dmul_rn(z.y, Wv.y), rv.y);
         if (!isfinite(b0)) { bad = 1; b0 = 0.; }
         if (!isfinite(b1)) { bad = 1; b1 = 0.; }
-        fzr.add(b0, my_zr);
-        fzr.add(b1, my_zr);
+        const double rb0 = fzr.add_lazy(b0), rb1 = fzr1.add_lazy(b1);
+        if (ra0 != 0. || ra1 != 0. || rb0 != 0. || rb1 != 0.) {  // rare: residues the expansions cannot hold
+            sa::accumulate(my_rr, ra0, 1); sa::accumulate(my_rr, ra1, 1);
+            sa::accumulate(my_zr, rb0, 1); sa::accumulate(my_zr, rb1, 1);
+        }
         pv = pn; av = an; xv = xn; rv = rn; Pv = Pn; Wv = Wn;
         i = inext;
     }
@@ -137,12 +143,14 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
         fzr.add(b0, my_zr);
     }
     if (CHECK) {
-        frr.flush(my_rr);
-        if (sa::block_finish<PCG_WARPS>(smem, bad, slot, 1) && threadIdx.x == 0 && !st->dist) pcg_after_rr(st, slot.result + 1, iter);
+        frr.merge(frr1, my_rr);
+        frr.flush_warp(my_rr);
+        if (sa::block_finish<1>(my_rr, bad, slot, 1) && threadIdx.x == 0 && !st->dist) pcg_after_rr(st, slot.result + 1, iter);
         __syncthreads();
     }
-    fzr.flush(my_zr);
-    if (sa::block_finish<PCG_WARPS>(smem + PCG_WARPS * sa::BINS, bad, slot, 2) && threadIdx.x == 0 && !st->dist)
+    fzr.merge(fzr1, my_zr);
+    fzr.flush_warp(my_zr);
+    if (sa::block_finish<1>(my_zr, bad, slot, 2) && threadIdx.x == 0 && !st->dist)
         pcg_after_zr(st, slot.result + 2, iter);
 }
 
@@ -171,18 +179,31 @@ __global__ void pcg_scalar_kernel(PcgState* st, dgb_dot_result* res, int iter, i
     }
 }
 
-// K3 (pcg.h:182): axpby(1, ap, beta, p): p = p*beta; p = fma(1, ap, p)
+// K3 (pcg.h:182): axpby(1, ap, beta, p): p = p*beta; p = fma(1, ap, p).  Pure stream (24 B/dof): full occupancy, four
+// front-batched 128-bit loads per operand and thread, 8 CTAs per SM (the layout of the blas1 kernels).
 __global__ void __launch_bounds__(PCG_THREADS)
 pcg_direction_kernel(size_t n, const double* __restrict__ z, double* __restrict__ p, const PcgState* st) {
     if (st->done) return;
+    constexpr int U = 4;
     const double beta = st->beta;
     const size_t T = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nvec = n / 2;
-    for (size_t i = tid; i < nvec; i += T) {
-        double2 zv = ld2(z + 2 * i), pv = ld2(p + 2 * i);
-        pv.x = __fma_rn(1., zv.x, __dmul_rn(pv.x, beta));
-        pv.y = __fma_rn(1., zv.y, __dmul_rn(pv.y, beta));
-        st2(p + 2 * i, pv);
+    for (size_t base = tid; base < nvec; base += (size_t)U * T) {
+        double2 zv[U], pv[U];
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t i = base + (size_t)u * T;
+            if (i < nvec) { zv[u] = ld2(z + 2 * i); pv[u] = ld2(p + 2 * i); }
+        }
+#pragma unroll
+        for (int u = 0; u < U; u++) {
+            const size_t i = base + (size_t)u * T;
+            if (i < nvec) {
+                pv[u].x = __fma_rn(1., zv[u].x, __dmul_rn(pv[u].x, beta));
+                pv[u].y = __fma_rn(1., zv[u].y, __dmul_rn(pv[u].y, beta));
+                st2(p + 2 * i, pv[u]);
+            }
+        }
     }
     if ((n & 1) && tid == 0) p[n - 1] = __fma_rn(1., z[n - 1], __dmul_rn(p[n - 1], beta));
 }
@@ -297,6 +318,12 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
     const bool fused = A.fusable && identity_chi && !A.chi_weight_jump && (dist || !getenv("DGB_ELLIPTIC_UNFUSED"));
     FusedDot fd{W, s.slot, s.st};
     const unsigned g2 = grid_for(n, 2);
+    unsigned g3;
+    {
+        size_t want = (n / 2 + (size_t)PCG_THREADS * 4 - 1) / ((size_t)PCG_THREADS * 4), cap = (size_t)sm_count() * 8;
+        if (want == 0) want = 1;
+        g3 = (unsigned)(want < cap ? want : cap);
+    }
     int i = 1;
     while (i < max_iter) {
         int stop = i + s.check_every < max_iter ? i + s.check_every : max_iter;
@@ -320,7 +347,7 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
             DGB_LAUNCHED();
             if (dist && (e = dist_finish<3>(s, comm, check ? 1 : 2, check ? 2 : 1, i, check, st))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n][2], st);
-            pcg_direction_kernel<<<g2, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st);
+            pcg_direction_kernel<<<g3, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st);
             DGB_LAUNCHED();
             if ((e = halo(s.p))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n++][3], st);
@@ -364,8 +391,8 @@ static int pcg_alloc(Pcg* s, size_t n) {
     DGB_CUDA(cudaMemset(s->st, 0, sizeof(PcgState)));
     DGB_CUDA(cudaMallocHost(&s->st_host, sizeof(PcgState)));
     const int ns = 4;
-    DGB_CUDA(cudaMalloc(&s->slot.gacc, ns * sa::BINS * sizeof(long long)));
-    DGB_CUDA(cudaMemset(s->slot.gacc, 0, ns * sa::BINS * sizeof(long long)));
+    DGB_CUDA(cudaMalloc(&s->slot.gacc, ns * sa::GACC_WORDS * sizeof(long long)));
+    DGB_CUDA(cudaMemset(s->slot.gacc, 0, ns * sa::GACC_WORDS * sizeof(long long)));
     DGB_CUDA(cudaMalloc(&s->slot.gstatus, ns * sizeof(int)));
     DGB_CUDA(cudaMemset(s->slot.gstatus, 0, ns * sizeof(int)));
     DGB_CUDA(cudaMalloc(&s->slot.ticket, ns * sizeof(unsigned int)));

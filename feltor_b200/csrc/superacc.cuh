@@ -26,6 +26,8 @@ constexpr int DIGITS = 56;
 constexpr int KRX = 8;
 constexpr int F_WORDS = 20;
 constexpr int NF = 3;  // FPE size in registers
+constexpr int SPREAD = 16;  // global accumulators per dot: CTAs spread their partials to cut same-address atomic contention
+constexpr int GACC_WORDS = SPREAD * BINS;  // int64 words of global scratch per slot
 
 // error-free transformation: a + b = r + s exactly (Knuth TwoSum, 6 flops, no branch)
 __device__ __forceinline__ double two_sum(double a, double b, double& s) {
@@ -124,39 +126,80 @@ __device__ inline double round_normalized(const long long* acc, int negative) {
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Per-thread floating point expansion
-struct Fpe {
-    double a[NF];
+// Per-thread floating point expansion of NFP doubles.  NFP = 3 absorbs ~2^100 of dynamic range without touching the
+// shared accumulator (standalone dots, which are memory bound anyway); NFP = 2 costs 12 instead of 18 FP64 adds per
+// element and still never spills for data whose products span less than ~2^40 -- the choice for dots fused into
+// FP64-pipe-bound kernels.  Either way the result is exact: what the expansion cannot hold goes to the accumulator.
+template <int NFP>
+struct FpeT {
+    double a[NFP];
     __device__ __forceinline__ void clear() {
 #pragma unroll
-        for (int i = 0; i < NF; i++) a[i] = 0.0;
+        for (int i = 0; i < NFP; i++) a[i] = 0.0;
     }
     // add x; a residue the expansion cannot hold is spilled (exactly) to `acc` (shared, stride 1).  The expansion
     // itself stays valid: after the cascade a[] + residue equals the old a[] + x exactly.
     __device__ __forceinline__ void add(double x, long long* acc) {
 #pragma unroll
-        for (int i = 0; i < NF; i++) {
+        for (int i = 0; i < NFP; i++) {
             double s;
             a[i] = two_sum(a[i], x, s);
             x = s;
         }
         if (x != 0.0) accumulate(acc, x, 1);
     }
+    // the same without the spill: returns the residue (almost always 0.0).  Lets a caller run several independent
+    // expansions through the FP64 pipe interleaved and test all residues with ONE branch (the cascade of one add is a
+    // chain of 6 NFP dependent operations; a branch after every element would serialise the chains).
+    __device__ __forceinline__ double add_lazy(double x) {
+#pragma unroll
+        for (int i = 0; i < NFP; i++) {
+            double s;
+            a[i] = two_sum(a[i], x, s);
+            x = s;
+        }
+        return x;
+    }
+    // fold another expansion into this one (exact)
+    __device__ __forceinline__ void merge(FpeT& o, long long* acc) {
+#pragma unroll
+        for (int i = 0; i < NFP; i++) { add(o.a[i], acc); o.a[i] = 0.0; }
+    }
     __device__ __forceinline__ void flush(long long* acc) {
 #pragma unroll
-        for (int i = 0; i < NF; i++) {
+        for (int i = 0; i < NFP; i++) {
             accumulate(acc, a[i], 1);
             a[i] = 0.0;
         }
     }
+    // exact warp-level reduction by shuffles, then lane 0 flushes: 3 instead of 96 accumulator updates per warp.
+    // All 32 lanes must call.  (A lane that has handed its expansion to a partner adds nothing afterwards, so every
+    // value -- including residues spilled on the way -- reaches the accumulator exactly once.)
+    __device__ __forceinline__ void flush_warp(long long* acc) {
+        const int lane = threadIdx.x & 31;
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) {
+            double v[NFP];
+#pragma unroll
+            for (int i = 0; i < NFP; i++) v[i] = __shfl_down_sync(0xffffffffu, a[i], off);
+            if (lane < off) {
+#pragma unroll
+                for (int i = 0; i < NFP; i++) add(v[i], acc);
+            }
+        }
+        if (lane == 0) flush(acc);
+        else clear();
+        __syncwarp();
+    }
 };
+using Fpe = FpeT<NF>;
 
 // ---------------------------------------------------------------------------------------------------------
 // Block- and grid-level reduction used by every kernel that carries a fused dot.
 // Shared memory: NWARPS accumulators of BINS words (stride 1, accumulator w at smem + w*BINS).
 // Global scratch ("slot"): partials[gridDim.x * BINS], status flags, a ticket; result record.
 struct DotSlot {
-    long long* gacc;          // [nslots][BINS] global accumulators, zero between launches
+    long long* gacc;          // [nslots][SPREAD][BINS] global accumulators, zero between launches
     int* gstatus;             // [nslots] OR of the per-block status flags, zero between launches
     unsigned int* ticket;     // [nslots] zero-initialised, reset by the finishing block
     dgb_dot_result* result;   // device
@@ -173,21 +216,41 @@ __device__ inline void block_init(long long* smem) {
 // and lets the last block to arrive normalise, round and publish {acc, value, status}.
 // `status` = 1 if this thread saw a non-finite product.  All threads of the block must call.  Returns true in ALL
 // threads of the finishing block after the result is written (so callers can chain scalar post-processing).
+// the scalar tail of a reduction, kept out of line so that its registers (39-word loops, ldexp, ...) do not count
+// against the streaming loop of the calling kernel
+static __device__ __noinline__ void normalize_noinline(long long* acc) { normalize(acc, 1); }
+static __device__ __noinline__ void publish_result(long long* smem, const DotSlot& slot, int slot_idx) {
+    int negative = normalize(smem, 1);
+    dgb_dot_result* r = slot.result + slot_idx;
+    r->value = round_normalized(smem, negative);
+    r->status = __ldcg(slot.gstatus + slot_idx);
+    r->pad = 0;
+    slot.gstatus[slot_idx] = 0;
+    slot.ticket[slot_idx] = 0;
+    __threadfence();
+}
+
 template <int NWARPS>
 __device__ inline bool block_finish(long long* smem, int status, const DotSlot& slot, int slot_idx = 0) {
     __shared__ int s_last;
     int any_bad = __syncthreads_or(status);
-    // 1. normalise each warp accumulator (one thread each), then sum word-wise (NWARPS <= 32 -> no overflow)
-    if (threadIdx.x < NWARPS) normalize(smem + threadIdx.x * BINS, 1);
-    __syncthreads();
     long long sum = 0;
-    if (threadIdx.x < BINS) {
+    if (NWARPS == 1) {
+        // one accumulator per block (the usual case: expansions are reduced by shuffles first, see flush_warp)
+        if (threadIdx.x < BINS) sum = smem[threadIdx.x];
+    } else {
+        // 1. normalise each warp accumulator (one thread each), then sum word-wise (NWARPS <= 32 -> no overflow)
+        if (threadIdx.x < NWARPS) normalize_noinline(smem + threadIdx.x * BINS);
+        __syncthreads();
+        if (threadIdx.x < BINS) {
 #pragma unroll
-        for (int w = 0; w < NWARPS; w++) sum += smem[w * BINS + threadIdx.x];
+            for (int w = 0; w < NWARPS; w++) sum += smem[w * BINS + threadIdx.x];
+        }
     }
     __syncthreads();
-    long long* gacc = slot.gacc + (size_t)slot_idx * BINS;
-    // 2. word-parallel atomic accumulation into the global accumulator
+    long long* gbase = slot.gacc + (size_t)slot_idx * GACC_WORDS;
+    long long* gacc = gbase + (blockIdx.x % SPREAD) * BINS;
+    // 2. word-parallel atomic accumulation into one of the SPREAD global accumulators of the slot
     if (threadIdx.x < BINS && sum != 0) add_word(gacc, threadIdx.x, sum, 1);
     if (threadIdx.x == 0 && any_bad) atomicOr(slot.gstatus + slot_idx, 1);
     __threadfence();
@@ -200,22 +263,30 @@ __device__ inline bool block_finish(long long* smem, int status, const DotSlot& 
     if (!s_last) return false;
     // 3. last block: fetch, reset, normalise, round
     __threadfence();
+    // the copies hold arbitrary int64 digits: add low 56 bits and signed high parts separately (no overflow), the
+    // high parts carry into the next word
+    __shared__ long long s_hi[BINS];
     if (threadIdx.x < BINS) {
-        smem[threadIdx.x] = __ldcg(gacc + threadIdx.x);
-        gacc[threadIdx.x] = 0;  // ready for the next launch on the same stream
+        long long lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < SPREAD; k++) {
+            const long long v = __ldcg(gbase + k * BINS + threadIdx.x);
+            gbase[k * BINS + threadIdx.x] = 0;  // ready for the next launch on the same stream
+            const long long h = v >> DIGITS;
+            hi += h;
+            lo += v - (long long)((unsigned long long)h << DIGITS);
+        }
+        if (threadIdx.x == BINS - 1) { lo += (long long)((unsigned long long)hi << DIGITS); hi = 0; }  // top word keeps its sign
+        smem[threadIdx.x] = lo;
+        s_hi[threadIdx.x] = hi;
     }
     __syncthreads();
-    if (threadIdx.x == 0) {
-        int negative = normalize(smem, 1);
-        dgb_dot_result* r = slot.result + slot_idx;
-        for (int i = 0; i < BINS; i++) r->acc[i] = smem[i];
-        r->value = round_normalized(smem, negative);
-        r->status = __ldcg(slot.gstatus + slot_idx);
-        r->pad = 0;
-        slot.gstatus[slot_idx] = 0;
-        slot.ticket[slot_idx] = 0;
-        __threadfence();
-    }
+    if (threadIdx.x > 0 && threadIdx.x < BINS) smem[threadIdx.x] += s_hi[threadIdx.x - 1];
+    __syncthreads();
+    if (threadIdx.x == 0) publish_result(smem, slot, slot_idx);
+    __syncthreads();
+    if (threadIdx.x < BINS) slot.result[slot_idx].acc[threadIdx.x] = smem[threadIdx.x];  // the normalised words
+    __threadfence();
     __syncthreads();
     return true;
 }
