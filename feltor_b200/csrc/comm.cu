@@ -10,6 +10,8 @@
 #include "superacc.cuh"
 #include <dlfcn.h>
 #include <cstring>
+#include <cstdlib>
+#include <vector>
 
 namespace dgb {
 
@@ -25,6 +27,7 @@ struct NcclApi {
     ncclResult_t (*CommInitRank)(ncclComm_t*, int, ncclUniqueId, int) = nullptr;
     ncclResult_t (*CommDestroy)(ncclComm_t) = nullptr;
     ncclResult_t (*AllReduce)(const void*, void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
+    ncclResult_t (*AllGather)(const void*, void*, size_t, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Send)(const void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*Recv)(void*, size_t, int, int, ncclComm_t, cudaStream_t) = nullptr;
     ncclResult_t (*GroupStart)() = nullptr;
@@ -40,7 +43,7 @@ static NcclApi* nccl() {
         if (!api.lib) api.lib = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
         if (api.lib) {
 #define BIND(name) *(void**)(&api.name) = dlsym(api.lib, "nccl" #name)
-            BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(AllReduce); BIND(Send); BIND(Recv);
+            BIND(GetUniqueId); BIND(CommInitRank); BIND(CommDestroy); BIND(AllReduce); BIND(AllGather); BIND(Send); BIND(Recv);
             BIND(GroupStart); BIND(GroupEnd); BIND(GetErrorString);
 #undef BIND
         }
@@ -62,9 +65,133 @@ static NcclApi* nccl() {
 struct Comm {
     ncclComm_t comm = nullptr;
     int rank = 0, size = 1;
+    // peer-memory exchange (comm.cuh)
+    bool p2p = false;
+    long long* local = nullptr;
+    long long* peer[P2P_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    unsigned long long epoch[P2P_CHANNELS] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 int comm_rank(const Comm* c) { return c ? c->rank : 0; }
 int comm_size(const Comm* c) { return c ? c->size : 1; }
+
+P2pView comm_p2p_view(Comm* c) {
+    P2pView v;
+    for (int r = 0; r < P2P_MAX_RANKS; r++) v.peer[r] = c ? c->peer[r] : nullptr;
+    v.rank = c ? c->rank : 0;
+    v.size = c ? c->size : 1;
+    v.enabled = c && c->p2p ? 1 : 0;
+    return v;
+}
+unsigned long long comm_p2p_next_epoch(Comm* c, int first, int count) {
+    // all channels of one call advance together; a channel that sat out some calls catches up to the maximum so that
+    // every channel of the call carries the SAME epoch on every rank (ranks issue identical call sequences)
+    unsigned long long e = 0;
+    for (int k = first; k < first + count; k++) e = c->epoch[k] > e ? c->epoch[k] : e;
+    e += 1;
+    for (int k = first; k < first + count; k++) c->epoch[k] = e;
+    return e;
+}
+
+// map every rank's exchange buffer into this process (CUDA IPC; the handles travel through an ncclAllGather)
+static int comm_p2p_setup(Comm* c) {
+    const char* off = getenv("DGB_NO_P2P");
+    if ((off && atoi(off)) || c->size > P2P_MAX_RANKS || c->size < 2 || !nccl()->AllGather) return 0;
+    DGB_CUDA(cudaMalloc(&c->local, P2P_BYTES));
+    DGB_CUDA(cudaMemset(c->local, 0, P2P_BYTES));
+    DGB_CUDA(cudaDeviceSynchronize());
+    cudaIpcMemHandle_t mine;
+    cudaError_t ce = cudaIpcGetMemHandle(&mine, c->local);
+    // every rank must take part in the gather even if its own handle could not be made: flag it with zeros
+    unsigned char* dev = nullptr;
+    const size_t HB = sizeof(cudaIpcMemHandle_t) + 8;
+    DGB_CUDA(cudaMalloc(&dev, HB * c->size));
+    std::vector<unsigned char> host(HB * c->size, 0);
+    if (ce == cudaSuccess) { memcpy(host.data() + HB * c->rank, &mine, sizeof(mine)); host[HB * c->rank + sizeof(mine)] = 1; }
+    else cudaGetLastError();
+    DGB_CUDA(cudaMemcpy(dev + HB * c->rank, host.data() + HB * c->rank, HB, cudaMemcpyHostToDevice));
+    DGB_NCCL(nccl()->AllGather(dev + HB * c->rank, dev, HB, 0 /* ncclInt8 */, c->comm, nullptr));
+    DGB_CUDA(cudaDeviceSynchronize());
+    DGB_CUDA(cudaMemcpy(host.data(), dev, HB * c->size, cudaMemcpyDeviceToHost));
+    cudaFree(dev);
+    bool ok = true;
+    for (int r = 0; r < c->size; r++) ok = ok && host[HB * r + sizeof(mine)] == 1;
+    for (int r = 0; r < c->size && ok; r++) {
+        if (r == c->rank) { c->peer[r] = c->local; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, host.data() + HB * r, sizeof(h));
+        void* p = nullptr;
+        if (cudaIpcOpenMemHandle(&p, h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); ok = false; break; }
+        c->peer[r] = reinterpret_cast<long long*>(p);
+    }
+    // agree on the outcome (a rank that failed to map a peer must not leave the others spinning on its flags)
+    long long* flag = nullptr;
+    DGB_CUDA(cudaMalloc(&flag, 8));
+    long long hv = ok ? 0 : 1;
+    DGB_CUDA(cudaMemcpy(flag, &hv, 8, cudaMemcpyHostToDevice));
+    DGB_NCCL(nccl()->AllReduce(flag, flag, 1, ncclInt64, ncclSum, c->comm, nullptr));
+    DGB_CUDA(cudaDeviceSynchronize());
+    DGB_CUDA(cudaMemcpy(&hv, flag, 8, cudaMemcpyDeviceToHost));
+    cudaFree(flag);
+    c->p2p = hv == 0;
+    if (getenv("DGB_COMM_VERBOSE"))
+        fprintf(stderr, "dgb_comm rank %d/%d: peer-memory dot exchange %s\n", c->rank, c->size, c->p2p ? "enabled" : "unavailable (NCCL allreduce)");
+    return 0;
+}
+
+int comm_p2p_map(Comm* c, void* basep, void** peers) {
+    if (!c || !c->p2p) return 1;
+    cudaIpcMemHandle_t mine;
+    cudaError_t ce = cudaIpcGetMemHandle(&mine, basep);
+    const size_t HB = sizeof(cudaIpcMemHandle_t) + 8;
+    unsigned char* dev = nullptr;
+    DGB_CUDA(cudaMalloc(&dev, HB * c->size));
+    std::vector<unsigned char> host(HB * c->size, 0);
+    if (ce == cudaSuccess) { memcpy(host.data() + HB * c->rank, &mine, sizeof(mine)); host[HB * c->rank + sizeof(mine)] = 1; }
+    else cudaGetLastError();
+    DGB_CUDA(cudaMemcpy(dev + HB * c->rank, host.data() + HB * c->rank, HB, cudaMemcpyHostToDevice));
+    DGB_NCCL(nccl()->AllGather(dev + HB * c->rank, dev, HB, 0 /* ncclInt8 */, c->comm, nullptr));
+    DGB_CUDA(cudaDeviceSynchronize());
+    DGB_CUDA(cudaMemcpy(host.data(), dev, HB * c->size, cudaMemcpyDeviceToHost));
+    bool ok = true;
+    for (int r = 0; r < c->size; r++) ok = ok && host[HB * r + sizeof(mine)] == 1;
+    for (int r = 0; r < c->size; r++) peers[r] = nullptr;
+    for (int r = 0; r < c->size && ok; r++) {
+        if (r == c->rank) { peers[r] = basep; continue; }
+        cudaIpcMemHandle_t h;
+        memcpy(&h, host.data() + HB * r, sizeof(h));
+        if (cudaIpcOpenMemHandle(&peers[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); peers[r] = nullptr; ok = false; }
+    }
+    long long hv = ok ? 0 : 1;
+    DGB_CUDA(cudaMemcpy(dev, &hv, 8, cudaMemcpyHostToDevice));
+    DGB_NCCL(nccl()->AllReduce(dev, dev, 1, ncclInt64, ncclSum, c->comm, nullptr));
+    DGB_CUDA(cudaDeviceSynchronize());
+    DGB_CUDA(cudaMemcpy(&hv, dev, 8, cudaMemcpyDeviceToHost));
+    cudaFree(dev);
+    if (hv != 0) { comm_p2p_unmap(c, peers); return 1; }
+    return 0;
+}
+void comm_p2p_unmap(Comm* c, void** peers) {
+    if (!c) return;
+    for (int r = 0; r < c->size; r++) {
+        if (r != c->rank && peers[r]) cudaIpcCloseMemHandle(peers[r]);
+        peers[r] = nullptr;
+    }
+}
+
+__global__ void __launch_bounds__(32) p2p_barrier_kernel(P2pView v, int lower, int upper, unsigned long long epoch) {
+    const int t = threadIdx.x;
+    const int who = t == 0 ? lower : (t == 1 ? upper : -1);
+    if (who < 0 || (t == 1 && upper == lower)) return;
+    p2p_store(p2p_rec(v.peer[who], 7, epoch, v.rank), 1ull, epoch);
+    p2p_wait(p2p_rec(v.peer[v.rank], 7, epoch, who), epoch);
+}
+int comm_p2p_neighbour_barrier(Comm* c, int lower, int upper, cudaStream_t st) {
+    if (!c || !c->p2p) { set_error("peer-memory barrier without peer memory"); return DGB_ERR_INVALID; }
+    const unsigned long long epoch = comm_p2p_next_epoch(c, 7, 1);
+    p2p_barrier_kernel<<<1, 32, 0, st>>>(comm_p2p_view(c), lower, upper, epoch);
+    DGB_LAUNCHED();
+    return 0;
+}
 
 int comm_allreduce_i64(Comm* c, long long* buf, size_t count, cudaStream_t st) {
     if (!c || c->size == 1) return 0;
@@ -116,6 +243,21 @@ __global__ void superacc_finalize_kernel(dgb_dot_result* r, int nrec) {
     r[k].pad = 0;
 }
 
+// peer-memory variant of the global dot: exchange + normalise + round in one launch (channels 4..)
+__global__ void __launch_bounds__(64) p2p_dot_kernel(P2pView v, dgb_dot_result* r, int nrec, unsigned long long epoch) {
+    // records use channels 4.. but are indexed from 0 in r: shift the pointer so that record k sits at index 4 + k
+    p2p_allreduce_records(v, reinterpret_cast<long long*>(r) - 4 * 41, 4, nrec, epoch);
+    const int k = threadIdx.x;
+    if (k >= nrec) return;
+    long long acc[sa::BINS];
+    for (int i = 0; i < sa::BINS; i++) acc[i] = r[k].acc[i];
+    int neg = sa::normalize(acc, 1);
+    for (int i = 0; i < sa::BINS; i++) r[k].acc[i] = acc[i];
+    r[k].value = sa::round_normalized(acc, neg);
+    r[k].status = r[k].status != 0 || r[k].pad != 0;
+    r[k].pad = 0;
+}
+
 }  // namespace dgb
 
 using namespace dgb;
@@ -140,6 +282,8 @@ int dgb_comm_create(dgb_comm** out, const char* id128, int rank, int nranks) {
         memcpy(id.internal, id128, 128);
         ncclResult_t r = n->CommInitRank(&c->comm, nranks, id, rank);
         if (r != 0) { delete c; set_error("ncclCommInitRank failed with %d", r); return DGB_ERR_INVALID; }
+        int e = comm_p2p_setup(c);
+        if (e) { delete c; return e; }
     }
     *out = reinterpret_cast<dgb_comm*>(c);
     return 0;
@@ -147,6 +291,9 @@ int dgb_comm_create(dgb_comm** out, const char* id128, int rank, int nranks) {
 int dgb_comm_destroy(dgb_comm* h) {
     Comm* c = reinterpret_cast<Comm*>(h);
     if (!c) return 0;
+    for (int r = 0; r < c->size; r++)
+        if (c->p2p && r != c->rank && c->peer[r]) cudaIpcCloseMemHandle(c->peer[r]);
+    cudaFree(c->local);
     if (c->comm && nccl() && nccl()->CommDestroy) nccl()->CommDestroy(c->comm);
     delete c;
     return 0;
@@ -159,6 +306,12 @@ int dgb_comm_halo_rows(dgb_comm* h, double* interior, size_t row_len, size_t nro
 int dgb_comm_allreduce_dot(dgb_comm* h, dgb_dot_result* result_dev, int nrecords, dgb_stream_t s) {
     Comm* c = reinterpret_cast<Comm*>(h);
     if (nrecords < 1) return 0;
+    if (c && c->p2p && nrecords <= P2P_CHANNELS - 4) {  // channels 0..3 belong to the PCG workspace, 4.. to this entry point
+        const unsigned long long epoch = comm_p2p_next_epoch(c, 4, nrecords);
+        p2p_dot_kernel<<<1, 64, 0, as_stream(s)>>>(comm_p2p_view(c), result_dev, nrecords, epoch);
+        DGB_LAUNCHED();
+        return 0;
+    }
     int e = comm_allreduce_i64(c, reinterpret_cast<long long*>(result_dev), (size_t)nrecords * sizeof(dgb_dot_result) / 8, as_stream(s));
     if (e) return e;
     superacc_finalize_kernel<<<1, 32, 0, as_stream(s)>>>(result_dev, nrecords);

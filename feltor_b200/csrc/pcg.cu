@@ -25,6 +25,10 @@ struct Pcg {
     double *r = nullptr, *p = nullptr, *ap = nullptr;
     double* p_base = nullptr;  // allocation behind p (p may be offset by the ghost rows of a slab)
     size_t p_cap = 0;
+    // peer-memory halo (multi-GPU): the p buffers of all ranks mapped into this process
+    void* p_peers[P2P_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    Comm* p_peers_comm = nullptr;
+    bool p_mapped = false;
     PcgState* st = nullptr;       // device
     PcgState* st_host = nullptr;  // pinned
     sa::DotSlot slot;             // 4 slots: 0 pAp, 1 rWr, 2 zWr, 3 setup dots
@@ -166,7 +170,10 @@ __device__ inline void finalize_record(dgb_dot_result* r) {
     r->pad = 0;
 }
 template <int MODE>
-__global__ void pcg_scalar_kernel(PcgState* st, dgb_dot_result* res, int iter, int check) {
+__global__ void __launch_bounds__(64) pcg_scalar_kernel(PcgState* st, dgb_dot_result* res, int iter, int check, P2pView pv, int first,
+                                                        int count, unsigned long long epoch) {
+    // peer-memory path: the exchange of the local records happens here (comm.cuh); NCCL path: already summed
+    if (pv.enabled) p2p_allreduce_records(pv, reinterpret_cast<long long*>(res), first, count, epoch);
     if (threadIdx.x != 0) return;
     if (MODE >= 2 && st->done) return;
     if (MODE == 0) finalize_record(res + 3);
@@ -181,8 +188,12 @@ __global__ void pcg_scalar_kernel(PcgState* st, dgb_dot_result* res, int iter, i
 
 // K3 (pcg.h:182): axpby(1, ap, beta, p): p = p*beta; p = fma(1, ap, p).  Pure stream (24 B/dof): full occupancy, four
 // front-batched 128-bit loads per operand and thread, 8 CTAs per SM (the layout of the blas1 kernels).
+// Multi-GPU: the bottom / top `gcnt` doubles (the rows the neighbours need) are ALSO stored straight into the upper ghost
+// rows of the lower neighbour (`rem_lo`) / the lower ghost rows of the upper neighbour (`rem_up`) through peer memory --
+// the halo exchange of the next operator application rides in this kernel, a neighbour barrier follows.
 __global__ void __launch_bounds__(PCG_THREADS)
-pcg_direction_kernel(size_t n, const double* __restrict__ z, double* __restrict__ p, const PcgState* st) {
+pcg_direction_kernel(size_t n, const double* __restrict__ z, double* __restrict__ p, const PcgState* st, double* rem_lo,
+                     double* rem_up, size_t gcnt) {
     if (st->done) return;
     constexpr int U = 4;
     const double beta = st->beta;
@@ -202,6 +213,8 @@ pcg_direction_kernel(size_t n, const double* __restrict__ z, double* __restrict_
                 pv[u].x = __fma_rn(1., zv[u].x, __dmul_rn(pv[u].x, beta));
                 pv[u].y = __fma_rn(1., zv[u].y, __dmul_rn(pv[u].y, beta));
                 st2(p + 2 * i, pv[u]);
+                if (rem_lo && 2 * i < gcnt) st2(rem_lo + 2 * i, pv[u]);
+                if (rem_up && 2 * i >= n - gcnt) st2(rem_up + (2 * i - (n - gcnt)), pv[u]);
             }
         }
     }
@@ -245,9 +258,14 @@ static int fetch_result(Pcg& s, int si, cudaStream_t st) {
 // dist: complete the dot(s) in slots [first, first+count) across ranks, then run the scalar hook MODE
 template <int MODE>
 static int dist_finish(Pcg& s, Comm* comm, int first, int count, int iter, int check, cudaStream_t st) {
-    int e = comm_allreduce_i64(comm, reinterpret_cast<long long*>(s.results + first), (size_t)count * sizeof(dgb_dot_result) / 8, st);
-    if (e) return e;
-    pcg_scalar_kernel<MODE><<<1, 32, 0, st>>>(s.st, s.results, iter, check);
+    const P2pView pv = comm_p2p_view(comm);
+    unsigned long long epoch = 0;
+    if (pv.enabled) epoch = comm_p2p_next_epoch(comm, first, count);
+    else {
+        int e = comm_allreduce_i64(comm, reinterpret_cast<long long*>(s.results + first), (size_t)count * sizeof(dgb_dot_result) / 8, st);
+        if (e) return e;
+    }
+    pcg_scalar_kernel<MODE><<<1, 64, 0, st>>>(s.st, s.results, iter, check, pv, first, count, epoch);
     DGB_LAUNCHED();
     return 0;
 }
@@ -265,6 +283,7 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
     const size_t row_len = dist ? (size_t)A.Nx * A.n : 0;
     const size_t ghost_rows = dist ? (size_t)A.slab_ghost * A.n : 0, gh = ghost_rows * row_len;
     if (s.p_cap < n + 2 * gh) {
+        if (s.p_mapped) { comm_p2p_unmap(s.p_peers_comm, s.p_peers); s.p_mapped = false; }
         cudaFree(s.p_base);
         s.p_base = nullptr;
         DGB_CUDA(cudaMalloc(&s.p_base, (n + 2 * gh) * sizeof(double)));
@@ -272,6 +291,33 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
         s.p_cap = n + 2 * gh;
     }
     s.p = s.p_base + gh;
+    // peer-memory halo: map the p buffers of all ranks once per allocation (collective)
+    double *rem_lo = nullptr, *rem_up = nullptr;
+    int nb_lower = -1, nb_upper = -1;
+    bool p2p_halo = false;
+    if (dist && comm_size(comm) > 1) {
+        if (!s.p_mapped || s.p_peers_comm != comm) {
+            if (s.p_mapped) comm_p2p_unmap(s.p_peers_comm, s.p_peers);
+            DGB_CUDA(cudaStreamSynchronize(st));
+            const int m = comm_p2p_map(comm, s.p_base, s.p_peers);
+            if (m > 1) return m;
+            s.p_mapped = m == 0;
+            s.p_peers_comm = comm;
+        }
+        const int rank = comm_rank(comm), size = comm_size(comm);
+        nb_lower = rank - 1; nb_upper = rank + 1;
+        if (nb_lower < 0) nb_lower = A.wrapy ? size - 1 : -1;
+        if (nb_upper >= size) nb_upper = A.wrapy ? 0 : -1;
+        // every rank must take the same decision: equal slab heights are not required, but the neighbour's layout is
+        // [gh | n_nb | gh] with ITS n -- its upper ghost starts at gh + n_nb, which we do not know; so only the LOWER ghost
+        // of the upper neighbour (offset 0) and, for equal n, the upper ghost of the lower neighbour are addressable.
+        // bench/solver slabs are equal-sized whenever Ny divides by the rank count; otherwise NCCL does the exchange.
+        p2p_halo = s.p_mapped && gh > 0 && (n % 2 == 0) && (gh % 2 == 0) && A.Ny % size == 0 && A.slab_rows == A.Ny / size;
+        if (p2p_halo) {
+            if (nb_lower >= 0) rem_lo = reinterpret_cast<double*>(s.p_peers[nb_lower]) + gh + n;  // its upper ghost rows
+            if (nb_upper >= 0) rem_up = reinterpret_cast<double*>(s.p_peers[nb_upper]);           // its lower ghost rows
+        }
+    }
     auto halo = [&](double* v) -> int {
         if (!dist) return 0;
         return comm_halo_rows(comm, v, row_len, (size_t)A.slab_rows * A.n, ghost_rows, A.wrapy, st);
@@ -347,9 +393,10 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
             DGB_LAUNCHED();
             if (dist && (e = dist_finish<3>(s, comm, check ? 1 : 2, check ? 2 : 1, i, check, st))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n][2], st);
-            pcg_direction_kernel<<<g3, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st);
+            pcg_direction_kernel<<<g3, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st, rem_lo, rem_up, gh);
             DGB_LAUNCHED();
-            if ((e = halo(s.p))) return e;
+            if (p2p_halo) { if ((e = comm_p2p_neighbour_barrier(comm, nb_lower, nb_upper, st))) return e; }
+            else if ((e = halo(s.p))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n++][3], st);
         }
         if ((e = fetch_state(s, st))) return e;
@@ -416,6 +463,7 @@ void pcg_delete(Pcg* s) {
     if (s->ev_ready)
         for (int k = 0; k < Pcg::PROF_MAX; k++)
             for (int j = 0; j < 4; j++) cudaEventDestroy(s->ev[k][j]);
+    if (s->p_mapped) comm_p2p_unmap(s->p_peers_comm, s->p_peers);
     cudaFree(s->r); cudaFree(s->p_base); cudaFree(s->ap); cudaFree(s->st); cudaFreeHost(s->st_host);
     cudaFree(s->slot.gacc); cudaFree(s->slot.gstatus); cudaFree(s->slot.ticket);
     cudaFree(s->results); cudaFreeHost(s->results_host);
