@@ -222,6 +222,28 @@ struct FTensorMul2d {  // multiply.h:18-32; v = {lambda,t00,t01,t10,t11,in0,in1,
         v[7] = __fma_rn(l, tmp0, temp);
     }
 };
+struct FUpwindAxpby {  // evaluate(y, Axpby(a,b), UpwindProduct(), v, back, forw): advection.h:112-120, functors.h:312-337
+    static constexpr int NV = 4; static constexpr unsigned RMASK = 0xf, WMASK = 0x8;
+    double a, b;
+    __device__ void operator()(double (&v)[4]) const {
+        const double up = __dmul_rn(v[0], v[0] >= 0. ? v[1] : v[2]);
+        v[3] = __fma_rn(a, up, __dmul_rn(v[3], b));
+    }
+};
+struct FTensorDot2dAxpby {  // scalar_product2d (multiply.h:493-512, TensorDot2d :135-150); v = {lambda,v0,v1,t00,t01,t10,t11,mu,w0,w1,y}
+    static constexpr int NV = 11; static constexpr unsigned RMASK = 0x7ff, WMASK = 0x400;
+    double a, b, lambda_s, mu_s;
+    unsigned present;  // bit k set: array k present, else implicit constant (lambda_s, identity tensor, mu_s)
+    __device__ void operator()(double (&v)[11]) const {
+        const double l = (present & 1u) ? v[0] : lambda_s, m = (present & 128u) ? v[7] : mu_s;
+        const double t00 = (present & 8u) ? v[3] : 1., t01 = (present & 16u) ? v[4] : 0.;
+        const double t10 = (present & 32u) ? v[5] : 0., t11 = (present & 64u) ? v[6] : 1.;
+        const double tmp0 = __fma_rn(t00, v[8], __dmul_rn(t01, v[9]));
+        const double tmp1 = __fma_rn(t10, v[8], __dmul_rn(t11, v[9]));
+        const double r = __dmul_rn(__dmul_rn(l, m), __fma_rn(v[1], tmp0, __dmul_rn(v[2], tmp1)));
+        v[10] = __fma_rn(a, r, __dmul_rn(v[10], b));
+    }
+};
 template <int OP>
 struct FUnary {
     static constexpr int NV = 2; static constexpr unsigned RMASK = 1, WMASK = 2;
@@ -256,6 +278,18 @@ __global__ void __launch_bounds__(256) embedded_pair_sum_kernel(EpsParams P, dou
         }
         y[i] = a;
         yt[i] = at;
+    }
+}
+
+// evaluate(y, Axpby(alpha, beta), PairSum(), a_0, x_0, ..., a_{nk-1}, x_{nk-1}) (subroutines.h:123-143, 260-274):
+// y = fma(alpha, fma(a_0, x_0, fma(a_1, x_1, ... a_last * x_last)), y * beta) -- the dense-matrix gemv of the time steppers
+// (blas2_densematrix.h:38-74)
+__global__ void __launch_bounds__(256) pair_sum_axpby_kernel(EpsParams P, double alpha, double beta, double* __restrict__ y, size_t n) {
+    const size_t T = (size_t)gridDim.x * blockDim.x;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += T) {
+        double sum = __dmul_rn(P.b[P.nk - 1], P.k[P.nk - 1][i]);
+        for (int s = P.nk - 2; s >= 0; s--) sum = __fma_rn(P.b[s], P.k[s][i], sum);
+        y[i] = __fma_rn(alpha, sum, __dmul_rn(y[i], beta));
     }
 }
 
@@ -322,6 +356,17 @@ int dgb_tensor_multiply2d(size_t n, const double* lambda, double lambda_s, const
     return launch_ew(FTensorMul2d{lambda_s, mu, present}, pack<9>({lambda, t00, t01, t10, t11, in0, in1, out0, out1}),
                      n, s);
 }
+int dgb_upwind_axpby(size_t n, double alpha, const double* v, const double* back, const double* forw, double beta, double* y,
+                     dgb_stream_t s) {
+    return launch_ew(FUpwindAxpby{alpha, beta}, pack<4>({v, back, forw, y}), n, s);
+}
+int dgb_tensor_dot2d(size_t n, double alpha, const double* lambda, double lambda_s, const double* v0, const double* v1,
+                     const double* t00, const double* t01, const double* t10, const double* t11, const double* mu, double mu_s,
+                     const double* w0, const double* w1, double beta, double* y, dgb_stream_t s) {
+    unsigned present = (lambda ? 1u : 0u) | (t00 ? 8u : 0u) | (t01 ? 16u : 0u) | (t10 ? 32u : 0u) | (t11 ? 64u : 0u) | (mu ? 128u : 0u);
+    return launch_ew(FTensorDot2dAxpby{alpha, beta, lambda_s, mu_s, present},
+                     pack<11>({lambda, v0, v1, t00, t01, t10, t11, mu, w0, w1, y}), n, s);
+}
 int dgb_embedded_pair_sum(size_t n, double* y, double* yt, double b0, double bt0, int nk, const double* b,
                           const double* bt, const double* const* k, dgb_stream_t s) {
     if (nk < 0 || nk > 16) { set_error("dgb_embedded_pair_sum: nk=%d outside [0,16]", nk); return DGB_ERR_UNSUPPORTED; }
@@ -331,6 +376,18 @@ int dgb_embedded_pair_sum(size_t n, double* y, double* yt, double b0, double bt0
     P.b0 = b0; P.bt0 = bt0; P.nk = nk;
     size_t want = (n + 255) / 256, cap = (size_t)sm_count() * 8;
     embedded_pair_sum_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(s)>>>(P, y, yt, n);
+    DGB_LAUNCHED();
+    return 0;
+}
+int dgb_pair_sum_axpby(size_t n, double alpha, int nk, const double* a, const double* const* x, double beta, double* y,
+                       dgb_stream_t s) {
+    if (nk < 1 || nk > 8) { set_error("dgb_pair_sum_axpby: nk = %d not in 1..8", nk); return DGB_ERR_INVALID; }
+    if (n == 0) return 0;
+    EpsParams P;
+    for (int i = 0; i < nk; i++) { P.k[i] = x[i]; P.b[i] = a[i]; P.bt[i] = 0.; }
+    P.b0 = 0.; P.bt0 = 0.; P.nk = nk;
+    size_t want = (n + 255) / 256, cap = (size_t)sm_count() * 8;
+    pair_sum_axpby_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(s)>>>(P, alpha, beta, y, n);
     DGB_LAUNCHED();
     return 0;
 }

@@ -17,6 +17,9 @@ namespace dgb {
 extern "C" int dgb_tensor_multiply2d(size_t, const double*, double, const double*, const double*, const double*,
                                      const double*, const double*, const double*, double, double*, double*, dgb_stream_t);
 extern "C" int dgb_axpbypgz(size_t, double, const double*, double, const double*, double, double*, dgb_stream_t);
+extern "C" int dgb_tensor_dot2d(size_t, double, const double*, double, const double*, const double*, const double*, const double*,
+                                const double*, const double*, const double*, double, const double*, const double*, double, double*,
+                                dgb_stream_t);
 
 __global__ void __launch_bounds__(256)
 elliptic_finish_kernel(size_t n, double alpha, const double* __restrict__ temp, const double* __restrict__ vol,
@@ -65,8 +68,33 @@ static int elliptic2d_unfused(Elliptic2dPlan& p, double alpha, const double* x, 
     return 0;
 }
 
+extern "C" int dgb_pointwise_dot(size_t, double, const double*, const double*, double, double*, dgb_stream_t);
+extern "C" int dgb_axpby(size_t, double, const double*, double, double*, dgb_stream_t);
+static int elliptic2d_symv_plain(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
+                                 bool force_unfused);
+
+// GeneralHelmholtz::symv (helmholtz.h:74-80): only the two-operand form exists in the reference
 int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                     bool force_unfused) {
+    if (!p.helm) return elliptic2d_symv_plain(p, alpha, x, beta, y, st, force_unfused);
+    if (alpha != 1. || beta != 0.) {
+        set_error("dgb_elliptic2d_symv: a Helmholtz plan supports symv(x, y) only (alpha = 1, beta = 0), as the reference");
+        return DGB_ERR_UNSUPPORTED;
+    }
+    if (!force_unfused && elliptic2d_walker_supported(p) && !p.chi[0] && !p.chi[1] && !p.chi[2] && !p.chi[3] && !p.chi_weight_jump &&
+        p.sigma && x != y)
+        return elliptic2d_fused_launch(p, 1., x, 0., y, st);  // the walker applies the Helmholtz epilogue itself
+    int e = 0;
+    if (p.helm_alpha != 0.) { if ((e = elliptic2d_symv_plain(p, 1., x, 0., y, st, true))) return e; }
+    dgb_stream_t s = reinterpret_cast<dgb_stream_t>(st);
+    const size_t n = p.slab ? (size_t)p.slab_rows * p.n * p.Nx * p.n : p.size;
+    if (p.helm_chi) return dgb_pointwise_dot(n, 1., p.helm_chi, x, -p.helm_alpha, y, s);
+    // chi = 1: z *= b; z = fma(1*1, x, z)
+    return dgb_axpby(n, 1., x, -p.helm_alpha, y, s);
+}
+
+static int elliptic2d_symv_plain(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
+                                 bool force_unfused) {
     if (!p.sigma) { set_error("dgb_elliptic2d_symv: sigma has not been set"); return DGB_ERR_INVALID; }
     if (x == y) { set_error("dgb_elliptic2d_symv: x must not alias y"); return DGB_ERR_INVALID; }
     static int env_unfused = -1;
@@ -199,6 +227,23 @@ int dgb_elliptic2d_set_chi(dgb_elliptic2d* h, const double* xx, const double* xy
     Elliptic2dPlan* p = reinterpret_cast<Elliptic2dPlan*>(h);
     p->chi[0] = xx; p->chi[1] = xy; p->chi[2] = yx; p->chi[3] = yy;
     return 0;
+}
+int dgb_elliptic2d_set_helmholtz(dgb_elliptic2d* h, int enable, double alpha, const double* chi) {
+    Elliptic2dPlan* p = reinterpret_cast<Elliptic2dPlan*>(h);
+    p->helm = enable != 0; p->helm_alpha = alpha; p->helm_chi = chi;
+    return 0;
+}
+int dgb_elliptic2d_variation(dgb_elliptic2d* h, double alpha, const double* lambda, const double* phi, double beta, double* sigma,
+                             dgb_stream_t s) {
+    Elliptic2dPlan& p = *reinterpret_cast<Elliptic2dPlan*>(h);
+    if (p.slab) { set_error("dgb_elliptic2d_variation: not available on a slab plan"); return DGB_ERR_UNSUPPORTED; }
+    int e = ensure_temps(p);
+    if (e) return e;
+    cudaStream_t st = as_stream(s);
+    if ((e = ell_symv(p.rightx, 1., phi, 0., p.tx, st, false))) return e;   // elliptic.h:499
+    if ((e = ell_symv(p.righty, 1., phi, 0., p.ty, st, false))) return e;   // :500
+    return dgb_tensor_dot2d(p.size, alpha, lambda, 1., p.tx, p.ty, p.chi[0], p.chi[1], p.chi[2], p.chi[3], lambda, 1., p.tx, p.ty,
+                            beta, sigma, s);                                 // :501
 }
 int dgb_elliptic2d_set_jfactor(dgb_elliptic2d* h, double jfactor) { reinterpret_cast<Elliptic2dPlan*>(h)->jfactor = jfactor; return 0; }
 int dgb_elliptic2d_set_slab(dgb_elliptic2d* h, int yoff, int rows, int ghost) {

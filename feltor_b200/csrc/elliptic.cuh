@@ -22,9 +22,14 @@ struct Elliptic2dPlan {
     // sigma operands carry slab_ghost ghost cell rows on either side (filled by the halo exchange)
     bool slab = false;
     int slab_yoff = 0, slab_rows = 0, slab_ghost = 0;
+    // GeneralHelmholtz mode (helmholtz.h:74-80): symv(x, y) = chi x - helm_alpha (Elliptic x)
+    bool helm = false;
+    double helm_alpha = 0.;
+    const double* helm_chi = nullptr;  // borrowed, nullptr = 1
     void* walk_part[2] = {nullptr, nullptr};  // work partitions of the walker kernel (plain / fused-dot variant)
 };
 void elliptic2d_walker_release(Elliptic2dPlan& p);
+bool elliptic2d_walker_supported(const Elliptic2dPlan& p);
 
 int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                     bool force_unfused);

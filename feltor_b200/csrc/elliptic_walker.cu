@@ -52,6 +52,9 @@ struct WalkArgs {
     const double* w;  // weights of the fused dot
     double* y;
     double alpha, beta, jfactor;
+    int helm;                 // GeneralHelmholtz epilogue: y = chi x - helm_alpha y (helmholtz.h:74-80)
+    double helm_alpha;
+    const double* helm_chi;
     sa::DotSlot slot;
     PcgState* pcg;
 };
@@ -536,6 +539,16 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
 #pragma unroll
                             for (int kx = 0; kx < N; kx++) acc[ky][kx] = __fma_rn(A.alpha, acc[ky][kx], 0.);
                     }
+                    if (A.helm) {  // pointwiseDot(1., chi, x, -helm_alpha, y): y *= -helm_alpha; y = fma(1*chi, x, y)
+                        const double mha = -A.helm_alpha;
+#pragma unroll
+                        for (int ky = 0; ky < N; ky++)
+#pragma unroll
+                            for (int kx = 0; kx < N; kx++) {
+                                const double c = A.helm_chi ? __ldg(A.helm_chi + gb + (size_t)ky * LD + kx) : 1.;
+                                acc[ky][kx] = __fma_rn(__dmul_rn(1., c), x0[ky * RP + eo + kx], __dmul_rn(acc[ky][kx], mha));
+                            }
+                    }
                     if (A.tma_store) {
 #pragma unroll
                         for (int ky = 0; ky < N; ky++)
@@ -700,6 +713,7 @@ static int wlaunch(Elliptic2dPlan& p, double alpha, const double* x, double beta
     A.fy_hi = std::min({p.righty.i_hi, p.lefty.i_hi, p.jumpy.i_hi});
     A.sigma = p.sigma; A.vol = p.vol; A.x = x; A.y = y; A.w = nullptr;
     A.alpha = alpha; A.beta = beta; A.jfactor = p.jfactor;
+    A.helm = p.helm ? 1 : 0; A.helm_alpha = p.helm_alpha; A.helm_chi = p.helm_chi;
     A.pcg = nullptr; A.slot = sa::DotSlot{nullptr, nullptr, nullptr, nullptr};
     if (DOT) { A.w = fd->w; A.slot = fd->slot; A.pcg = fd->pcg; }
     CUtensorMap mx, ms, mw, my;
@@ -740,7 +754,7 @@ void elliptic2d_walker_release(Elliptic2dPlan& p) {
 bool elliptic2d_walker_supported(const Elliptic2dPlan& p) {
     static int off = -1;
     if (off < 0) { const char* e = getenv("DGB_ELLIPTIC_TILE"); off = (e && atoi(e)) ? 1 : 0; }
-    return !off && p.fusable && (p.n == 2 || p.n == 3) && p.Nx >= 5 && p.Ny >= 5;
+    return !off && p.fusable && (p.n == 2 || p.n == 3) && p.Nx >= 5 && p.Ny >= 5 && !(p.helm && p.helm_alpha == 0.);
 }
 
 int elliptic2d_walker_launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,

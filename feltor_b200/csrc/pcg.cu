@@ -361,7 +361,8 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
     if ((e = fetch_result(s, 3, st))) return e;
     if (std::sqrt(s.results_host[3].value) < tol) { *iterations = 0; return 0; }  // pcg.h:157
     const bool identity_chi = !A.chi[0] && !A.chi[1] && !A.chi[2] && !A.chi[3];
-    const bool fused = A.fusable && identity_chi && !A.chi_weight_jump && (dist || !getenv("DGB_ELLIPTIC_UNFUSED"));
+    const bool fused = A.fusable && identity_chi && !A.chi_weight_jump && (dist || !getenv("DGB_ELLIPTIC_UNFUSED")) &&
+                       (!A.helm || elliptic2d_walker_supported(A));  // only the walker knows the Helmholtz epilogue
     FusedDot fd{W, s.slot, s.st};
     const unsigned g2 = grid_for(n, 2);
     unsigned g3;

@@ -1,0 +1,314 @@
+"""The toefl right-hand side on libdgb200.so: mirror of toefl::Explicit (src/toefl/toefl.h:8-310) and of the dg classes
+it is built from -- dg::Helmholtz (inc/dg/helmholtz.h:27-82), dg::Advection (inc/dg/advection.h:60-120),
+dg::Extrapolation (inc/dg/extrapolation.h:225-460) and the fixed-step explicit Runge-Kutta stepper dg::ERKStep
+(inc/dg/runge_kutta.h:300-400) -- same member names, same call sequence, every arithmetic step a dgb_* call.
+Like the rest of feltor_b200/*.py this is harness code over the C ABI (tests, benchmarks), not the product.
+
+Models implemented: "global" (the default input of the reference) and "local".
+"""
+import ctypes as C
+import numpy as np
+import torch
+from ._lib import lib
+from ._dev import ptr, stream, dvec
+from . import blas1, topology as T
+from .elliptic import Elliptic2d, MultigridCG2d
+
+d = C.c_double
+
+
+def _zeros(n):
+    return torch.zeros(n, dtype=torch.float64, device="cuda")
+
+
+class Helmholtz:
+    """dg::GeneralHelmholtz<dg::Elliptic2d> (helmholtz.h:27-82): chi x - alpha Elliptic x; usable wherever the solvers
+    take an Elliptic2d (dgb_elliptic2d_set_helmholtz switches the plan's two-operand symv)."""
+
+    def __init__(self, alpha, elliptic):
+        self.E, self.alpha = elliptic, alpha
+        self.h = elliptic.h
+        self.size = elliptic.size
+        self._chi = None
+        lib().elliptic2d_set_helmholtz(self.h, 1, d(alpha), None)
+
+    def weights(self):
+        return self.E.weights()
+
+    def precond(self):
+        return self.E.precond()
+
+    def set_chi(self, chi):
+        self._chi = chi.clone()
+        lib().elliptic2d_set_helmholtz(self.h, 1, d(self.alpha), ptr(self._chi))
+
+    def symv(self, x, y):
+        self.E.symv(x, y)
+
+
+class Advection:
+    """dg::Advection (advection.h:60-120): upwind discretisation of v . grad f"""
+
+    def __init__(self, g, bcx=None, bcy=None):
+        bcx = g.bc[0] if bcx is None else bcx
+        bcy = g.bc[1] if bcy is None else bcy
+        self.dxf = T.derivative(0, g, bcx, T.FORWARD)
+        self.dyf = T.derivative(1, g, bcy, T.FORWARD)
+        self.dxb = T.derivative(0, g, bcx, T.BACKWARD)
+        self.dyb = T.derivative(1, g, bcy, T.BACKWARD)
+        self.t0, self.t1 = _zeros(g.size), _zeros(g.size)
+
+    def upwind(self, alpha, vx, vy, f, beta, result):
+        n = f.numel()
+        self.dxb.symv(1., f, 0., self.t0)
+        self.dxf.symv(1., f, 0., self.t1)
+        lib().upwind_axpby(n, d(alpha), ptr(vx), ptr(self.t0), ptr(self.t1), d(beta), ptr(result), stream())
+        self.dyb.symv(1., f, 0., self.t0)
+        self.dyf.symv(1., f, 0., self.t1)
+        lib().upwind_axpby(n, d(alpha), ptr(vy), ptr(self.t0), ptr(self.t1), d(1.), ptr(result), stream())
+
+
+class Extrapolation:
+    """dg::Extrapolation (extrapolation.h:225-460): polynomial through up to `max` past solutions"""
+
+    def __init__(self, max_, copyable):
+        self.max, self.counter = max_, 0
+        self.x = [copyable.clone() for _ in range(max_)]
+        self.t = [0.] * max_
+
+    def extrapolate(self, t, new_x):
+        c, tt, x = self.counter, self.t, self.x
+        if c == 0:
+            blas1.copy(0., new_x)
+        elif c == 1:
+            blas1.copy(x[0], new_x)
+        elif c == 3:
+            raise NotImplementedError("parabolic extrapolation is not used by toefl")
+        else:
+            f0 = (t - tt[1]) / (tt[0] - tt[1])
+            f1 = (t - tt[0]) / (tt[1] - tt[0])
+            blas1.axpby(f0, x[0], f1, x[1], new_x)
+
+    def update(self, t_new, new_entry):
+        if self.max == 0:
+            return
+        for i in range(self.counter):
+            if abs(t_new - self.t[i]) < 1e-14:
+                blas1.copy(new_entry, self.x[i])
+                return
+        if self.counter < self.max:
+            self.counter += 1
+        self.x = [self.x[-1]] + self.x[:-1]  # std::rotate by one towards the back
+        self.t = [self.t[-1]] + self.t[:-1]
+        self.t[0] = t_new
+        blas1.copy(new_entry, self.x[0])
+
+
+class Parameters:
+    """toefl::Parameters (src/toefl/parameters.h) from the same JSON dictionary"""
+
+    def __init__(self, js):
+        g = js["grid"]
+        self.n, self.Nx, self.Ny, self.lx, self.ly = g["n"], g["Nx"], g["Ny"], float(g["lx"]), float(g["ly"])
+        e = js["elliptic"]
+        self.num_stages = e["stages"]
+        self.eps_pol = [float(e["eps_pol"][0])] + [float(v) * float(e["eps_pol"][0]) for v in e["eps_pol"][1:self.num_stages]]
+        self.eps_gamma = [float(e["eps_gamma"][0])] + [float(v) * float(e["eps_gamma"][0]) for v in e["eps_gamma"][1:self.num_stages]]
+        self.pol_dir = {"forward": T.FORWARD, "backward": T.BACKWARD, "centered": T.CENTERED}[e["direction"]]
+        self.diff_dir = T.CENTERED
+        i = js["init"]
+        self.amp, self.sigma, self.posX, self.posY = float(i["amplitude"]), float(i["sigma"]), float(i["posX"]), float(i["posY"])
+        self.flr = i.get("flr", "none")
+        bcs = {"PER": T.PER, "DIR": T.DIR, "NEU": T.NEU, "DIR_NEU": T.DIR_NEU, "NEU_DIR": T.NEU_DIR}
+        self.bcx, self.bcy = bcs[js["bc"][0]], bcs[js["bc"][1]]
+        m = js["model"]
+        self.model = m.get("type", "global")
+        self.nu = float(m["nu"])
+        self.boussinesq, self.tau, self.friction, self.kappa = False, 0., 0., 0.
+        if self.model in ("local", "global"):
+            self.kappa, self.tau = float(m["curvature"]), float(m["tau"])
+            if self.model == "global":
+                self.boussinesq = bool(m["boussinesq"])
+        else:
+            raise NotImplementedError("toefl model %r" % self.model)
+
+
+class Explicit:
+    """toefl::Explicit<CartesianGrid2d, DMatrix, DVec> (src/toefl/toefl.h)"""
+
+    def __init__(self, p):
+        self.p = p
+        g = T.Grid([0., 0.], [p.lx, p.ly], p.n, [p.Nx, p.Ny], [p.bcx, p.bcy])
+        self.grid, n = g, g.size
+        self.chi, self.omega, self.uE2 = _zeros(n), _zeros(n), _zeros(n)
+        # dg::LinearX (toefl.h:63, functors.h): a*x + b, which the reference's host compiler contracts to fma(a, x, b);
+        # Fraction arithmetic is exact and float() rounds once, i.e. this IS the fused result
+        from fractions import Fraction
+        a, b = Fraction(p.kappa), Fraction(1. - p.kappa * p.posX * p.lx)
+        line = np.array([float(a * Fraction(float(x)) + b) for x in g.abscissas(0)])
+        self.binv = dvec(np.ascontiguousarray(np.broadcast_to(line, (g.shape(1), g.shape(0))).reshape(-1)))
+        self.phi = [_zeros(n), _zeros(n)]
+        self.dxphi, self.dyphi = [_zeros(n), _zeros(n)], [_zeros(n), _zeros(n)]
+        self.ype, self.lapy, self.v = [_zeros(n), _zeros(n)], [_zeros(n), _zeros(n)], [_zeros(n), _zeros(n)]
+        self.gamma_n = _zeros(n)
+        self.laplaceM = Elliptic2d(g, direction=p.diff_dir)
+        self.adv = Advection(g)
+        self.multigrid = MultigridCG2d(g, p.num_stages)
+        self.old_phi, self.old_psi, self.old_gammaN = (Extrapolation(2, self.chi) for _ in range(3))
+        self.multi_chi = self.multigrid.project(self.chi)
+        self.multi_pol = [Elliptic2d(self.multigrid.grid(u), direction=p.pol_dir, jfactor=1.) for u in range(p.num_stages)]
+        self.multi_gamma1 = [Helmholtz(-0.5 * p.tau, Elliptic2d(self.multigrid.grid(u), direction=p.pol_dir))
+                             for u in range(p.num_stages)]
+        self.centered = [T.derivative(0, g, p.bcx, T.CENTERED), T.derivative(1, g, p.bcy, T.CENTERED)]
+        self.ncalls = 0
+        self.numbers = {}  # PCG iterations per stage of the last solves: "gammaN", "pol", "gammaPhi"
+
+    def gamma_inv(self):
+        return self.multi_gamma1[0]
+
+    def initial_condition(self):
+        """src/toefl/toefl.cpp:50-72"""
+        p, g = self.p, self.grid
+        x0, y0, s = p.posX * p.lx, p.posY * p.ly, p.sigma
+        gauss = g.evaluate(lambda x, y: p.amp * np.exp(-((x - x0) * (x - x0) / 2. / s / s + (y - y0) * (y - y0) / 2. / s / s)))
+        y = [dvec(gauss), dvec(gauss)]
+        if p.tau != 0 and p.flr == "gamma_inv":
+            self.gamma_inv().symv(y[0], y[1])
+        return y
+
+    def compute_psi(self, t):
+        p = self.p
+        if p.tau == 0.:
+            blas1.axpby(1., self.phi[0], 0., self.phi[1])
+        else:
+            self.old_psi.extrapolate(t, self.phi[1])
+            self.numbers["gammaPhi"] = self.multigrid.solve(self.multi_gamma1, self.phi[1], self.phi[0], p.eps_gamma)
+            self.old_psi.update(t, self.phi[1])
+        lib().elliptic2d_variation(self.multi_pol[0].h, d(1.), None, ptr(self.phi[0]), d(0.), ptr(self.uE2), stream())
+        if p.model == "global":
+            blas1.pointwiseDot(1., self.binv, self.binv, self.uE2, 0., self.uE2)
+            blas1.axpby(-0.5, self.uE2, 1., self.phi[1])
+
+    def polarisation(self, t, y):
+        p = self.p
+        if p.model == "global":
+            # chi = (nt + 1) binv binv, same rounding sequence as the device lambda of toefl.h:116-119
+            blas1.copy(y[1], self.chi)
+            blas1.plus(self.chi, 1.)
+            blas1.pointwiseDot(self.chi, self.binv, self.chi)
+            blas1.pointwiseDot(self.chi, self.binv, self.chi)
+            if not p.boussinesq:
+                self.multi_chi = self.multigrid.project(self.chi)
+                for u in range(3):
+                    self.multi_pol[u].set_chi(self.multi_chi[u])
+        if p.tau == 0.:
+            blas1.axpby(1., y[1], 0., self.gamma_n)
+        else:
+            self.old_gammaN.extrapolate(t, self.gamma_n)
+            self.numbers["gammaN"] = self.multigrid.solve(self.multi_gamma1, self.gamma_n, y[1], p.eps_gamma)
+            self.old_gammaN.update(t, self.gamma_n)
+        blas1.axpby(-1., y[0], 1., self.gamma_n, self.omega)
+        if p.model == "global" and p.boussinesq:
+            blas1.pointwiseDivide(self.omega, self.chi, self.omega)
+        self.old_phi.extrapolate(t, self.phi[0])
+        self.numbers["pol"] = self.multigrid.solve(self.multi_pol, self.phi[0], self.omega, p.eps_pol)
+        self.old_phi.update(t, self.phi[0])
+
+    def __call__(self, t, y, yp):
+        p = self.p
+        self.ncalls += 1
+        self.polarisation(t, y)
+        self.compute_psi(t)
+        tau = [-1., p.tau]
+        for u in range(2):
+            blas1.copy(y[u], self.ype[u])
+            if p.model == "global":
+                blas1.plus(self.ype[u], 1.)
+        for u in range(2):
+            self.centered[0].symv(1., self.phi[u], 0., self.dxphi[u])
+            self.centered[1].symv(1., self.phi[u], 0., self.dyphi[u])
+            if p.model == "global":
+                blas1.pointwiseDot(-1., self.binv, self.dyphi[u], 0., self.v[0])
+                blas1.pointwiseDot(+1., self.binv, self.dxphi[u], 0., self.v[1])
+            else:
+                blas1.axpby(-1., self.dyphi[u], 0., self.v[0])
+                blas1.axpby(+1., self.dxphi[u], 0., self.v[1])
+            blas1.plus(self.v[1], -tau[u] * p.kappa)
+            self.adv.upwind(-1., self.v[0], self.v[1], y[u], 0., yp[u])
+            if p.model == "global":
+                blas1.pointwiseDot(p.kappa, self.ype[u], self.dyphi[u], 1., yp[u])
+            else:
+                blas1.axpby(p.kappa, self.dyphi[u], 1., yp[u])
+        for u in range(2):
+            self.laplaceM.symv(-1., y[u], 0., self.lapy[u])
+            blas1.axpby(p.nu, self.lapy[u], 1., yp[u])
+
+
+# Butcher tableaus of inc/dg/tableau.h used here: name -> (a, b, bt, c, fsal)
+TABLEAUS = {
+    "Bogacki-Shampine-4-2-3": ([[0, 0, 0, 0], [0.5, 0, 0, 0], [0, 0.75, 0, 0], [2. / 9., 1. / 3., 4. / 9., 0.]],
+                               [2. / 9., 1. / 3., 4. / 9., 0.], [7. / 24., 1. / 4., 1. / 3., 1. / 8.], [0., 0.5, 3. / 4., 1.], True),
+    "Runge-Kutta-4-4": ([[0, 0, 0, 0], [0.5, 0, 0, 0], [0, 0.5, 0, 0], [0, 0, 1., 0]], [1. / 6., 1. / 3., 1. / 3., 1. / 6.],
+                        [1. / 6., 1. / 3., 1. / 3., 1. / 6.], [0, 0.5, 0.5, 1.], False),
+}
+
+
+def dense_gemv(alpha, ks, x, beta, y):
+    """blas2::gemv(alpha, dg::asDenseMatrix(ks), x, beta, y) (blas2_densematrix.h:38-74): chunks of 8 / 4 / 2 / 1 columns"""
+    size, n = len(x), y.numel()
+
+    def pair_sum(cols, b):
+        A = (C.c_double * len(cols))(*[x[j] for j in cols])
+        X = (C.c_void_p * len(cols))(*[ks[j].data_ptr() for j in cols])
+        lib().pair_sum_axpby(n, d(alpha), len(cols), A, X, d(b), ptr(y), stream())
+
+    i = 0
+    for i in range(size // 8):
+        pair_sum(range(i * 8, i * 8 + 8), beta if i == 0 else 1.)
+    i = size // 8
+    l = 0
+    if size % 8 >= 4:
+        pair_sum(range(i * 8, i * 8 + 4), beta if size < 8 else 1.)
+        l = 1
+    k = 0
+    if (size % 8) % 4 >= 2:
+        pair_sum(range(i * 8 + l * 4, i * 8 + l * 4 + 2), beta if size < 4 else 1.)
+        k = 1
+    if ((size % 8) % 4) % 2 == 1:
+        j = i * 8 + l * 4 + k * 2
+        blas1.axpby(alpha * x[j], ks[j], beta if size < 2 else 1., y)
+
+
+class ERKStep:
+    """dg::ERKStep for std::array<DVec,2> (runge_kutta.h:300-400): same stage logic including FSAL, same kernels for the
+    stage sums (dense gemv, EmbeddedPairSum) => bitwise the reference's arithmetic."""
+
+    def __init__(self, tableau, copyable):
+        self.a, self.b, self.bt, self.c, self.fsal = TABLEAUS[tableau]
+        self.s = len(self.b)
+        self.k = [[v.clone() for v in copyable] for _ in range(self.s)]
+        self.rkd = [self.b[j] - self.bt[j] for j in range(self.s)]  # ButcherTableau::d (tableau.h:124)
+        self.t1 = 1e300
+
+    def step(self, rhs, t0, u0, u1, dt, delta):
+        s = self.s
+        if t0 != self.t1:
+            rhs(t0, u0, self.k[0])
+        for i in range(1, s):
+            tu = float(np.float64(dt) * np.float64(self.c[i]) + np.float64(t0))  # DG_FMA on the host: see note below
+            for q in range(2):
+                blas1.copy(u0[q], delta[q])
+                dense_gemv(dt, [self.k[l][q] for l in range(i)], self.a[i][:i], 1., delta[q])
+            rhs(tu, delta, self.k[i])
+        for q in range(2):
+            blas1.copy(u0[q], u1[q])
+            # detail::gemm({dt,dt}, k, {b, d}, {1., 0.}, {u1, delta}) (runge_kutta.h:24-64) for s = 4 columns
+            assert s == 4, "only four-stage tableaus are wired up"
+            blas1.embedded_pair_sum(u1[q], delta[q], 1., 0., [dt * v for v in self.b], [dt * v for v in self.rkd],
+                                    [self.k[j][q] for j in range(s)])
+        self.t1 = t1 = t0 + dt
+        if not self.fsal:
+            rhs(t1, u1, self.k[0])
+        else:
+            self.k[0], self.k[s - 1] = self.k[s - 1], self.k[0]
+        return t1

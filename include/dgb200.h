@@ -103,6 +103,20 @@ DGB_API int dgb_embedded_pair_sum(size_t n, double* y, double* yt, double b0, do
 /* blas1::transform with a unary functor of inc/dg/functors.h (y = op(x)); op codes below */
 enum { DGB_OP_EXP = 0, DGB_OP_LN = 1, DGB_OP_SQRT = 2, DGB_OP_INVERT = 3, DGB_OP_ABS = 4, DGB_OP_SQUARE = 5,
        DGB_OP_INVSQRT = 6 };
+/* y = alpha * v * (v >= 0 ? back : forw) + beta * y: blas1::evaluate(y, Axpby(alpha,beta), UpwindProduct(), v, back, forw)
+ * as used by dg::Advection::upwind (advection.h:112-120, functors.h:312-337) */
+DGB_API int dgb_upwind_axpby(size_t n, double alpha, const double* v, const double* back, const double* forw, double beta,
+                             double* y, dgb_stream_t s);
+/* y = alpha * lambda mu (v . T w) + beta y: dg::tensor::scalar_product2d (multiply.h:493-512).  NULL lambda / mu mean the
+ * scalars given next to them, NULL tensor entries the identity tensor. */
+DGB_API int dgb_tensor_dot2d(size_t n, double alpha, const double* lambda, double lambda_s, const double* v0, const double* v1,
+                             const double* t00, const double* t01, const double* t10, const double* t11, const double* mu,
+                             double mu_s, const double* w0, const double* w1, double beta, double* y, dgb_stream_t s);
+/* y = alpha * PairSum(a_0, x_0, ..., a_{nk-1}, x_{nk-1}) + beta * y with the reference's nesting
+ * fma(a_0, x_0, fma(a_1, x_1, ... a_last x_last)) (subroutines.h:123-143): the dense-matrix gemv behind the
+ * Runge-Kutta / multistep stage sums (blas2_densematrix.h:38-74); a: host array, x: host array of device pointers, nk <= 8 */
+DGB_API int dgb_pair_sum_axpby(size_t n, double alpha, int nk, const double* a_host, const double* const* x, double beta,
+                               double* y, dgb_stream_t s);
 DGB_API int dgb_transform(size_t n, int op, const double* x, double* y, dgb_stream_t s);          /* blas1.h:585 */
 
 /* ---------------------------------------------------------------------------------------------------
@@ -264,6 +278,14 @@ DGB_API int dgb_elliptic2d_set_vol(dgb_elliptic2d* plan, const double* vol);    
 DGB_API int dgb_elliptic2d_set_chi(dgb_elliptic2d* plan, const double* xx, const double* xy, const double* yx,
                                    const double* yy);                             /* m_chi; NULL = identity entry */
 DGB_API int dgb_elliptic2d_set_jfactor(dgb_elliptic2d* plan, double jfactor);
+/* dg::GeneralHelmholtz<Elliptic2d> (helmholtz.h:27-82): with enable != 0 the two-operand symv of the plan (and with it
+ * PCG / MultigridCG2d on the plan) computes  y = chi x - alpha (Elliptic x)  exactly as
+ * `symv(m_matrix, x, y); pointwiseDot(1., m_chi, x, -m_alpha, y)`; chi == NULL is the default chi = 1. */
+DGB_API int dgb_elliptic2d_set_helmholtz(dgb_elliptic2d* plan, int enable, double alpha, const double* chi);
+/* Elliptic2d::variation (elliptic.h:497-502): sigma = alpha lambda^2 (grad phi . chi . grad phi) + beta sigma with the
+ * plan's right derivatives and chi tensor; lambda == NULL means 1 */
+DGB_API int dgb_elliptic2d_variation(dgb_elliptic2d* plan, double alpha, const double* lambda, const double* phi, double beta,
+                                     double* sigma, dgb_stream_t s);
 /* size of the operator; *fused = 1 if the one-pass kernel applies to these matrices (else the composition runs) */
 DGB_API int dgb_elliptic2d_size(const dgb_elliptic2d* plan, size_t* size, int* fused);
 DGB_API int dgb_elliptic2d_symv(dgb_elliptic2d* plan, double alpha, const double* x, double beta, double* y,

@@ -1,0 +1,156 @@
+"""toefl (config 3 of BASELINE.json): the right-hand side toefl::Explicit, its building blocks and fixed-step
+dg::ERKStep on libdgb200.so against the UNMODIFIED reference (src/toefl/toefl.h, OpenMP backend): committed golden
+vectors (tests/golden/toefl_golden.npz, generator beside it) and, when oracle/_ref/libdgref_toefl.so travelled along,
+the live reference on other sizes.  Everything is compared BITWISE: state, potentials, per-stage PCG iteration counts.
+(CG amplifies a 1-ulp perturbation of its input to ~1e-8 of the solution within a few dozen iterations -- it is the bit
+equality of every building block that makes the 1e-12 bar of the north star reachable at all.)"""
+import ctypes as C
+import os
+import numpy as np
+import pytest
+from util import same_bits, rng
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_backend
+    gpu_backend.require_library_loaded()
+    return gpu_backend
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "toefl_golden.npz"))
+
+
+@pytest.fixture(scope="module")
+def reft():
+    from oracle import reftoefl
+    return reftoefl if reftoefl.available() else None
+
+
+def params(n, N, model):
+    from oracle import reftoefl
+    return reftoefl.default_params(n, N, N, model__type=model)
+
+
+def run_steps(G, js, y0, y1, steps, dt=0.5):
+    import torch
+    from feltor_b200 import toefl as TF
+    ex = TF.Explicit(TF.Parameters(js))
+    u0 = [G.make(y0), G.make(y1)]
+    u1 = [torch.zeros_like(u0[0]), torch.zeros_like(u0[0])]
+    delta = [torch.zeros_like(u0[0]), torch.zeros_like(u0[0])]
+    erk = TF.ERKStep("Bogacki-Shampine-4-2-3", u0)
+    t = 0.
+    for _ in range(steps):
+        t = erk.step(ex, t, u0, u1, dt, delta)
+        u0, u1 = u1, u0
+    return ex, u0
+
+
+@pytest.mark.parametrize("model", ["global", "local"])
+def test_toefl_steps_vs_golden(G, gold, model):
+    js = params(3, 24, model)
+    ex, u = run_steps(G, js, gold[model + "_init0"], gold[model + "_init1"], 3)
+    assert same_bits(G.get(ex.binv), gold[model + "_binv"])
+    assert same_bits(G.get(u[0]), gold[model + "_y0"])
+    assert same_bits(G.get(u[1]), gold[model + "_y1"])
+    assert same_bits(G.get(ex.phi[0]), gold[model + "_phi0"])
+    assert same_bits(G.get(ex.phi[1]), gold[model + "_phi1"])
+    assert ex.ncalls == 10  # FSAL: 4 + 3 + 3 right-hand-side evaluations
+
+
+@pytest.mark.parametrize("model", ["global", "local"])
+def test_toefl_rhs_vs_golden(G, gold, model):
+    import torch
+    from feltor_b200 import toefl as TF
+    ex = TF.Explicit(TF.Parameters(params(3, 24, model)))
+    y = [G.make(gold[model + "_y0"]), G.make(gold[model + "_y1"])]
+    yp = [torch.zeros_like(y[0]), torch.zeros_like(y[0])]  # Advection::upwind scales its output by beta = 0 (NaN would stay, as in the reference)
+    ex(0., y, yp)
+    assert same_bits(G.get(yp[0]), gold[model + "_rhs0"])
+    assert same_bits(G.get(yp[1]), gold[model + "_rhs1"])
+    assert same_bits(G.get(ex.phi[0]), gold[model + "_rhsphi0"])
+    assert same_bits(G.get(ex.phi[1]), gold[model + "_rhsphi1"])
+
+
+def test_toefl_building_blocks_vs_live_reference(G, reft):
+    """Advection::upwind, Elliptic::variation, the Helmholtz and the chi-weighted polarisation multigrid solves"""
+    if reft is None:
+        pytest.skip("oracle/_ref/libdgref_toefl.so not present")
+    import torch
+    from feltor_b200 import toefl as TF
+    from feltor_b200._lib import lib
+    from feltor_b200._dev import ptr, stream
+    js = params(3, 40, "global")
+    ref = reft.RefToefl(js)
+    ex = TF.Explicit(TF.Parameters(js))
+    n, r = ref.size, rng(7)
+    assert same_bits(G.get(ex.binv), ref.binv())
+    f, vx, vy, res = (r.uniform(-1, 1, n) for _ in range(4))
+    out = G.make(res)
+    ex.adv.upwind(-1., G.make(vx), G.make(vy), G.make(f), 0.5, out)
+    assert same_bits(G.get(out), ref.upwind(-1., vx, vy, f, 0.5, res))
+    phi = ex.grid.evaluate(lambda x, y: np.sin(0.05 * x) * np.cos(0.03 * y))
+    u = torch.zeros(n, dtype=torch.float64, device="cuda")  # Axpby(alpha, 0) scales the old value: NaN would stay, as in the reference
+    lib().elliptic2d_variation(ex.multi_pol[0].h, C.c_double(1.), None, ptr(G.make(phi)), C.c_double(0.), ptr(u), stream())
+    assert same_bits(G.get(u), ref.variation(phi))
+    b = ex.grid.evaluate(lambda x, y: np.exp(-((x - 60) ** 2 + (y - 100) ** 2) / 200.))
+    x = G.make(np.zeros(n))
+    num = ex.multigrid.solve(ex.multi_gamma1, x, G.make(b), ex.p.eps_gamma)
+    xr, numr = ref.helmholtz_solve(np.zeros(n), b)
+    assert num == numr and same_bits(G.get(x), xr)
+    chi = 1. + b
+    mc = ex.multigrid.project(G.make(chi))
+    for k in range(3):
+        ex.multi_pol[k].set_chi(mc[k])
+    x = G.make(np.zeros(n))
+    num = ex.multigrid.solve(ex.multi_pol, x, G.make(b), ex.p.eps_pol)
+    xr, numr = ref.pol_solve(chi, np.zeros(n), b)
+    assert num == numr and same_bits(G.get(x), xr)
+
+
+@pytest.mark.parametrize("N,steps", [(48, 4), (64, 2)])
+def test_toefl_steps_vs_live_reference(G, reft, N, steps):
+    if reft is None:
+        pytest.skip("oracle/_ref/libdgref_toefl.so not present")
+    js = params(3, N, "global")
+    ref = reft.RefToefl(js)
+    y0, y1 = ref.init()
+    ra, rb, _ = ref.erk("Bogacki-Shampine-4-2-3", 0., 0.5, steps, y0, y1)
+    ex, u = run_steps(G, js, y0, y1, steps)
+    assert same_bits(G.get(u[0]), ra) and same_bits(G.get(u[1]), rb)
+    assert same_bits(G.get(ex.phi[0]), ref.phi(0)) and same_bits(G.get(ex.phi[1]), ref.phi(1))
+    # the initial condition built on the device agrees to rounding (host exp / contraction differ in the last bit)
+    yi = ex.initial_condition()
+    assert np.abs(G.get(yi[0]) - y0).max() <= 4e-16 and np.abs(G.get(yi[1]) - y1).max() <= 2e-15
+
+
+def test_helmholtz_symv_fused_equals_composition(G):
+    """the walker's Helmholtz epilogue == Elliptic symv followed by pointwiseDot(1, chi, x, -alpha, y), with and without chi"""
+    import torch
+    from feltor_b200 import blas1, topology as T
+    from feltor_b200.elliptic import Elliptic2d
+    from feltor_b200.toefl import Helmholtz
+    g = T.Grid([0., 0.], [3., 2.], 3, [36, 28], [T.DIR, T.PER])
+    r = rng(3)
+    x, chi = G.make(r.uniform(-1, 1, g.size)), G.make(1. + r.uniform(0, 1, g.size))
+    for direction in (T.FORWARD, T.CENTERED):
+        E = Elliptic2d(g, direction=direction)
+        ref_y = torch.empty_like(x)
+        E.symv(x, ref_y)
+        H = Helmholtz(-0.37, Elliptic2d(g, direction=direction))
+        y = torch.full_like(x, float("nan"))
+        H.symv(x, y)
+        expect = ref_y.clone()
+        blas1.axpby(1., x, 0.37, expect)
+        assert same_bits(G.get(y), G.get(expect))
+        H.set_chi(chi)
+        H.symv(x, y)
+        expect = ref_y.clone()
+        blas1.pointwiseDot(1., chi, x, 0.37, expect)
+        assert same_bits(G.get(y), G.get(expect))

@@ -1,0 +1,27 @@
+"""CPU: pins the wrapped reference toefl (oracle/_ref/libdgref_toefl.so) to the committed golden vectors, so that a GPU
+failure against the fixture cannot be a stale fixture.  Skipped when the reference tree / wrapper is not available."""
+import os
+import numpy as np
+import pytest
+from util import same_bits
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.mark.parametrize("model", ["global", "local"])
+def test_reference_reproduces_golden(model):
+    from oracle import reftoefl as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libdgref_toefl.so not built (needs /root/reference)")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "toefl_golden.npz"))
+    ref = R.RefToefl(R.default_params(3, 24, 24, model__type=model))
+    y0, y1 = ref.init()
+    assert same_bits(y0, gold[model + "_init0"]) and same_bits(y1, gold[model + "_init1"])
+    a, b, _ = ref.erk("Bogacki-Shampine-4-2-3", 0., 0.5, 3, y0, y1)
+    assert same_bits(a, gold[model + "_y0"]) and same_bits(b, gold[model + "_y1"])
+    assert same_bits(ref.phi(0), gold[model + "_phi0"])
+
+
+def test_toefl_harness_has_no_oracle_import():
+    src = open(os.path.join(ROOT, "feltor_b200", "toefl.py")).read()
+    assert "oracle" not in src.replace("oracle/", "")
