@@ -285,7 +285,7 @@ def main():
                 "d2h_bytes_per_step": ndof * 8},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "elliptic2d_fused_kernel<3,2,dot> (Elliptic apply + dot(p,W,Ap))",
+        "roofline": {"bound": "hbm", "kernel": "elliptic2d_walker_kernel<3,fwd,dot> (Elliptic apply + dot(p,W,Ap))",
                      "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
                      "frac": achieved / peak if achieved else None, "traffic": traffic,
                      "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms},
