@@ -458,6 +458,16 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
             DGB_PHASE_FENCE();
             if (emit) {
                 const double* x0 = xrow(iy);
+                // beta != 0 / curvilinear volume: the epilogue reads y / vol with lane-strided loads; pull the lines into L1
+                // now so that the latency is gone by then (hot loops use beta == 0, vol == nullptr)
+                if ((A.beta != 0. || A.vol != nullptr) && outlane) {
+                    const size_t gp = (size_t)(iy * N) * LD + (size_t)gx * N;
+#pragma unroll
+                    for (int ky = 0; ky < N; ky++) {
+                        if (A.beta != 0.) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.y + gp + (size_t)ky * LD));
+                        if (A.vol != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.vol + gp + (size_t)ky * LD));
+                    }
+                }
                 const int ym = fast ? 0 : w_ymat(iy, A);
                 const bool on = fast || gx >= 0;
                 // ---- GX(iy) for my cell, then the neighbours' by shuffle
@@ -523,14 +533,22 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                 if (outlane) {
                     const size_t gb = (size_t)(iy * N) * LD + (size_t)gx * N;
                     if (A.vol != nullptr || A.beta != 0.) {
+                        double yo[N][N], vo[N][N];  // all loads first: their latencies overlap
 #pragma unroll
                         for (int ky = 0; ky < N; ky++)
 #pragma unroll
                             for (int kx = 0; kx < N; kx++) {
                                 const size_t g = gb + (size_t)ky * LD + kx;
+                                yo[ky][kx] = A.beta == 0. ? 0. : A.y[g];
+                                vo[ky][kx] = A.vol ? __ldg(A.vol + g) : 1.;
+                            }
+#pragma unroll
+                        for (int ky = 0; ky < N; ky++)
+#pragma unroll
+                            for (int kx = 0; kx < N; kx++) {
                                 double t = acc[ky][kx];
-                                if (A.vol) t = __ddiv_rn(t, __ldg(A.vol + g));
-                                const double b = A.beta == 0. ? 0. : __dmul_rn(A.y[g], A.beta);
+                                if (A.vol) t = __ddiv_rn(t, vo[ky][kx]);
+                                const double b = A.beta == 0. ? 0. : __dmul_rn(yo[ky][kx], A.beta);
                                 acc[ky][kx] = __fma_rn(A.alpha, t, b);
                             }
                     } else {

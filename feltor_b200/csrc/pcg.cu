@@ -75,13 +75,14 @@ pcg_dot3_kernel(size_t n, const double* __restrict__ x, const double* __restrict
     }
 }
 
-// K2 (pcg.h:167-181)
-template <bool CHECK>
-__global__ void __launch_bounds__(PCG_THREADS)
+// K2 (pcg.h:167-181).  PREFETCH: the six 128-bit loads of the next trip are in flight while this trip is reduced (2 CTAs
+// per SM); otherwise the kernel relies on occupancy (BPS CTAs per SM).
+template <bool CHECK, bool PREFETCH, int BPS>
+__global__ void __launch_bounds__(PCG_THREADS, BPS)
 pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ ap, double* __restrict__ x,
                   double* __restrict__ r, const double* __restrict__ P, const double* __restrict__ W, PcgState* st,
                   sa::DotSlot slot, int iter) {
-    __shared__ long long smem[2 * sa::BINS];  // one accumulator per dot and block
+    __shared__ long long smem[2 * sa::BINS];  // one accumulator per dot and block: [0] rr (slot 1), [1] zr (slot 2)
     if (st->done) return;
     const double alpha = st->alpha, malpha = -alpha;
     sa::block_init<2>(smem);
@@ -95,14 +96,17 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
     int bad = 0;
     const size_t T = (size_t)gridDim.x * blockDim.x, tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
     const size_t nvec = n / 2;
-    // software pipeline: the six 128-bit loads of the next trip are in flight while this trip is reduced
     size_t i = tid;
     double2 pv, av, xv, rv, Pv, Wv;
-    if (i < nvec) { pv = ld2(p + 2 * i); av = ld2(ap + 2 * i); xv = ld2(x + 2 * i); rv = ld2(r + 2 * i); Pv = ld2(P + 2 * i); Wv = ld2(W + 2 * i); }
+    if (PREFETCH && i < nvec) { pv = ld2(p + 2 * i); av = ld2(ap + 2 * i); xv = ld2(x + 2 * i); rv = ld2(r + 2 * i); Pv = ld2(P + 2 * i); Wv = ld2(W + 2 * i); }
     while (i < nvec) {
         const size_t inext = i + T;
         double2 pn, an, xn, rn, Pn, Wn;
-        if (inext < nvec) { pn = ld2(p + 2 * inext); an = ld2(ap + 2 * inext); xn = ld2(x + 2 * inext); rn = ld2(r + 2 * inext); Pn = ld2(P + 2 * inext); Wn = ld2(W + 2 * inext); }
+        if (PREFETCH) {
+            if (inext < nvec) { pn = ld2(p + 2 * inext); an = ld2(ap + 2 * inext); xn = ld2(x + 2 * inext); rn = ld2(r + 2 * inext); Pn = ld2(P + 2 * inext); Wn = ld2(W + 2 * inext); }
+        } else {
+            pv = ld2(p + 2 * i); av = ld2(ap + 2 * i); xv = ld2(x + 2 * i); rv = ld2(r + 2 * i); Pv = ld2(P + 2 * i); Wv = ld2(W + 2 * i);
+        }
         // Axpby(alpha,1): y = y*1; y = fma(alpha, x, y)   (subroutines.h:260-274)
         xv.x = __fma_rn(alpha, pv.x, __dmul_rn(xv.x, 1.));
         xv.y = __fma_rn(alpha, pv.y, __dmul_rn(xv.y, 1.));
@@ -128,7 +132,7 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
             sa::accumulate(my_rr, ra0, 1); sa::accumulate(my_rr, ra1, 1);
             sa::accumulate(my_zr, rb0, 1); sa::accumulate(my_zr, rb1, 1);
         }
-        pv = pn; av = an; xv = xn; rv = rn; Pv = Pn; Wv = Wn;
+        if (PREFETCH) { pv = pn; av = an; xv = xn; rv = rn; Pv = Pn; Wv = Wn; }
         i = inext;
     }
     if ((n & 1) && tid == 0) {
@@ -146,16 +150,15 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
         if (!isfinite(b0)) { bad = 1; b0 = 0.; }
         fzr.add(b0, my_zr);
     }
-    if (CHECK) {
-        frr.merge(frr1, my_rr);
-        frr.flush_warp(my_rr);
-        if (sa::block_finish<1>(my_rr, bad, slot, 1) && threadIdx.x == 0 && !st->dist) pcg_after_rr(st, slot.result + 1, iter);
-        __syncthreads();
-    }
+    // both dots leave together: one fence / ticket sequence
+    if (CHECK) { frr.merge(frr1, my_rr); frr.flush_warp(my_rr); }
     fzr.merge(fzr1, my_zr);
     fzr.flush_warp(my_zr);
-    if (sa::block_finish<1>(my_zr, bad, slot, 2) && threadIdx.x == 0 && !st->dist)
+    const bool last = CHECK ? sa::block_finish_multi<2>(smem, bad, slot, 1) : sa::block_finish_multi<1>(my_zr, bad, slot, 2);
+    if (last && threadIdx.x == 0 && !st->dist) {
+        if (CHECK) pcg_after_rr(st, slot.result + 1, iter);
         pcg_after_zr(st, slot.result + 2, iter);
+    }
 }
 
 // multi-GPU: after the integer allreduce of the local accumulators, one thread normalises, rounds and runs the hook
@@ -191,7 +194,7 @@ __global__ void __launch_bounds__(64) pcg_scalar_kernel(PcgState* st, dgb_dot_re
 // Multi-GPU: the bottom / top `gcnt` doubles (the rows the neighbours need) are ALSO stored straight into the upper ghost
 // rows of the lower neighbour (`rem_lo`) / the lower ghost rows of the upper neighbour (`rem_up`) through peer memory --
 // the halo exchange of the next operator application rides in this kernel, a neighbour barrier follows.
-__global__ void __launch_bounds__(PCG_THREADS)
+__global__ void __launch_bounds__(PCG_THREADS, 4)
 pcg_direction_kernel(size_t n, const double* __restrict__ z, double* __restrict__ p, const PcgState* st, double* rem_lo,
                      double* rem_up, size_t gcnt) {
     if (st->done) return;
@@ -365,6 +368,8 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
                        (!A.helm || elliptic2d_walker_supported(A));  // only the walker knows the Helmholtz epilogue
     FusedDot fd{W, s.slot, s.st};
     const unsigned g2 = grid_for(n, 2);
+    static int k2_variant = -1;  // experiment knob: 0 register prefetch, 2 CTAs/SM   1 no prefetch, 4 CTAs/SM   2 no prefetch, 3 CTAs/SM
+    if (k2_variant < 0) { const char* ev = getenv("DGB_PCG_K2_VARIANT"); k2_variant = ev ? atoi(ev) : 0; }
     unsigned g3;
     {
         size_t want = (n / 2 + (size_t)PCG_THREADS * 4 - 1) / ((size_t)PCG_THREADS * 4), cap = (size_t)sm_count() * 8;
@@ -387,10 +392,16 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
             }
             if (dist && (e = dist_finish<2>(s, comm, 0, 1, i, 0, st))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n][1], st);
-            if (check)
-                pcg_update_kernel<true><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
-            else
-                pcg_update_kernel<false><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+            if (k2_variant == 0) {
+                if (check) pcg_update_kernel<true, true, 2><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+                else pcg_update_kernel<false, true, 2><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+            } else if (k2_variant == 1) {
+                if (check) pcg_update_kernel<true, false, 4><<<2 * g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+                else pcg_update_kernel<false, false, 4><<<2 * g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+            } else {
+                if (check) pcg_update_kernel<true, false, 3><<<g2 / 2 * 3, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+                else pcg_update_kernel<false, false, 3><<<g2 / 2 * 3, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+            }
             DGB_LAUNCHED();
             if (dist && (e = dist_finish<3>(s, comm, check ? 1 : 2, check ? 2 : 1, i, check, st))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n][2], st);

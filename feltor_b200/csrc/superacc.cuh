@@ -291,5 +291,53 @@ __device__ inline bool block_finish(long long* smem, int status, const DotSlot& 
     return true;
 }
 
+// K dots of one kernel finished together: accumulators smem[k * BINS ..], slots slot0 .. slot0 + K - 1, ONE fence /
+// ticket sequence (the ticket of slot0).  K <= 4, blockDim.x >= 64 K.  Thread group k = threads [64 k, 64 k + 39).
+template <int K>
+__device__ inline bool block_finish_multi(long long* smem, int status, const DotSlot& slot, int slot0) {
+    __shared__ int s_last;
+    __shared__ long long s_hi[K * BINS];
+    const int any_bad = __syncthreads_or(status);
+    const int grp = threadIdx.x >> 6, t = threadIdx.x & 63;
+    if (grp < K && t < BINS) {
+        const long long v = smem[grp * BINS + t];
+        if (v != 0) add_word(slot.gacc + (size_t)(slot0 + grp) * GACC_WORDS + (blockIdx.x % SPREAD) * BINS, t, v, 1);
+    }
+    if (threadIdx.x < K && any_bad) atomicOr(slot.gstatus + slot0 + threadIdx.x, 1);
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int tk = atomicAdd(slot.ticket + slot0, 1u);
+        s_last = (tk == gridDim.x * gridDim.y * gridDim.z - 1);
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    if (grp < K && t < BINS) {
+        long long* gbase = slot.gacc + (size_t)(slot0 + grp) * GACC_WORDS;
+        long long lo = 0, hi = 0;
+#pragma unroll
+        for (int k = 0; k < SPREAD; k++) {
+            const long long v = __ldcg(gbase + k * BINS + t);
+            gbase[k * BINS + t] = 0;
+            const long long h = v >> DIGITS;
+            hi += h;
+            lo += v - (long long)((unsigned long long)h << DIGITS);
+        }
+        if (t == BINS - 1) { lo += (long long)((unsigned long long)hi << DIGITS); hi = 0; }
+        smem[grp * BINS + t] = lo;
+        s_hi[grp * BINS + t] = hi;
+    }
+    __syncthreads();
+    if (grp < K && t > 0 && t < BINS) smem[grp * BINS + t] += s_hi[grp * BINS + t - 1];
+    __syncthreads();
+    if (grp < K && t == 0) publish_result(smem + grp * BINS, slot, slot0 + grp);
+    __syncthreads();
+    if (grp < K && t < BINS) slot.result[slot0 + grp].acc[t] = smem[grp * BINS + t];
+    __threadfence();
+    __syncthreads();
+    return true;
+}
+
 }  // namespace sa
 }  // namespace dgb
