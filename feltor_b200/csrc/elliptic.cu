@@ -73,6 +73,11 @@ extern "C" int dgb_axpby(size_t, double, const double*, double, double*, dgb_str
 static int elliptic2d_symv_plain(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                                  bool force_unfused);
 
+static bool env_unfused_helm() {
+    static int v = -1;
+    if (v < 0) { const char* e = getenv("DGB_ELLIPTIC_UNFUSED"); v = (e && atoi(e)) ? 1 : 0; }
+    return v != 0;
+}
 // GeneralHelmholtz::symv (helmholtz.h:74-80): only the two-operand form exists in the reference
 int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                     bool force_unfused) {
@@ -81,9 +86,9 @@ int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double bet
         set_error("dgb_elliptic2d_symv: a Helmholtz plan supports symv(x, y) only (alpha = 1, beta = 0), as the reference");
         return DGB_ERR_UNSUPPORTED;
     }
-    if (!force_unfused && elliptic2d_walker_supported(p) && !p.chi[0] && !p.chi[1] && !p.chi[2] && !p.chi[3] && !p.chi_weight_jump &&
-        p.sigma && x != y)
-        return elliptic2d_fused_launch(p, 1., x, 0., y, st);  // the walker applies the Helmholtz epilogue itself
+    if (!force_unfused && !env_unfused_helm() && p.fusable && p.helm_alpha != 0. && !p.chi[0] && !p.chi[1] && !p.chi[2] && !p.chi[3] &&
+        !p.chi_weight_jump && p.sigma && x != y)
+        return elliptic2d_fused_launch(p, 1., x, 0., y, st);  // both fused kernels apply the Helmholtz epilogue themselves
     int e = 0;
     if (p.helm_alpha != 0.) { if ((e = elliptic2d_symv_plain(p, 1., x, 0., y, st, true))) return e; }
     dgb_stream_t s = reinterpret_cast<dgb_stream_t>(st);

@@ -38,6 +38,9 @@ struct FusedArgs {
     const double* x;
     double* y;
     double alpha, beta, jfactor;
+    int helm;                 // GeneralHelmholtz epilogue: y = chi x - helm_alpha y (helmholtz.h:74-80)
+    double helm_alpha;
+    const double* helm_chi;
     // optional fused dot(x, w, y) of the PCG step (pcg.h:165-166): products round(round(x*w)*y)
     const double* dot_w;
     sa::DotSlot slot;
@@ -326,7 +329,11 @@ __device__ __forceinline__ void compute_tile(const FusedArgs& A, const EllipticC
             double t = so[i * OC + 32 * j];
             if (A.vol) t = __ddiv_rn(t, vin[i][j]);
             const double b = A.beta == 0. ? 0. : __dmul_rn(yin[i][j], A.beta);
-            const double v = __fma_rn(A.alpha, t, b);
+            double v = __fma_rn(A.alpha, t, b);
+            if (A.helm) {  // pointwiseDot(1., chi, x, -helm_alpha, y): y *= -helm_alpha; y = fma(1*chi, x, y)
+                const double c = A.helm_chi ? __ldg(A.helm_chi + gbase + (size_t)i * LDG + 32 * j) : 1.;
+                v = __fma_rn(__dmul_rn(1., c), sxr[i * XC + 32 * j], __dmul_rn(v, -A.helm_alpha));
+            }
             A.y[gbase + (size_t)i * LDG + 32 * j] = v;
             if (DOT) {
                 double pr = __dmul_rn(__dmul_rn(sxr[i * XC + 32 * j], win[i][j]), v);
@@ -426,6 +433,7 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
     A.ntiles = A.ntx * ((A.Ny + TY - 1) / TY);
     A.sigma = p.sigma; A.vol = p.vol; A.x = x; A.y = y;
     A.alpha = alpha; A.beta = beta; A.jfactor = p.jfactor;
+    A.helm = p.helm ? 1 : 0; A.helm_alpha = p.helm_alpha; A.helm_chi = p.helm_chi;
     A.dot_w = nullptr; A.pcg = nullptr; A.slot = sa::DotSlot{nullptr, nullptr, nullptr, nullptr};
     if (DOT) { A.dot_w = fd->w; A.slot = fd->slot; A.pcg = fd->pcg; }
     CUtensorMap mx, ms;

@@ -365,7 +365,7 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
     if (std::sqrt(s.results_host[3].value) < tol) { *iterations = 0; return 0; }  // pcg.h:157
     const bool identity_chi = !A.chi[0] && !A.chi[1] && !A.chi[2] && !A.chi[3];
     const bool fused = A.fusable && identity_chi && !A.chi_weight_jump && (dist || !getenv("DGB_ELLIPTIC_UNFUSED")) &&
-                       (!A.helm || elliptic2d_walker_supported(A));  // only the walker knows the Helmholtz epilogue
+                       (!A.helm || A.helm_alpha != 0.);
     FusedDot fd{W, s.slot, s.st};
     const unsigned g2 = grid_for(n, 2);
     static int k2_variant = -1;  // experiment knob: 0 register prefetch, 2 CTAs/SM   1 no prefetch, 4 CTAs/SM   2 no prefetch, 3 CTAs/SM
@@ -378,7 +378,16 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
     }
     int i = 1;
     while (i < max_iter) {
-        int stop = i + s.check_every < max_iter ? i + s.check_every : max_iter;
+        // a batch ends where the host looks at the device state.  Convergence can only be raised by an iteration that
+        // tests the residual (i % test_frequency == 0), so with test_frequency > 1 the batch ends right after such an
+        // iteration instead of at an arbitrary one (coarse multigrid stages test every 10th iteration, multigrid.h:646)
+        int stop = i + s.check_every;
+        if (test_frequency > 1) {
+            const int next_test = (i / test_frequency + 1) * test_frequency;  // first tested iteration >= i (i itself if divisible: handled by +1 below)
+            stop = (i % test_frequency == 0 ? i : next_test) + 1;
+            while (stop - i < s.check_every / 2) stop += test_frequency;       // keep batches from getting tiny
+        }
+        if (stop > max_iter) stop = max_iter;
         for (; i < stop; i++) {
             const bool prof = s.profile && s.prof_n < Pcg::PROF_MAX;
             const int check = i % test_frequency == 0;

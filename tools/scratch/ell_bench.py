@@ -26,7 +26,7 @@ for bcx, bcy, name in ((T.DIR, T.PER, "DIRxPER"), (T.PER, T.PER, "PERxPER")):
         t = float(np.median(ts))
         print(f"{name} {dname}: fused {t:7.1f} us  {24*g.size/t/1e3:7.1f} GB/s  bitwise==unfused: {same}", flush=True)
 g = T.Grid([0., 0.], [np.pi, 2 * np.pi], 3, [N, N], [T.DIR, T.PER])
-E = Elliptic2d(g, T.DIR, T.PER, T.FORWARD, 1.0)
+E = Elliptic2d(g, T.DIR, T.PER, T.CENTERED if os.environ.get("DIRN") == "cen" else T.FORWARD, 1.0)
 E.set_chi(torch.from_numpy(g.evaluate(lambda x, y: 1. + 0.9 * np.sin(x) * np.sin(y)).copy()).cuda())
 b = torch.from_numpy(g.evaluate(lambda x, y: np.sin(x) * np.sin(y)).copy()).cuda()
 x = torch.zeros_like(b)
