@@ -258,6 +258,21 @@ DGB_API int dgb_ds_centered_fused(int num_rows, int nplanes, const int* plus_pos
                                   const double* minus_val, double alpha, const double* f, const double* bphi,
                                   double delta_phi, double beta, double* g, dgb_stream_t s);
 
+/* Dedicated gather layout for the field-line interpolation matrices (north star item 4): the CSR matrix is converted
+ * once into sliced ELL (32-row slices, entries of a slice stored [k][lane]) so that a warp reads indices / values
+ * coalesced; summation order = CSR order, results bitwise equal to dgb_csr_spmv_planes / dgb_ds_centered_fused. */
+typedef struct dgb_gather_plan dgb_gather_plan;
+DGB_API int dgb_gather_plan_create(dgb_gather_plan** plan, int num_rows, int num_cols, const int* row_offsets_dev,
+                                   const int* cols_dev, const double* vals_dev, dgb_stream_t s);
+DGB_API int dgb_gather_plan_destroy(dgb_gather_plan* plan);
+/* y[pl] = alpha M x[(pl + shift) mod nplanes] + beta y[pl] for all planes (Fieldaligned::ePlus/eMinus core) */
+DGB_API int dgb_gather_spmv_planes(const dgb_gather_plan* plan, double alpha, const double* x, double beta, double* y,
+                                   int nplanes, int shift, dgb_stream_t s);
+/* DS::centered(alpha, f, beta, g) (ds.h:481-485), periodic z, one launch */
+DGB_API int dgb_gather_ds_centered(const dgb_gather_plan* plus, const dgb_gather_plan* minus, int nplanes, double alpha,
+                                   const double* f, const double* bphi, double delta_phi, double beta, double* g,
+                                   dgb_stream_t s);
+
 /* ---------------------------------------------------------------------------------------------------
  * Fused Elliptic2d: replaces the 8-kernel composition of Elliptic2d::symv inc/dg/elliptic.h:428-458
  *   y = alpha/vol * [ -Lx sigma (chi_xx Rx + chi_xy Ry) x - Ly sigma (chi_yx Rx + chi_yy Ry) x

@@ -113,3 +113,42 @@ def test_ds_formulas_and_fused_centered(G):
         lib().ds_apply(2, N, C.c_double(al), ptr(d["fm"]), ptr(d["fp"]), None, None, ptr(d["bphi"]), None, C.c_double(dphi),
                        C.c_double(beta), ptr(g2), stream())
         assert same_bits(G.get(g1), G.get(g2)), beta
+
+
+@pytest.mark.parametrize("n,nz,maxlen", [(700, 7, 35), (1000, 64, 90), (33, 1, 5), (4096, 9, 40)])
+def test_gather_plan_equals_csr_kernels(G, n, nz, maxlen):
+    """the sliced-ELL gather plan (dgb_gather_*) == the CSR kernels bit for bit: all-planes SpMV for every beta / shift,
+    fused DS::centered; ragged rows including empty ones"""
+    from feltor_b200 import lib
+    from feltor_b200._dev import ptr, stream
+    r = rng(n + nz)
+    pos, idx, val = stencil_csr(r, n, 30, maxlen)
+    counts = np.diff(pos)
+    # make some rows empty
+    keep = r.uniform(0, 1, n) > 0.05
+    sel = np.repeat(keep, counts)
+    idx, val = idx[sel], val[sel]
+    pos = np.concatenate([[0], np.cumsum(counts * keep)]).astype(np.int32)
+    mpos, midx, mval = stencil_csr(r, n, 25, maxlen)
+    dP, dM = dev_csr(G, pos, idx, val), dev_csr(G, mpos, midx, mval)
+    hp, hm = C.c_void_p(), C.c_void_p()
+    lib().gather_plan_create(C.byref(hp), n, n, ptr(dP[0]), ptr(dP[1]), ptr(dP[2]), stream())
+    lib().gather_plan_create(C.byref(hm), n, n, ptr(dM[0]), ptr(dM[1]), ptr(dM[2]), stream())
+    f, y0 = r.uniform(-1, 1, n * nz), r.uniform(-1, 1, n * nz)
+    df = G.make(f)
+    for alpha, beta, shift in ((1., 0., 1), (0.7, 1., -1), (-1.3, 0.4, 0)):
+        a = G.make(y0 if beta != 0. else np.full(n * nz, np.nan))
+        b = G.make(y0 if beta != 0. else np.full(n * nz, np.nan))
+        lib().csr_spmv_planes(n, n, ptr(dP[0]), ptr(dP[1]), ptr(dP[2]), C.c_double(alpha), ptr(df), C.c_double(beta), ptr(a), nz, shift, stream())
+        lib().gather_spmv_planes(hp, C.c_double(alpha), ptr(df), C.c_double(beta), ptr(b), nz, shift, stream())
+        assert same_bits(G.get(a), G.get(b)), (alpha, beta, shift)
+    bphi = G.make(r.uniform(0.5, 1.5, n * nz))
+    for beta in (0., -0.3):
+        a = G.make(y0 if beta != 0. else np.full(n * nz, np.nan))
+        b = G.make(y0 if beta != 0. else np.full(n * nz, np.nan))
+        lib().ds_centered_fused(n, nz, ptr(dP[0]), ptr(dP[1]), ptr(dP[2]), ptr(dM[0]), ptr(dM[1]), ptr(dM[2]), C.c_double(0.7),
+                                ptr(df), ptr(bphi), C.c_double(0.1), C.c_double(beta), ptr(a), stream())
+        lib().gather_ds_centered(hp, hm, nz, C.c_double(0.7), ptr(df), ptr(bphi), C.c_double(0.1), C.c_double(beta), ptr(b), stream())
+        assert same_bits(G.get(a), G.get(b)), beta
+    lib().gather_plan_destroy(hp)
+    lib().gather_plan_destroy(hm)
