@@ -202,6 +202,21 @@ int ref_csr_symv(int nrows, int ncols, int nnz, const int* pos, const int* idx, 
     return 0;
 }
 
+// handle-based variant: the matrix is built once (what Fieldaligned does), only the symv is timed / repeated
+void* ref_csr_create(int nrows, int ncols, int nnz, const int* pos, const int* idx, const double* val) {
+    thrust::host_vector<int> p(pos, pos + nrows + 1), c(idx, idx + nnz);
+    thrust::host_vector<double> v(val, val + nnz);
+    dg::IHMatrix hm(nrows, ncols, p, c, v);
+    return new dg::IDMatrix(hm);
+}
+void ref_csr_free(void* h) { delete (dg::IDMatrix*)h; }
+int ref_csr_apply(void* h, int nrows, int ncols, double alpha, const double* x, double beta, double* y) {
+    CView vx(x, ncols);
+    VView vy(y, nrows);
+    try { dg::blas2::symv(alpha, *(dg::IDMatrix*)h, vx, beta, vy); } catch (std::exception& e) { return 1; }
+    return 0;
+}
+
 // ---------------------------------------------------------------- blas1 (inc/dg/blas1.h)
 void ref_copy(int n, const double* x, double* y) { CView a(x, n); VView b(y, n); dg::blas1::copy(a, b); }
 void ref_scal(int n, double* x, double a) { VView v(x, n); dg::blas1::scal(v, a); }

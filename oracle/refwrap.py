@@ -161,6 +161,24 @@ def csr_symv(nrows, ncols, pos, idx, val, alpha, x, beta, y):
                               C.c_double(beta), dp(y))
 
 
+class Csr:
+    """the reference's IDMatrix built once (Fieldaligned keeps its interpolation matrices), symv per call"""
+
+    def __init__(self, nrows, ncols, pos, idx, val):
+        lib().ref_csr_create.restype = C.c_void_p
+        self.nrows, self.ncols = nrows, ncols
+        self.h = C.c_void_p(lib().ref_csr_create(nrows, ncols, len(val), ip(pos), ip(idx), dp(val)))
+
+    def symv(self, alpha, x, beta, y):
+        return lib().ref_csr_apply(self.h, self.nrows, self.ncols, C.c_double(alpha), dp(x), C.c_double(beta), dp(y))
+
+    def __del__(self):
+        try:
+            lib().ref_csr_free(self.h)
+        except Exception:
+            pass
+
+
 def dot2(x, y):
     acc = np.zeros(39, dtype=np.int64)
     st = lib().ref_dot2(x.size, dp(x), dp(y), lp(acc))

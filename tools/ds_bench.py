@@ -106,12 +106,13 @@ for name, cpd in (("dg (36 per row)", 2), ("cubic (81 per row)", 3)):
             hf = f.cpu().numpy()
             hb = bphi.cpu().numpy()
             tp, tm, hg = np.zeros(size), np.zeros(size), np.zeros(size)
+            rP, rM = R.Csr(rows, rows, hP[0], hP[1], hP[2]), R.Csr(rows, rows, hM[0], hM[1], hM[2])
             t0 = time.time()
             for k in range(Nz):  # Fieldaligned::ePlus / eMinus: one symv per plane (fieldaligned.h:850-912), then the formula
-                R.csr_symv(rows, rows, hP[0], hP[1], hP[2], 1., hf[((k + 1) % Nz) * rows:((k + 1) % Nz + 1) * rows], 0., tp[k * rows:(k + 1) * rows])
-                R.csr_symv(rows, rows, hM[0], hM[1], hM[2], 1., hf[((k - 1) % Nz) * rows:((k - 1) % Nz + 1) * rows], 0., tm[k * rows:(k + 1) * rows])
+                rP.symv(1., hf[((k + 1) % Nz) * rows:((k + 1) % Nz + 1) * rows], 0., tp[k * rows:(k + 1) * rows])
+                rM.symv(1., hf[((k - 1) % Nz) * rows:((k - 1) % Nz + 1) * rows], 0., tm[k * rows:(k + 1) * rows])
             hg[:] = 1. * hb * (tp - tm) / 2. / dphi
             tr = time.time() - t0
-            print(f"{name:20s} reference OpenMP CSR x {2*Nz} planes + numpy formula {tr*1e6:9.1f} us  {alg/tr/1e9:8.1f} GB/s  ({R.lib().ref_get_max_threads()} host threads)", flush=True)
+            print(f"{name:20s} reference OpenMP CSR x {2*Nz} planes + numpy formula {tr*1e6:9.1f} us  {alg/tr/1e9:8.2f} GB/s  ({R.lib().ref_get_max_threads()} host threads)", flush=True)
     t2 = timeit(composed, args.reps)
     print(f"{name:20s} ePlus + eMinus + formula {t2*1e6:9.1f} us  {alg/t2/1e9:8.1f} GB/s  {alg/t2/1e9/PEAK*100:5.1f}% (same algorithmic bytes)", flush=True)
