@@ -305,7 +305,8 @@ __device__ __forceinline__ void ld_cell(const double* slot, int e, double (&dst)
         for (int b = 0; b < N; b++) dst[a][b] = slot[a * RP + e + b];
 }
 
-template <int N, int DIRK, bool DOT>
+// PLAIN: alpha-only epilogue (beta == 0, no volume form, no Helmholtz term) known at compile time -- the hot variants
+template <int N, int DIRK, bool DOT, bool PLAIN>
 __global__ void __launch_bounds__((WL<N, DIRK, DOT>::THREADS), 1)
 elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_constant__ EllipticCoef<N, Offs<DIRK>::BPL> C,
                          const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_s,
@@ -460,7 +461,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                 const double* x0 = xrow(iy);
                 // beta != 0 / curvilinear volume: the epilogue reads y / vol with lane-strided loads; pull the lines into L1
                 // now so that the latency is gone by then (hot loops use beta == 0, vol == nullptr)
-                if ((A.beta != 0. || A.vol != nullptr) && outlane) {
+                if (!PLAIN && (A.beta != 0. || A.vol != nullptr) && outlane) {
                     const size_t gp = (size_t)(iy * N) * LD + (size_t)gx * N;
 #pragma unroll
                     for (int ky = 0; ky < N; ky++) {
@@ -532,7 +533,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                 }
                 if (outlane) {
                     const size_t gb = (size_t)(iy * N) * LD + (size_t)gx * N;
-                    if (A.vol != nullptr || A.beta != 0.) {
+                    if (!PLAIN && (A.vol != nullptr || A.beta != 0.)) {
                         double yo[N][N], vo[N][N];  // all loads first: their latencies overlap
 #pragma unroll
                         for (int ky = 0; ky < N; ky++)
@@ -557,7 +558,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
 #pragma unroll
                             for (int kx = 0; kx < N; kx++) acc[ky][kx] = __fma_rn(A.alpha, acc[ky][kx], 0.);
                     }
-                    if (A.helm) {  // pointwiseDot(1., chi, x, -helm_alpha, y): y *= -helm_alpha; y = fma(1*chi, x, y)
+                    if (!PLAIN && A.helm) {  // pointwiseDot(1., chi, x, -helm_alpha, y): y *= -helm_alpha; y = fma(1*chi, x, y)
                         const double mha = -A.helm_alpha;
 #pragma unroll
                         for (int ky = 0; ky < N; ky++)
@@ -705,14 +706,14 @@ static int build_partition(WalkPartition& P, int Nx, int Ny, int UL, int HL, int
     return 0;
 }
 
-template <int N, int DIRK, bool DOT>
+template <int N, int DIRK, bool DOT, bool PLAIN>
 static int wlaunch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st, const FusedDot* fd) {
     constexpr int B = Offs<DIRK>::BPL;
     using L = WL<N, DIRK, DOT>;
     static bool configured = false;
     static int no_tma = -1;
     if (!configured) {
-        DGB_CUDA(cudaFuncSetAttribute(elliptic2d_walker_kernel<N, DIRK, DOT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+        DGB_CUDA(cudaFuncSetAttribute(elliptic2d_walker_kernel<N, DIRK, DOT, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
         configured = true;
     }
     if (no_tma < 0) { const char* e = getenv("DGB_NO_TMA"); no_tma = (e && atoi(e)) ? 1 : 0; }
@@ -753,7 +754,7 @@ static int wlaunch(Elliptic2dPlan& p, double alpha, const double* x, double beta
     EllipticCoef<N, B> C;
     fill<N, B>(C.rx, p.rightx); fill<N, B>(C.ry, p.righty); fill<N, B>(C.lx, p.leftx); fill<N, B>(C.ly, p.lefty);
     fill<N, 3>(C.jx, p.jumpx); fill<N, 3>(C.jy, p.jumpy);
-    elliptic2d_walker_kernel<N, DIRK, DOT><<<grid, L::THREADS, L::BYTES, st>>>(A, C, mx, ms, mw, my);
+    elliptic2d_walker_kernel<N, DIRK, DOT, PLAIN><<<grid, L::THREADS, L::BYTES, st>>>(A, C, mx, ms, mw, my);
     DGB_LAUNCHED();
     return 0;
 }
@@ -785,9 +786,11 @@ bool elliptic2d_walker_supported(const Elliptic2dPlan& p) {
 
 int elliptic2d_walker_launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                              const FusedDot* fd) {
-#define DGB_WCASE(NN, DD)                                                         \
-    case NN * 10 + DD:                                                            \
-        return fd ? wlaunch<NN, DD, true>(p, 1., x, 0., y, st, fd) : wlaunch<NN, DD, false>(p, alpha, x, beta, y, st, nullptr);
+    const bool plain = !p.helm && !p.vol && (fd || beta == 0.);
+#define DGB_WCASE(NN, DD)                                                                                          \
+    case NN * 10 + DD:                                                                                             \
+        if (fd) return plain ? wlaunch<NN, DD, true, true>(p, 1., x, 0., y, st, fd) : wlaunch<NN, DD, true, false>(p, 1., x, 0., y, st, fd); \
+        return plain ? wlaunch<NN, DD, false, true>(p, alpha, x, beta, y, st, nullptr) : wlaunch<NN, DD, false, false>(p, alpha, x, beta, y, st, nullptr);
     switch (p.n * 10 + p.dirk) {
         DGB_WCASE(2, 0) DGB_WCASE(2, 1) DGB_WCASE(2, 2)
         DGB_WCASE(3, 0) DGB_WCASE(3, 1) DGB_WCASE(3, 2)
