@@ -127,3 +127,14 @@ OPS = {"exp": 0, "ln": 1, "sqrt": 2, "invert": 3, "abs": 4, "square": 5, "invsqr
 def transform(x, y, op):
     """blas1.h:585 with a functor of inc/dg/functors.h named by `op`."""
     lib().transform(_n(x, y), OPS[op], ptr(x), ptr(y), stream())
+
+
+REDUCE = {"sum": 0, "max": 1, "min": 2, "or": 3}
+UNARY = {"identity": 0, "abs": 1, "square": 2, "isnan": 3, "isnotfinite": 4}
+
+
+def reduce(x, init, op, unary="identity"):
+    """blas1.h:213-223 for the closed set of (binary, unary) functors of include/dgb200.h"""
+    out = C.c_double()
+    lib().reduce(x.numel(), ptr(x), REDUCE[op], UNARY[unary], d(init), C.byref(out), stream())
+    return out.value

@@ -133,6 +133,13 @@ typedef struct dgb_dot_result {
     int32_t status;             /* 0 ok, 1 a product was NaN/Inf (blas1.h:161) */
     int32_t pad;
 } dgb_dot_result;
+/* dg::blas1::reduce(x, init, binary_op, unary_op) (blas1.h:213-223, blas1_cuda.cuh:96-102) for the (op, unary) pairs the
+ * library and the applications use; synchronous like the reference (returns the value on the host).  Max / min / or are
+ * order independent; SUM is a plain floating-point sum (not reproducible, as in the reference) -- the exact sums are
+ * dgb_dot2/3 with a scalar operand (blas1::vdot, dot(1., x)). */
+enum { DGB_REDUCE_SUM = 0, DGB_REDUCE_MAX = 1, DGB_REDUCE_MIN = 2, DGB_REDUCE_OR = 3 };
+enum { DGB_UNARY_IDENTITY = 0, DGB_UNARY_ABS = 1, DGB_UNARY_SQUARE = 2, DGB_UNARY_ISNAN = 3, DGB_UNARY_ISNOTFINITE = 4 };
+DGB_API int dgb_reduce(size_t n, const double* x, int op, int unary, double init, double* result_host, dgb_stream_t s);
 typedef struct dgb_dot_ws dgb_dot_ws; /* device scratch: per-block partial superaccumulators + ticket */
 DGB_API int dgb_dot_ws_create(dgb_dot_ws** ws);
 DGB_API int dgb_dot_ws_destroy(dgb_dot_ws* ws);

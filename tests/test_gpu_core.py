@@ -290,3 +290,30 @@ def test_ell_full_size_properties(G):
     y = torch.empty_like(x)
     G.symv(m, 1., c, 0., y)
     assert float(y.abs().max()) < 1e-9
+
+
+@pytest.mark.parametrize("n", [1, 31, 1000, 300001])
+def test_reduce_closed_set(G, n):
+    """blas1::reduce for max / min / logical-or (order independent: exact) and sum (to rounding); blas1_t.cpp reduce snippets"""
+    from feltor_b200 import blas1
+    r = rng(n)
+    x = r.uniform(-3, 3, n)
+    dx = G.make(x)
+    assert blas1.reduce(dx, -1e300, "max") == x.max()
+    assert blas1.reduce(dx, 1e10, "min") == min(1e10, x.min())
+    assert blas1.reduce(dx, 0., "max", "abs") == np.abs(x).max()
+    assert blas1.reduce(dx, 0., "or", "isnan") == 0.
+    assert abs(blas1.reduce(dx, 0., "sum", "square") - np.sum(x * x)) <= 1e-12 * np.sum(x * x)
+    x[n // 2] = np.nan
+    assert blas1.reduce(G.make(x), 0., "or", "isnan") == 1.
+    x[n // 2] = np.inf
+    assert blas1.reduce(G.make(x), 0., "or", "isnan") == 0. and blas1.reduce(G.make(x), 0., "or", "isnotfinite") == 1.
+
+
+def test_vdot_is_the_exact_dot_with_a_scalar_operand(G):
+    """blas1::vdot(identity, x) / dot(1., x): the superaccumulator kernels accept scalar operands (SURVEY 8b)"""
+    from feltor_b200 import blas2
+    x = wide(rng(5), 5000, -40, 40)
+    got = blas2.dot(1., G.make(x))
+    import math
+    assert got == math.fsum(x)
