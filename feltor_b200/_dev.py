@@ -19,7 +19,10 @@ def ptr(t):
 
 def dvec(a):
     """Host numpy array -> device tensor (dtype preserved)."""
-    return torch.from_numpy(np.ascontiguousarray(a)).cuda()
+    a = np.ascontiguousarray(a)
+    if not a.flags.writeable:  # e.g. a broadcast view: torch refuses to wrap read-only memory silently
+        a = a.copy()
+    return torch.from_numpy(a).cuda()
 
 
 def hvec(t):
