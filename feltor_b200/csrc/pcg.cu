@@ -151,9 +151,13 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
         fzr.add(b0, my_zr);
     }
     // both dots leave together: one fence / ticket sequence
-    if (CHECK) { frr.merge(frr1, my_rr); frr.flush_warp(my_rr); }
     fzr.merge(fzr1, my_zr);
-    fzr.flush_warp(my_zr);
+    if (CHECK) {
+        frr.merge(frr1, my_rr);
+        sa::flush_warp2(frr, my_rr, fzr, my_zr);
+    } else {
+        fzr.flush_warp(my_zr);
+    }
     const bool last = CHECK ? sa::block_finish_multi<2>(smem, bad, slot, 1) : sa::block_finish_multi<1>(my_zr, bad, slot, 2);
     if (last && threadIdx.x == 0 && !st->dist) {
         if (CHECK) pcg_after_rr(st, slot.result + 1, iter);

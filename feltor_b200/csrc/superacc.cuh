@@ -184,7 +184,8 @@ struct FpeT {
             for (int i = 0; i < NFP; i++) v[i] = __shfl_down_sync(0xffffffffu, a[i], off);
             if (lane < off) {
 #pragma unroll
-                for (int i = 0; i < NFP; i++) add(v[i], acc);
+                for (int i = 0; i < NFP; i++)
+                    if (v[i] != 0.0) add(v[i], acc);  // the tail components are usually zero: skip their add cascades
             }
         }
         if (lane == 0) flush(acc);
@@ -193,6 +194,38 @@ struct FpeT {
     }
 };
 using Fpe = FpeT<NF>;
+
+// flush_warp for two expansions at once: the two shuffle trees are independent, so their add cascades interleave in the
+// FP64 pipe and the serial tail of a kernel that carries two dots is about as long as for one
+template <int NFP>
+__device__ __forceinline__ void flush_warp2(FpeT<NFP>& p, long long* pacc, FpeT<NFP>& q, long long* qacc) {
+    const int lane = threadIdx.x & 31;
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        double v[NFP], w[NFP], rv[NFP], rw[NFP];
+#pragma unroll
+        for (int i = 0; i < NFP; i++) {
+            v[i] = __shfl_down_sync(0xffffffffu, p.a[i], off);
+            w[i] = __shfl_down_sync(0xffffffffu, q.a[i], off);
+        }
+        if (lane < off) {
+            bool spill = false;
+#pragma unroll
+            for (int i = 0; i < NFP; i++) {
+                rv[i] = p.add_lazy(v[i]);
+                rw[i] = q.add_lazy(w[i]);
+                spill = spill || rv[i] != 0.0 || rw[i] != 0.0;
+            }
+            if (spill) {
+#pragma unroll 1
+                for (int i = 0; i < NFP; i++) { accumulate(pacc, rv[i], 1); accumulate(qacc, rw[i], 1); }
+            }
+        }
+    }
+    if (lane == 0) { p.flush(pacc); q.flush(qacc); }
+    else { p.clear(); q.clear(); }
+    __syncwarp();
+}
 
 // ---------------------------------------------------------------------------------------------------------
 // Block- and grid-level reduction used by every kernel that carries a fused dot.
@@ -220,7 +253,7 @@ __device__ inline void block_init(long long* smem) {
 // against the streaming loop of the calling kernel
 static __device__ __noinline__ void normalize_noinline(long long* acc) { normalize(acc, 1); }
 static __device__ __noinline__ void publish_result(long long* smem, const DotSlot& slot, int slot_idx) {
-    int negative = normalize(smem, 1);
+    int negative = normalize(smem, 1);  // after prenormalize() below the carry chain is short but must still run in order
     dgb_dot_result* r = slot.result + slot_idx;
     r->value = round_normalized(smem, negative);
     r->status = __ldcg(slot.gstatus + slot_idx);
