@@ -95,7 +95,30 @@ inline EncodeTiledFn encode_fn() {
     return fn;
 }
 // 2-d map over a row-major (rows x ld) array of doubles with a (box_r x box_c) box; false if TMA cannot describe it
+inline bool make_map_uncached(CUtensorMap* m, const double* base, int rows, int ld, int box_r, int box_c);
+// Encoding a tensor map is a driver call of a few microseconds; solvers apply the same operator to the same buffers
+// thousands of times, so the last few descriptors are kept (keyed by everything that goes into them).
 inline bool make_map(CUtensorMap* m, const double* base, int rows, int ld, int box_r, int box_c) {
+    struct Entry { const double* base; int rows, ld, br, bc; bool ok; CUtensorMap map; };
+    constexpr int NE = 16;
+    static Entry cache[NE];
+    static int used = 0, next = 0;
+    for (int i = 0; i < used; i++) {
+        const Entry& e = cache[i];
+        if (e.base == base && e.rows == rows && e.ld == ld && e.br == box_r && e.bc == box_c) {
+            if (e.ok) *m = e.map;
+            return e.ok;
+        }
+    }
+    Entry& e = cache[next];
+    next = (next + 1) % NE;
+    if (used < NE) used++;
+    e.base = base; e.rows = rows; e.ld = ld; e.br = box_r; e.bc = box_c;
+    e.ok = make_map_uncached(&e.map, base, rows, ld, box_r, box_c);
+    if (e.ok) *m = e.map;
+    return e.ok;
+}
+inline bool make_map_uncached(CUtensorMap* m, const double* base, int rows, int ld, int box_r, int box_c) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return false;
     if ((reinterpret_cast<uintptr_t>(base) & 15u) || ((size_t)ld * sizeof(double)) % 16 || box_c > 256 || box_r > 256) return false;
