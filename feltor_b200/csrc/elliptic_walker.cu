@@ -33,7 +33,11 @@ namespace dgb {
 #ifndef DGB_WALK_PD
 #define DGB_WALK_PD 1
 #endif
+#ifndef DGB_WALK_WRING
+#define DGB_WALK_WRING 1  // 1: the weights of the fused dot come through their own TMA ring; 0: lane-strided global loads
+#endif                    // behind an L1 prefetch (frees two ring slots per warp; measured slower: 128 vs 122 us at 12 warps)
 constexpr int WALK_MAX_WARPS = DGB_WALK_WARPS, WALK_PD = DGB_WALK_PD;
+constexpr bool WALK_WRING = DGB_WALK_WRING != 0;
 constexpr int WNOROW = -(1 << 30);
 // keeps the compiler from hoisting the next phase's shared-memory loads above this point (register pressure)
 #define DGB_PHASE_FENCE() asm volatile("" ::: "memory")
@@ -75,7 +79,7 @@ struct WL {
     static constexpr int SLOT = (N * RP * 8 + 127) / 128 * 128 / 8;       // doubles per slot (128-B aligned)
     static constexpr int OP = UL * N;                                      // row pitch of the output staging buffer
     static constexpr int OSLOT = (N * OP * 8 + 127) / 128 * 128 / 8;
-    static constexpr int XOFF = 0, SOFF = XOFF + SX * SLOT, WOFF = SOFF + SS * SLOT, OOFF = WOFF + (DOT ? SW : 0) * SLOT,
+    static constexpr int XOFF = 0, SOFF = XOFF + SX * SLOT, WOFF = SOFF + SS * SLOT, OOFF = WOFF + ((DOT && WALK_WRING) ? SW : 0) * SLOT,
                          BOFF = OOFF + OSLOT, WARP_DOUBLES = BOFF + 16;  // 16 doubles: up to 16 mbarriers
     static constexpr int FIT = (227 * 1024 - 4096) / (WARP_DOUBLES * 8);  // warps whose rings fit into one SM
     // warps come in multiples of 4 (one per scheduler, the register file is per scheduler): 12 warps leave 168
@@ -360,7 +364,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
         while (pt < te) {
             const int r = p_iy0 - HL + pj, rs = r - WX + LY, rw = r - WX;
             const bool needS = rs >= p_iy0 - NP + LY && rs <= p_iy1 - 1 + LY;
-            const bool needW = DOT && rw >= p_iy0 && rw <= p_iy1 - 1;
+            const bool needW = DOT && WALK_WRING && rw >= p_iy0 && rw <= p_iy1 - 1;
             if (xp - xr >= (unsigned)SX || (needS && sp - sr >= (unsigned)SS) || (needW && wp - wr >= (unsigned)SW)) break;
             double* dx = Xr + (xp % SX) * SLOT;
             double* ds = Sr + (sp % SS) * SLOT;
@@ -461,6 +465,11 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                 const double* x0 = xrow(iy);
                 // beta != 0 / curvilinear volume: the epilogue reads y / vol with lane-strided loads; pull the lines into L1
                 // now so that the latency is gone by then (hot loops use beta == 0, vol == nullptr)
+                if (DOT && !WALK_WRING && outlane) {  // weights of the fused dot: same treatment
+                    const size_t gp = (size_t)(iy * N) * LD + (size_t)gx * N;
+#pragma unroll
+                    for (int ky = 0; ky < N; ky++) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.w + gp + (size_t)ky * LD));
+                }
                 if (!PLAIN && (A.beta != 0. || A.vol != nullptr) && outlane) {
                     const size_t gp = (size_t)(iy * N) * LD + (size_t)gx * N;
 #pragma unroll
@@ -581,7 +590,14 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                     }
                     if (DOT) {
                         double WV[N][N], XC[N][N];
-                        ld_cell<N, RP>(wrow(iy), eo, WV);
+                        if (WALK_WRING) {
+                            ld_cell<N, RP>(wrow(iy), eo, WV);
+                        } else {
+#pragma unroll
+                            for (int ky = 0; ky < N; ky++)
+#pragma unroll
+                                for (int kx = 0; kx < N; kx++) WV[ky][kx] = __ldg(A.w + gb + (size_t)ky * LD + kx);
+                        }
                         ld_cell<N, RP>(x0, eo, XC);
                         double res[N][N];
                         bool spill = false;
@@ -741,7 +757,7 @@ static int wlaunch(Elliptic2dPlan& p, double alpha, const double* x, double beta
     const int ld = p.Nx * N;
     A.tma_load = !no_tma && make_map(&mx, x - gh, (A.Ny + 2 * A.ghost) * N, ld, N, L::RP) &&
                  make_map(&ms, p.sigma - gh, (A.Ny + 2 * A.ghost) * N, ld, N, L::RP) &&
-                 (!DOT || make_map(&mw, A.w, A.Ny * N, ld, N, L::RP));
+                 (!DOT || !WALK_WRING || make_map(&mw, A.w, A.Ny * N, ld, N, L::RP));
     A.tma_store = !no_tma && make_map(&my, y, A.Ny * N, ld, N, L::OP);
     // one persistent CTA per SM; the work is cut into one cost-weighted piece per warp
     const int grid = sm_count(), nwarps = grid * L::WARPS;
