@@ -24,6 +24,7 @@
 //     of the tile kernel and of the reference's OpenMP backend.
 #include "elliptic_dev.cuh"
 #include <vector>
+#include <type_traits>
 
 namespace dgb {
 
@@ -310,7 +311,9 @@ __device__ __forceinline__ void ld_cell(const double* slot, int e, double (&dst)
 }
 
 // PLAIN: alpha-only epilogue (beta == 0, no volume form, no Helmholtz term) known at compile time -- the hot variants
-template <int N, int DIRK, bool DOT, bool PLAIN>
+// ALLTMA: every load and store of this launch goes through TMA (no periodic seam in x, all operands describable) -- the
+// LDGSTS / direct-store alternatives are compiled out
+template <int N, int DIRK, bool DOT, bool PLAIN, bool ALLTMA>
 __global__ void __launch_bounds__((WL<N, DIRK, DOT>::THREADS), 1)
 elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_constant__ EllipticCoef<N, Offs<DIRK>::BPL> C,
                          const __grid_constant__ CUtensorMap map_x, const __grid_constant__ CUtensorMap map_s,
@@ -357,7 +360,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
         const int cl = t.x * UL - HL;
         p_iy0 = t.y; p_iy1 = t.z;
         p_cs = cl * N - ((cl * N) & 1);
-        p_manual = !A.tma_load || (A.wrapx && (cl < 0 || cl + 32 > A.Nx));
+        p_manual = ALLTMA ? 0 : (!A.tma_load || (A.wrapx && (cl < 0 || cl + 32 > A.Nx)));
     };
     ptask();
     auto produce = [&]() {
@@ -385,7 +388,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                 }
                 if (needW) tma_load_2d(dw, &map_w, b, p_cs, rw * N);  // w has no ghost rows
             }
-            cp_async_commit();  // one (possibly empty) LDGSTS group per tick: group index == tick index
+            if (!ALLTMA) cp_async_commit();  // one (possibly empty) LDGSTS group per tick: group index == tick index
             xp++; sp += needS ? 1u : 0u; wp += needW ? 1u : 0u; tickp++;
             if (++pj == p_iy1 - p_iy0 + HL + WX) { pt++; pj = 0; ptask(); }
         }
@@ -398,7 +401,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
         const int c0 = task.x * UL, iy0 = task.y, iy1 = task.z;
         const int cl = c0 - HL;                              // cell column of lane 0
         const int sh = (cl * N) & 1;                         // the box starts at an even element column
-        const bool manual = !A.tma_load || (A.wrapx && (cl < 0 || cl + 32 > A.Nx));
+        const bool manual = ALLTMA ? false : (!A.tma_load || (A.wrapx && (cl < 0 || cl + 32 > A.Nx)));
         const int fx = iy0 - HL, nticks = iy1 - iy0 + HL + WX, s0row = iy0 - NP + LY;
         const int gx = gcell(cl + lane, A.Nx, A.wrapx);      // my cell column (wrapped), -1 if it does not exist
         const bool outlane = lane >= HL && lane < HL + UL && cl + lane < A.Nx;
@@ -428,6 +431,11 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
             const bool fast = fastx && fasty;
             const bool emit = iy >= iy0;
 
+            double acc[N][N];  // [ky][kx] the cell's outputs (valid when emit)
+            // the whole stencil part of the step exists twice, FAST (interior rows everywhere, constant-bank blocks) and
+            // general, selected by ONE warp-uniform branch
+            auto stencils = [&](auto fast_tag) {
+                constexpr bool FAST = decltype(fast_tag)::value;
             // ---- GY(R) = sigma(R) * (Ry x)(R), R = iy + LY: operands are the cell's own column in rows R-1, R, R+1
             {
                 const int R = iy + LY;
@@ -440,7 +448,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
 #pragma unroll
                     for (int b = 0; b < N; b++) g[a][b] = 0.;
                 bool ong = true;
-                if (fast) {
+                if (FAST) {
                     stencil_mem<N, RK, true, 1, RP, true>(A.ry, C.ry, 0, pa, pb, pc, 1., g);
                 } else {
                     const int my = w_ymat(R, A);
@@ -478,8 +486,8 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                         if (A.vol != nullptr) asm volatile("prefetch.global.L1 [%0];" ::"l"(A.vol + gp + (size_t)ky * LD));
                     }
                 }
-                const int ym = fast ? 0 : w_ymat(iy, A);
-                const bool on = fast || gx >= 0;
+                const int ym = FAST ? 0 : w_ymat(iy, A);
+                const bool on = FAST || gx >= 0;
                 // ---- GX(iy) for my cell, then the neighbours' by shuffle
                 double gxv[N][N], gxm[N][N], gxp[N][N];
                 {
@@ -488,7 +496,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
 #pragma unroll
                         for (int b = 0; b < N; b++) gxv[a][b] = 0.;
                     if (on) {
-                        if (fast) stencil_mem<N, RK, true, RP, 1, false>(A.rx, C.rx, 0, x0 + el, x0 + eo, x0 + er, 1., gxv);
+                        if (FAST) stencil_mem<N, RK, true, RP, 1, false>(A.rx, C.rx, 0, x0 + el, x0 + eo, x0 + er, 1., gxv);
                         else stencil_mem<N, RK, false, RP, 1, false>(A.rx, C.rx, gx, x0 + el, x0 + eo, x0 + er, 1., gxv);
                         double S0[N][N];
                         ld_cell<N, RP>(srow(iy), eo, S0);
@@ -507,36 +515,41 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                 }
                 DGB_PHASE_FENCE();
                 // ---- the cell's n x n outputs
-                double acc[N][N];  // [ky][kx]
 #pragma unroll
                 for (int a = 0; a < N; a++)
 #pragma unroll
                     for (int b = 0; b < N; b++) acc[a][b] = 0.;
                 if (on) {
                     // Ly ty (alpha = 1, beta = 0): GY rows iy-1, iy, iy+1 = gy[-1-LLO], gy[-LLO], gy[1-LLO]
-                    if (fast) stencil_lines<N, LK, true, true>(A.ly, C.ly, 0, gy[LK == 0 ? 0 : -1 - LLO], gy[-LLO], gy[LK == 1 ? -LLO : 1 - LLO], 1., acc);
-                    else stencil_lines<N, LK, false, true>(A.ly, C.ly, ym, gy[LK == 0 ? 0 : -1 - LLO], gy[-LLO], gy[LK == 1 ? -LLO : 1 - LLO], 1., acc);
+                    if (FAST) stencil_lines<N, LK, true, true>(A.ly, C.ly, 0, gy[LK == 0 ? 0 : -1 - LLO], gy[-LLO], gy[LK == 1 ? -LLO : 1 - LLO], 1., acc);
+                        else stencil_lines<N, LK, false, true>(A.ly, C.ly, ym, gy[LK == 0 ? 0 : -1 - LLO], gy[-LLO], gy[LK == 1 ? -LLO : 1 - LLO], 1., acc);
                     // - Lx tx - t   (alpha = -1, beta = -1)
 #pragma unroll
                     for (int a = 0; a < N; a++)
 #pragma unroll
                         for (int b = 0; b < N; b++) acc[a][b] = __dmul_rn(acc[a][b], -1.);
-                    if (fast) stencil_lines<N, LK, true, false>(A.lx, C.lx, 0, gxm, gxv, gxp, -1., acc);
-                    else stencil_lines<N, LK, false, false>(A.lx, C.lx, gx, gxm, gxv, gxp, -1., acc);
+                    if (FAST) stencil_lines<N, LK, true, false>(A.lx, C.lx, 0, gxm, gxv, gxp, -1., acc);
+                        else stencil_lines<N, LK, false, false>(A.lx, C.lx, gx, gxm, gxv, gxp, -1., acc);
                     DGB_PHASE_FENCE();
                     if (A.jfactor != 0.) {
-                        if (fast) stencil_mem<N, 2, true, RP, 1, false>(A.jx, C.jx, 0, x0 + el, x0 + eo, x0 + er, A.jfactor, acc);
+                        if (FAST) stencil_mem<N, 2, true, RP, 1, false>(A.jx, C.jx, 0, x0 + el, x0 + eo, x0 + er, A.jfactor, acc);
                         else stencil_mem<N, 2, false, RP, 1, false>(A.jx, C.jx, gx, x0 + el, x0 + eo, x0 + er, A.jfactor, acc);
                         DGB_PHASE_FENCE();
                         const double* xd = xrow(iy - 1) + eo;
                         const double* xu = xrow(iy + 1) + eo;
-                        if (fast) stencil_mem<N, 2, true, 1, RP, true>(A.jy, C.jy, 0, xd, x0 + eo, xu, A.jfactor, acc);
+                        if (FAST) stencil_mem<N, 2, true, 1, RP, true>(A.jy, C.jy, 0, xd, x0 + eo, xu, A.jfactor, acc);
                         else stencil_mem<N, 2, false, 1, RP, true>(A.jy, C.jy, ym, xd, x0 + eo, xu, A.jfactor, acc);
                     }
                 }
                 DGB_PHASE_FENCE();
+                }
+            };
+            if (fast) stencils(std::true_type{});
+            else stencils(std::false_type{});
+            if (emit) {
+                const double* x0 = xrow(iy);
                 // ---- epilogue  y = fma(alpha, t/vol, beta*y)  (+ the exact dot); staged for the TMA store
-                if (A.tma_store) {
+                if (ALLTMA || A.tma_store) {
                     if (lane == 0) bulk_wait_read<0>();  // the previous store has read the staging buffer
                     __syncwarp();
                 }
@@ -577,7 +590,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                                 acc[ky][kx] = __fma_rn(__dmul_rn(1., c), x0[ky * RP + eo + kx], __dmul_rn(acc[ky][kx], mha));
                             }
                     }
-                    if (A.tma_store) {
+                    if (ALLTMA || A.tma_store) {
 #pragma unroll
                         for (int ky = 0; ky < N; ky++)
 #pragma unroll
@@ -616,7 +629,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                         }
                     }
                 }
-                if (A.tma_store) {
+                if (ALLTMA || A.tma_store) {
                     fence_async_smem();
                     __syncwarp();
                     if (lane == 0) {
@@ -643,8 +656,8 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
             produce();
         }
     }
-    cp_async_wait<0>();
-    if (A.tma_store && lane == 0) bulk_wait<0>();
+    if (!ALLTMA) cp_async_wait<0>();
+    if ((ALLTMA || A.tma_store) && lane == 0) bulk_wait<0>();
     if (DOT) {
 #pragma unroll
         for (int k = 1; k < N; k++) fpe[0].merge(fpe[k], dsm);
@@ -722,16 +735,25 @@ static int build_partition(WalkPartition& P, int Nx, int Ny, int UL, int HL, int
     return 0;
 }
 
+template <int N, int DIRK, bool DOT, bool PLAIN, bool ALLTMA>
+static int wlaunch_go(const WalkArgs& A, const EllipticCoef<N, Offs<DIRK>::BPL>& C, const CUtensorMap& mx, const CUtensorMap& ms,
+                      const CUtensorMap& mw, const CUtensorMap& my, int grid, cudaStream_t st) {
+    using L = WL<N, DIRK, DOT>;
+    static bool configured = false;
+    if (!configured) {
+        DGB_CUDA(cudaFuncSetAttribute(elliptic2d_walker_kernel<N, DIRK, DOT, PLAIN, ALLTMA>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
+        configured = true;
+    }
+    elliptic2d_walker_kernel<N, DIRK, DOT, PLAIN, ALLTMA><<<grid, L::THREADS, L::BYTES, st>>>(A, C, mx, ms, mw, my);
+    DGB_LAUNCHED();
+    return 0;
+}
+
 template <int N, int DIRK, bool DOT, bool PLAIN>
 static int wlaunch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st, const FusedDot* fd) {
     constexpr int B = Offs<DIRK>::BPL;
     using L = WL<N, DIRK, DOT>;
-    static bool configured = false;
     static int no_tma = -1;
-    if (!configured) {
-        DGB_CUDA(cudaFuncSetAttribute(elliptic2d_walker_kernel<N, DIRK, DOT, PLAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L::BYTES));
-        configured = true;
-    }
     if (no_tma < 0) { const char* e = getenv("DGB_NO_TMA"); no_tma = (e && atoi(e)) ? 1 : 0; }
     WalkArgs A;
     A.rx = view(p.rightx); A.ry = view(p.righty); A.lx = view(p.leftx); A.ly = view(p.lefty);
@@ -770,9 +792,8 @@ static int wlaunch(Elliptic2dPlan& p, double alpha, const double* x, double beta
     EllipticCoef<N, B> C;
     fill<N, B>(C.rx, p.rightx); fill<N, B>(C.ry, p.righty); fill<N, B>(C.lx, p.leftx); fill<N, B>(C.ly, p.lefty);
     fill<N, 3>(C.jx, p.jumpx); fill<N, 3>(C.jy, p.jumpy);
-    elliptic2d_walker_kernel<N, DIRK, DOT, PLAIN><<<grid, L::THREADS, L::BYTES, st>>>(A, C, mx, ms, mw, my);
-    DGB_LAUNCHED();
-    return 0;
+    if (A.tma_load && A.tma_store && !A.wrapx) return wlaunch_go<N, DIRK, DOT, PLAIN, true>(A, C, mx, ms, mw, my, grid, st);
+    return wlaunch_go<N, DIRK, DOT, PLAIN, false>(A, C, mx, ms, mw, my, grid, st);
 }
 
 void elliptic2d_walker_release(Elliptic2dPlan& p) {
