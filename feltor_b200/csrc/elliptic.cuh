@@ -29,7 +29,7 @@ struct Elliptic2dPlan {
     void* walk_part[2] = {nullptr, nullptr};  // work partitions of the walker kernel (plain / fused-dot variant)
 };
 void elliptic2d_walker_release(Elliptic2dPlan& p);
-bool elliptic2d_walker_supported(const Elliptic2dPlan& p);
+bool elliptic2d_walker_supported(const Elliptic2dPlan& p, bool with_dot = false);
 
 int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                     bool force_unfused);

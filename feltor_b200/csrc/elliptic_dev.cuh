@@ -148,6 +148,6 @@ inline void fill(double (&dst)[BPL][N][N], const EllDev& m) {
 
 int elliptic2d_walker_launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                              const FusedDot* fd);
-bool elliptic2d_walker_supported(const Elliptic2dPlan& p);
+
 
 }  // namespace dgb

@@ -475,7 +475,7 @@ int elliptic2d_fused_launch(Elliptic2dPlan& p, double alpha, const double* x, do
 }
 // y = A x fused with dot(x, w, y) and the PCG alpha update (pcg.h:165-166)
 int elliptic2d_fused_launch_dot(Elliptic2dPlan& p, const double* x, double* y, cudaStream_t st, const FusedDot& fd) {
-    if (elliptic2d_walker_supported(p)) return elliptic2d_walker_launch(p, 1., x, 0., y, st, &fd);
+    if (elliptic2d_walker_supported(p, true)) return elliptic2d_walker_launch(p, 1., x, 0., y, st, &fd);
     return dispatch<true>(p, 1., x, 0., y, st, &fd);
 }
 

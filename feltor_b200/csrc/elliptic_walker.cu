@@ -807,7 +807,7 @@ void elliptic2d_walker_release(Elliptic2dPlan& p) {
     }
 }
 
-bool elliptic2d_walker_supported(const Elliptic2dPlan& p) {
+bool elliptic2d_walker_supported(const Elliptic2dPlan& p, bool with_dot) {
     static int off = -1;
     if (off < 0) { const char* e = getenv("DGB_ELLIPTIC_TILE"); off = (e && atoi(e)) ? 1 : 0; }
     static int force = -1;
@@ -817,8 +817,10 @@ bool elliptic2d_walker_supported(const Elliptic2dPlan& p) {
     // measured on B200 (n = 3): the walker wins for the one-sided discretisations from ~512^2 cells on (87 vs 119 us at
     // 1024^2); below that each warp gets too few rows to amortise its pipeline fill, and the centered stencil (28 useful
     // lanes, 250 registers, 8 warps) only draws level with the tile kernel at 1024^2
+    // (118 vs 156 us for the plain apply, equal with the fused dot, where it runs on 8 warps)
     const long long cells = (long long)p.Nx * (p.slab ? p.slab_rows : p.Ny);
-    return p.dirk != 2 && cells >= 400 * 400;
+    if (p.dirk == 2) return !with_dot && cells >= 700 * 700;
+    return cells >= 400 * 400;
 }
 
 int elliptic2d_walker_launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
