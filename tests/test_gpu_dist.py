@@ -15,7 +15,8 @@ def G():
     return gpu_backend
 
 
-@pytest.mark.parametrize("N,bcx,bcy,d", [([40, 24], 1, 0, 0), ([37, 19], 4, 0, 2), ([33, 40], 1, 1, 1), ([64, 16], 0, 0, 0)])
+@pytest.mark.parametrize("N,bcx,bcy,d", [([40, 24], 1, 0, 0), ([37, 19], 4, 0, 2), ([33, 40], 1, 1, 1), ([64, 16], 0, 0, 0),
+                                        ([416, 420], 1, 0, 0), ([420, 416], 0, 0, 1)])  # the last two: large enough for the walker kernel
 def test_slab_symv_equals_global(G, N, bcx, bcy, d):
     from feltor_b200 import topology as T
     from feltor_b200.elliptic import Elliptic2d

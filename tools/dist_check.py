@@ -53,6 +53,34 @@ for N, bcx, bcy, d in (([40, 24], T.DIR, T.PER, T.FORWARD), ([37, 21], T.NEU, T.
     same_dot = val == blas2.dot(dvec(x), E.weights(), dvec(x))
     print(f"rank {rank}/{size} N={N} bc=({bcx},{bcy}) dir={d}: symv {same_symv} pcg {same_pcg} (it {its} vs {it1}) dot {same_dot}", flush=True)
     ok = ok and same_symv and same_pcg and same_dot
+# a grid large enough that every rank's slab takes the walker kernel (>= 400^2 cells per rank) and the peer-memory halo
+# path (equal slabs): symv and a fixed number of PCG iterations, bitwise against the single-GPU run
+N, bcx, bcy, d = [416, 416 * size], T.DIR, T.PER, T.FORWARD
+g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, N, [bcx, bcy])
+r = np.random.default_rng(11)
+chi = 1. + r.uniform(0, 1, g.size)
+x = r.uniform(-1, 1, g.size)
+b = g.evaluate(lambda xx, yy: np.sin(xx) * np.sin(yy) * (1 + np.cos(3 * yy)))
+E = Elliptic2d(g, bcx, bcy, d, 1.0)
+E.set_chi(dvec(chi))
+y = torch.zeros(g.size, dtype=torch.float64, device="cuda")
+E.symv(dvec(x), y)
+p1 = PCG(g.size, 41)
+p1.set_throw_on_fail(False)
+xs1 = torch.zeros(g.size, dtype=torch.float64, device="cuda")
+it1 = p1.solve(E, xs1, dvec(b), E.precond(), E.weights(), 1e-30, 1.0, 1)
+S = SlabElliptic2d(comm, g, bcx, bcy, d, 1.0)
+S.set_chi(dvec(S.local(chi)))
+ys = torch.full((S.size,), float("nan"), dtype=torch.float64, device="cuda")
+S.symv(dvec(S.local(x)), ys)
+same_symv = np.array_equal(hvec(ys).view(np.int64), S.local(hvec(y)).view(np.int64))
+p2 = DistPCG(comm, S.size, 41)
+p2.throw_on_fail = False
+xs = torch.zeros(S.size, dtype=torch.float64, device="cuda")
+its = p2.solve(S, xs, dvec(S.local(b)), S.precond(), S.weights(), 1e-30, 1.0, 1)
+same_pcg = its == it1 and np.array_equal(hvec(xs).view(np.int64), S.local(hvec(xs1)).view(np.int64))
+print(f"rank {rank}/{size} N={N} (walker slabs): symv {same_symv} pcg-40-iterations {same_pcg}", flush=True)
+ok = ok and same_symv and same_pcg
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
