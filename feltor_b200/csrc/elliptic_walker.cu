@@ -675,21 +675,22 @@ struct WalkPartition {
     int* d_tbegin = nullptr;
     int ntasks = 0;
 };
-// measured on B200 (n = 3, 1024^2): a boundary column costs ~2 interior ones, a column filled by LDGSTS ~4
-static double walk_weight(bool manual) {
+// measured on B200 (n = 3, 1024^2): a boundary column costs ~2.3 interior ones, a column filled by LDGSTS ~3
+static double walk_weight(bool manual, bool dot = false) {
     static double wb = -1., wm = -1.;
     if (wb < 0.) {
         const char* e = getenv("DGB_WALK_SLOW_WEIGHT");
-        wb = e ? atof(e) : 2.0;
+        wb = e ? atof(e) : 2.3;
         if (wb < 1.) wb = 1.;
         e = getenv("DGB_WALK_MANUAL_WEIGHT");
-        wm = e ? atof(e) : 4.0;
+        wm = e ? atof(e) : 3.0;
         if (wm < 1.) wm = 1.;
     }
+    if (!manual && dot && !getenv("DGB_WALK_SLOW_WEIGHT")) return 2.0;  // the fused-dot variant (8 warps): measured optimum
     return manual ? wm : wb;
 }
 static int build_partition(WalkPartition& P, int Nx, int Ny, int UL, int HL, int nwarps, int fx_lo, int fx_hi, bool wrapx,
-                           bool tma, int min_rows, cudaStream_t st) {
+                           bool tma, int min_rows, bool dot, cudaStream_t st) {
     const int key = (tma ? 1 : 0) | (wrapx ? 2 : 0) | (fx_lo << 2) | (fx_hi << 12);
     if (P.Nx == Nx && P.Ny == Ny && P.nwarps == nwarps && P.UL == UL && P.key == key && P.d_tasks) return 0;
     const int ncols = (Nx + UL - 1) / UL;
@@ -699,29 +700,47 @@ static int build_partition(WalkPartition& P, int Nx, int Ny, int UL, int HL, int
         const int cl = c * UL - HL;
         const bool fast = cl >= fx_lo && cl + 32 <= fx_hi;
         const bool manual = !tma || (wrapx && (cl < 0 || cl + 32 > Nx));
-        wcol[c] = manual ? walk_weight(true) : (fast ? 1. : walk_weight(false));
+        wcol[c] = manual ? walk_weight(true) : (fast ? 1. : walk_weight(false, dot));
         total += wcol[c] * Ny;
     }
-    // walk along the cost line; warp g ends where the accumulated cost reaches (g + 1) * total / nwarps.  A piece is at
-    // least min_rows rows long (the ring depth) unless the whole column is shorter.
+    // Every warp gets a budget B of cost units (one unit = one interior cell row); a piece costs rows * weight plus a fixed
+    // overhead (GY-only step, leading rows, pipeline fill).  Pieces are laid along the columns in order; the smallest B
+    // for which nwarps warps hold everything is found by bisection.  A piece is at least min_rows rows long (the ring
+    // depth) unless the whole column is shorter.
+    static double ovh = -1.;
+    if (ovh < 0.) { const char* e = getenv("DGB_WALK_TASK_OVERHEAD"); ovh = e ? atof(e) : 2.0; if (ovh < 0.) ovh = 0.; }
     std::vector<int4> tasks;
-    std::vector<int> tbegin(nwarps + 1, 0);
-    int c = 0, row = 0;
-    double cum = 0.;
-    for (int g = 0; g < nwarps; g++) {
-        tbegin[g] = (int)tasks.size();
-        const double end = g == nwarps - 1 ? total + 1. : total * (g + 1) / nwarps;
-        while (c < ncols && cum < end - 1e-9) {
-            const int avail = Ny - row;
-            int take = (int)((end - cum) / wcol[c] + 0.5);
-            if (take < min_rows) take = min_rows;
-            if (take > avail || avail - take < min_rows) take = avail;
-            tasks.push_back(make_int4(c, row, row + take, 0));
-            cum += take * wcol[c];
+    std::vector<int> tbegin;
+    auto assign = [&](double B, bool keep) -> int {
+        if (keep) { tasks.clear(); tbegin.assign(1, 0); }
+        int g = 0, c = 0, row = 0;
+        double budget = B;
+        while (c < ncols) {
+            const int left = Ny - row;
+            int fit = (int)((budget - ovh) / wcol[c] + 1e-9);
+            if (fit < min_rows && fit < left) {  // not worth starting a piece here: next warp
+                if (budget >= B - 1e-9) fit = std::min(left, min_rows);  // a fresh warp always takes at least the minimum
+                else { g++; budget = B; if (keep) tbegin.push_back((int)tasks.size()); continue; }
+            }
+            int take = std::min(fit, left);
+            if (left - take > 0 && left - take < min_rows)  // do not leave a stub shorter than the ring depth behind
+                take = (left - min_rows >= min_rows) ? left - min_rows : left;
+            if (take < 1) take = std::min(left, min_rows);
+            if (keep) tasks.push_back(make_int4(c, row, row + take, 0));
+            budget -= take * wcol[c] + ovh;
             row += take;
             if (row >= Ny) { c++; row = 0; }
         }
+        return g + 1;
+    };
+    double lo = total / nwarps, hi = 2. * total / nwarps + ovh * 4. + (double)min_rows * walk_weight(true);
+    while (assign(hi, false) > nwarps) hi *= 1.5;
+    for (int it = 0; it < 40; it++) {
+        const double mid = 0.5 * (lo + hi);
+        if (assign(mid, false) <= nwarps) hi = mid; else lo = mid;
     }
+    assign(hi, true);
+    while ((int)tbegin.size() < nwarps + 1) tbegin.push_back((int)tasks.size());
     tbegin[nwarps] = (int)tasks.size();
     cudaFree(P.d_tasks); cudaFree(P.d_tbegin);
     P.d_tasks = nullptr; P.d_tbegin = nullptr;
@@ -786,7 +805,7 @@ static int wlaunch(Elliptic2dPlan& p, double alpha, const double* x, double beta
     void*& slot = p.walk_part[DOT ? 1 : 0];
     if (!slot) slot = new WalkPartition();
     WalkPartition& P = *reinterpret_cast<WalkPartition*>(slot);
-    int e = build_partition(P, p.Nx, A.Ny, L::UL, L::HL, nwarps, A.fx_lo, A.fx_hi, A.wrapx, A.tma_load, L::SX, st);
+    int e = build_partition(P, p.Nx, A.Ny, L::UL, L::HL, nwarps, A.fx_lo, A.fx_hi, A.wrapx, A.tma_load, L::SX, DOT, st);
     if (e) return e;
     A.tasks = P.d_tasks; A.tbegin = P.d_tbegin;
     EllipticCoef<N, B> C;
