@@ -834,11 +834,10 @@ bool elliptic2d_walker_supported(const Elliptic2dPlan& p, bool with_dot) {
     if (off || !p.fusable || !(p.n == 2 || p.n == 3) || p.Nx < 5 || p.Ny < 5 || (p.helm && p.helm_alpha == 0.)) return false;
     if (force) return true;
     // measured on B200 (n = 3): the walker wins for the one-sided discretisations from ~512^2 cells on (87 vs 119 us at
-    // 1024^2); below that each warp gets too few rows to amortise its pipeline fill, and the centered stencil (28 useful
-    // lanes, 250 registers, 8 warps) only draws level with the tile kernel at 1024^2
-    // (118 vs 156 us for the plain apply, equal with the fused dot, where it runs on 8 warps)
+    // 1024^2); below that each warp gets too few rows to amortise its pipeline fill.  The centered stencil (28 useful
+    // lanes, 250 registers, 8 warps) gains less: 118 vs 156 us for the plain apply, +3..6 % in PCG with the fused dot
     const long long cells = (long long)p.Nx * (p.slab ? p.slab_rows : p.Ny);
-    if (p.dirk == 2) return !with_dot && cells >= 700 * 700;
+    (void)with_dot;  // measured again with the budget partition: the walker wins from ~400^2 cells on for every variant
     return cells >= 400 * 400;
 }
 
