@@ -222,6 +222,25 @@ struct FTensorMul2d {  // multiply.h:18-32; v = {lambda,t00,t01,t10,t11,in0,in1,
         v[7] = __fma_rn(l, tmp0, temp);
     }
 };
+struct FArakawa {  // ArakawaFunctor (arakawa.h:125-145); v = {lhs, rhs, dxlhs, dylhs, dxrhs, dyrhs}, the last three are in/out
+    static constexpr int NV = 6; static constexpr unsigned RMASK = 0x3f, WMASK = 0x38;
+    __device__ void operator()(double (&v)[6]) const {
+        const double third = 1. / 3., mthird = -(1. / 3.);
+        const double lhs = v[0], rhs = v[1], dxlhs = v[2], dylhs = v[3], dxrhs = v[4], dyrhs = v[5];
+        double result = 0.;
+        result = __fma_rn(__dmul_rn(third, dxlhs), dyrhs, result);
+        result = __fma_rn(__dmul_rn(mthird, dylhs), dxrhs, result);
+        double temp = 0.;
+        temp = __fma_rn(__dmul_rn(third, lhs), dyrhs, temp);
+        v[5] = result;
+        temp = __fma_rn(__dmul_rn(mthird, dylhs), rhs, temp);
+        v[3] = temp;
+        temp = 0.;
+        temp = __fma_rn(__dmul_rn(third, dxlhs), rhs, temp);
+        temp = __fma_rn(__dmul_rn(mthird, lhs), dxrhs, temp);
+        v[4] = temp;
+    }
+};
 struct FUpwindAxpby {  // evaluate(y, Axpby(a,b), UpwindProduct(), v, back, forw): advection.h:112-120, functors.h:312-337
     static constexpr int NV = 4; static constexpr unsigned RMASK = 0xf, WMASK = 0x8;
     double a, b;
@@ -355,6 +374,10 @@ int dgb_tensor_multiply2d(size_t n, const double* lambda, double lambda_s, const
     unsigned present = (lambda ? 1u : 0u) | (t00 ? 2u : 0u) | (t01 ? 4u : 0u) | (t10 ? 8u : 0u) | (t11 ? 16u : 0u);
     return launch_ew(FTensorMul2d{lambda_s, mu, present}, pack<9>({lambda, t00, t01, t10, t11, in0, in1, out0, out1}),
                      n, s);
+}
+int dgb_arakawa_functor(size_t n, const double* lhs, const double* rhs, const double* dxlhs, double* dylhs, double* dxrhs,
+                        double* dyrhs, dgb_stream_t s) {
+    return launch_ew(FArakawa{}, pack<6>({lhs, rhs, dxlhs, dylhs, dxrhs, dyrhs}), n, s);
 }
 int dgb_upwind_axpby(size_t n, double alpha, const double* v, const double* back, const double* forw, double beta, double* y,
                      dgb_stream_t s) {

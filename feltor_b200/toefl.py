@@ -68,6 +68,31 @@ class Advection:
         lib().upwind_axpby(n, d(alpha), ptr(vy), ptr(self.t0), ptr(self.t1), d(1.), ptr(result), stream())
 
 
+class ArakawaX:
+    """dg::ArakawaX (arakawa.h:30-170): Poisson bracket {lhs, rhs} on a Cartesian grid (perp volume 1)"""
+
+    def __init__(self, g, bcx=None, bcy=None):
+        bcx = g.bc[0] if bcx is None else bcx
+        bcy = g.bc[1] if bcy is None else bcy
+        n = g.size
+        self.dxlhs, self.dxrhs, self.dylhs, self.dyrhs = (_zeros(n) for _ in range(4))
+        self.bdxf = T.derivative(0, g, bcx, T.CENTERED)
+        self.bdyf = T.derivative(1, g, bcy, T.CENTERED)
+        self.chi = torch.ones(n, dtype=torch.float64, device="cuda")  # 1 / perp_vol
+
+    def __call__(self, *a):
+        """(lhs, rhs, result) | (alpha, lhs, rhs, beta, result)"""
+        alpha, lhs, rhs, beta, result = (1., a[0], a[1], 0., a[2]) if len(a) == 3 else a
+        self.bdxf.symv(1., lhs, 0., self.dxlhs)
+        self.bdyf.symv(1., lhs, 0., self.dylhs)
+        self.bdxf.symv(1., rhs, 0., self.dxrhs)
+        self.bdyf.symv(1., rhs, 0., self.dyrhs)
+        lib().arakawa_functor(lhs.numel(), ptr(lhs), ptr(rhs), ptr(self.dxlhs), ptr(self.dylhs), ptr(self.dxrhs), ptr(self.dyrhs), stream())
+        self.bdxf.symv(1., self.dylhs, 1., self.dyrhs)
+        self.bdyf.symv(1., self.dxrhs, 1., self.dyrhs)
+        blas1.pointwiseDot(alpha, self.chi, self.dyrhs, beta, result)
+
+
 class Extrapolation:
     """dg::Extrapolation (extrapolation.h:225-460): polynomial through up to `max` past solutions"""
 

@@ -103,6 +103,9 @@ DGB_API int dgb_embedded_pair_sum(size_t n, double* y, double* yt, double b0, do
 /* blas1::transform with a unary functor of inc/dg/functors.h (y = op(x)); op codes below */
 enum { DGB_OP_EXP = 0, DGB_OP_LN = 1, DGB_OP_SQRT = 2, DGB_OP_INVERT = 3, DGB_OP_ABS = 4, DGB_OP_SQUARE = 5,
        DGB_OP_INVSQRT = 6 };
+/* the pointwise step of dg::ArakawaX::operator() (arakawa.h:125-145,156): dylhs, dxrhs, dyrhs are overwritten */
+DGB_API int dgb_arakawa_functor(size_t n, const double* lhs, const double* rhs, const double* dxlhs, double* dylhs,
+                                double* dxrhs, double* dyrhs, dgb_stream_t s);
 /* y = alpha * v * (v >= 0 ? back : forw) + beta * y: blas1::evaluate(y, Axpby(alpha,beta), UpwindProduct(), v, back, forw)
  * as used by dg::Advection::upwind (advection.h:112-120, functors.h:312-337) */
 DGB_API int dgb_upwind_axpby(size_t n, double alpha, const double* v, const double* back, const double* forw, double beta,

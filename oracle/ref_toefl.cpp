@@ -131,6 +131,14 @@ void ref_toefl_upwind(void* hh, double alpha, const double* vx, const double* vy
     adv.upwind(alpha, a, b, c, beta, r);
     std::copy(r.begin(), r.end(), result);
 }
+void ref_toefl_arakawa(void* hh, double alpha, const double* lhs, const double* rhs, double beta, double* result) {
+    RefToefl* h = (RefToefl*)hh;
+    const size_t n = h->grid.size();
+    dg::ArakawaX<dg::CartesianGrid2d, dg::DMatrix, DVec> ar(h->grid);
+    DVec a(lhs, lhs + n), b(rhs, rhs + n), r(result, result + n);
+    ar(alpha, a, b, beta, r);
+    std::copy(r.begin(), r.end(), result);
+}
 void ref_toefl_variation(void* hh, const double* phi, double* out) {
     RefToefl* h = (RefToefl*)hh;
     const size_t n = h->grid.size();

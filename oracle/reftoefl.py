@@ -31,6 +31,7 @@ def lib():
         _lib.ref_toefl_pol_solve.argtypes = [C.c_void_p] * 5
         _lib.ref_toefl_upwind.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         _lib.ref_toefl_variation.argtypes = [C.c_void_p] * 3
+        _lib.ref_toefl_arakawa.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
         _lib.ref_toefl_binv.argtypes = [C.c_void_p] * 2
     return _lib
 
@@ -94,6 +95,11 @@ class RefToefl:
     def upwind(self, alpha, vx, vy, f, beta, result):
         r = np.array(result, copy=True)
         lib().ref_toefl_upwind(self.h, alpha, _p(np.ascontiguousarray(vx)), _p(np.ascontiguousarray(vy)), _p(np.ascontiguousarray(f)), beta, _p(r))
+        return r
+
+    def arakawa(self, alpha, lhs, rhs, beta, result):
+        r = np.array(result, copy=True)
+        lib().ref_toefl_arakawa(self.h, alpha, _p(np.ascontiguousarray(lhs)), _p(np.ascontiguousarray(rhs)), beta, _p(r))
         return r
 
     def variation(self, phi):

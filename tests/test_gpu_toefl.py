@@ -95,6 +95,10 @@ def test_toefl_building_blocks_vs_live_reference(G, reft):
     out = G.make(res)
     ex.adv.upwind(-1., G.make(vx), G.make(vy), G.make(f), 0.5, out)
     assert same_bits(G.get(out), ref.upwind(-1., vx, vy, f, 0.5, res))
+    ar = TF.ArakawaX(ex.grid)
+    out = G.make(res)
+    ar(0.7, G.make(f), G.make(vx), -0.4, out)
+    assert same_bits(G.get(out), ref.arakawa(0.7, f, vx, -0.4, res))
     phi = ex.grid.evaluate(lambda x, y: np.sin(0.05 * x) * np.cos(0.03 * y))
     u = torch.zeros(n, dtype=torch.float64, device="cuda")  # Axpby(alpha, 0) scales the old value: NaN would stay, as in the reference
     lib().elliptic2d_variation(ex.multi_pol[0].h, C.c_double(1.), None, ptr(G.make(phi)), C.c_double(0.), ptr(u), stream())
