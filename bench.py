@@ -150,6 +150,64 @@ def reference_arm(args, rank, world):
     print(json.dumps(out), flush=True)
 
 
+def secondary_workload(args, rank):
+    """configs 3 (toefl) and 4 (DS) of BASELINE.json on one GPU: GPU leg from tools/{toefl,ds}_bench.py, CPU baseline = the
+    unmodified reference (oracle/_ref) on a bounded sample; one JSON line"""
+    if rank != 0:
+        return
+    sys.path.insert(0, os.path.join(ROOT, "tools"))
+    if args.workload == "toefl":
+        import toefl_bench
+        out, y_init = toefl_bench.run(args.cells, args.steps, max(args.warmup, 2), 0.5)
+        line = {"metric": "toefl_steps_per_second", "value": out["steps_per_s"], "unit": "steps/s", "n_gpus": 1, "steps": args.steps,
+                "warmup": max(args.warmup, 2), "ms_per_step": out["ms_per_step"], "higher_is_better": True, "dtype": "f64",
+                "data": "synthetic", "config": {"workload": out["workload"]}, "detail": out, "gpu_launches": out["kernel_launches"]}
+        if not args.no_cpu_baseline:
+            from oracle import reftoefl as R
+            if R.available():
+                ref = R.RefToefl(toefl_bench.params(args.cells))
+                nref = 2
+                sys.stdout.flush()
+                saved, devnull = os.dup(1), os.open(os.devnull, os.O_WRONLY)
+                os.dup2(devnull, 1)  # the reference prints its solver statistics to stdout (toefl.h: set_benchmark(true))
+                try:
+                    _, _, rsec = ref.erk("Bogacki-Shampine-4-2-3", 0., 0.5, nref, y_init[0], y_init[1])
+                finally:
+                    os.dup2(saved, 1)
+                    os.close(devnull)
+                    os.close(saved)
+                line["cpu_baseline"] = {"value": nref / rsec, "unit": "steps/s", "cores": os.cpu_count(), "kind": "reference",
+                                        "sample": "%d steps from the same initial state (toefl::Explicit + dg::ERKStep, OpenMP)" % nref}
+        print(json.dumps(line), flush=True)
+        return
+    import ds_bench
+    import numpy as np_
+    rows = ds_bench.run(96, 64, 20)
+    line = {"metric": "ds_centered_gbs", "value": rows[0]["gather_plan_gbs"], "unit": "GB/s", "n_gpus": 1, "higher_is_better": True,
+            "dtype": "f64", "data": "synthetic", "config": {"workload": "DS::centered n=3 96x96x64, synthetic field-line matrices (dg: 36 per row)"},
+            "detail": rows, "roofline": {"bound": "hbm", "achieved": rows[0]["gather_plan_gbs"], "peak": peaks()[0], "unit": "GB/s",
+                                         "frac": rows[0]["gather_plan_gbs"] / peaks()[0], "traffic": None}}
+    if not args.no_cpu_baseline:
+        from oracle import refwrap as R
+        if R.available():
+            rng = np_.random.default_rng(0)
+            nrows, Nz = (3 * 96) ** 2, 64
+            size = nrows * Nz
+            hf = rng.uniform(-1, 1, size)
+            rng.uniform(0.5, 1.5, size)
+            P, M = ds_bench.interpolation_matrix(rng, 96, 2), ds_bench.interpolation_matrix(rng, 96, 2)
+            rP, rM = R.Csr(nrows, nrows, *P), R.Csr(nrows, nrows, *M)
+            tp, tm = np_.zeros(size), np_.zeros(size)
+            t0 = time.time()
+            for k in range(Nz):  # Fieldaligned::ePlus / eMinus: one symv per plane (fieldaligned.h:850-912)
+                rP.symv(1., hf[((k + 1) % Nz) * nrows:((k + 1) % Nz + 1) * nrows], 0., tp[k * nrows:(k + 1) * nrows])
+                rM.symv(1., hf[((k - 1) % Nz) * nrows:((k - 1) % Nz + 1) * nrows], 0., tm[k * nrows:(k + 1) * nrows])
+            sec = time.time() - t0
+            line["cpu_baseline"] = {"value": rows[0]["algorithmic_bytes"] / sec / 1e9, "unit": "GB/s", "cores": R.lib().ref_get_max_threads(),
+                                    "kind": "reference", "sample": "the 128 plane-wise CSR symv of one DS::centered (reference OpenMP kernel), formula excluded"}
+    print(json.dumps(line), flush=True)
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -159,11 +217,16 @@ def main():
     ap.add_argument("--ref-iters", type=int, default=10, help="PCG iterations per step of the CPU reference arm")
     ap.add_argument("--cells", type=int, default=1024)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="pcg", choices=["pcg", "toefl", "ds"],
+                    help="pcg: the headline (config 2); toefl: config 3; ds: config 4 -- the two secondary workloads print their own "
+                         "JSON line (single GPU) with the reference's CPU path timed beside them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.workload != "pcg":
+        return secondary_workload(args, rank)
     if args.impl == "reference":
         return reference_arm(args, rank, world)
 

@@ -102,7 +102,7 @@ class Ell:
 
     @classmethod
     def from_like(cls, m):
-        """from any object with the oracle's Ell attributes (oracle/refwrap.Ell)"""
+        """from any object that carries the EllSparseBlockMat fields (num_rows, ..., data, cols_idx, data_idx)"""
         return cls(m.num_rows, m.num_cols, m.bpl, m.n, m.left_size, m.right_size, m.data, m.cols_idx, m.data_idx,
                    m.right_range)
 
