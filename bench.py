@@ -332,13 +332,23 @@ def main():
         return
     peak, peak_kind = peaks()
     k1_ms = prof[0].value / max(pn.value, 1)
-    k1_bytes = 32 * ndof  # read p, sigma, W; write Ap  (24 B/dof apply + 8 B/dof weights of the fused dot)
-    achieved = k1_bytes / (k1_ms * 1e-3) / 1e9 if k1_ms > 0 else None
-    traffic = None
+    k2_ms = prof[1].value / max(pn.value, 1)
+    # algorithmic bytes per launch: K1 = fused Elliptic apply + dot: read p, sigma, W, write Ap = 32 B/dof;
+    # K2 = update + two dots: read p, Ap, x, r, P, W, write x, r, z = 72 B/dof
     try:
-        traffic = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))["elliptic2d_fused_dot_bytes_per_launch"]
+        tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
     except Exception:
-        pass
+        tr = {}
+    kernels = [
+        {"kernel": "elliptic2d_walker_kernel<3,fwd,dot> (Elliptic apply + dot(p,W,Ap))", "bytes_per_launch": 32 * ndof, "ms_per_launch": k1_ms,
+         "traffic": tr.get("elliptic2d_fused_dot_bytes_per_launch")},
+        {"kernel": "pcg_update_kernel (x, r, z = P r updates + dot(r,W,r), dot(z,W,r))", "bytes_per_launch": 72 * ndof, "ms_per_launch": k2_ms,
+         "traffic": tr.get("pcg_update_bytes_per_launch")},
+    ]
+    for k in kernels:
+        k["achieved"] = k["bytes_per_launch"] / (k["ms_per_launch"] * 1e-3) / 1e9 if k["ms_per_launch"] > 0 else None
+        k["frac"] = k["achieved"] / peak if k["achieved"] else None
+    dom = max(kernels, key=lambda k: k["ms_per_launch"])  # the dominant kernel of the step = the one with the largest share of it
     value = its / (ms * 1e-3)
     out = {
         "metric": "pcg_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": world,
@@ -352,10 +362,11 @@ def main():
                 "d2h_bytes_per_step": ndof * 8},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": "elliptic2d_walker_kernel<3,fwd,dot> (Elliptic apply + dot(p,W,Ap))",
-                     "achieved": achieved, "peak": peak, "peak_kind": peak_kind, "unit": "GB/s",
-                     "frac": achieved / peak if achieved else None, "traffic": traffic,
-                     "bytes_per_launch": k1_bytes, "ms_per_launch": k1_ms},
+        "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "peak_kind": peak_kind,
+                     "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"], "bytes_per_launch": dom["bytes_per_launch"],
+                     "ms_per_launch": dom["ms_per_launch"]},
+        "roofline_other_kernels": [{kk: k[kk] for kk in ("kernel", "achieved", "frac", "traffic", "bytes_per_launch", "ms_per_launch")}
+                                   for k in kernels if k is not dom],
         "kernels_ms_per_iteration": {"apply_dot": k1_ms, "update_dots": prof[1].value / max(pn.value, 1),
                                      "direction": prof[2].value / max(pn.value, 1)},
         "pcg_gbs_at_128B_per_dof": 128 * ndof * value / world / 1e9,
