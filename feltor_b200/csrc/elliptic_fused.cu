@@ -45,6 +45,8 @@ struct FusedArgs {
     const double* dot_w;
     sa::DotSlot slot;
     PcgState* pcg;
+    P2pView p2p;
+    unsigned long long epoch;
 };
 
 // out[k] = fma(a, sum_q C[d][k][q] * s[(off_d*N + q)*stride], out[k]) for the slots d of block-row `cell` of M
@@ -400,7 +402,7 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
     }
     if (DOT) {
         fpe.flush_warp(dsm);
-        if (sa::block_finish<1>(dsm, bad, A.slot, 0) && tid == 0 && !A.pcg->dist) pcg_after_pAp(A.pcg, A.slot.result);
+        fused_dot_finish(sa::block_finish<1>(dsm, bad, A.slot, 0), A.pcg, A.slot.result, A.p2p, A.epoch);
     }
 }
 
@@ -435,7 +437,8 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
     A.alpha = alpha; A.beta = beta; A.jfactor = p.jfactor;
     A.helm = p.helm ? 1 : 0; A.helm_alpha = p.helm_alpha; A.helm_chi = p.helm_chi;
     A.dot_w = nullptr; A.pcg = nullptr; A.slot = sa::DotSlot{nullptr, nullptr, nullptr, nullptr};
-    if (DOT) { A.dot_w = fd->w; A.slot = fd->slot; A.pcg = fd->pcg; }
+    A.p2p = P2pView{}; A.p2p.enabled = 0; A.epoch = 0;
+    if (DOT) { A.dot_w = fd->w; A.slot = fd->slot; A.pcg = fd->pcg; A.p2p = fd->p2p; A.epoch = fd->epoch; }
     CUtensorMap mx, ms;
     memset(&mx, 0, sizeof(mx));
     memset(&ms, 0, sizeof(ms));

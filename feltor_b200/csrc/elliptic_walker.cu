@@ -62,6 +62,8 @@ struct WalkArgs {
     const double* helm_chi;
     sa::DotSlot slot;
     PcgState* pcg;
+    P2pView p2p;               // multi-GPU: the finishing block exchanges the dot record over peer memory (pcg.cuh)
+    unsigned long long epoch;
 };
 
 template <int N, int DIRK, bool DOT>
@@ -662,7 +664,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
 #pragma unroll
         for (int k = 1; k < N; k++) fpe[0].merge(fpe[k], dsm);
         fpe[0].flush_warp(dsm);
-        if (sa::block_finish<1>(dsm, bad, A.slot, 0) && threadIdx.x == 0 && !A.pcg->dist) pcg_after_pAp(A.pcg, A.slot.result);
+        fused_dot_finish(sa::block_finish<1>(dsm, bad, A.slot, 0), A.pcg, A.slot.result, A.p2p, A.epoch);
     }
 }
 
@@ -791,7 +793,8 @@ static int wlaunch(Elliptic2dPlan& p, double alpha, const double* x, double beta
     A.alpha = alpha; A.beta = beta; A.jfactor = p.jfactor;
     A.helm = p.helm ? 1 : 0; A.helm_alpha = p.helm_alpha; A.helm_chi = p.helm_chi;
     A.pcg = nullptr; A.slot = sa::DotSlot{nullptr, nullptr, nullptr, nullptr};
-    if (DOT) { A.w = fd->w; A.slot = fd->slot; A.pcg = fd->pcg; }
+    A.p2p = P2pView{}; A.p2p.enabled = 0; A.epoch = 0;
+    if (DOT) { A.w = fd->w; A.slot = fd->slot; A.pcg = fd->pcg; A.p2p = fd->p2p; A.epoch = fd->epoch; }
     CUtensorMap mx, ms, mw, my;
     memset(&mx, 0, sizeof(mx)); memset(&ms, 0, sizeof(ms)); memset(&mw, 0, sizeof(mw)); memset(&my, 0, sizeof(my));
     const long long gh = (long long)A.ghost * N * p.Nx * N;  // doubles in the ghost rows below the slab

@@ -77,11 +77,11 @@ pcg_dot3_kernel(size_t n, const double* __restrict__ x, const double* __restrict
 
 // K2 (pcg.h:167-181).  PREFETCH: the six 128-bit loads of the next trip are in flight while this trip is reduced (2 CTAs
 // per SM); otherwise the kernel relies on occupancy (BPS CTAs per SM).
-template <bool CHECK, bool PREFETCH, int BPS>
+template <bool CHECK, bool PREFETCH, int BPS, bool P2P>  // P2P: the finishing block exchanges the dots over peer memory
 __global__ void __launch_bounds__(PCG_THREADS, BPS)
 pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ ap, double* __restrict__ x,
                   double* __restrict__ r, const double* __restrict__ P, const double* __restrict__ W, PcgState* st,
-                  sa::DotSlot slot, int iter) {
+                  sa::DotSlot slot, int iter, P2pView peer, unsigned long long epoch) {
     __shared__ long long smem[2 * sa::BINS];  // one accumulator per dot and block: [0] rr (slot 1), [1] zr (slot 2)
     if (st->done) return;
     const double alpha = st->alpha, malpha = -alpha;
@@ -159,7 +159,17 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
         fzr.flush_warp(my_zr);
     }
     const bool last = CHECK ? sa::block_finish_multi<2>(smem, bad, slot, 1) : sa::block_finish_multi<1>(my_zr, bad, slot, 2);
-    if (last && threadIdx.x == 0 && !st->dist) {
+    if (!last) return;
+    if (st->dist) {
+        if (!P2P || !peer.enabled) return;  // NCCL path: allreduce + pcg_scalar_kernel follow on the stream
+        // peer-memory path: this (the finishing) block exchanges the records with the other ranks right here
+        p2p_allreduce_records(peer, reinterpret_cast<long long*>(slot.result), CHECK ? 1 : 2, CHECK ? 2 : 1, epoch);
+        if (threadIdx.x == 0) {
+            if (CHECK) finalize_record(slot.result + 1);
+            finalize_record(slot.result + 2);
+        }
+    }
+    if (threadIdx.x == 0) {
         if (CHECK) pcg_after_rr(st, slot.result + 1, iter);
         pcg_after_zr(st, slot.result + 2, iter);
     }
@@ -167,15 +177,6 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
 
 // multi-GPU: after the integer allreduce of the local accumulators, one thread normalises, rounds and runs the hook
 //   MODE 0: res[3] only   MODE 1: nrmzr_old = dot (pcg.h:160)   MODE 2: alpha (pcg.h:166)   MODE 3: K2 hooks
-__device__ inline void finalize_record(dgb_dot_result* r) {
-    long long acc[sa::BINS];
-    for (int i = 0; i < sa::BINS; i++) acc[i] = r->acc[i];
-    int neg = sa::normalize(acc, 1);
-    for (int i = 0; i < sa::BINS; i++) r->acc[i] = acc[i];
-    r->value = sa::round_normalized(acc, neg);
-    r->status = r->status != 0 || r->pad != 0;
-    r->pad = 0;
-}
 template <int MODE>
 __global__ void __launch_bounds__(64) pcg_scalar_kernel(PcgState* st, dgb_dot_result* res, int iter, int check, P2pView pv, int first,
                                                         int count, unsigned long long epoch) {
@@ -370,7 +371,15 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
     const bool identity_chi = !A.chi[0] && !A.chi[1] && !A.chi[2] && !A.chi[3];
     const bool fused = A.fusable && identity_chi && !A.chi_weight_jump && (dist || !getenv("DGB_ELLIPTIC_UNFUSED")) &&
                        (!A.helm || A.helm_alpha != 0.);
-    FusedDot fd{W, s.slot, s.st};
+    const P2pView pview = comm_p2p_view(comm);
+    // The finishing block of K1/K2 can run the peer-memory exchange itself (one launch less per dot); measured at 2 GPUs this
+    // is 3 % SLOWER than the separate 64-thread exchange kernel (the serial tail of a 300-CTA kernel gets longer), so it is
+    // opt-in: DGB_P2P_IN_KERNEL=1
+    static int in_kernel = -1;
+    if (in_kernel < 0) { const char* ev = getenv("DGB_P2P_IN_KERNEL"); in_kernel = (ev && atoi(ev)) ? 1 : 0; }
+    const bool p2p_dots = dist && pview.enabled && in_kernel;
+    FusedDot fd{W, s.slot, s.st, pview, 0ull};
+    if (!p2p_dots) fd.p2p.enabled = 0;
     const unsigned g2 = grid_for(n, 2);
     static int k2_variant = -1;  // experiment knob: 0 register prefetch, 2 CTAs/SM   1 no prefetch, 4 CTAs/SM   2 no prefetch, 3 CTAs/SM
     if (k2_variant < 0) { const char* ev = getenv("DGB_PCG_K2_VARIANT"); k2_variant = ev ? atoi(ev) : 0; }
@@ -397,26 +406,32 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
             const int check = i % test_frequency == 0;
             if (prof) cudaEventRecord(s.ev[s.prof_n][0], st);
             if (fused) {
+                if (p2p_dots) fd.epoch = comm_p2p_next_epoch(comm, 0, 1);
                 if ((e = elliptic2d_fused_launch_dot(A, s.p, s.ap, st, fd))) return e;
             } else {
                 if ((e = elliptic2d_symv(A, 1., s.p, 0., s.ap, st, false))) return e;
                 pcg_dot3_kernel<2><<<g1, PCG_THREADS, 0, st>>>(n, s.p, W, s.ap, s.slot, 0, s.st);
                 DGB_LAUNCHED();
             }
-            if (dist && (e = dist_finish<2>(s, comm, 0, 1, i, 0, st))) return e;
+            if (dist && !(fused && p2p_dots) && (e = dist_finish<2>(s, comm, 0, 1, i, 0, st))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n][1], st);
+#define DGB_K2(C_, P_, B_) (p2p_dots ? pcg_update_kernel<C_, P_, B_, true> : pcg_update_kernel<C_, P_, B_, false>)
+            P2pView k2v = pview;
+            k2v.enabled = p2p_dots ? 1 : 0;
+            const unsigned long long k2e = p2p_dots ? comm_p2p_next_epoch(comm, check ? 1 : 2, check ? 2 : 1) : 0ull;
             if (k2_variant == 0) {
-                if (check) pcg_update_kernel<true, true, 2><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
-                else pcg_update_kernel<false, true, 2><<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+                if (check) DGB_K2(true, true, 2)<<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
+                else DGB_K2(false, true, 2)<<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
             } else if (k2_variant == 1) {
-                if (check) pcg_update_kernel<true, false, 4><<<2 * g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
-                else pcg_update_kernel<false, false, 4><<<2 * g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+                if (check) DGB_K2(true, false, 4)<<<2 * g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
+                else DGB_K2(false, false, 4)<<<2 * g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
             } else {
-                if (check) pcg_update_kernel<true, false, 3><<<g2 / 2 * 3, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
-                else pcg_update_kernel<false, false, 3><<<g2 / 2 * 3, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i);
+                if (check) DGB_K2(true, false, 3)<<<g2 / 2 * 3, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
+                else DGB_K2(false, false, 3)<<<g2 / 2 * 3, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
             }
+#undef DGB_K2
             DGB_LAUNCHED();
-            if (dist && (e = dist_finish<3>(s, comm, check ? 1 : 2, check ? 2 : 1, i, check, st))) return e;
+            if (dist && !p2p_dots && (e = dist_finish<3>(s, comm, check ? 1 : 2, check ? 2 : 1, i, check, st))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n][2], st);
             pcg_direction_kernel<<<g3, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st, rem_lo, rem_up, gh);
             DGB_LAUNCHED();

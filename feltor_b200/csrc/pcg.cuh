@@ -1,6 +1,7 @@
 // Internal: device-resident PCG scalars and the hooks fused kernels call when a dot product completes.
 #pragma once
 #include "superacc.cuh"
+#include "comm.cuh"
 
 namespace dgb {
 
@@ -18,7 +19,21 @@ struct FusedDot {
     const double* w;
     sa::DotSlot slot;
     PcgState* pcg;
+    // multi-GPU with peer memory: the finishing block of the kernel exchanges the record itself (comm.cuh) and runs the hook
+    P2pView p2p;
+    unsigned long long epoch;
 };
+
+// normalise + round a summed record in place (status = number of ranks that met NaN/Inf)
+__device__ inline void finalize_record(dgb_dot_result* r) {
+    long long acc[sa::BINS];
+    for (int i = 0; i < sa::BINS; i++) acc[i] = r->acc[i];
+    int neg = sa::normalize(acc, 1);
+    for (int i = 0; i < sa::BINS; i++) r->acc[i] = acc[i];
+    r->value = sa::round_normalized(acc, neg);
+    r->status = r->status != 0 || r->pad != 0;
+    r->pad = 0;
+}
 
 // pcg.h:166  alpha = nrmzr_old / dot(p, W, ap)
 __device__ __forceinline__ void pcg_after_pAp(PcgState* st, const dgb_dot_result* r) {
@@ -41,6 +56,16 @@ __device__ __forceinline__ void pcg_after_zr(PcgState* st, const dgb_dot_result*
     st->nrmzr_old = nw;
     st->cur = iter;
     if (zr->status) { st->status = 1; st->done = 1; st->iter = iter; }
+}
+
+// what the finishing block of a fused apply + dot(p,W,Ap) kernel does once the local record is published.  `last` is true
+// in ALL threads of that block (>= 64 threads).
+__device__ inline void fused_dot_finish(bool last, PcgState* st, dgb_dot_result* results, const P2pView& pv, unsigned long long epoch) {
+    if (!last) return;
+    if (!st->dist) { if (threadIdx.x == 0) pcg_after_pAp(st, results); return; }
+    if (!pv.enabled) return;  // NCCL path: the host enqueues the allreduce and the scalar kernel
+    p2p_allreduce_records(pv, reinterpret_cast<long long*>(results), 0, 1, epoch);
+    if (threadIdx.x == 0) { finalize_record(results); pcg_after_pAp(st, results); }
 }
 
 struct Elliptic2dPlan;
