@@ -691,10 +691,9 @@ static double walk_weight(bool manual, bool dot = false) {
     if (!manual && dot && !getenv("DGB_WALK_SLOW_WEIGHT")) return 2.0;  // the fused-dot variant (8 warps): measured optimum
     return manual ? wm : wb;
 }
-static int build_partition(WalkPartition& P, int Nx, int Ny, int UL, int HL, int nwarps, int fx_lo, int fx_hi, bool wrapx,
-                           bool tma, int min_rows, bool dot, cudaStream_t st) {
-    const int key = (tma ? 1 : 0) | (wrapx ? 2 : 0) | (fx_lo << 2) | (fx_hi << 12);
-    if (P.Nx == Nx && P.Ny == Ny && P.nwarps == nwarps && P.UL == UL && P.key == key && P.d_tasks) return 0;
+// host part (no CUDA): tasks[] = (warp column, first row, end row, 0), tbegin[g] .. tbegin[g+1] = the tasks of warp g
+static void partition_host(int Nx, int Ny, int UL, int HL, int nwarps, int fx_lo, int fx_hi, bool wrapx, bool tma, int min_rows,
+                           bool dot, std::vector<int4>& tasks, std::vector<int>& tbegin) {
     const int ncols = (Nx + UL - 1) / UL;
     std::vector<double> wcol(ncols);
     double total = 0.;
@@ -711,8 +710,6 @@ static int build_partition(WalkPartition& P, int Nx, int Ny, int UL, int HL, int
     // depth) unless the whole column is shorter.
     static double ovh = -1.;
     if (ovh < 0.) { const char* e = getenv("DGB_WALK_TASK_OVERHEAD"); ovh = e ? atof(e) : 2.0; if (ovh < 0.) ovh = 0.; }
-    std::vector<int4> tasks;
-    std::vector<int> tbegin;
     auto assign = [&](double B, bool keep) -> int {
         if (keep) { tasks.clear(); tbegin.assign(1, 0); }
         int g = 0, c = 0, row = 0;
@@ -744,6 +741,15 @@ static int build_partition(WalkPartition& P, int Nx, int Ny, int UL, int HL, int
     assign(hi, true);
     while ((int)tbegin.size() < nwarps + 1) tbegin.push_back((int)tasks.size());
     tbegin[nwarps] = (int)tasks.size();
+}
+
+static int build_partition(WalkPartition& P, int Nx, int Ny, int UL, int HL, int nwarps, int fx_lo, int fx_hi, bool wrapx,
+                           bool tma, int min_rows, bool dot, cudaStream_t st) {
+    const int key = (tma ? 1 : 0) | (wrapx ? 2 : 0) | (fx_lo << 2) | (fx_hi << 12);
+    if (P.Nx == Nx && P.Ny == Ny && P.nwarps == nwarps && P.UL == UL && P.key == key && P.d_tasks) return 0;
+    std::vector<int4> tasks;
+    std::vector<int> tbegin;
+    partition_host(Nx, Ny, UL, HL, nwarps, fx_lo, fx_hi, wrapx, tma, min_rows, dot, tasks, tbegin);
     cudaFree(P.d_tasks); cudaFree(P.d_tbegin);
     P.d_tasks = nullptr; P.d_tbegin = nullptr;
     DGB_CUDA(cudaMalloc(&P.d_tasks, (tasks.size() + 1) * sizeof(int4)));
@@ -817,6 +823,23 @@ static int wlaunch(Elliptic2dPlan& p, double alpha, const double* x, double beta
     if (A.tma_load && A.tma_store && !A.wrapx) return wlaunch_go<N, DIRK, DOT, PLAIN, true>(A, C, mx, ms, mw, my, grid, st);
     return wlaunch_go<N, DIRK, DOT, PLAIN, false>(A, C, mx, ms, mw, my, grid, st);
 }
+
+}  // namespace dgb
+// test hook (host only, no device needed): the work partition of the walker kernel for an Nx x Ny cell grid whose cells
+// [fx_lo, fx_hi) are interior in x.  tasks_out: 3 ints per piece (warp column, first row, end row), tbegin_out: nwarps + 1.
+extern "C" int dgb_debug_walker_partition(int Nx, int Ny, int centered, int nwarps, int fx_lo, int fx_hi, int wrapx, int tma, int dot,
+                                          int* tasks_out, int max_tasks, int* ntasks, int* tbegin_out) {
+    const int HL = centered ? 2 : 1, UL = 32 - 2 * HL, min_rows = (centered ? 2 : 1) + 2 + dgb::WALK_PD;
+    std::vector<int4> tasks;
+    std::vector<int> tbegin;
+    dgb::partition_host(Nx, Ny, UL, HL, nwarps, fx_lo, fx_hi, wrapx != 0, tma != 0, min_rows, dot != 0, tasks, tbegin);
+    *ntasks = (int)tasks.size();
+    if ((int)tasks.size() > max_tasks) { dgb::set_error("dgb_debug_walker_partition: %zu pieces, room for %d", tasks.size(), max_tasks); return DGB_ERR_INVALID; }
+    for (size_t k = 0; k < tasks.size(); k++) { tasks_out[3 * k] = tasks[k].x; tasks_out[3 * k + 1] = tasks[k].y; tasks_out[3 * k + 2] = tasks[k].z; }
+    for (int g = 0; g <= nwarps; g++) tbegin_out[g] = tbegin[g];
+    return 0;
+}
+namespace dgb {
 
 void elliptic2d_walker_release(Elliptic2dPlan& p) {
     for (int k = 0; k < 2; k++) {

@@ -303,6 +303,9 @@ DGB_API int dgb_elliptic2d_set_vol(dgb_elliptic2d* plan, const double* vol);    
 DGB_API int dgb_elliptic2d_set_chi(dgb_elliptic2d* plan, const double* xx, const double* xy, const double* yx,
                                    const double* yy);                             /* m_chi; NULL = identity entry */
 DGB_API int dgb_elliptic2d_set_jfactor(dgb_elliptic2d* plan, double jfactor);
+/* test hook, host only: the work partition the warp-walker kernel would use (tasks_out: column, first row, end row per piece) */
+DGB_API int dgb_debug_walker_partition(int Nx, int Ny, int centered, int nwarps, int fx_lo, int fx_hi, int wrapx, int tma, int dot,
+                                       int* tasks_out, int max_tasks, int* ntasks, int* tbegin_out);
 /* dg::GeneralHelmholtz<Elliptic2d> (helmholtz.h:27-82): with enable != 0 the two-operand symv of the plan (and with it
  * PCG / MultigridCG2d on the plan) computes  y = chi x - alpha (Elliptic x)  exactly as
  * `symv(m_matrix, x, y); pointwiseDot(1., m_chi, x, -m_alpha, y)`; chi == NULL is the default chi = 1. */
