@@ -1,13 +1,16 @@
 // dg::Elliptic2d: y = alpha/vol [ -Lx sigma (chi_xx Rx + chi_xy Ry) - Ly sigma (chi_yx Rx + chi_yy Ry) + jfactor (Jx + Jy) ] x + beta y
-// Replaces the 8-launch composition of Elliptic2d::symv (inc/dg/elliptic.h:428-458).
-//  * elliptic2d_symv_unfused: the same composition on our kernels (6 Ell symv + tensor multiply + divide) --
-//    the general path (any chi tensor, chi-weighted jumps, any matrix structure).
-//  * elliptic2d_fused_kernel: ONE pass.  A CTA owns a tile of TX x TY cells; it stages x and sigma (with a halo) in
-//    shared memory, computes the fluxes tx = sigma Rx x, ty = sigma Ry x for the tile plus the one-cell ring the
-//    adjoint derivative reaches into, and then one thread per cell replays the reference's rounding sequence for
-//    its n x n outputs in registers.  HBM traffic: read x, read sigma, write y (24 B/dof, +8 if beta != 0, +8 vol).
-//    The n x n blocks of interior rows are kernel parameters (constant-bank DFMA operands); boundary cells look
-//    their blocks up in global memory.
+// Replaces the 8-launch composition of Elliptic2d::symv (inc/dg/elliptic.h:428-458).  Three implementations, chosen per call:
+//  * elliptic2d_walker_kernel (elliptic_walker.cu), the default from ~400^2 cells on: one warp per strip of cell columns
+//    walking along y, warp-private TMA rings, fluxes in registers / shuffles, TMA store; ONE pass, 24 B/dof of HBM traffic
+//    (+8 if beta != 0, +8 vol).  Also carries the fused exact dot of PCG, the Helmholtz epilogue and the slab (multi-GPU) mode.
+//  * elliptic2d_fused_kernel (elliptic_fused.cu), small grids and n = 4: a CTA owns a tile of 32 x 8 cells staged by TMA,
+//    fluxes through shared memory, one thread per cell; same traffic, same options.
+//  * elliptic2d_symv_unfused (this file): the reference's composition on our kernels (6 Ell symv + tensor multiply +
+//    divide) -- the general path (any chi tensor, chi-weighted jumps, any matrix structure) and the test comparator
+//    (every fused result is checked bitwise against it).
+// The n x n blocks of interior rows are kernel parameters (uniform / constant-bank operands of the DFMAs); boundary cells
+// look their blocks up in global memory.  This file also holds the GeneralHelmholtz mode (helmholtz.h:74-80) and
+// Elliptic::variation (elliptic.h:497-502).
 #include "elliptic.cuh"
 #include <cstdlib>
 
