@@ -5,6 +5,8 @@
 // A Feltor tree would instead plug the C ABI into its own dispatch seams; this header is the
 // stand-alone way to program against the library from C++.
 #pragma once
+#include <algorithm>
+#include <cmath>
 #include <cstddef>
 #include <stdexcept>
 #include <string>
@@ -125,6 +127,46 @@ inline double dot(const DVec& x, const DVec& w, const DVec& y) {
 inline double dot(const DVec& w, const DVec& x) { return dot(x, w, x); }
 }  // namespace blas2
 
+// dg::DMatrix = EllSparseBlockMat<double, thrust::device_vector> (inc/dg/backend/sparseblockmat.h:44-188)
+class DMatrix {
+    dgb_ell* m_m = nullptr;
+  public:
+    DMatrix() = default;
+    explicit DMatrix(dgb_ellh* host) {  // takes ownership of the host description
+        dgb_ell_host v;
+        check(dgb_ellh_view(host, &v));
+        int e = dgb_ell_create(&m_m, &v);
+        dgb_ellh_destroy(host);
+        check(e);
+    }
+    DMatrix(const DMatrix&) = delete;
+    DMatrix(DMatrix&& o) noexcept { std::swap(m_m, o.m_m); }
+    DMatrix& operator=(DMatrix&& o) noexcept { std::swap(m_m, o.m_m); return *this; }
+    ~DMatrix() { if (m_m) dgb_ell_destroy(m_m); }
+    void symv(double alpha, const DVec& x, double beta, DVec& y) const { check(dgb_ell_symv(m_m, alpha, x.data(), beta, y.data(), nullptr)); }
+};
+namespace create {  // inc/dg/topology/derivatives.h:36-60
+inline DMatrix dx(const Grid2d& g, bc b, direction d = centered) { dgb_ellh* m; check(dgb_topo_derivative(&m, &g.g, 0, b, d)); return DMatrix(m); }
+inline DMatrix dy(const Grid2d& g, bc b, direction d = centered) { dgb_ellh* m; check(dgb_topo_derivative(&m, &g.g, 1, b, d)); return DMatrix(m); }
+}
+namespace blas2 {
+inline void symv(const DMatrix& m, const DVec& x, DVec& y) { m.symv(1., x, 0., y); }
+inline void symv(double alpha, const DMatrix& m, const DVec& x, double beta, DVec& y) { m.symv(alpha, x, beta, y); }
+}
+namespace blas1 {
+inline void pointwiseDot(double a, const DVec& x1, const DVec& x2, const DVec& x3, double b, DVec& y) {  // blas1.h:457
+    if (a == 0.) return scal(y, b);
+    check(dgb_pointwise_dot3(y.size(), a, x1.data(), x2.data(), x3.data(), b, y.data(), nullptr));
+}
+enum class reduce_op { sum = DGB_REDUCE_SUM, max = DGB_REDUCE_MAX, min = DGB_REDUCE_MIN, logical_or = DGB_REDUCE_OR };
+enum class unary_op { identity = DGB_UNARY_IDENTITY, abs = DGB_UNARY_ABS, square = DGB_UNARY_SQUARE, isnan = DGB_UNARY_ISNAN, isnotfinite = DGB_UNARY_ISNOTFINITE };
+inline double reduce(const DVec& x, double init, reduce_op op, unary_op u = unary_op::identity) {  // blas1.h:213-223, closed functor set
+    double out = 0;
+    check(dgb_reduce(x.size(), x.data(), (int)op, (int)u, init, &out, nullptr));
+    return out;
+}
+}
+
 // dg::Elliptic2d<CartesianGrid2d, DMatrix, DVec> (inc/dg/elliptic.h:233-516)
 class Elliptic2d {
     dgb_elliptic2d* m_plan = nullptr;
@@ -165,7 +207,106 @@ class Elliptic2d {
     void set_jfactor(double j) { check(dgb_elliptic2d_set_jfactor(m_plan, j)); }
     void symv(const DVec& x, DVec& y) { symv(1., x, 0., y); }
     void symv(double alpha, const DVec& x, double beta, DVec& y) { check(dgb_elliptic2d_symv(m_plan, alpha, x.data(), beta, y.data(), nullptr)); }
+    // sigma = alpha lambda^2 (grad phi . chi . grad phi) + beta sigma   (elliptic.h:469-502)
+    void variation(const DVec& phi, DVec& sigma) { variation(1., nullptr, phi, 0., sigma); }
+    void variation(double alpha, const DVec* lambda, const DVec& phi, double beta, DVec& sigma) {
+        check(dgb_elliptic2d_variation(m_plan, alpha, lambda ? lambda->data() : nullptr, phi.data(), beta, sigma.data(), nullptr));
+    }
     dgb_elliptic2d* plan() { return m_plan; }
+    const dgb_elliptic2d* plan() const { return m_plan; }
+};
+
+// dg::Helmholtz<Geometry, DMatrix, DVec> = GeneralHelmholtz<Elliptic2d, DVec> (inc/dg/helmholtz.h:27-95): chi x - alpha Elliptic x.
+// The Elliptic plan carries the Helmholtz term, so PCG / MultigridCG2d run on it unchanged.
+class Helmholtz {
+    double m_alpha;
+    Elliptic2d m_matrix;
+    DVec m_chi;
+    bool m_has_chi = false;
+  public:
+    Helmholtz(double alpha, Elliptic2d&& matrix) : m_alpha(alpha), m_matrix(std::move(matrix)) {
+        check(dgb_elliptic2d_set_helmholtz(m_matrix.plan(), 1, m_alpha, nullptr));
+    }
+    Helmholtz(Helmholtz&&) = default;
+    const DVec& weights() const { return m_matrix.weights(); }
+    const DVec& precond() const { return m_matrix.precond(); }
+    double alpha() const { return m_alpha; }
+    void set_chi(const DVec& chi) {
+        m_chi = chi; m_has_chi = true;
+        check(dgb_elliptic2d_set_helmholtz(m_matrix.plan(), 1, m_alpha, m_chi.data()));
+    }
+    void symv(const DVec& x, DVec& y) { m_matrix.symv(x, y); }
+    Elliptic2d& matrix() { return m_matrix; }
+    dgb_elliptic2d* plan() { return m_matrix.plan(); }
+};
+
+// dg::Advection<Geometry, DMatrix, DVec> (inc/dg/advection.h:60-120)
+class Advection {
+    DVec m_temp0, m_temp1;
+    DMatrix m_dxf, m_dyf, m_dxb, m_dyb;
+  public:
+    explicit Advection(const Grid2d& g) : Advection(g, g.bcx(), g.bcy()) {}
+    Advection(const Grid2d& g, bc bcx, bc bcy)
+        : m_temp0(g.size(), 1.), m_temp1(g.size(), 1.), m_dxf(create::dx(g, bcx, forward)), m_dyf(create::dy(g, bcy, forward)),
+          m_dxb(create::dx(g, bcx, backward)), m_dyb(create::dy(g, bcy, backward)) {}
+    void upwind(double alpha, const DVec& vx, const DVec& vy, const DVec& f, double beta, DVec& result) {
+        blas2::symv(m_dxb, f, m_temp0);
+        blas2::symv(m_dxf, f, m_temp1);
+        check(dgb_upwind_axpby(f.size(), alpha, vx.data(), m_temp0.data(), m_temp1.data(), beta, result.data(), nullptr));
+        blas2::symv(m_dyb, f, m_temp0);
+        blas2::symv(m_dyf, f, m_temp1);
+        check(dgb_upwind_axpby(f.size(), alpha, vy.data(), m_temp0.data(), m_temp1.data(), 1., result.data(), nullptr));
+    }
+};
+
+// dg::ArakawaX<Geometry, DMatrix, DVec> (inc/dg/arakawa.h:30-170), Cartesian grids (perpendicular volume 1)
+class ArakawaX {
+    DVec m_dxlhs, m_dxrhs, m_dylhs, m_dyrhs, m_chi;
+    DMatrix m_bdxf, m_bdyf;
+  public:
+    explicit ArakawaX(const Grid2d& g) : ArakawaX(g, g.bcx(), g.bcy()) {}
+    ArakawaX(const Grid2d& g, bc bcx, bc bcy)
+        : m_dxlhs(g.size(), 1.), m_dxrhs(g.size(), 1.), m_dylhs(g.size(), 1.), m_dyrhs(g.size(), 1.), m_chi(g.size(), 1.),
+          m_bdxf(create::dx(g, bcx, centered)), m_bdyf(create::dy(g, bcy, centered)) {}
+    void operator()(const DVec& lhs, const DVec& rhs, DVec& result) { (*this)(1., lhs, rhs, 0., result); }
+    void operator()(double alpha, const DVec& lhs, const DVec& rhs, double beta, DVec& result) {
+        blas2::symv(m_bdxf, lhs, m_dxlhs);
+        blas2::symv(m_bdyf, lhs, m_dylhs);
+        blas2::symv(m_bdxf, rhs, m_dxrhs);
+        blas2::symv(m_bdyf, rhs, m_dyrhs);
+        check(dgb_arakawa_functor(lhs.size(), lhs.data(), rhs.data(), m_dxlhs.data(), m_dylhs.data(), m_dxrhs.data(), m_dyrhs.data(), nullptr));
+        blas2::symv(1., m_bdxf, m_dylhs, 1., m_dyrhs);
+        blas2::symv(1., m_bdyf, m_dxrhs, 1., m_dyrhs);
+        blas1::pointwiseDot(alpha, m_chi, m_dyrhs, beta, result);
+    }
+};
+
+// dg::Extrapolation<DVec> (inc/dg/extrapolation.h:225-460), constant / linear extrapolation
+class Extrapolation {
+    unsigned m_max = 0, m_counter = 0;
+    std::vector<DVec> m_x;
+    std::vector<double> m_t;
+  public:
+    Extrapolation() = default;
+    Extrapolation(unsigned max, const DVec& copyable) { set_max(max, copyable); }
+    void set_max(unsigned max, const DVec& copyable) { m_counter = 0; m_x.assign(max, copyable); m_t.assign(max, 0.); m_max = max; }
+    void extrapolate(double t, DVec& new_x) const {
+        if (m_counter == 0) return blas1::copy(0., new_x);
+        if (m_counter == 1) return blas1::copy(m_x[0], new_x);
+        if (m_counter == 3) throw Error(DGB_ERR_UNSUPPORTED, "dgb200: parabolic extrapolation is not implemented");
+        double f0 = (t - m_t[1]) / (m_t[0] - m_t[1]), f1 = (t - m_t[0]) / (m_t[1] - m_t[0]);
+        blas1::axpby(f0, m_x[0], f1, m_x[1], new_x);
+    }
+    void update(double t_new, const DVec& new_entry) {
+        if (m_max == 0) return;
+        for (unsigned i = 0; i < m_counter; i++)
+            if (std::abs(t_new - m_t[i]) < 1e-14) { blas1::copy(new_entry, m_x[i]); return; }
+        if (m_counter < m_max) m_counter++;
+        std::rotate(m_x.rbegin(), m_x.rbegin() + 1, m_x.rend());
+        std::rotate(m_t.rbegin(), m_t.rbegin() + 1, m_t.rend());
+        m_t[0] = t_new;
+        blas1::copy(new_entry, m_x[0]);
+    }
 };
 
 // dg::PCG<DVec> (inc/dg/pcg.h:25-199)
@@ -190,6 +331,10 @@ class PCG {
         if (e == DGB_ERR_NOCONVERGE && !m_throw) return (unsigned)it;
         check(e);
         return (unsigned)it;
+    }
+    unsigned solve(Helmholtz& A, DVec& x, const DVec& b, const DVec& P, const DVec& W, double eps = 1e-12,
+                   double nrmb_correction = 1., int test_frequency = 1) {
+        return solve(A.matrix(), x, b, P, W, eps, nrmb_correction, test_frequency);  // the plan carries the Helmholtz term
     }
 };
 
@@ -221,6 +366,14 @@ class MultigridCG2d {
     }
     std::vector<unsigned> solve(std::vector<Elliptic2d>& ops, DVec& x, const DVec& b, double eps) {
         return solve(ops, x, b, std::vector<double>(m_stages, eps));
+    }
+    std::vector<unsigned> solve(std::vector<Helmholtz>& ops, DVec& x, const DVec& b, std::vector<double> eps) {
+        std::vector<dgb_elliptic2d*> A;
+        std::vector<const double*> P, W;
+        for (auto& o : ops) { A.push_back(o.plan()); P.push_back(o.precond().data()); W.push_back(o.weights().data()); }
+        std::vector<int> num(m_stages);
+        check(dgb_multigrid2d_solve(m_mg, A.data(), P.data(), W.data(), x.data(), b.data(), eps.data(), num.data(), nullptr));
+        return std::vector<unsigned>(num.begin(), num.end());
     }
 };
 

@@ -1,0 +1,45 @@
+// C++ host program against include/dg_b200.hpp: the operators toefl::Explicit is built from (Helmholtz multigrid solve,
+// Advection::upwind, ArakawaX, Elliptic::variation, Extrapolation, blas1::reduce) on the toefl grid; prints exact-dot
+// checksums that tests/test_cpp_host.py compares with the Python harness (both call the same C ABI).
+//   operators_demo <N>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include "dg_b200.hpp"
+using namespace dgb200;
+int main(int argc, char** argv) {
+    unsigned N = argc > 1 ? atoi(argv[1]) : 48;
+    Grid2d grid(0, 200, 0, 200, 3, N, N, DIR, PER);
+    DVec w(create::weights(grid));
+    DVec f(evaluate([](double x, double y) { return sin(0.05 * x) * cos(0.03 * y); }, grid));
+    DVec vx(evaluate([](double x, double y) { return cos(0.02 * x) - 0.3; }, grid)), vy(evaluate([](double x, double y) { return sin(0.04 * y) + 0.1; }, grid));
+    DVec b(evaluate([](double x, double y) { return exp(-((x - 60) * (x - 60) + (y - 100) * (y - 100)) / 200.); }, grid));
+    // Helmholtz multigrid solve (toefl.h:75-83,155: Gamma^{-1})
+    MultigridCG2d mg(grid, 3);
+    std::vector<Helmholtz> gamma;
+    for (unsigned u = 0; u < 3; u++) gamma.emplace_back(-0.5, Elliptic2d(mg.grid(u), centered));
+    DVec x(grid.size(), 0.);
+    std::vector<unsigned> num = mg.solve(gamma, x, b, std::vector<double>{1e-7, 1e-7, 1e-7});
+    printf("helmholtz iterations: %u %u %u\n", num[0], num[1], num[2]);
+    printf("helmholtz checksum: %.17g\n", blas2::dot(x, w, x));
+    // Advection::upwind, ArakawaX, variation
+    DVec r(grid.size(), 0.25);
+    Advection adv(grid);
+    adv.upwind(-1., vx, vy, f, 0.5, r);
+    printf("upwind checksum: %.17g\n", blas2::dot(r, w, r));
+    ArakawaX arakawa(grid);
+    arakawa(0.7, f, b, -0.4, r);
+    printf("arakawa checksum: %.17g\n", blas2::dot(r, w, r));
+    Elliptic2d pol(grid, centered, 1.);
+    DVec s(grid.size(), 0.);
+    pol.variation(f, s);
+    printf("variation checksum: %.17g\n", blas2::dot(s, w, s));
+    // Extrapolation (linear) and reduce
+    Extrapolation ex(2, f);
+    ex.update(0., f);
+    ex.update(0.5, b);
+    ex.extrapolate(1.0, s);
+    printf("extrapolation checksum: %.17g\n", blas2::dot(s, w, s));
+    printf("max: %.17g min: %.17g\n", blas1::reduce(s, -1e300, blas1::reduce_op::max), blas1::reduce(s, 1e300, blas1::reduce_op::min));
+    return 0;
+}

@@ -10,14 +10,70 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 EXE = os.path.join(ROOT, "tests", "cpp", "poisson_demo")
 
 
-def build():
-    src = os.path.join(ROOT, "tests", "cpp", "poisson_demo.cpp")
+EXE2 = os.path.join(ROOT, "tests", "cpp", "operators_demo")
+
+
+def build(exe=EXE, name="poisson_demo"):
+    src = os.path.join(ROOT, "tests", "cpp", name + ".cpp")
     hdr = os.path.join(ROOT, "include", "dg_b200.hpp")
-    if os.path.exists(EXE) and os.path.getmtime(EXE) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
+    if os.path.exists(exe) and os.path.getmtime(exe) > max(os.path.getmtime(src), os.path.getmtime(hdr)):
         return
     subprocess.check_call(["g++", "-std=c++17", "-O2", "-I" + os.path.join(ROOT, "include"), src,
                            "-L" + os.path.join(ROOT, "feltor_b200"), "-ldgb200",
-                           "-Wl,-rpath," + os.path.join(ROOT, "feltor_b200"), "-Wl,-rpath,$ORIGIN/../../feltor_b200", "-o", EXE])
+                           "-Wl,-rpath," + os.path.join(ROOT, "feltor_b200"), "-Wl,-rpath,$ORIGIN/../../feltor_b200", "-o", exe])
+
+
+def test_cpp_operators_demo_builds():
+    build(EXE2, "operators_demo")
+    assert os.path.exists(EXE2)
+
+
+@pytest.mark.gpu
+def test_cpp_operators_demo_matches_harness():
+    """Helmholtz multigrid solve, Advection::upwind, ArakawaX, variation, Extrapolation, reduce through include/dg_b200.hpp
+    give the same exact-dot checksums as the Python harness (which is itself bit-identical to the reference classes)"""
+    import ctypes as C
+    import math
+    import torch
+    import gpu_backend as G
+    from feltor_b200 import blas1, blas2, toefl as TF, topology as T
+    from feltor_b200._lib import lib
+    from feltor_b200._dev import ptr, stream
+    from feltor_b200.elliptic import Elliptic2d, MultigridCG2d
+    if not os.path.exists(EXE2):
+        build(EXE2, "operators_demo")
+    N = 48
+    out = subprocess.run([EXE2, str(N)], capture_output=True, text=True, timeout=300)
+    assert out.returncode == 0, out.stdout + out.stderr
+    val = {m.group(1): float(m.group(2)) for m in re.finditer(r"(\w+) checksum: (\S+)", out.stdout)}
+    its = [int(v) for v in re.search(r"helmholtz iterations: (\d+) (\d+) (\d+)", out.stdout).groups()]
+    mx, mn = [float(v) for v in re.search(r"max: (\S+) min: (\S+)", out.stdout).groups()]
+    g = T.Grid([0., 0.], [200., 200.], 3, [N, N], [T.DIR, T.PER])
+    w = G.make(g.weights())
+    ev = lambda f: G.make(g.evaluate(f, vectorized=False))
+    f = ev(lambda x, y: math.sin(0.05 * x) * math.cos(0.03 * y))
+    vx, vy = ev(lambda x, y: math.cos(0.02 * x) - 0.3), ev(lambda x, y: math.sin(0.04 * y) + 0.1)
+    b = ev(lambda x, y: math.exp(-((x - 60) * (x - 60) + (y - 100) * (y - 100)) / 200.))
+    mg = MultigridCG2d(g, 3)
+    gamma = [TF.Helmholtz(-0.5, Elliptic2d(mg.grid(u), direction=T.CENTERED)) for u in range(3)]
+    x = torch.zeros_like(b)
+    assert mg.solve(gamma, x, b, [1e-7] * 3) == its
+    assert blas2.dot(x, w, x) == val["helmholtz"]
+    r = torch.full_like(b, 0.25)
+    TF.Advection(g).upwind(-1., vx, vy, f, 0.5, r)
+    assert blas2.dot(r, w, r) == val["upwind"]
+    TF.ArakawaX(g)(0.7, f, b, -0.4, r)
+    assert blas2.dot(r, w, r) == val["arakawa"]
+    pol = Elliptic2d(g, direction=T.CENTERED, jfactor=1.)
+    s = torch.zeros_like(b)
+    lib().elliptic2d_variation(pol.h, C.c_double(1.), None, ptr(f), C.c_double(0.), ptr(s), stream())
+    assert blas2.dot(s, w, s) == val["variation"]
+    ex = TF.Extrapolation(2, f)
+    ex.update(0., f)
+    ex.update(0.5, b)
+    ex.extrapolate(1.0, s)
+    assert blas2.dot(s, w, s) == val["extrapolation"]
+    assert blas1.reduce(s, -1e300, "max") == mx and blas1.reduce(s, 1e300, "min") == mn
 
 
 def test_cpp_host_only():
