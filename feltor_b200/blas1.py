@@ -112,6 +112,16 @@ def tensor_multiply2d(lam, t, in0, in1, mu, out0, out1):
                             ptr(in0), ptr(in1), d(mu), ptr(out0), ptr(out1), stream())
 
 
+def tensor_multiply3d(lam, t, ins, mu, outs):
+    """dg::tensor::multiply3d, inc/dg/topology/multiply.h:34-58,243; t = 9 tensors/None (row major) or None."""
+    larr = None if isinstance(lam, (int, float)) else lam
+    ls = float(lam) if larr is None else 1.0
+    T = (C.c_void_p * 9)(*[None if a is None else a.data_ptr() for a in (t or [None] * 9)])
+    I = (C.c_void_p * 3)(*[a.data_ptr() for a in ins])
+    O = (C.c_void_p * 3)(*[a.data_ptr() for a in outs])
+    lib().tensor_multiply3d(_n(*ins, *outs), ptr(larr), d(ls), T, I, d(mu), O, stream())
+
+
 def embedded_pair_sum(y, yt, b0, bt0, b, bt, ks):
     """subroutines.h:179-204 as used by ERKStep (runge_kutta.h:35-62)."""
     nk = len(ks)

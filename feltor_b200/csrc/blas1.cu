@@ -222,6 +222,26 @@ struct FTensorMul2d {  // multiply.h:18-32; v = {lambda,t00,t01,t10,t11,in0,in1,
         v[7] = __fma_rn(l, tmp0, temp);
     }
 };
+struct FTensorMul3d {  // multiply.h:34-58; v = {lambda, t00..t22 (row major), in0,in1,in2, out0,out1,out2}
+    static constexpr int NV = 16; static constexpr unsigned RMASK = 0xffff, WMASK = 0xe000;
+    double lambda_s, mu;
+    unsigned present;  // bit 0: lambda array, bit 1+k: tensor component k present, else the identity's constant
+    __device__ void operator()(double (&v)[16]) const {
+        double l = (present & 1u) ? v[0] : lambda_s;
+        double t[9];
+#pragma unroll
+        for (int k = 0; k < 9; k++) t[k] = (present >> (1 + k)) & 1u ? v[1 + k] : (k % 4 == 0 ? 1. : 0.);
+        double tmp0 = __fma_rn(t[0], v[10], __fma_rn(t[1], v[11], __dmul_rn(t[2], v[12])));
+        double tmp1 = __fma_rn(t[3], v[10], __fma_rn(t[4], v[11], __dmul_rn(t[5], v[12])));
+        double tmp2 = __fma_rn(t[6], v[10], __fma_rn(t[7], v[11], __dmul_rn(t[8], v[12])));
+        double temp = __dmul_rn(v[15], mu);
+        v[15] = __fma_rn(l, tmp2, temp);
+        temp = __dmul_rn(v[14], mu);
+        v[14] = __fma_rn(l, tmp1, temp);
+        temp = __dmul_rn(v[13], mu);
+        v[13] = __fma_rn(l, tmp0, temp);
+    }
+};
 struct FArakawa {  // ArakawaFunctor (arakawa.h:125-145); v = {lhs, rhs, dxlhs, dylhs, dxrhs, dyrhs}, the last three are in/out
     static constexpr int NV = 6; static constexpr unsigned RMASK = 0x3f, WMASK = 0x38;
     __device__ void operator()(double (&v)[6]) const {
@@ -374,6 +394,22 @@ int dgb_tensor_multiply2d(size_t n, const double* lambda, double lambda_s, const
     unsigned present = (lambda ? 1u : 0u) | (t00 ? 2u : 0u) | (t01 ? 4u : 0u) | (t10 ? 8u : 0u) | (t11 ? 16u : 0u);
     return launch_ew(FTensorMul2d{lambda_s, mu, present}, pack<9>({lambda, t00, t01, t10, t11, in0, in1, out0, out1}),
                      n, s);
+}
+int dgb_tensor_multiply3d(size_t n, const double* lambda, double lambda_s, const double* const t[9], const double* const in[3],
+                          double mu, double* const out[3], dgb_stream_t s) {
+    if (!in || !out || !in[0] || !in[1] || !in[2] || !out[0] || !out[1] || !out[2]) {
+        set_error("dgb_tensor_multiply3d: in/out vectors required");
+        return DGB_ERR_INVALID;
+    }
+    unsigned present = lambda ? 1u : 0u;
+    Pack<16> pk;
+    pk.p[0] = const_cast<double*>(lambda);
+    for (int k = 0; k < 9; k++) {
+        pk.p[1 + k] = t ? const_cast<double*>(t[k]) : nullptr;
+        if (pk.p[1 + k]) present |= 2u << k;
+    }
+    for (int k = 0; k < 3; k++) { pk.p[10 + k] = const_cast<double*>(in[k]); pk.p[13 + k] = out[k]; }
+    return launch_ew(FTensorMul3d{lambda_s, mu, present}, pk, n, s);
 }
 int dgb_arakawa_functor(size_t n, const double* lhs, const double* rhs, const double* dxlhs, double* dylhs, double* dxrhs,
                         double* dyrhs, dgb_stream_t s) {

@@ -1,5 +1,6 @@
 // dg::geo::Fieldaligned::ePlus / eMinus (inc/geometries/fieldaligned.h:850-912) and the parallel-derivative
-// formulas ds_forward/backward/centered, ds_forward2/backward2, dss_centered (inc/geometries/ds.h:744-852,84-106).
+// formulas ds_forward/backward/centered, ds_forward2/backward2, dss_centered, dssd_centered, ds_div*, ds_average
+// (inc/geometries/ds.h:744-1000,84-135).
 //  * dgb_fa_eplus / dgb_fa_eminus: the 2-d interpolation matrix is applied to ALL planes in one launch
 //    (csr_planes_kernel), then the ghost-cell fix-up of the last / first plane for non-periodic z with the same
 //    three blas1 steps the reference performs.
@@ -17,7 +18,8 @@ extern "C" int dgb_axpbyz(size_t, double, const double*, double, const double*, 
 extern "C" int dgb_axpby(size_t, double, const double*, double, double*, dgb_stream_t);
 extern "C" int dgb_pointwise_dot(size_t, double, const double*, const double*, double, double*, dgb_stream_t);
 
-enum { DS_FORWARD = 0, DS_BACKWARD = 1, DS_CENTERED = 2, DS_FORWARD2 = 3, DS_BACKWARD2 = 4, DSS_CENTERED = 5 };
+enum { DS_FORWARD = 0, DS_BACKWARD = 1, DS_CENTERED = 2, DS_FORWARD2 = 3, DS_BACKWARD2 = 4, DSS_CENTERED = 5,
+       DSSD_CENTERED = 6, DS_DIV_BACKWARD = 7, DS_DIV_FORWARD = 8, DS_DIV_CENTERED = 9, DS_AVERAGE = 10 };
 
 // a, b, c: the shifted fields in the argument order of the reference lambdas; bm, b0, bp: bphi on the minus/own/plus plane
 template <int KIND>
@@ -37,6 +39,42 @@ __device__ __forceinline__ double ds_formula(double alpha, double beta, double d
         v = __ddiv_rn(__dmul_rn(__dmul_rn(alpha, b0), __dsub_rn(__dmul_rn(bP2, fp2), __dmul_rn(bM2, fm2))), delta);
     }
     return beta == 0. ? v : __dadd_rn(v, __dmul_rn(beta, g));
+}
+
+// the formulas that also need the volume form sqrtG on the three planes (ds.h:111-135, 903-1000)
+template <int KIND>
+__device__ __forceinline__ double ds_vol_formula(double alpha, double beta, double delta, double g, double a, double b, double c,
+                                                  double Gm, double G0, double Gp, double bm, double b0, double bp) {
+    double v;
+    if (KIND == DSSD_CENTERED) {    // DSSDCentered: a = fm, b = f, c = fp
+        double bP2 = __ddiv_rn(__dadd_rn(bp, b0), 2.), bM2 = __ddiv_rn(__dadd_rn(bm, b0), 2.);
+        double fm2 = __ddiv_rn(__dsub_rn(b, a), delta), fp2 = __ddiv_rn(__dsub_rn(c, b), delta);
+        double gp2 = __ddiv_rn(__ddiv_rn(__dadd_rn(Gp, G0), G0), 2.), gm2 = __ddiv_rn(__ddiv_rn(__dadd_rn(Gm, G0), G0), 2.);
+        double t1 = __dmul_rn(__dmul_rn(__dmul_rn(gp2, fp2), bP2), bP2), t2 = __dmul_rn(__dmul_rn(__dmul_rn(bM2, bM2), gm2), fm2);
+        v = __ddiv_rn(__dmul_rn(alpha, __dsub_rn(t1, t2)), delta);
+    } else if (KIND == DS_DIV_BACKWARD)  // a = fm, b = f: alpha*(bP0*G0*f - bPm*Gm*fm)/G0/delta
+        v = __ddiv_rn(__ddiv_rn(__dmul_rn(alpha, __dsub_rn(__dmul_rn(__dmul_rn(b0, G0), b), __dmul_rn(__dmul_rn(bm, Gm), a))), G0), delta);
+    else if (KIND == DS_DIV_FORWARD)     // a = f, b = fp: alpha*(bPp*Gp*fp - bP0*G0*f)/G0/delta
+        v = __ddiv_rn(__ddiv_rn(__dmul_rn(alpha, __dsub_rn(__dmul_rn(__dmul_rn(bp, Gp), b), __dmul_rn(__dmul_rn(b0, G0), a))), G0), delta);
+    else if (KIND == DS_DIV_CENTERED)    // a = fm, b = fp: alpha*(fp*Gp*bPp - fm*Gm*bPm)/G0/2/delta
+        v = __ddiv_rn(__ddiv_rn(__ddiv_rn(__dmul_rn(alpha, __dsub_rn(__dmul_rn(__dmul_rn(b, Gp), bp), __dmul_rn(__dmul_rn(a, Gm), bm))), G0), 2.), delta);
+    else                                 // ds_average: a = fm, b = fp: alpha*(fp+fm)/2
+        v = __ddiv_rn(__dmul_rn(alpha, __dadd_rn(b, a)), 2.);
+    return beta == 0. ? v : __dadd_rn(v, __dmul_rn(beta, g));
+}
+
+template <int KIND>
+__global__ void __launch_bounds__(256)
+ds_vol_kernel(size_t n, double alpha, double beta, double delta, const double* __restrict__ a, const double* __restrict__ b,
+              const double* __restrict__ c, const double* __restrict__ Gm, const double* __restrict__ G0,
+              const double* __restrict__ Gp, const double* __restrict__ bm, const double* __restrict__ b0,
+              const double* __restrict__ bp, double* __restrict__ g) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        double cc = c ? c[i] : 0.;
+        double go = beta == 0. ? 0. : g[i];
+        g[i] = ds_vol_formula<KIND>(alpha, beta, delta, go, a[i], b[i], cc, Gm ? Gm[i] : 0., G0 ? G0[i] : 1., Gp ? Gp[i] : 0.,
+                                    bm ? bm[i] : 0., b0 ? b0[i] : 0., bp ? bp[i] : 0.);
+    }
 }
 
 template <int KIND>
@@ -124,6 +162,28 @@ int dgb_ds_apply(int kind, size_t n, double alpha, const double* a, const double
         case DSS_CENTERED: ds_kernel<DSS_CENTERED><<<grid, 256, 0, st>>>(n, alpha, beta, delta_phi, a, b, c, bphi_m, bphi, bphi_p, g); break;
         default: set_error("dgb_ds_apply: unknown kind %d", kind); return DGB_ERR_INVALID;
     }
+    DGB_LAUNCHED();
+    return 0;
+}
+
+// kind: 6 dssd_centered (a=fm,b=f,c=fp) 7 ds_divBackward (a=fm,b=f) 8 ds_divForward (a=f,b=fp) 9 ds_divCentered (a=fm,b=fp)
+//       10 ds_average (a=fm,b=fp; no metric fields);  ds.h:881-1000
+int dgb_ds_apply_vol(int kind, size_t n, double alpha, const double* a, const double* b, const double* c, const double* sqrtG_m,
+                     const double* sqrtG, const double* sqrtG_p, const double* bphi_m, const double* bphi, const double* bphi_p,
+                     double delta_phi, double beta, double* g, dgb_stream_t s) {
+    if (n == 0) return 0;
+    bool ok = a && b && g;
+    if (kind == DSSD_CENTERED) ok = ok && c && sqrtG_m && sqrtG && sqrtG_p && bphi_m && bphi && bphi_p;
+    else if (kind == DS_DIV_BACKWARD) ok = ok && sqrtG_m && sqrtG && bphi_m && bphi;
+    else if (kind == DS_DIV_FORWARD) ok = ok && sqrtG_p && sqrtG && bphi_p && bphi;
+    else if (kind == DS_DIV_CENTERED) ok = ok && sqrtG_m && sqrtG && sqrtG_p && bphi_m && bphi_p;
+    else if (kind != DS_AVERAGE) { set_error("dgb_ds_apply_vol: unknown kind %d", kind); return DGB_ERR_INVALID; }
+    if (!ok) { set_error("dgb_ds_apply_vol: missing operand for kind %d", kind); return DGB_ERR_INVALID; }
+    cudaStream_t st = as_stream(s);
+    unsigned grid = ew_grid(n);
+#define DGB_DSV(K) case K: ds_vol_kernel<K><<<grid, 256, 0, st>>>(n, alpha, beta, delta_phi, a, b, c, sqrtG_m, sqrtG, sqrtG_p, bphi_m, bphi, bphi_p, g); break;
+    switch (kind) { DGB_DSV(DSSD_CENTERED) DGB_DSV(DS_DIV_BACKWARD) DGB_DSV(DS_DIV_FORWARD) DGB_DSV(DS_DIV_CENTERED) DGB_DSV(DS_AVERAGE) }
+#undef DGB_DSV
     DGB_LAUNCHED();
     return 0;
 }

@@ -96,6 +96,10 @@ DGB_API int dgb_pointwise_divide_xy(size_t n, const double* x1, const double* x2
 DGB_API int dgb_tensor_multiply2d(size_t n, const double* lambda, double lambda_s, const double* t00,
                                   const double* t01, const double* t10, const double* t11, const double* in0,
                                   const double* in1, double mu, double* out0, double* out1, dgb_stream_t s);
+/* TensorMultiply3d (multiply.h:34-58): the same for 3 components; t = HOST array of 9 device pointers (row major,
+ * NULL entries / NULL t = identity), in / out = HOST arrays of 3 device pointers (out may alias in) */
+DGB_API int dgb_tensor_multiply3d(size_t n, const double* lambda, double lambda_s, const double* const t[9],
+                                  const double* const in[3], double mu, double* const out[3], dgb_stream_t s);
 /* EmbeddedPairSum (subroutines.h:179-204, used by ERKStep runge_kutta.h:35-62):
  * y = b0*y + sum_s b[s]*k[s], yt = bt0*yt + sum_s bt[s]*k[s];  b, bt, k are HOST arrays (k of device pointers), nk <= 16 */
 DGB_API int dgb_embedded_pair_sum(size_t n, double* y, double* yt, double b0, double bt0, int nk, const double* b_host,
@@ -262,6 +266,13 @@ DGB_API int dgb_fa_shift(int plus, int num_rows, int nplanes, const int* pos, co
 DGB_API int dgb_ds_apply(int kind, size_t n, double alpha, const double* a, const double* b, const double* c,
                          const double* bphi_m, const double* bphi, const double* bphi_p, double delta_phi, double beta,
                          double* g, dgb_stream_t s);
+/* dssd_centered / ds_divBackward / ds_divForward / ds_divCentered / ds_average (ds.h:881-1000): kind 6..10, operands in
+ * the argument order of the reference functions (6: fm,f,fp  7: fm,f  8: f,fp  9: fm,fp  10: fm,fp); sqrtG_* = fa.sqrtGm/
+ * sqrtG/sqrtGp, bphi_* = fa.bphiM/bphi/bphiP; fields a kind does not use may be NULL */
+DGB_API int dgb_ds_apply_vol(int kind, size_t n, double alpha, const double* a, const double* b, const double* c,
+                             const double* sqrtG_m, const double* sqrtG, const double* sqrtG_p, const double* bphi_m,
+                             const double* bphi, const double* bphi_p, double delta_phi, double beta, double* g,
+                             dgb_stream_t s);
 /* DS::centered(alpha, f, beta, g) (ds.h:481-485) for periodic z fused into one kernel (gather f+, f-, formula) */
 DGB_API int dgb_ds_centered_fused(int num_rows, int nplanes, const int* plus_pos, const int* plus_idx,
                                   const double* plus_val, const int* minus_pos, const int* minus_idx,

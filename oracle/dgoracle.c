@@ -96,6 +96,59 @@ ORC_API void orc_tensor_multiply2d(int n, const double* lambda, double lambda_s,
         out0[i] = fma(l, tmp0, temp);
     }
 }
+/* TensorMultiply3d inc/dg/topology/multiply.h:34-58; t = 9 row-major component pointers (NULL = identity's constant) */
+ORC_API void orc_tensor_multiply3d(int n, const double* lambda, double lambda_s, const double* const* t,
+                                   const double* const* in, double mu, double* const* out) {
+    for (int i = 0; i < n; i++) {
+        double l = lambda ? lambda[i] : lambda_s, T[9];
+        for (int k = 0; k < 9; k++) T[k] = (t && t[k]) ? t[k][i] : (k % 4 == 0 ? 1. : 0.);
+        double i0 = in[0][i], i1 = in[1][i], i2 = in[2][i];
+        double tmp0 = fma(T[0], i0, fma(T[1], i1, T[2] * i2));
+        double tmp1 = fma(T[3], i0, fma(T[4], i1, T[5] * i2));
+        double tmp2 = fma(T[6], i0, fma(T[7], i1, T[8] * i2));
+        double temp = out[2][i] * mu;
+        out[2][i] = fma(l, tmp2, temp);
+        temp = out[1][i] * mu;
+        out[1][i] = fma(l, tmp1, temp);
+        temp = out[0][i] * mu;
+        out[0][i] = fma(l, tmp0, temp);
+    }
+}
+/* The parallel-derivative formulas inc/geometries/ds.h:743-1000 (+ functors :67-135) written left to right with
+ * separately rounded operations (the reference's are user lambdas whose contraction is up to its compiler, so parity
+ * with a compiled reference is to ~1e-14, not bitwise).  kind and operand order as dgb_ds_apply / dgb_ds_apply_vol:
+ * 0 forward (a=f,b=fp) 1 backward (a=f,b=fm) 2 centered (a=fm,b=fp) 3 forward2 (f,fp,fpp) 4 backward2 (f,fm,fmm)
+ * 5 dss_centered (fm,f,fp) 6 dssd_centered (fm,f,fp) 7 divBackward (fm,f) 8 divForward (f,fp) 9 divCentered (fm,fp)
+ * 10 average (fm,fp) */
+ORC_API void orc_ds_apply(int kind, int n, double alpha, const double* a, const double* b, const double* c,
+                          const double* Gm, const double* G0, const double* Gp, const double* bm, const double* b0,
+                          const double* bp, double delta, double beta, double* g) {
+    for (int i = 0; i < n; i++) {
+        double v = 0.;
+        switch (kind) {
+            case 0: v = alpha * b0[i] * (b[i] - a[i]) / delta; break;
+            case 1: v = alpha * b0[i] * (a[i] - b[i]) / delta; break;
+            case 2: v = alpha * b0[i] * (b[i] - a[i]) / 2. / delta; break;
+            case 3: v = alpha * b0[i] * (-3. * a[i] + 4. * b[i] - c[i]) / 2. / delta; break;
+            case 4: v = alpha * b0[i] * (3. * a[i] - 4. * b[i] + c[i]) / 2. / delta; break;
+            case 5: case 6: {
+                double bP2 = (bp[i] + b0[i]) / 2., bM2 = (bm[i] + b0[i]) / 2.;
+                double fm2 = (b[i] - a[i]) / delta, fp2 = (c[i] - b[i]) / delta;
+                if (kind == 5) v = alpha * b0[i] * (bP2 * fp2 - bM2 * fm2) / delta;
+                else {
+                    double gp2 = (Gp[i] + G0[i]) / G0[i] / 2., gm2 = (Gm[i] + G0[i]) / G0[i] / 2.;
+                    v = alpha * (gp2 * fp2 * bP2 * bP2 - bM2 * bM2 * gm2 * fm2) / delta;
+                }
+                break;
+            }
+            case 7: v = alpha * (b0[i] * G0[i] * b[i] - bm[i] * Gm[i] * a[i]) / G0[i] / delta; break;
+            case 8: v = alpha * (bp[i] * Gp[i] * b[i] - b0[i] * G0[i] * a[i]) / G0[i] / delta; break;
+            case 9: v = alpha * (b[i] * Gp[i] * bp[i] - a[i] * Gm[i] * bm[i]) / G0[i] / 2. / delta; break;
+            case 10: v = alpha * (b[i] + a[i]) / 2.; break;
+        }
+        g[i] = beta == 0. ? v : v + beta * g[i];
+    }
+}
 /* EmbeddedPairSum subroutines.h:179-204: y = b0*y + sum b_i k_i ; yt likewise.  k = array of pointers */
 ORC_API void orc_embedded_pair_sum(int n, double* y, double* yt, double b0, double bt0, int nk, const double* b,
                                    const double* bt, const double* const* k) {

@@ -85,6 +85,22 @@ def tensor_multiply2d(lam, t, in0, in1, mu, out0, out1):
                                 d(mu), dp(out0), dp(out1))
 
 
+def tensor_multiply3d(lam, t, ins, mu, outs):
+    """lam: array or float; t = 9 arrays/None (row major) or None; ins, outs: 3 arrays each."""
+    larr = lam if isinstance(lam, np.ndarray) else None
+    ls = 1.0 if larr is not None else float(lam)
+    T = (c_dp * 9)(*[dp(a) for a in (t or [None] * 9)])
+    lib().orc_tensor_multiply3d(ins[0].size, dp(larr), d(ls), T, (c_dp * 3)(*[dp(a) for a in ins]), d(mu),
+                                (c_dp * 3)(*[dp(a) for a in outs]))
+
+
+def ds_apply(kind, alpha, a, b, c, G, bphi, delta, beta, g):
+    """inc/geometries/ds.h:743-1000; G = (sqrtGm, sqrtG, sqrtGp) or None, bphi = (bphiM, bphi, bphiP)"""
+    G = G or (None, None, None)
+    lib().orc_ds_apply(kind, a.size, d(alpha), dp(a), dp(b), dp(c), dp(G[0]), dp(G[1]), dp(G[2]), dp(bphi[0]), dp(bphi[1]),
+                       dp(bphi[2]), d(delta), d(beta), dp(g))
+
+
 def embedded_pair_sum(y, yt, b0, bt0, b, bt, ks):
     b = np.ascontiguousarray(b, dtype=np.float64)
     bt = np.ascontiguousarray(bt, dtype=np.float64)

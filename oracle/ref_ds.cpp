@@ -1,0 +1,62 @@
+// TEST INFRASTRUCTURE (never linked into or called by the product).
+// The UNMODIFIED free functions dg::geo::ds_* / dss_centered / dssd_centered / ds_div* / ds_average of the reference
+// (inc/geometries/ds.h:743-1016) and dg::TensorMultiply3d (inc/dg/topology/multiply.h:34-58), instantiated on a mock
+// FieldAligned that only hands out the metric fields those templates ask for (deltaPhi, bphi*, sqrtG*).
+// Built by oracle/Makefile into oracle/_ref/libdgref_ds.so from the sources where they lie under /root/reference.
+#include <cstdint>
+#include <vector>
+#include <omp.h>
+#include "dg/algorithm.h"
+#include "dg/geometries/geometries.h"
+
+namespace {
+using Vec = thrust::host_vector<double>;
+struct MockFA {
+    double delta;
+    Vec gm, g0, gp, bm, b0, bp;
+    double deltaPhi() const { return delta; }
+    const Vec& sqrtGm() const { return gm; }
+    const Vec& sqrtG() const { return g0; }
+    const Vec& sqrtGp() const { return gp; }
+    const Vec& bphiM() const { return bm; }
+    const Vec& bphi() const { return b0; }
+    const Vec& bphiP() const { return bp; }
+};
+Vec mk(const double* p, int n) { return p ? Vec(p, p + n) : Vec(n, 0.); }
+}  // namespace
+
+extern "C" {
+// kind 0..5 as dgb_ds_apply, 6 dssd_centered, 7 ds_divBackward (a=fm,b=f), 8 ds_divForward (a=f,b=fp),
+// 9 ds_divCentered (a=fm,b=fp), 10 ds_average (a=fm,b=fp)
+void ref_ds_apply(int kind, int n, double alpha, const double* a, const double* b, const double* c, const double* gm,
+                  const double* g0, const double* gp, const double* bm, const double* b0, const double* bp, double delta,
+                  double beta, double* g) {
+    MockFA fa{delta, mk(gm, n), mk(g0, n), mk(gp, n), mk(bm, n), mk(b0, n), mk(bp, n)};
+    Vec va = mk(a, n), vb = mk(b, n), vc = mk(c, n), vg(g, g + n);
+    switch (kind) {
+        case 0: dg::geo::ds_forward(fa, alpha, va, vb, beta, vg); break;
+        case 1: dg::geo::ds_backward(fa, alpha, vb, va, beta, vg); break;       // (fm, f)
+        case 2: dg::geo::ds_centered(fa, alpha, va, vb, beta, vg); break;       // (fm, fp)
+        case 3: dg::geo::ds_forward2(fa, alpha, va, vb, vc, beta, vg); break;   // (f, fp, fpp)
+        case 4: dg::geo::ds_backward2(fa, alpha, vc, vb, va, beta, vg); break;  // (fmm, fm, f)
+        case 5: dg::geo::dss_centered(fa, alpha, va, vb, vc, beta, vg); break;  // (fm, f, fp)
+        case 6: dg::geo::dssd_centered(fa, alpha, va, vb, vc, beta, vg); break;
+        case 7: dg::geo::ds_divBackward(fa, alpha, va, vb, beta, vg); break;
+        case 8: dg::geo::ds_divForward(fa, alpha, va, vb, beta, vg); break;
+        case 9: dg::geo::ds_divCentered(fa, alpha, va, vb, beta, vg); break;
+        case 10: dg::geo::ds_average(fa, alpha, va, vb, beta, vg); break;
+    }
+    for (int i = 0; i < n; i++) g[i] = vg[i];
+}
+// t: 9 arrays (row major), in/out: 3 arrays each
+void ref_tensor_multiply3d(int n, const double* lambda, const double* const* t, const double* const* in, double mu,
+                           double* const* out) {
+    Vec l = mk(lambda, n), T[9], I[3], O[3];
+    for (int k = 0; k < 9; k++) T[k] = mk(t[k], n);
+    for (int k = 0; k < 3; k++) { I[k] = mk(in[k], n); O[k] = mk(out[k], n); }
+    dg::blas1::subroutine(dg::TensorMultiply3d(), l, T[0], T[1], T[2], T[3], T[4], T[5], T[6], T[7], T[8], I[0], I[1], I[2], mu,
+                          O[0], O[1], O[2]);
+    for (int k = 0; k < 3; k++)
+        for (int i = 0; i < n; i++) out[k][i] = O[k][i];
+}
+}

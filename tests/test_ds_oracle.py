@@ -1,0 +1,51 @@
+"""CPU: pins the oracle's parallel-derivative formulas (orc_ds_apply) and TensorMultiply3d against fixtures produced by
+the UNMODIFIED reference functions (tests/golden/make_golden_ds.py -> ds_golden.npz).  TensorMultiply3d is written with
+explicit DG_FMA in the reference: bit-exact.  The ds formulas are user lambdas that the reference's compiler is free to
+contract (g++ -O2 -mfma does): tolerance 1e-13 relative to the operand scale, stated here."""
+import os
+import numpy as np
+import pytest
+from oracle import orc
+from util import same_bits
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ARGS = {0: ("f", "fp", None), 1: ("f", "fm", None), 2: ("fm", "fp", None), 3: ("f", "fp", "fpp"), 4: ("f", "fm", "fmm"),
+        5: ("fm", "f", "fp"), 6: ("fm", "f", "fp"), 7: ("fm", "f", None), 8: ("f", "fp", None), 9: ("fm", "fp", None),
+        10: ("fm", "fp", None)}
+DS_TOL = 1e-13
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(os.path.join(ROOT, "tests", "golden", "ds_golden.npz"))
+
+
+def ds_close(got, want):
+    scale = np.maximum(np.abs(want), 1.0)
+    return np.max(np.abs(got - want) / scale) < DS_TOL
+
+
+@pytest.mark.parametrize("kind", range(11))
+def test_ds_formulas_fixture(gold, kind):
+    a, b, c = ARGS[kind]
+    G = tuple(gold["ds/" + k] for k in ("Gm", "G0", "Gp"))
+    B = tuple(gold["ds/" + k] for k in ("bm", "b0", "bp"))
+    for beta in (-0.3, 0.0):
+        g = gold["ds/g0"].copy() if beta != 0. else np.full_like(gold["ds/g0"], np.nan)
+        orc.ds_apply(kind, 0.7, gold["ds/" + a], gold["ds/" + b], gold["ds/" + c] if c else None, G, B,
+                     float(gold["ds/delta"][0]), beta, g)
+        assert ds_close(g, gold[f"ds/kind{kind}/beta{int(beta != 0)}"]), (kind, beta)
+
+
+def test_tensor_multiply3d_fixture(gold):
+    t, ins = list(gold["t3d/t"]), list(gold["t3d/in"])
+    o = [a.copy() for a in gold["t3d/out0"]]
+    orc.tensor_multiply3d(gold["t3d/lambda"], t, ins, 0.3, o)
+    assert same_bits(np.stack(o), gold["t3d/out"])
+    o = [a.copy() for a in ins]
+    orc.tensor_multiply3d(gold["t3d/lambda"], t, o, 0., o)
+    assert same_bits(np.stack(o), gold["t3d/out_alias"])
+    # identity tensor, scalar lambda: out = 2 in (temp = out*mu as in the reference: no NaN overwrite for mu = 0)
+    o = [np.zeros_like(a) for a in ins]
+    orc.tensor_multiply3d(2., None, ins, 0., o)
+    assert same_bits(np.stack(o), 2. * np.stack(ins))

@@ -60,6 +60,32 @@ def test_blas1_vs_oracle(G, n):
         assert same_bits(np.stack(a), np.stack([G.get(t) for t in b])), ("op", k, n)
 
 
+def test_tensor_multiply3d(G):
+    """TensorMultiply3d (multiply.h:34-58): fixture of the unmodified reference, oracle, aliasing, identity, odd/unaligned"""
+    import os
+    from feltor_b200 import blas1
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ds_golden.npz"))
+    t, ins, lam = [G.make(a) for a in gold["t3d/t"]], [G.make(a) for a in gold["t3d/in"]], G.make(gold["t3d/lambda"])
+    o = [G.make(a) for a in gold["t3d/out0"]]
+    blas1.tensor_multiply3d(lam, t, ins, 0.3, o)
+    assert same_bits(np.stack([G.get(a) for a in o]), gold["t3d/out"])
+    o = [G.make(a) for a in gold["t3d/in"]]
+    blas1.tensor_multiply3d(lam, t, o, 0., o)
+    assert same_bits(np.stack([G.get(a) for a in o]), gold["t3d/out_alias"])
+    # sparse tensor (some components implicit), scalar lambda, operands offset by one element -> scalar path
+    r = rng(31)
+    n = 777
+    hv = [r.uniform(-2, 2, n + 1) for _ in range(10)]
+    dv = [G.make(a) for a in hv]
+    ht = [hv[0][1:].copy(), None, hv[1][1:].copy(), None, None, hv[2][1:].copy(), hv[3][1:].copy(), None, None]
+    dt = [dv[0][1:], None, dv[1][1:], None, None, dv[2][1:], dv[3][1:], None, None]
+    hi, ho = [hv[4 + k][1:].copy() for k in range(3)], [hv[7 + k][1:].copy() for k in range(3)]
+    orc.tensor_multiply3d(-1.5, ht, hi, 0.25, ho)
+    do = [dv[7 + k][1:] for k in range(3)]
+    blas1.tensor_multiply3d(-1.5, dt, [dv[4 + k][1:] for k in range(3)], 0.25, do)
+    assert same_bits(np.stack(ho), np.stack([G.get(a) for a in do]))
+
+
 def test_blas1_unaligned_views_and_tensor(G):
     """operands offset by one element (8-byte aligned only) take the scalar path; TensorMultiply2d; EmbeddedPairSum"""
     from feltor_b200 import blas1

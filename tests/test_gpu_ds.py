@@ -115,6 +115,55 @@ def test_ds_formulas_and_fused_centered(G):
         assert same_bits(G.get(g1), G.get(g2)), beta
 
 
+ARGS = {0: ("f", "fp", None), 1: ("f", "fm", None), 2: ("fm", "fp", None), 3: ("f", "fp", "fpp"), 4: ("f", "fm", "fmm"),
+        5: ("fm", "f", "fp"), 6: ("fm", "f", "fp"), 7: ("fm", "f", None), 8: ("f", "fp", None), 9: ("fm", "fp", None),
+        10: ("fm", "fp", None)}
+
+
+@pytest.mark.parametrize("kind", range(11))
+def test_ds_formulas_golden_and_oracle(G, kind):
+    """all eleven ds.h:743-1000 formulas: bit-identical to the oracle restatement (same rounding sequence), and within
+    1e-13 of the fixture computed by the unmodified reference functions (their lambdas are contracted by its compiler);
+    beta = 0 overwrites NaN"""
+    import os
+    from feltor_b200 import lib
+    from feltor_b200._dev import ptr, stream
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ds_golden.npz"))
+    a, b, c = ARGS[kind]
+    dv = {k: G.make(gold["ds/" + k]) for k in ("f", "fm", "fp", "fmm", "fpp", "Gm", "G0", "Gp", "bm", "b0", "bp")}
+    n, delta = gold["ds/f"].size, float(gold["ds/delta"][0])
+    for beta in (-0.3, 0.0):
+        g0 = gold["ds/g0"].copy() if beta != 0. else np.full(n, np.nan)
+        g = G.make(g0)
+        cc = ptr(dv[c]) if c else None
+        if kind < 6:
+            lib().ds_apply(kind, n, C.c_double(0.7), ptr(dv[a]), ptr(dv[b]), cc, ptr(dv["bm"]), ptr(dv["b0"]), ptr(dv["bp"]),
+                           C.c_double(delta), C.c_double(beta), ptr(g), stream())
+        else:
+            lib().ds_apply_vol(kind, n, C.c_double(0.7), ptr(dv[a]), ptr(dv[b]), cc, ptr(dv["Gm"]), ptr(dv["G0"]), ptr(dv["Gp"]),
+                               ptr(dv["bm"]), ptr(dv["b0"]), ptr(dv["bp"]), C.c_double(delta), C.c_double(beta), ptr(g), stream())
+        got = G.get(g)
+        want = g0.copy()
+        orc.ds_apply(kind, 0.7, gold["ds/" + a], gold["ds/" + b], gold["ds/" + c] if c else None,
+                     tuple(gold["ds/" + k] for k in ("Gm", "G0", "Gp")), tuple(gold["ds/" + k] for k in ("bm", "b0", "bp")),
+                     delta, beta, want)
+        assert same_bits(got, want), (kind, beta)
+        ref = gold[f"ds/kind{kind}/beta{int(beta != 0)}"]
+        assert np.max(np.abs(got - ref) / np.maximum(np.abs(ref), 1.)) < 1e-13, (kind, beta)
+
+
+def test_ds_apply_vol_rejects_missing_operands(G):
+    from feltor_b200 import lib, DgbError
+    from feltor_b200._dev import ptr, stream
+    x = G.make(np.ones(8))
+    with pytest.raises(DgbError):
+        lib().ds_apply_vol(7, 8, C.c_double(1.), ptr(x), ptr(x), None, None, ptr(x), None, ptr(x), ptr(x), None,
+                           C.c_double(1.), C.c_double(0.), ptr(x), stream())
+    with pytest.raises(DgbError):
+        lib().ds_apply_vol(11, 8, C.c_double(1.), ptr(x), ptr(x), None, None, None, None, None, None, None,
+                           C.c_double(1.), C.c_double(0.), ptr(x), stream())
+
+
 @pytest.mark.parametrize("n,nz,maxlen", [(700, 7, 35), (1000, 64, 90), (33, 1, 5), (4096, 9, 40)])
 def test_gather_plan_equals_csr_kernels(G, n, nz, maxlen):
     """the sliced-ELL gather plan (dgb_gather_*) == the CSR kernels bit for bit: all-planes SpMV for every beta / shift,
