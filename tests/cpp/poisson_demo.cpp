@@ -44,5 +44,11 @@ int main(int argc, char** argv) {
     DVec y(grid.size(), 0.);
     unsigned it = pcg.solve(multi_pol[0], y, b, multi_pol[0].precond(), multi_pol[0].weights(), 1e-6);
     printf("pcg iterations: %u\n", it);
+    // the generic solve (any operator with symv / any callable): same iteration, unfused -- must agree bit for bit
+    DVec z(grid.size(), 0.);
+    Elliptic2d& A = multi_pol[0];
+    unsigned itg = pcg.solve([&A](const DVec& in, DVec& out) { A.symv(in, out); }, z, b, A.precond(), A.weights(), 1e-6);
+    blas1::axpby(1., y, -1., z);
+    printf("generic pcg iterations: %u difference %.17g checksum %.17g\n", itg, blas2::dot(A.weights(), z), blas2::dot(A.weights(), y));
     return err < 1e-4 ? 0 : 1;
 }

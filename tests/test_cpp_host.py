@@ -94,7 +94,10 @@ def test_cpp_poisson_demo_matches_harness():
     out = subprocess.run([EXE, "48", "32", "3"], capture_output=True, text=True, timeout=300)
     assert out.returncode == 0, out.stdout + out.stderr
     num = [int(v) for v in re.search(r"multigrid iterations:((?: \d+)+)", out.stdout).group(1).split()]
-    it = int(re.search(r"pcg iterations: (\d+)", out.stdout).group(1))
+    it = int(re.search(r"^pcg iterations: (\d+)", out.stdout, flags=re.M).group(1))
+    m = re.search(r"generic pcg iterations: (\d+) difference (\S+) checksum (\S+)", out.stdout)
+    # the unfused generic PCG::solve (callable operator) == the fused solver, bit for bit
+    assert int(m.group(1)) == it and float(m.group(2)) == 0.0
     g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, [48, 32], [T.DIR, T.PER])
     amp = 0.9
     import math
@@ -110,3 +113,5 @@ def test_cpp_poisson_demo_matches_harness():
     assert mg.solve(ops, x, G.make(b), 1e-6) == num
     y = G.make(np.zeros(g.size))
     assert PCG(g.size, 100000).solve(ops[0], y, G.make(b), ops[0].precond(), ops[0].weights(), 1e-6) == it
+    from feltor_b200 import blas2
+    assert blas2.dot(y, ops[0].weights(), y) == float(m.group(3))
