@@ -182,3 +182,12 @@ def symv(*a):
             return blas1.pointwiseDot(M, x, y)
         return blas1.pointwiseDot(alpha, M, x, beta, y)
     return M.symv(alpha, x, beta, y)
+
+
+STENCILS = {"median": 0, "swm": 1, "average": 2, "symv": 3}
+
+
+def stencil(kind, pos, idx, val, x, y, alpha=0.0):
+    """blas2::stencil(f, M, x, y) (blas2.h:454) with f = CSRMedianFilter / CSRSWMFilter(alpha) / CSRAverageFilter /
+    CSRSymvFilter (topology/filter.h:174-266); pos, idx int32 device tensors, val float64 or None."""
+    lib().csr_stencil(STENCILS[kind], pos.numel() - 1, ptr(pos), ptr(idx), ptr(val), d(alpha), ptr(x), ptr(y), stream())

@@ -222,6 +222,11 @@ struct FTensorMul2d {  // multiply.h:18-32; v = {lambda,t00,t01,t10,t11,in0,in1,
         v[7] = __fma_rn(l, tmp0, temp);
     }
 };
+struct FTolerance {  // detail::Tolerance (adaptive.h:123-134): delta = delta / (rtol*|u0| + atol); v = {u0, delta}
+    static constexpr int NV = 2; static constexpr unsigned RMASK = 3, WMASK = 2;
+    double rtol, atol;
+    __device__ void operator()(double (&v)[2]) const { v[1] = __ddiv_rn(v[1], __fma_rn(rtol, fabs(v[0]), atol)); }
+};
 struct FTensorMul3d {  // multiply.h:34-58; v = {lambda, t00..t22 (row major), in0,in1,in2, out0,out1,out2}
     static constexpr int NV = 16; static constexpr unsigned RMASK = 0xffff, WMASK = 0xe000;
     double lambda_s, mu;
@@ -410,6 +415,9 @@ int dgb_tensor_multiply3d(size_t n, const double* lambda, double lambda_s, const
     }
     for (int k = 0; k < 3; k++) { pk.p[10 + k] = const_cast<double*>(in[k]); pk.p[13 + k] = out[k]; }
     return launch_ew(FTensorMul3d{lambda_s, mu, present}, pk, n, s);
+}
+int dgb_adaptive_tolerance(size_t n, double rtol, double atol, const double* u0, double* delta, dgb_stream_t s) {
+    return launch_ew(FTolerance{rtol, atol}, pack<2>({u0, delta}), n, s);
 }
 int dgb_arakawa_functor(size_t n, const double* lhs, const double* rhs, const double* dxlhs, double* dylhs, double* dxrhs,
                         double* dyrhs, dgb_stream_t s) {

@@ -1,17 +1,18 @@
 """The toefl right-hand side on libdgb200.so: mirror of toefl::Explicit (src/toefl/toefl.h:8-310) and of the dg classes
 it is built from -- dg::Helmholtz (inc/dg/helmholtz.h:27-82), dg::Advection (inc/dg/advection.h:60-120),
-dg::Extrapolation (inc/dg/extrapolation.h:225-460) and the fixed-step explicit Runge-Kutta stepper dg::ERKStep
-(inc/dg/runge_kutta.h:300-400) -- same member names, same call sequence, every arithmetic step a dgb_* call.
+dg::Extrapolation (inc/dg/extrapolation.h:225-460), the explicit Runge-Kutta stepper dg::ERKStep
+(inc/dg/runge_kutta.h:300-400) and dg::Adaptive with its controllers (inc/dg/adaptive.h:22-395) -- same member names, same call sequence, every arithmetic step a dgb_* call.
 Like the rest of feltor_b200/*.py this is harness code over the C ABI (tests, benchmarks), not the product.
 
 Models implemented: "global" (the default input of the reference) and "local".
 """
 import ctypes as C
+import math
 import numpy as np
 import torch
 from ._lib import lib
 from ._dev import ptr, stream, dvec
-from . import blas1, topology as T
+from . import blas1, blas2, topology as T
 from .elliptic import Elliptic2d, MultigridCG2d
 
 d = C.c_double
@@ -337,3 +338,94 @@ class ERKStep:
         else:
             self.k[0], self.k[s - 1] = self.k[s - 1], self.k[0]
         return t1
+
+
+def i_control(dt, eps, embedded_order, order):
+    """adaptive.h:37-41"""
+    return dt[0] * math.pow(eps[0], -1. / float(embedded_order))
+
+
+def pi_control(dt, eps, embedded_order, order):
+    """adaptive.h:43-53"""
+    if dt[1] == 0:
+        return i_control(dt, eps, embedded_order, order)
+    factor = math.pow(eps[0], -0.8 / float(embedded_order)) * math.pow(eps[1], 0.31 / float(embedded_order))
+    return dt[0] * factor
+
+
+def pid_control(dt, eps, embedded_order, order):
+    """adaptive.h:71-85"""
+    if dt[1] == 0:
+        return i_control(dt, eps, embedded_order, order)
+    if dt[2] == 0:
+        return pi_control(dt, eps, embedded_order, order)
+    q = float(embedded_order)
+    factor = math.pow(eps[0], -0.58 / q) * math.pow(eps[1], 0.21 / q) * math.pow(eps[2], -0.1 / q)
+    return dt[0] * factor
+
+
+def pair_dot(x, y):
+    """blas1::dot of std::array<DVec,2> operands: the superaccumulators of the components are summed, normalised and
+    rounded once (blas1_dispatch_vector.h:153-176)"""
+    acc = np.zeros(blas2.BIN_COUNT, dtype=np.int64)
+    for a, b in zip(x, y):
+        part, _, st = blas2.superacc(a, b)
+        if st != 0:
+            raise FloatingPointError("dg::Error: dot product failed since one of the inputs contains NaN or Inf")
+        acc += part
+    lib().superacc_normalize_host(acc.ctypes.data_as(C.c_void_p))
+    lib().superacc_round_host.restype = C.c_double
+    return lib().superacc_round_host(acc.ctypes.data_as(C.c_void_p))
+
+
+def l2norm(x):
+    """adaptive.h:22"""
+    return math.sqrt(pair_dot(x, x))
+
+
+class Adaptive:
+    """dg::Adaptive<dg::ERKStep<std::array<DVec,2>>> (adaptive.h:232-395): embedded step, error scaled by
+    detail::Tolerance, controller with the step / error history, rejection with restart of the controller."""
+
+    def __init__(self, tableau, copyable, embedded_order=2, order=3):
+        self.stepper = ERKStep(tableau, copyable)
+        self.next = [v.clone() for v in copyable]
+        self.delta = [v.clone() for v in copyable]
+        self.size = float(sum(v.numel() for v in copyable))   # dot(1, 1) over both components, exact
+        self.embedded_order, self.order = embedded_order, order   # Bogacki-Shampine-4-2-3: q = 2, p = 3 (tableau.h)
+        self.eps0 = self.eps1 = self.eps2 = 1.
+        self.dt0 = self.dt1 = self.dt2 = 0.
+        self.failed, self.nfailed, self.nsteps = False, 0, 0
+
+    def step(self, rhs, t0, u0, u1, dt, control=pid_control, norm=l2norm, rtol=1e-5, atol=1e-6, reject_limit=2.):
+        """returns (t1, dt_next); u1 may be the same list as u0 (AdaptiveTimeloop::do_integrate calls it so)"""
+        t_next = self.stepper.step(rhs, t0, u0, self.next, dt, self.delta)
+        self.nsteps += 1
+        rs, as_ = rtol * math.sqrt(self.size), atol * math.sqrt(self.size)
+        for q in range(2):
+            lib().adaptive_tolerance(u0[q].numel(), d(rs), d(as_), ptr(u0[q]), ptr(self.delta[q]), stream())
+        self.eps0 = norm(self.delta)
+        self.dt0 = dt
+        if self.eps0 > reject_limit or math.isnan(self.eps0):
+            dt = control([self.dt0, 0., self.dt2], [self.eps0, self.eps1, self.eps2], self.embedded_order, self.order)
+            if abs(dt) > 0.9 * abs(self.dt0):
+                dt = 0.9 * self.dt0
+            self.failed = True
+            self.nfailed += 1
+            if u1 is not u0:
+                for q in range(2):
+                    blas1.copy(u0[q], u1[q])
+            return t0, dt
+        if self.eps0 < 1e-30:
+            dt = 1e14 * self.dt0
+            self.eps0 = 1e-30
+        else:
+            dt = control([self.dt0, self.dt1, self.dt2], [self.eps0, self.eps1, self.eps2], self.embedded_order, self.order)
+            if abs(dt) > 100 * abs(self.dt0):
+                dt = 100 * self.dt0
+        self.eps2, self.eps1 = self.eps1, self.eps0
+        self.dt2, self.dt1 = self.dt1, self.dt0
+        for q in range(2):
+            blas1.copy(self.next[q], u1[q])
+        self.failed = False
+        return t_next, dt

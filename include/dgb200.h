@@ -96,6 +96,9 @@ DGB_API int dgb_pointwise_divide_xy(size_t n, const double* x1, const double* x2
 DGB_API int dgb_tensor_multiply2d(size_t n, const double* lambda, double lambda_s, const double* t00,
                                   const double* t01, const double* t10, const double* t11, const double* in0,
                                   const double* in1, double mu, double* out0, double* out1, dgb_stream_t s);
+/* detail::Tolerance of dg::Adaptive (adaptive.h:123-134, used at :300): delta = delta / (rtol*|u0| + atol); the caller
+ * passes rtol, atol already scaled by sqrt(size) as the functor's constructor does */
+DGB_API int dgb_adaptive_tolerance(size_t n, double rtol, double atol, const double* u0, double* delta, dgb_stream_t s);
 /* TensorMultiply3d (multiply.h:34-58): the same for 3 components; t = HOST array of 9 device pointers (row major,
  * NULL entries / NULL t = identity), in / out = HOST arrays of 3 device pointers (out may alias in) */
 DGB_API int dgb_tensor_multiply3d(size_t n, const double* lambda, double lambda_s, const double* const t[9],
@@ -250,6 +253,14 @@ DGB_API int dgb_csr_spmv(int num_rows, int num_cols, const int* row_offsets, con
 DGB_API int dgb_csr_spmv_planes(int num_rows, int num_cols, const int* row_offsets, const int* cols,
                                 const double* vals, double alpha, const double* x, double beta, double* y,
                                 int nplanes, int shift, dgb_stream_t s);
+
+/* dg::blas2::stencil(f, M, x, y) / parallel_for (blas2.h:413-454, blas2_stencil.h:13-70) for the library's CSR stencil
+ * functors (topology/filter.h:174-266): the matrix only encodes the neighbourhood of each row (create::window_stencil).
+ * y[i] = lower median / switching median (alpha) / average of x over the stencil, or sum x*vals (test filter).
+ * x must not alias y. */
+enum { DGB_STENCIL_MEDIAN = 0, DGB_STENCIL_SWM = 1, DGB_STENCIL_AVERAGE = 2, DGB_STENCIL_SYMV = 3 };
+DGB_API int dgb_csr_stencil(int kind, int num_rows, const int* row_offsets, const int* cols, const double* vals,
+                            double alpha, const double* x, double* y, dgb_stream_t s);
 
 /* ---------------------------------------------------------------------------------------------------
  * dg::geo::Fieldaligned / dg::geo::DS apply path (inc/geometries/fieldaligned.h:806-912, ds.h:170-330,744-852).  The

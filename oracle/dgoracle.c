@@ -149,6 +149,43 @@ ORC_API void orc_ds_apply(int kind, int n, double alpha, const double* a, const 
         g[i] = beta == 0. ? v : v + beta * g[i];
     }
 }
+/* dg::blas2::stencil / parallel_for with the library's CSR stencil functors, inc/dg/topology/filter.h:84-266.
+ * The (lower) median is an order statistic -- rank (n+1)/2 of the stencil values -- so it is restated here by sorting;
+ * kind 0 CSRMedianFilter, 1 CSRSWMFilter(alpha), 2 CSRAverageFilter, 3 CSRSymvFilter */
+static int orc_cmp_double(const void* a, const void* b) {
+    double x = *(const double*)a, y = *(const double*)b;
+    return x < y ? -1 : x > y;
+}
+static double orc_row_median(int b, int e, const int* idx, const double* x, int use_dev, double center, double* scratch) {
+    int n = e - b;
+    for (int k = 0; k < n; k++) scratch[k] = use_dev ? fabs(x[idx[b + k]] - center) : x[idx[b + k]];
+    qsort(scratch, n, sizeof(double), orc_cmp_double);
+    return scratch[(n + 1) / 2 - 1];
+}
+ORC_API void orc_csr_stencil(int kind, int num_rows, const int* pos, const int* idx, const double* val, double alpha,
+                             const double* x, double* y) {
+    int maxn = 1;
+    for (int i = 0; i < num_rows; i++) if (pos[i + 1] - pos[i] > maxn) maxn = pos[i + 1] - pos[i];
+    double* scratch = (double*)malloc(sizeof(double) * maxn);
+    for (int i = 0; i < num_rows; i++) {
+        int b = pos[i], e = pos[i + 1], n = e - b;
+        if (kind == 0) y[i] = orc_row_median(b, e, idx, x, 0, 0., scratch);
+        else if (kind == 1) {
+            double med = orc_row_median(b, e, idx, x, 0, 0., scratch);
+            double amd = orc_row_median(b, e, idx, x, 1, med, scratch);
+            y[i] = fabs(x[i] - med) > alpha * amd ? med : x[i];
+        } else if (kind == 2) {
+            double t = 0;
+            for (int k = b; k < e; k++) t += x[idx[k]] / (double)n;
+            y[i] = t;
+        } else {
+            double t = 0;
+            for (int k = b; k < e; k++) t += x[idx[k]] * val[k];   /* y += x*v (test filter; contraction is up to the reference's compiler) */
+            y[i] = t;
+        }
+    }
+    free(scratch);
+}
 /* EmbeddedPairSum subroutines.h:179-204: y = b0*y + sum b_i k_i ; yt likewise.  k = array of pointers */
 ORC_API void orc_embedded_pair_sum(int n, double* y, double* yt, double b0, double bt0, int nk, const double* b,
                                    const double* bt, const double* const* k) {

@@ -101,6 +101,11 @@ def ds_apply(kind, alpha, a, b, c, G, bphi, delta, beta, g):
                        dp(bphi[2]), d(delta), d(beta), dp(g))
 
 
+def csr_stencil(kind, pos, idx, val, alpha, x, y):
+    """blas2::stencil with CSRMedianFilter (0) / CSRSWMFilter(alpha) (1) / CSRAverageFilter (2) / CSRSymvFilter (3)"""
+    lib().orc_csr_stencil(kind, len(pos) - 1, ip(pos), ip(idx), dp(val), d(alpha), dp(x), dp(y))
+
+
 def embedded_pair_sum(y, yt, b0, bt0, b, bt, ks):
     b = np.ascontiguousarray(b, dtype=np.float64)
     bt = np.ascontiguousarray(bt, dtype=np.float64)

@@ -60,3 +60,18 @@ void ref_tensor_multiply3d(int n, const double* lambda, const double* const* t, 
         for (int i = 0; i < n; i++) out[k][i] = O[k][i];
 }
 }
+
+// dg::blas2::parallel_for with the library's CSR stencil functors (inc/dg/topology/filter.h:174-266, blas2.h:413-454):
+// kind 0 CSRMedianFilter, 1 CSRSWMFilter(alpha), 2 CSRAverageFilter, 3 CSRSymvFilter
+extern "C" void ref_csr_stencil(int kind, int num_rows, int num_cols, const int* pos, const int* idx, const double* val,
+                                double alpha, const double* x, double* y) {
+    thrust::host_vector<int> p(pos, pos + num_rows + 1), c(idx, idx + pos[num_rows]);
+    Vec v(val, val + pos[num_rows]), vx(x, x + num_cols), vy(y, y + num_rows);
+    switch (kind) {
+        case 0: dg::blas2::parallel_for(dg::CSRMedianFilter(), num_rows, p, c, v, vx, vy); break;
+        case 1: dg::blas2::parallel_for(dg::CSRSWMFilter<double>(alpha), num_rows, p, c, v, vx, vy); break;
+        case 2: dg::blas2::parallel_for(dg::CSRAverageFilter(), num_rows, p, c, v, vx, vy); break;
+        case 3: dg::blas2::parallel_for(dg::CSRSymvFilter(), num_rows, p, c, v, vx, vy); break;
+    }
+    for (int i = 0; i < num_rows; i++) y[i] = vy[i];
+}

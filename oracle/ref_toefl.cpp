@@ -94,6 +94,26 @@ double ref_toefl_erk(void* hh, const char* tableau, double t0, double dt, int ns
     out2(y, y0, y1);
     return sec;
 }
+// nsteps calls of dg::Adaptive<dg::ERKStep>::step with dg::pid_control and dg::l2norm, u0 aliasing u1 the way
+// dg::AdaptiveTimeloop::do_integrate drives it (adaptive.h:232-395,640-685; src/toefl/toefl.cpp:88-91).
+// dt_io: initial / proposed next step, dts[k] = step proposed after call k, t_io: time; returns the number of failed steps
+int ref_toefl_adaptive(void* hh, const char* tableau, double* t_io, double* dt_io, int nsteps, double rtol, double atol,
+                       double* y0, double* y1, double* dts) {
+    RefToefl* h = (RefToefl*)hh;
+    const size_t n = h->grid.size();
+    Vec2 y;
+    in2(y0, y1, n, y);
+    dg::Adaptive<dg::ERKStep<Vec2>> adapt(tableau, y);
+    double t = *t_io, dt = *dt_io;
+    for (int k = 0; k < nsteps; k++) {
+        adapt.step(h->rhs, t, y, t, y, dt, dg::pid_control, dg::l2norm, rtol, atol);
+        if (dts) dts[k] = dt;
+    }
+    *t_io = t;
+    *dt_io = dt;
+    out2(y, y0, y1);
+    return (int)adapt.nfailed();
+}
 int ref_toefl_ncalls(void* hh) { return (int)((RefToefl*)hh)->rhs.ncalls(); }
 
 // ---- the building blocks of toefl::Explicit one by one (the class keeps them private), constructed as toefl.h:60-83 does

@@ -27,6 +27,8 @@ def lib():
         _lib.ref_toefl_erk.restype = C.c_double
         _lib.ref_toefl_erk.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         _lib.ref_toefl_ncalls.argtypes = [C.c_void_p]
+        _lib.ref_toefl_adaptive.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.ref_toefl_helmholtz_solve.argtypes = [C.c_void_p] * 4
         _lib.ref_toefl_pol_solve.argtypes = [C.c_void_p] * 5
         _lib.ref_toefl_upwind.argtypes = [C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p]
@@ -79,6 +81,14 @@ class RefToefl:
         a, b = np.array(y0, copy=True), np.array(y1, copy=True)
         sec = lib().ref_toefl_erk(self.h, tableau.encode(), t0, dt, nsteps, _p(a), _p(b))
         return a, b, sec
+
+    def adaptive(self, tableau, t0, dt0, nsteps, rtol, atol, y0, y1):
+        """nsteps calls of dg::Adaptive<ERKStep>::step (pid_control, l2norm); returns y0, y1, t, dts[], nfailed"""
+        a, b = np.array(y0, copy=True), np.array(y1, copy=True)
+        t, dt, dts = C.c_double(t0), C.c_double(dt0), np.zeros(nsteps)
+        nf = lib().ref_toefl_adaptive(self.h, tableau.encode(), C.byref(t), C.byref(dt), nsteps, C.c_double(rtol),
+                                      C.c_double(atol), _p(a), _p(b), _p(dts))
+        return a, b, t.value, dts, nf
 
     def helmholtz_solve(self, x, b):
         x = np.array(x, copy=True)

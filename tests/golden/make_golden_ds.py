@@ -49,5 +49,20 @@ o = [a.copy() for a in ins]   # in place (out aliases in), mu = 0
 L.ref_tensor_multiply3d(n, dp(lam), (c_dp * 9)(*[dp(a) for a in t]), (c_dp * 3)(*[dp(a) for a in o]), d(0.),
                         (c_dp * 3)(*[dp(a) for a in o]))
 out["t3d/out_alias"] = np.stack(o)
+# ---- blas2::stencil with the CSR filters on window-like stencils of 3, 4, 5, 9 and 12..25 points (ties included)
+L.ref_csr_stencil.argtypes = None
+nr = 500
+xs = np.round(r.uniform(-1, 1, nr), 1) + 0.0    # coarse values: many ties (+0.0: no negative zeros)
+xs[::7] = r.uniform(-1, 1, len(xs[::7]))
+counts = r.choice([3, 4, 5, 9, 12, 25], nr)
+pos = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+idx = np.concatenate([np.clip(i + r.integers(-12, 13, c), 0, nr - 1) for i, c in enumerate(counts)]).astype(np.int32)
+val = r.uniform(-1, 1, pos[-1])
+out["stencil/x"], out["stencil/pos"], out["stencil/idx"], out["stencil/val"] = xs, pos, idx, val
+c_ip = C.POINTER(C.c_int)
+for kind in range(4):
+    y = np.zeros(nr)
+    L.ref_csr_stencil(kind, nr, nr, pos.ctypes.data_as(c_ip), idx.ctypes.data_as(c_ip), dp(val), d(1.5), dp(xs), dp(y))
+    out[f"stencil/kind{kind}"] = y
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ds_golden.npz"), **out)
 print("wrote ds_golden.npz with", len(out), "arrays")

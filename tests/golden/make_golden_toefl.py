@@ -3,7 +3,7 @@
 (oracle/_ref/libdgref_toefl.so, built by oracle/Makefile from /root/reference/src/toefl/toefl.h).
 Cases: default input of src/toefl/input/default.json on a 24 x 24 grid (n = 3), models "global" and "local";
 stored: initial condition, the state and both potentials after 3 fixed Bogacki-Shampine-4-2-3 steps of dt = 0.5, and one
-right-hand-side evaluation (fresh object) at that state.   python tests/golden/make_golden_toefl.py"""
+right-hand-side evaluation (fresh object) at that state; plus two dg::Adaptive<ERKStep> runs (see below).   python tests/golden/make_golden_toefl.py"""
 import os
 import sys
 import numpy as np
@@ -25,5 +25,15 @@ for model in ("global", "local"):
     out[model + "_rhs0"], out[model + "_rhs1"] = p0, p1
     out[model + "_rhsphi0"], out[model + "_rhsphi1"] = fresh.phi(0), fresh.phi(1)
     out[model + "_binv"] = ref.binv()
+# dg::Adaptive<ERKStep> with pid_control / l2norm as src/toefl/toefl.cpp:88-91 drives it: (a) 8 steps from the timeloop's
+# initial guess dt = 1e-6 (growth limited to x100 per step), (b) 4 steps from dt = 60 (first step rejected, controller restart)
+js = R.default_params(3, 24, 24, model__type="global")
+for name, dt0, nsteps in (("adaptA", 1e-6, 8), ("adaptB", 60., 4)):
+    ref = R.RefToefl(js)
+    y0, y1 = ref.init()
+    a, b, t, dts, nf = ref.adaptive("Bogacki-Shampine-4-2-3", 0., dt0, nsteps, 1e-5, 1e-6, y0, y1)
+    out[name + "_y0"], out[name + "_y1"], out[name + "_dts"] = a, b, dts
+    out[name + "_t_nfailed"] = np.array([t, nf])
+    print(name, "t =", t, "dts =", dts, "failed", nf)
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "toefl_golden.npz"), **out)
 print("wrote", len(out), "arrays")

@@ -49,3 +49,11 @@ def test_tensor_multiply3d_fixture(gold):
     o = [np.zeros_like(a) for a in ins]
     orc.tensor_multiply3d(2., None, ins, 0., o)
     assert same_bits(np.stack(o), 2. * np.stack(ins))
+
+
+@pytest.mark.parametrize("kind", range(4))
+def test_csr_stencil_fixture(gold, kind):
+    """blas2::stencil with CSRMedianFilter / CSRSWMFilter / CSRAverageFilter / CSRSymvFilter (filter.h:174-266): bit-exact"""
+    y = np.full(gold["stencil/x"].size, np.nan)
+    orc.csr_stencil(kind, gold["stencil/pos"], gold["stencil/idx"], gold["stencil/val"], 1.5, gold["stencil/x"], y)
+    assert same_bits(y, gold[f"stencil/kind{kind}"])

@@ -60,6 +60,34 @@ def test_blas1_vs_oracle(G, n):
         assert same_bits(np.stack(a), np.stack([G.get(t) for t in b])), ("op", k, n)
 
 
+@pytest.mark.parametrize("kind", ["median", "swm", "average", "symv"])
+def test_csr_stencil(G, kind):
+    """blas2::stencil with the library's CSR filters: fixture of the unmodified reference + random stencils vs the oracle"""
+    import os
+    from feltor_b200 import blas2, DgbError
+    from feltor_b200._dev import dvec
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "ds_golden.npz"))
+    k = blas2.STENCILS[kind]
+    pos, idx, val = dvec(gold["stencil/pos"]), dvec(gold["stencil/idx"]), dvec(gold["stencil/val"])
+    x, y = G.make(gold["stencil/x"]), G.make(np.full(gold["stencil/x"].size, np.nan))
+    blas2.stencil(kind, pos, idx, val, x, y, alpha=1.5)
+    assert same_bits(G.get(y), gold[f"stencil/kind{k}"])
+    r = rng(50 + k)
+    n = 3001
+    counts = r.integers(1, 30, n)
+    hp = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    hi = np.concatenate([np.clip(i + r.integers(-40, 41, c), 0, n - 1) for i, c in enumerate(counts)]).astype(np.int32)
+    hv, hx = r.uniform(-1, 1, hp[-1]), np.round(r.uniform(-3, 3, n), 2) + 0.0
+    want = np.zeros(n)
+    orc.csr_stencil(k, hp, hi, hv, 0.8, hx, want)
+    dx, dy = G.make(hx), G.make(np.full(n, np.nan))
+    dp_, di_, dv_ = dvec(hp), dvec(hi), dvec(hv)
+    blas2.stencil(kind, dp_, di_, dv_, dx, dy, alpha=0.8)
+    assert same_bits(G.get(dy), want)
+    with pytest.raises(DgbError):
+        blas2.stencil(kind, dp_, di_, dv_, dx, dx, alpha=0.8)
+
+
 def test_tensor_multiply3d(G):
     """TensorMultiply3d (multiply.h:34-58): fixture of the unmodified reference, oracle, aliasing, identity, odd/unaligned"""
     import os

@@ -64,6 +64,24 @@ def test_toefl_steps_vs_golden(G, gold, model):
     assert ex.ncalls == 10  # FSAL: 4 + 3 + 3 right-hand-side evaluations
 
 
+@pytest.mark.parametrize("case,dt0,nsteps", [("adaptA", 1e-6, 8), ("adaptB", 60., 4)])
+def test_toefl_adaptive_vs_golden(G, gold, case, dt0, nsteps):
+    """dg::Adaptive<ERKStep> with pid_control / l2norm as src/toefl/toefl.cpp:88-91 drives it (adaptive.h:232-395):
+    state, every proposed step size, the time and the number of rejected steps are bit-identical to the reference's"""
+    from feltor_b200 import toefl as TF
+    js = params(3, 24, "global")
+    ex = TF.Explicit(TF.Parameters(js))
+    u = [G.make(gold["global_init0"]), G.make(gold["global_init1"])]
+    adapt = TF.Adaptive("Bogacki-Shampine-4-2-3", u)
+    t, dt, dts = 0., dt0, []
+    for _ in range(nsteps):
+        t, dt = adapt.step(ex, t, u, u, dt, TF.pid_control, TF.l2norm, 1e-5, 1e-6)
+        dts.append(dt)
+    assert same_bits(np.array(dts), gold[case + "_dts"]), (dts, gold[case + "_dts"])
+    assert t == gold[case + "_t_nfailed"][0] and adapt.nfailed == int(gold[case + "_t_nfailed"][1])
+    assert same_bits(G.get(u[0]), gold[case + "_y0"]) and same_bits(G.get(u[1]), gold[case + "_y1"])
+
+
 @pytest.mark.parametrize("model", ["global", "local"])
 def test_toefl_rhs_vs_golden(G, gold, model):
     import torch

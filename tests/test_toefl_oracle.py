@@ -22,6 +22,19 @@ def test_reference_reproduces_golden(model):
     assert same_bits(ref.phi(0), gold[model + "_phi0"])
 
 
+def test_reference_adaptive_reproduces_golden():
+    """dg::Adaptive<ERKStep> + pid_control + l2norm (adaptive.h:232-395), incl. a rejected step"""
+    from oracle import reftoefl as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libdgref_toefl.so not built (needs /root/reference)")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "toefl_golden.npz"))
+    ref = R.RefToefl(R.default_params(3, 24, 24, model__type="global"))
+    y0, y1 = ref.init()
+    a, b, t, dts, nf = ref.adaptive("Bogacki-Shampine-4-2-3", 0., 60., 4, 1e-5, 1e-6, y0, y1)
+    assert same_bits(a, gold["adaptB_y0"]) and same_bits(b, gold["adaptB_y1"]) and same_bits(dts, gold["adaptB_dts"])
+    assert t == gold["adaptB_t_nfailed"][0] and nf == int(gold["adaptB_t_nfailed"][1]) == 1
+
+
 def test_toefl_harness_has_no_oracle_import():
     src = open(os.path.join(ROOT, "feltor_b200", "toefl.py")).read()
     assert "oracle" not in src.replace("oracle/", "")
