@@ -429,3 +429,105 @@ class Adaptive:
             blas1.copy(self.next[q], u1[q])
         self.failed = False
         return t_next, dt
+
+
+def _host_fma(a, b, c):
+    """a*b + c with ONE rounding: the reference's host compiler contracts such expressions (g++ -O2 -mfma), exact
+    rational arithmetic reproduces that"""
+    from fractions import Fraction
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+# Shu-Osher tableaus (tableau.h:1262-1286): lower triangles alpha(i,k), beta(i,k), k <= i
+SHU_OSHER = {
+    "SSPRK-2-2": (2, [[1.], [0.5, 0.5]], [[1.], [0., 0.5]]),
+    "SSPRK-3-3": (3, [[1.], [3. / 4., 1. / 4.], [1. / 3., 0., 2. / 3.]], [[1.], [0., 1. / 4.], [0., 0., 2. / 3.]]),
+}
+# multistep tableaus (multistep_tableau.h:263-300): (order, a, b)
+MULTISTEP = {
+    "AB-1-1": (1, [1.], [1.]),
+    "AB-2-2": (2, [1., 0.], [1.5, -0.5]),
+    "AB-3-3": (3, [1., 0., 0.], [23. / 12., -4. / 3., 5. / 12.]),
+    "TVB-2-2": (2, [4. / 3., -1. / 3.], [4. / 3., -2. / 3.]),
+    "TVB-3-3": (3, [1.908535476882378, -1.334951446162515, 0.426415969280137],
+                [1.502575553858997, -1.654746338401493, 0.670051276940255]),
+}
+
+
+class ShuOsher:
+    """dg::ShuOsher with the identity limiter (runge_kutta.h:840-925) for std::array<DVec,2>"""
+
+    def __init__(self, tableau, copyable):
+        self.s, self.alpha, self.beta = SHU_OSHER[tableau]
+        self.u = [[v.clone() for v in copyable] for _ in range(self.s)]
+        self.k = [[v.clone() for v in copyable] for _ in range(self.s)]
+        self.t1 = 1e300
+
+    def step(self, rhs, t0, u0, u1, dt):
+        s, al, be = self.s, self.alpha, self.beta
+        ts = [t0] + [0.] * s
+        for q in range(2):
+            blas1.copy(u0[q], self.u[0][q])
+        if t0 != self.t1:
+            rhs(ts[0], self.u[0], self.k[0])
+        for i in range(1, s + 1):
+            out = u1 if i == s else self.u[i]
+            for q in range(2):
+                blas1.axpbypgz(al[i - 1][0], self.u[0][q], dt * be[i - 1][0], self.k[0][q], 0., out[q])
+            ts[i] = _host_fma(al[i - 1][0], ts[0], dt * be[i - 1][0])
+            for j in range(1, i):
+                for q in range(2):
+                    blas1.axpbypgz(al[i - 1][j], self.u[j][q], dt * be[i - 1][j], self.k[j][q], 1., out[q])
+                ts[i] = ts[i] + _host_fma(al[i - 1][j], ts[j], dt * be[i - 1][j])
+            if i != s:
+                rhs(ts[i], self.u[i], self.k[i])
+            else:
+                rhs(ts[i], u1, self.k[0])
+        self.t1 = ts[s]
+        return ts[s]
+
+
+class ExplicitMultistep:
+    """dg::ExplicitMultistep (multistep.h:59-100; FilteredExplicitMultistep::init/step :592-639 with the identity filter):
+    the first steps-1 steps are Shu-Osher Runge-Kutta steps of the same order, then
+    u = sum_i a_i u_{n-i} + dt b_i f_{n-i}"""
+
+    def __init__(self, tableau, copyable):
+        self.order, self.a, self.b = MULTISTEP[tableau]
+        self.steps = len(self.a)
+        self.u = [[v.clone() for v in copyable] for _ in range(self.steps)]
+        self.f = [[v.clone() for v in copyable] for _ in range(self.steps)]
+        self.counter = 0
+
+    def init(self, rhs, t0, u0, dt):
+        self.tu, self.dt = t0, dt
+        s = self.steps
+        for q in range(2):
+            blas1.copy(u0[q], self.u[s - 1][q])
+        rhs(self.tu, self.u[s - 1], self.f[s - 1])
+        self.counter = 0
+
+    def step(self, rhs, t, u):
+        """advances u in place, returns the new time"""
+        s = self.steps
+        if self.counter < s - 1:
+            rk = ShuOsher({1: "SSPRK-2-2", 2: "SSPRK-2-2", 3: "SSPRK-3-3"}[self.order], u)
+            t = rk.step(rhs, t, u, u, self.dt)
+            self.counter += 1
+            self.tu = t
+            m = s - 1 - self.counter
+            for q in range(2):
+                blas1.copy(u[q], self.u[m][q])
+            rhs(self.tu, self.u[m], self.f[m])
+            return t
+        t = self.tu = self.tu + self.dt
+        for q in range(2):
+            blas1.axpby(self.a[0], self.u[0][q], self.dt * self.b[0], self.f[0][q], u[q])
+            for i in range(1, s):
+                blas1.axpbypgz(self.a[i], self.u[i][q], self.dt * self.b[i], self.f[i][q], 1., u[q])
+        self.f = [self.f[-1]] + self.f[:-1]   # std::rotate: the oldest slot becomes slot 0
+        self.u = [self.u[-1]] + self.u[:-1]
+        for q in range(2):
+            blas1.copy(u[q], self.u[0][q])
+        rhs(self.tu, self.u[0], self.f[0])
+        return t

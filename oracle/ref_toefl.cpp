@@ -114,6 +114,22 @@ int ref_toefl_adaptive(void* hh, const char* tableau, double* t_io, double* dt_i
     out2(y, y0, y1);
     return (int)adapt.nfailed();
 }
+// dg::ExplicitMultistep (multistep.h:59-100, FilteredExplicitMultistep :514-639): init at t0, then nsteps steps of dt (the
+// first steps-1 are dg::ShuOsher steps, runge_kutta.h:883-910); ts[k] = time after step k
+void ref_toefl_multistep(void* hh, const char* tableau, double t0, double dt, int nsteps, double* y0, double* y1, double* ts) {
+    RefToefl* h = (RefToefl*)hh;
+    const size_t n = h->grid.size();
+    Vec2 y;
+    in2(y0, y1, n, y);
+    dg::ExplicitMultistep<Vec2> ms(tableau, y);
+    double t = t0;
+    ms.init(h->rhs, t, y, dt);
+    for (int k = 0; k < nsteps; k++) {
+        ms.step(h->rhs, t, y);
+        if (ts) ts[k] = t;
+    }
+    out2(y, y0, y1);
+}
 int ref_toefl_ncalls(void* hh) { return (int)((RefToefl*)hh)->rhs.ncalls(); }
 
 // ---- the building blocks of toefl::Explicit one by one (the class keeps them private), constructed as toefl.h:60-83 does

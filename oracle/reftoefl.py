@@ -27,6 +27,8 @@ def lib():
         _lib.ref_toefl_erk.restype = C.c_double
         _lib.ref_toefl_erk.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p]
         _lib.ref_toefl_ncalls.argtypes = [C.c_void_p]
+        _lib.ref_toefl_multistep.argtypes = [C.c_void_p, C.c_char_p, C.c_double, C.c_double, C.c_int, C.c_void_p, C.c_void_p,
+                                             C.c_void_p]
         _lib.ref_toefl_adaptive.argtypes = [C.c_void_p, C.c_char_p, C.c_void_p, C.c_void_p, C.c_int, C.c_double, C.c_double,
                                             C.c_void_p, C.c_void_p, C.c_void_p]
         _lib.ref_toefl_helmholtz_solve.argtypes = [C.c_void_p] * 4
@@ -89,6 +91,15 @@ class RefToefl:
         nf = lib().ref_toefl_adaptive(self.h, tableau.encode(), C.byref(t), C.byref(dt), nsteps, C.c_double(rtol),
                                       C.c_double(atol), _p(a), _p(b), _p(dts))
         return a, b, t.value, dts, nf
+
+    def ncalls(self):
+        return lib().ref_toefl_ncalls(self.h)
+
+    def multistep(self, tableau, t0, dt, nsteps, y0, y1):
+        """dg::ExplicitMultistep: init + nsteps steps; returns y0, y1, ts[]"""
+        a, b, ts = np.array(y0, copy=True), np.array(y1, copy=True), np.zeros(nsteps)
+        lib().ref_toefl_multistep(self.h, tableau.encode(), t0, dt, nsteps, _p(a), _p(b), _p(ts))
+        return a, b, ts
 
     def helmholtz_solve(self, x, b):
         x = np.array(x, copy=True)

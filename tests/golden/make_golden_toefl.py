@@ -35,5 +35,13 @@ for name, dt0, nsteps in (("adaptA", 1e-6, 8), ("adaptB", 60., 4)):
     out[name + "_y0"], out[name + "_y1"], out[name + "_dts"] = a, b, dts
     out[name + "_t_nfailed"] = np.array([t, nf])
     print(name, "t =", t, "dts =", dts, "failed", nf)
+# dg::ExplicitMultistep (multistep.h:59-100): init + steps; the first two steps are SSPRK-3-3 Shu-Osher steps
+for name, tab, dt, nsteps in (("msAB", "AB-3-3", 0.5, 6), ("msTVB", "TVB-3-3", 0.3, 5)):
+    ref = R.RefToefl(js)
+    y0, y1 = ref.init()
+    a, b, ts = ref.multistep(tab, 0., dt, nsteps, y0, y1)
+    out[name + "_y0"], out[name + "_y1"], out[name + "_ts"] = a, b, ts
+    out[name + "_ncalls"] = np.array([ref.ncalls()])
+    print(name, "ts =", ts, "rhs calls", ref.ncalls())
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "toefl_golden.npz"), **out)
 print("wrote", len(out), "arrays")

@@ -82,6 +82,24 @@ def test_toefl_adaptive_vs_golden(G, gold, case, dt0, nsteps):
     assert same_bits(G.get(u[0]), gold[case + "_y0"]) and same_bits(G.get(u[1]), gold[case + "_y1"])
 
 
+@pytest.mark.parametrize("case,tableau,dt,nsteps", [("msAB", "AB-3-3", 0.5, 6), ("msTVB", "TVB-3-3", 0.3, 5)])
+def test_toefl_multistep_vs_golden(G, gold, case, tableau, dt, nsteps):
+    """dg::ExplicitMultistep (multistep.h:59-100, :592-639) incl. its Shu-Osher start-up steps (runge_kutta.h:883-910):
+    state, step times and the number of right-hand-side calls bit-identical to the reference's"""
+    from feltor_b200 import toefl as TF
+    ex = TF.Explicit(TF.Parameters(params(3, 24, "global")))
+    u = [G.make(gold["global_init0"]), G.make(gold["global_init1"])]
+    ms = TF.ExplicitMultistep(tableau, u)
+    t, ts = 0., []
+    ms.init(ex, t, u, dt)
+    for _ in range(nsteps):
+        t = ms.step(ex, t, u)
+        ts.append(t)
+    assert same_bits(np.array(ts), gold[case + "_ts"])
+    assert ex.ncalls == int(gold[case + "_ncalls"][0])
+    assert same_bits(G.get(u[0]), gold[case + "_y0"]) and same_bits(G.get(u[1]), gold[case + "_y1"])
+
+
 @pytest.mark.parametrize("model", ["global", "local"])
 def test_toefl_rhs_vs_golden(G, gold, model):
     import torch
