@@ -321,7 +321,7 @@ class ERKStep:
         if t0 != self.t1:
             rhs(t0, u0, self.k[0])
         for i in range(1, s):
-            tu = float(np.float64(dt) * np.float64(self.c[i]) + np.float64(t0))  # DG_FMA on the host: see note below
+            tu = _host_fma(dt, self.c[i], t0)  # DG_FMA on the host (runge_kutta.h:376): one rounding
             for q in range(2):
                 blas1.copy(u0[q], delta[q])
                 dense_gemv(dt, [self.k[l][q] for l in range(i)], self.a[i][:i], 1., delta[q])

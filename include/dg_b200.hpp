@@ -6,6 +6,7 @@
 // stand-alone way to program against the library from C++.
 #pragma once
 #include <algorithm>
+#include <array>
 #include <type_traits>
 #include <cmath>
 #include <cstddef>
@@ -412,6 +413,162 @@ class MultigridCG2d {
         std::vector<int> num(m_stages);
         check(dgb_multigrid2d_solve(m_mg, A.data(), P.data(), W.data(), x.data(), b.data(), eps.data(), num.data(), nullptr));
         return std::vector<unsigned>(num.begin(), num.end());
+    }
+};
+
+// ---------------------------------------------------------------------------------------------------------------
+// Time steppers on std::array<DVec,2> (the container of toefl / feltor right-hand sides)
+// ---------------------------------------------------------------------------------------------------------------
+using DVec2 = std::array<DVec, 2>;
+
+// blas1::dot of recursive vectors: the superaccumulators of the components are summed, normalised and rounded ONCE
+// (blas1_dispatch_vector.h:153-176) -- not the sum of two rounded dots
+inline double dot(const DVec2& x, const DVec2& y) {
+    int64_t acc[DGB_BIN_COUNT] = {0};
+    for (int q = 0; q < 2; q++) {
+        int64_t part[DGB_BIN_COUNT];
+        double v;
+        int status = 0;
+        check(dgb_dot2(blas1::detail::ws(), x[q].size(), x[q].data(), y[q].data(), part, &v, &status, nullptr));
+        if (status != 0) throw Error(DGB_ERR_NOTFINITE, "dg::Error: dot product failed since one of the inputs contains NaN or Inf");
+        for (int k = 0; k < DGB_BIN_COUNT; k++) acc[k] += part[k];
+    }
+    check(dgb_superacc_normalize_host(acc));
+    return dgb_superacc_round_host(acc);
+}
+inline double l2norm(const DVec2& x) { return std::sqrt(dot(x, x)); }  // adaptive.h:22
+
+// controllers of inc/dg/adaptive.h:37-85
+inline double i_control(std::array<double, 3> dt, std::array<double, 3> eps, unsigned embedded_order, unsigned) {
+    return dt[0] * std::pow(eps[0], -1. / (double)embedded_order);
+}
+inline double pi_control(std::array<double, 3> dt, std::array<double, 3> eps, unsigned embedded_order, unsigned order) {
+    if (dt[1] == 0) return i_control(dt, eps, embedded_order, order);
+    double factor = std::pow(eps[0], -0.8 / (double)embedded_order) * std::pow(eps[1], 0.31 / (double)embedded_order);
+    return dt[0] * factor;
+}
+inline double pid_control(std::array<double, 3> dt, std::array<double, 3> eps, unsigned embedded_order, unsigned order) {
+    if (dt[1] == 0) return i_control(dt, eps, embedded_order, order);
+    if (dt[2] == 0) return pi_control(dt, eps, embedded_order, order);
+    double q = (double)embedded_order;
+    double factor = std::pow(eps[0], -0.58 / q) * std::pow(eps[1], 0.21 / q) * std::pow(eps[2], -0.1 / q);
+    return dt[0] * factor;
+}
+
+// dg::ButcherTableau (inc/dg/tableau.h): the embedded explicit tableaus wired up here
+struct ButcherTableau {
+    unsigned s, embedded_order, order;
+    std::vector<double> a, b, bt, c;  // a row major s x s
+    bool fsal;
+    static ButcherTableau get(const std::string& name) {
+        if (name == "Bogacki-Shampine-4-2-3")  // tableau.h:394-405
+            return {4, 2, 3, {0, 0, 0, 0, 0.5, 0, 0, 0, 0, 0.75, 0, 0, 2. / 9., 1. / 3., 4. / 9., 0.}, {2. / 9., 1. / 3., 4. / 9., 0.},
+                    {7. / 24., 1. / 4., 1. / 3., 1. / 8.}, {0., 0.5, 3. / 4., 1.}, true};
+        throw Error(DGB_ERR_UNSUPPORTED, "dgb200: tableau " + name + " is not wired up");
+    }
+};
+
+// dg::ERKStep<std::array<DVec,2>> (inc/dg/runge_kutta.h:300-400): embedded explicit Runge-Kutta step with FSAL; the stage
+// sums are the dense gemv (blas2_densematrix.h:38-74, chunks of 8/4/2/1 columns) and EmbeddedPairSum kernels
+class ERKStep {
+    ButcherTableau m_rk;
+    std::vector<DVec2> m_k;
+    double m_t1 = 1e300;
+    static void dense_gemv(double alpha, const std::vector<const double*>& cols, const double* x, double beta, DVec& y) {
+        const size_t size = cols.size();
+        auto pair_sum = [&](size_t first, int n, double b) {
+            std::vector<double> a(x + first, x + first + n);
+            check(dgb_pair_sum_axpby(y.size(), alpha, n, a.data(), cols.data() + first, b, y.data(), nullptr));
+        };
+        size_t i = 0;
+        for (; i < size / 8; i++) pair_sum(i * 8, 8, i == 0 ? beta : 1.);
+        size_t l = 0, k = 0;
+        if (size % 8 >= 4) { pair_sum(i * 8, 4, size < 8 ? beta : 1.); l = 1; }
+        if ((size % 8) % 4 >= 2) { pair_sum(i * 8 + l * 4, 2, size < 4 ? beta : 1.); k = 1; }
+        if (((size % 8) % 4) % 2 == 1) {
+            size_t j = i * 8 + l * 4 + k * 2;
+            check(dgb_axpby(y.size(), alpha * x[j], cols[j], size < 2 ? beta : 1., y.data(), nullptr));
+        }
+    }
+  public:
+    ERKStep() = default;
+    ERKStep(const std::string& tableau, const DVec2& copyable) : m_rk(ButcherTableau::get(tableau)), m_k(m_rk.s, copyable) {}
+    unsigned order() const { return m_rk.order; }
+    unsigned embedded_order() const { return m_rk.embedded_order; }
+    const DVec2& copyable() const { return m_k[0]; }
+    template <class RHS>
+    void step(RHS& rhs, double t0, const DVec2& u0, double& t1, DVec2& u1, double dt, DVec2& delta) {
+        const unsigned s = m_rk.s;
+        if (t0 != m_t1) rhs(t0, u0, m_k[0]);
+        for (unsigned i = 1; i < s; i++) {
+            const double tu = std::fma(dt, m_rk.c[i], t0);
+            for (int q = 0; q < 2; q++) {
+                blas1::copy(u0[q], delta[q]);
+                std::vector<const double*> cols;
+                for (unsigned l = 0; l < i; l++) cols.push_back(m_k[l][q].data());
+                dense_gemv(dt, cols, &m_rk.a[i * s], 1., delta[q]);
+            }
+            rhs(tu, delta, m_k[i]);
+        }
+        std::vector<double> b(s), d(s);
+        for (unsigned j = 0; j < s; j++) { b[j] = dt * m_rk.b[j]; d[j] = dt * (m_rk.b[j] - m_rk.bt[j]); }
+        for (int q = 0; q < 2; q++) {
+            blas1::copy(u0[q], u1[q]);
+            std::vector<const double*> cols;
+            for (unsigned j = 0; j < s; j++) cols.push_back(m_k[j][q].data());
+            check(dgb_embedded_pair_sum(u1[q].size(), u1[q].data(), delta[q].data(), 1., 0., (int)s, b.data(), d.data(), cols.data(), nullptr));
+        }
+        m_t1 = t1 = t0 + dt;
+        if (!m_rk.fsal) rhs(t1, u1, m_k[0]);
+        else std::swap(m_k[0], m_k[s - 1]);
+    }
+};
+
+// dg::Adaptive<dg::ERKStep<...>> (inc/dg/adaptive.h:232-395)
+class Adaptive {
+    ERKStep m_stepper;
+    DVec2 m_next, m_delta;
+    double m_size = 0, m_eps0 = 1, m_eps1 = 1, m_eps2 = 1, m_t_next = 0, m_dt0 = 0, m_dt1 = 0, m_dt2 = 0;
+    bool m_failed = false;
+    unsigned m_nfailed = 0, m_nsteps = 0;
+  public:
+    Adaptive(const std::string& tableau, const DVec2& copyable)
+        : m_stepper(tableau, copyable), m_next(copyable), m_delta(copyable), m_size((double)(copyable[0].size() + copyable[1].size())) {}
+    bool failed() const { return m_failed; }
+    unsigned nfailed() const { return m_nfailed; }
+    unsigned nsteps() const { return m_nsteps; }
+    double get_error() const { return m_eps0; }
+    // u1 may alias u0 (dg::AdaptiveTimeloop calls it so)
+    template <class RHS, class Control, class Norm>
+    void step(RHS& rhs, double t0, const DVec2& u0, double& t1, DVec2& u1, double& dt, Control control, Norm norm, double rtol,
+              double atol, double reject_limit = 2) {
+        m_stepper.step(rhs, t0, u0, m_t_next, m_next, dt, m_delta);
+        m_nsteps++;
+        const double rs = rtol * std::sqrt(m_size), as = atol * std::sqrt(m_size);  // detail::Tolerance (adaptive.h:123-134)
+        for (int q = 0; q < 2; q++) check(dgb_adaptive_tolerance(u0[q].size(), rs, as, u0[q].data(), m_delta[q].data(), nullptr));
+        m_eps0 = norm(m_delta);
+        m_dt0 = dt;
+        if (m_eps0 > reject_limit || std::isnan(m_eps0)) {
+            dt = control(std::array<double, 3>{m_dt0, 0, m_dt2}, std::array<double, 3>{m_eps0, m_eps1, m_eps2},
+                         m_stepper.embedded_order(), m_stepper.order());
+            if (std::fabs(dt) > 0.9 * std::fabs(m_dt0)) dt = 0.9 * m_dt0;
+            m_failed = true;
+            m_nfailed++;
+            if (&u0 != &u1) for (int q = 0; q < 2; q++) blas1::copy(u0[q], u1[q]);
+            t1 = t0;
+            return;
+        }
+        if (m_eps0 < 1e-30) { dt = 1e14 * m_dt0; m_eps0 = 1e-30; }
+        else {
+            dt = control(std::array<double, 3>{m_dt0, m_dt1, m_dt2}, std::array<double, 3>{m_eps0, m_eps1, m_eps2},
+                         m_stepper.embedded_order(), m_stepper.order());
+            if (std::fabs(dt) > 100 * std::fabs(m_dt0)) dt = 100 * m_dt0;
+        }
+        m_eps2 = m_eps1; m_eps1 = m_eps0;
+        m_dt2 = m_dt1; m_dt1 = m_dt0;
+        for (int q = 0; q < 2; q++) blas1::copy(m_next[q], u1[q]);
+        t1 = m_t_next;
+        m_failed = false;
     }
 };
 

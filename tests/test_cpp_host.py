@@ -23,6 +23,43 @@ def build(exe=EXE, name="poisson_demo"):
                            "-Wl,-rpath," + os.path.join(ROOT, "feltor_b200"), "-Wl,-rpath,$ORIGIN/../../feltor_b200", "-o", exe])
 
 
+EXE3 = os.path.join(ROOT, "tests", "cpp", "toefl_demo")
+
+
+def test_cpp_toefl_demo_builds():
+    build(EXE3, "toefl_demo")
+    assert os.path.exists(EXE3)
+
+
+@pytest.mark.gpu
+def test_cpp_toefl_demo_matches_reference_fixtures(tmp_path):
+    """toefl::Explicit + dg::ERKStep + dg::Adaptive written against include/dg_b200.hpp (tests/cpp/toefl_demo.cpp) reproduce
+    the fixtures of the unmodified reference bit for bit: exact-dot checksums of the state and both potentials after 3 fixed
+    steps, every adaptive step size, the end time and state of the adaptive run"""
+    from oracle import orc
+    if not os.path.exists(EXE3):
+        build(EXE3, "toefl_demo")
+    gold = np.load(os.path.join(ROOT, "tests", "golden", "toefl_golden.npz"))
+    init = tmp_path / "init.bin"
+    np.concatenate([gold["global_init0"], gold["global_init1"]]).tofile(init)
+    out = subprocess.run([EXE3, "24", "3", "8", str(init)], capture_output=True, text=True, timeout=600)
+    assert out.returncode == 0, out.stdout + out.stderr
+    xdot = lambda a: orc.dot2(a, a)[0]
+    m = re.search(r"erk checksum: (\S+) (\S+) phi (\S+) (\S+) calls (\d+)", out.stdout)
+    got = [float(m.group(k)) for k in range(1, 5)]
+    assert got == [xdot(gold["global_y0"]), xdot(gold["global_y1"]), xdot(gold["global_phi0"]), xdot(gold["global_phi1"])]
+    assert int(m.group(5)) == 10
+    dts = [float(v) for v in re.search(r"adaptive dts:((?: \S+)+)", out.stdout).group(1).split()]
+    assert dts == list(gold["adaptA_dts"])
+    m = re.search(r"adaptive checksum: (\S+) (\S+) t (\S+) failed (\d+)", out.stdout)
+    assert [float(m.group(1)), float(m.group(2))] == [xdot(gold["adaptA_y0"]), xdot(gold["adaptA_y1"])]
+    assert float(m.group(3)) == gold["adaptA_t_nfailed"][0] and int(m.group(4)) == int(gold["adaptA_t_nfailed"][1])
+    # the initial condition computed in the demo itself agrees with the reference's to rounding of the host exp() argument
+    own = subprocess.run([EXE3, "24", "0", "0"], capture_output=True, text=True, timeout=600)
+    c = [float(v) for v in re.search(r"init checksum: (\S+) (\S+)", own.stdout).groups()]
+    assert abs(c[0] - xdot(gold["global_init0"])) < 1e-12 * c[0] and abs(c[1] - xdot(gold["global_init1"])) < 1e-12 * c[1]
+
+
 def test_cpp_operators_demo_builds():
     build(EXE2, "operators_demo")
     assert os.path.exists(EXE2)
