@@ -270,6 +270,25 @@ int dgb_elliptic2d_size(const dgb_elliptic2d* h, size_t* size, int* fused) {
 int dgb_elliptic2d_symv(dgb_elliptic2d* h, double alpha, const double* x, double beta, double* y, dgb_stream_t s) {
     return elliptic2d_symv(*reinterpret_cast<Elliptic2dPlan*>(h), alpha, x, beta, y, as_stream(s), false);
 }
+// Elliptic3d with set_compute_in_2d(true) (elliptic.h:557-797, the mode src/feltor/feltor.h uses): the 3-d operator is the 2-d
+// one on every plane; sigma (= chi*vol) and the Helmholtz chi are 3-d fields, vol and the chi tensor are shared by the planes
+int dgb_elliptic2d_symv_planes(dgb_elliptic2d* h, int nplanes, const double* sigma3d, double alpha, const double* x, double beta,
+                               double* y, dgb_stream_t s) {
+    Elliptic2dPlan& p = *reinterpret_cast<Elliptic2dPlan*>(h);
+    if (p.slab) { set_error("dgb_elliptic2d_symv_planes: not available on a slab plan"); return DGB_ERR_UNSUPPORTED; }
+    if (nplanes < 0 || !sigma3d || !x || !y) { set_error("dgb_elliptic2d_symv_planes: invalid argument"); return DGB_ERR_INVALID; }
+    const double *sigma0 = p.sigma, *helm0 = p.helm_chi;
+    const size_t n = (size_t)p.size;
+    int e = 0;
+    for (int k = 0; k < nplanes && !e; k++) {
+        p.sigma = sigma3d + k * n;
+        if (helm0) p.helm_chi = helm0 + k * n;
+        e = elliptic2d_symv(p, alpha, x + k * n, beta, y + k * n, as_stream(s), false);
+    }
+    p.sigma = sigma0;
+    p.helm_chi = helm0;
+    return e;
+}
 int dgb_elliptic2d_symv_unfused(dgb_elliptic2d* h, double alpha, const double* x, double beta, double* y, dgb_stream_t s) {
     return elliptic2d_symv(*reinterpret_cast<Elliptic2dPlan*>(h), alpha, x, beta, y, as_stream(s), true);
 }

@@ -74,6 +74,53 @@ class Elliptic2d:
             pass
 
 
+class Elliptic3d:
+    """dg::Elliptic3d with set_compute_in_2d(true) (inc/dg/elliptic.h:557-797, the mode src/feltor/feltor.h uses) on a
+    CartesianGrid3d or a CylindricalGrid3d (x = R, y = Z, z = phi: vol = R): the 2-d plan applied to every plane."""
+
+    def __init__(self, g, direction=T.FORWARD, jfactor=1.0, chi_weight_jump=False, cylindrical=False):
+        assert g.ndim == 3
+        self.grid = g
+        self.perp = T.Grid(g.x0[:2], g.x1[:2], g.n[0], g.N[:2], g.bc[:2])
+        self.op = Elliptic2d(self.perp, direction=direction, jfactor=jfactor, chi_weight_jump=chi_weight_jump)
+        self.nplanes, self.size = g.shape(2), g.size
+        w = g.weights()
+        if cylindrical:
+            R = np.ascontiguousarray(np.broadcast_to(g.abscissas(0), (g.shape(1), g.shape(0))).reshape(-1))
+            # the volume form as the reference computes it: g^pp = 1/R/R (base_geometry.h:336-344), vol = 1/sqrt(det)
+            # (multiply.h:389, functors.h:82-88) -- R up to rounding, and the roundings must be the same
+            R = 1. / np.sqrt((1. / R) / R)
+            self._vol2d = dvec(R)
+            lib().elliptic2d_set_vol(self.op.h, ptr(self._vol2d))
+            self._vol = dvec(np.tile(R, self.nplanes))
+            w = w * np.tile(R, self.nplanes)          # create::volume = tensor::volume(metric) * weights
+        else:
+            self._vol2d, self._vol = None, None
+        self._weights = dvec(w)
+        self._precond = torch.ones(self.size, dtype=torch.float64, device="cuda")
+        self._sigma = self._vol.clone() if cylindrical else torch.ones(self.size, dtype=torch.float64, device="cuda")
+
+    def weights(self):
+        return self._weights
+
+    def precond(self):
+        return self._precond
+
+    def set_chi(self, sigma):
+        """elliptic.h:636-645: m_sigma = sigma*vol, precond = 1/sigma"""
+        if self._vol is None:
+            blas1.copy(sigma, self._sigma)
+        else:
+            blas1.pointwiseDot(sigma, self._vol, self._sigma)
+        blas1.pointwiseDivide(torch.ones_like(sigma), sigma, self._precond)
+
+    def symv(self, *a):
+        alpha, x, beta, y = (1., a[0], 0., a[1]) if len(a) == 2 else a
+        if x.numel() != self.size or y.numel() != self.size:
+            raise ValueError("dg::Error: vector size does not match the operator")
+        lib().elliptic2d_symv_planes(self.op.h, self.nplanes, ptr(self._sigma), d(alpha), ptr(x), d(beta), ptr(y), stream())
+
+
 class PCG:
     """dg::PCG<DVec> (pcg.h:25-199): solve(A, x, b, P, W, eps, nrmb_correction, test_frequency) -> iterations"""
 

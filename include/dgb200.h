@@ -341,6 +341,11 @@ DGB_API int dgb_elliptic2d_size(const dgb_elliptic2d* plan, size_t* size, int* f
 DGB_API int dgb_elliptic2d_symv(dgb_elliptic2d* plan, double alpha, const double* x, double beta, double* y,
                                 dgb_stream_t s);
 /* the unfused composition on the same plan (6 Ell symv + 2 blas1), kept for A/B tests and as the general path */
+/* dg::Elliptic3d with set_compute_in_2d(true) (elliptic.h:557-797,677): nplanes applications of the 2-d operator on the
+ * consecutive planes of 3-d vectors x, y.  sigma3d = chi*vol on every plane (what Elliptic3d::set_chi stores in m_sigma);
+ * a Helmholtz chi set on the plan is likewise read per plane; vol / the chi tensor of the plan are 2-d fields. */
+DGB_API int dgb_elliptic2d_symv_planes(dgb_elliptic2d* plan, int nplanes, const double* sigma3d, double alpha,
+                                       const double* x, double beta, double* y, dgb_stream_t s);
 DGB_API int dgb_elliptic2d_symv_unfused(dgb_elliptic2d* plan, double alpha, const double* x, double beta, double* y,
                                         dgb_stream_t s);
 

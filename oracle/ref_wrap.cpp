@@ -321,6 +321,34 @@ void ref_elliptic2d_variation(void* h, double alpha, const double* lambda, const
 void ref_elliptic2d_weights(void* h, double* out) { copy_out(((Ell2d*)h)->weights(), out); }
 void ref_elliptic2d_precond(void* h, double* out) { copy_out(((Ell2d*)h)->precond(), out); }
 
+// ---------------------------------------------------------------- Elliptic3d (inc/dg/elliptic.h:557-797)
+// y = alpha Elliptic3d(x) + beta y with set_compute_in_2d(true) (the mode the feltor application uses, src/feltor/feltor.h)
+// on a CartesianGrid3d (cylindrical = 0) or a CylindricalGrid3d (x = R, y = Z, z = phi; vol = R); chi = scalar field or NULL.
+// weights/precond (optional outputs) as the class reports them
+void ref_elliptic3d_symv(const RefGrid* g, int cylindrical, int dir, double jfactor, int chi_weight_jump, const double* chi,
+                         double alpha, const double* x, double beta, double* y, double* weights, double* precond) {
+    auto run = [&](auto& e) {
+        size_t n = e.weights().size();
+        e.set_compute_in_2d(true);
+        if (chi) { CView s(chi, n); e.set_chi(s); }
+        CView vx(x, n);
+        VView vy(y, n);
+        e.symv(alpha, vx, beta, vy);
+        if (weights) copy_out(e.weights(), weights);
+        if (precond) copy_out(e.precond(), precond);
+    };
+    if (cylindrical) {
+        dg::CylindricalGrid3d grid(g->x0[0], g->x1[0], g->x0[1], g->x1[1], g->x0[2], g->x1[2], g->n[0], g->N[0], g->N[1], g->N[2],
+                                   (dg::bc)g->bc[0], (dg::bc)g->bc[1], (dg::bc)g->bc[2]);
+        dg::Elliptic3d<dg::CylindricalGrid3d, DMatrix, DVec> e(grid, (dg::direction)dir, jfactor, (bool)chi_weight_jump);
+        run(e);
+    } else {
+        dg::CartesianGrid3d grid = g3(g);
+        dg::Elliptic3d<dg::CartesianGrid3d, DMatrix, DVec> e(grid, (dg::direction)dir, jfactor, (bool)chi_weight_jump);
+        run(e);
+    }
+}
+
 // ---------------------------------------------------------------- PCG (inc/dg/pcg.h:136-195)
 // returns number of iterations (max_iter if not converged; throw_on_fail is disabled).
 // seconds (optional) receives the wall time of solve() only.

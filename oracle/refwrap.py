@@ -267,3 +267,13 @@ class Multigrid:
             lib().ref_multigrid_free(self.h)
         except Exception:
             pass
+
+
+def elliptic3d_symv(g, cylindrical, direction, jfactor, chi_weight_jump, chi, alpha, x, beta, y):
+    """dg::Elliptic3d with set_compute_in_2d(true) (elliptic.h:557-797); g: RefGrid (ndim 3); returns (y, weights, precond)"""
+    n = x.size
+    out, w, p = np.array(y, copy=True), np.empty(n), np.empty(n)
+    lib().ref_elliptic3d_symv(C.byref(g), int(cylindrical), int(direction), C.c_double(jfactor), int(chi_weight_jump),
+                              dp(chi) if chi is not None else None, C.c_double(alpha), dp(np.ascontiguousarray(x)),
+                              C.c_double(beta), dp(out), dp(w), dp(p))
+    return out, w, p

@@ -1,0 +1,54 @@
+"""GPU: dg::Elliptic3d in its compute-in-2d mode (inc/dg/elliptic.h:557-797, the mode src/feltor/feltor.h runs) through
+dgb_elliptic2d_symv_planes, against the UNMODIFIED reference class (oracle/_ref/libdgref.so, live) on Cartesian and
+cylindrical 3-d grids.  Tolerance of the north star for symv: 1e-12 relative (measured: bit-identical)."""
+import numpy as np
+import pytest
+from util import same_bits, rng
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(scope="module")
+def G():
+    import gpu_backend
+    gpu_backend.require_library_loaded()
+    return gpu_backend
+
+
+@pytest.mark.parametrize("cyl", [False, True])
+@pytest.mark.parametrize("direction", [0, 2])
+@pytest.mark.parametrize("chi_weight_jump", [False, True])
+def test_elliptic3d_compute_in_2d(G, cyl, direction, chi_weight_jump):
+    from oracle import refwrap as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libdgref.so not present")
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic3d
+    x0, x1 = ([3., -1., 0.], [5., 1., 2 * np.pi]) if cyl else ([0., 0., 0.], [1., 2., 3.])
+    N, bc = [12, 10, 5], [T.DIR, T.NEU if cyl else T.PER, T.PER]
+    g = T.Grid(x0, x1, [3, 3, 1], N, bc)
+    rg = R.grid(x0, x1, 3, N, bc)
+    r = rng(7 + 2 * cyl + direction)
+    n = g.size
+    x, y0, chi = r.uniform(-1, 1, n), r.uniform(-1, 1, n), r.uniform(0.5, 2., n)
+    op = Elliptic3d(g, direction=direction, jfactor=0.7, chi_weight_jump=chi_weight_jump, cylindrical=cyl)
+    for use_chi, (alpha, beta) in ((False, (1., 0.)), (True, (1., 0.)), (True, (-0.5, 0.3))):
+        want, w, p = R.elliptic3d_symv(rg, cyl, direction, 0.7, chi_weight_jump, chi if use_chi else None, alpha, x, beta, y0)
+        if use_chi:
+            op.set_chi(G.make(chi))
+        y = G.make(y0 if beta != 0. else np.full(n, np.nan))
+        op.symv(alpha, G.make(x), beta, y)
+        got = G.get(y)
+        scale = np.abs(want).max()
+        assert np.abs(got - want).max() <= 1e-12 * scale, (cyl, direction, use_chi, np.abs(got - want).max() / scale)
+        assert same_bits(got, want), "within tolerance but not bit-identical"
+        assert same_bits(G.get(op.weights()), w) and same_bits(G.get(op.precond()), p)
+
+
+def test_elliptic3d_rejects_wrong_size(G):
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic3d
+    g = T.Grid([0., 0., 0.], [1., 1., 1.], [3, 3, 1], [4, 4, 3], [T.PER, T.PER, T.PER])
+    op = Elliptic3d(g)
+    with pytest.raises(ValueError):
+        op.symv(G.make(np.zeros(7)), G.make(np.zeros(g.size)))
