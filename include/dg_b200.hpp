@@ -572,4 +572,150 @@ class Adaptive {
     }
 };
 
+// dg::ShuOsher<std::array<DVec,2>> with the identity limiter (inc/dg/runge_kutta.h:840-925); tableaus tableau.h:1262-1286
+class ShuOsher {
+    unsigned m_s = 0;
+    std::vector<std::vector<double>> m_alpha, m_beta;  // lower triangles alpha(i,k), beta(i,k), k <= i
+    std::vector<DVec2> m_u, m_k;
+    double m_t1 = 1e300;
+  public:
+    ShuOsher(const std::string& tableau, const DVec2& copyable) {
+        if (tableau == "SSPRK-2-2") { m_s = 2; m_alpha = {{1.}, {0.5, 0.5}}; m_beta = {{1.}, {0., 0.5}}; }
+        else if (tableau == "SSPRK-3-3") { m_s = 3; m_alpha = {{1.}, {3. / 4., 1. / 4.}, {1. / 3., 0., 2. / 3.}}; m_beta = {{1.}, {0., 1. / 4.}, {0., 0., 2. / 3.}}; }
+        else throw Error(DGB_ERR_UNSUPPORTED, "dgb200: Shu-Osher tableau " + tableau + " is not wired up");
+        m_u.assign(m_s, copyable);
+        m_k.assign(m_s, copyable);
+    }
+    template <class RHS>
+    void step(RHS& rhs, double t0, const DVec2& u0, double& t1, DVec2& u1, double dt) {
+        const unsigned s = m_s;
+        std::vector<double> ts(s + 1);
+        ts[0] = t0;
+        for (int q = 0; q < 2; q++) blas1::copy(u0[q], m_u[0][q]);
+        if (t0 != m_t1) rhs(ts[0], m_u[0], m_k[0]);
+        for (unsigned i = 1; i <= s; i++) {
+            DVec2& out = i == s ? u1 : m_u[i];
+            for (int q = 0; q < 2; q++) blas1::axpbypgz(m_alpha[i - 1][0], m_u[0][q], dt * m_beta[i - 1][0], m_k[0][q], 0., out[q]);
+            ts[i] = std::fma(m_alpha[i - 1][0], ts[0], dt * m_beta[i - 1][0]);  // one rounding, as the reference's compiler contracts it
+            for (unsigned j = 1; j < i; j++) {
+                for (int q = 0; q < 2; q++) blas1::axpbypgz(m_alpha[i - 1][j], m_u[j][q], dt * m_beta[i - 1][j], m_k[j][q], 1., out[q]);
+                ts[i] += std::fma(m_alpha[i - 1][j], ts[j], dt * m_beta[i - 1][j]);
+            }
+            if (i != s) rhs(ts[i], m_u[i], m_k[i]);
+            else rhs(ts[i], u1, m_k[0]);
+        }
+        m_t1 = t1 = ts[s];
+    }
+};
+
+// dg::ExplicitMultistep<std::array<DVec,2>> (inc/dg/multistep.h:59-100; FilteredExplicitMultistep::init/step :592-639 with the
+// identity filter); tableaus multistep_tableau.h:263-300
+class ExplicitMultistep {
+    unsigned m_order = 0, m_counter = 0;
+    std::vector<double> m_a, m_b;
+    std::vector<DVec2> m_u, m_f;
+    double m_tu = 0, m_dt = 0;
+  public:
+    ExplicitMultistep(const std::string& tableau, const DVec2& copyable) {
+        if (tableau == "AB-1-1") { m_order = 1; m_a = {1.}; m_b = {1.}; }
+        else if (tableau == "AB-2-2") { m_order = 2; m_a = {1., 0.}; m_b = {1.5, -0.5}; }
+        else if (tableau == "AB-3-3") { m_order = 3; m_a = {1., 0., 0.}; m_b = {23. / 12., -4. / 3., 5. / 12.}; }
+        else if (tableau == "TVB-2-2") { m_order = 2; m_a = {4. / 3., -1. / 3.}; m_b = {4. / 3., -2. / 3.}; }
+        else if (tableau == "TVB-3-3") {
+            m_order = 3;
+            m_a = {1.908535476882378, -1.334951446162515, 0.426415969280137};
+            m_b = {1.502575553858997, -1.654746338401493, 0.670051276940255};
+        } else throw Error(DGB_ERR_UNSUPPORTED, "dgb200: multistep tableau " + tableau + " is not wired up");
+        m_u.assign(m_a.size(), copyable);
+        m_f.assign(m_a.size(), copyable);
+    }
+    template <class RHS>
+    void init(RHS& rhs, double t0, const DVec2& u0, double dt) {
+        m_tu = t0; m_dt = dt;
+        const size_t s = m_a.size();
+        for (int q = 0; q < 2; q++) blas1::copy(u0[q], m_u[s - 1][q]);
+        rhs(m_tu, m_u[s - 1], m_f[s - 1]);
+        m_counter = 0;
+    }
+    template <class RHS>
+    void step(RHS& rhs, double& t, DVec2& u) {
+        const size_t s = m_a.size();
+        if (m_counter < s - 1) {  // start-up: a Runge-Kutta step of the same order
+            ShuOsher rk(m_order <= 2 ? "SSPRK-2-2" : "SSPRK-3-3", u);
+            rk.step(rhs, t, u, t, u, m_dt);
+            m_counter++;
+            m_tu = t;
+            for (int q = 0; q < 2; q++) blas1::copy(u[q], m_u[s - 1 - m_counter][q]);
+            rhs(m_tu, m_u[s - 1 - m_counter], m_f[s - 1 - m_counter]);
+            return;
+        }
+        t = m_tu = m_tu + m_dt;
+        for (int q = 0; q < 2; q++) {
+            blas1::axpby(m_a[0], m_u[0][q], m_dt * m_b[0], m_f[0][q], u[q]);
+            for (size_t i = 1; i < s; i++) blas1::axpbypgz(m_a[i], m_u[i][q], m_dt * m_b[i], m_f[i][q], 1., u[q]);
+        }
+        std::rotate(m_f.rbegin(), m_f.rbegin() + 1, m_f.rend());
+        std::rotate(m_u.rbegin(), m_u.rbegin() + 1, m_u.rend());
+        for (int q = 0; q < 2; q++) blas1::copy(u[q], m_u[0][q]);
+        rhs(m_tu, m_u[0], m_f[0]);
+    }
+};
+
+// dg::CartesianGrid3d / dg::CylindricalGrid3d (inc/dg/topology/base_geometry.h:230-350): n polynomial coefficients in x and y,
+// one per cell in z
+struct Grid3d {
+    dgb_grid g{};
+    bool cylindrical = false;
+    Grid3d(double x0, double x1, double y0, double y1, double z0, double z1, unsigned n, unsigned Nx, unsigned Ny, unsigned Nz,
+           bc bcx = PER, bc bcy = PER, bc bcz = PER, bool cylindrical_ = false) : cylindrical(cylindrical_) {
+        g.ndim = 3;
+        g.x0[0] = x0; g.x1[0] = x1; g.x0[1] = y0; g.x1[1] = y1; g.x0[2] = z0; g.x1[2] = z1;
+        g.n[0] = g.n[1] = (int)n; g.n[2] = 1;
+        g.N[0] = (int)Nx; g.N[1] = (int)Ny; g.N[2] = (int)Nz;
+        g.bc[0] = bcx; g.bc[1] = bcy; g.bc[2] = bcz;
+    }
+    size_t size() const { size_t s; check(dgb_topo_size(&g, &s)); return s; }
+    unsigned Nz() const { return (unsigned)g.N[2]; }
+    Grid2d perp_grid() const { return Grid2d(g.x0[0], g.x1[0], g.x0[1], g.x1[1], (unsigned)g.n[0], (unsigned)g.N[0], (unsigned)g.N[1], (bc)g.bc[0], (bc)g.bc[1]); }
+    HVec weights() const { HVec w(size()); check(dgb_topo_weights(&g, w.data())); return w; }
+};
+
+// dg::Elliptic3d<Geometry, DMatrix, DVec> in its compute-in-2d mode (inc/dg/elliptic.h:557-797, set_compute_in_2d(true) -- the mode
+// src/feltor/feltor.h uses): the 2-d plan applied to every plane; cylindrical grids carry vol = 1/sqrt(1/R/R)
+class Elliptic3d {
+    Elliptic2d m_perp;
+    DVec m_weights, m_precond, m_sigma, m_vol, m_vol2d;
+    unsigned m_planes = 0;
+  public:
+    Elliptic3d(const Grid3d& g, direction dir = forward, double jfactor = 1., bool chi_weight_jump = false)
+        : m_perp(g.perp_grid(), dir, jfactor, chi_weight_jump), m_planes(g.Nz()) {
+        HVec w = g.weights();
+        const size_t n = g.size(), n2 = n / m_planes;
+        m_precond = DVec(n, 1.);
+        m_sigma = DVec(n, 1.);
+        if (g.cylindrical) {
+            HVec R = g.perp_grid().abscissas(0), vol(n), vol2d(n2);
+            for (size_t i = 0; i < n2; i++) { double r = R[i % R.size()]; vol2d[i] = 1. / std::sqrt(1. / r / r); }  // base_geometry.h:336-344, multiply.h:389
+            for (size_t i = 0; i < n; i++) { vol[i] = vol2d[i % n2]; w[i] *= vol[i]; }                        // create::volume
+            m_vol = DVec(vol);
+            m_vol2d = DVec(vol2d);
+            m_sigma = m_vol;
+            check(dgb_elliptic2d_set_vol(m_perp.plan(), m_vol2d.data()));
+        }
+        m_weights = DVec(w);
+    }
+    const DVec& weights() const { return m_weights; }
+    const DVec& precond() const { return m_precond; }
+    void set_chi(const DVec& sigma) {  // elliptic.h:636-645
+        if (m_vol.size()) blas1::pointwiseDot(sigma, m_vol, m_sigma);
+        else blas1::copy(sigma, m_sigma);
+        DVec one(sigma.size(), 1.);
+        blas1::pointwiseDivide(one, sigma, m_precond);
+    }
+    void symv(const DVec& x, DVec& y) { symv(1., x, 0., y); }
+    void symv(double alpha, const DVec& x, double beta, DVec& y) {
+        check(dgb_elliptic2d_symv_planes(m_perp.plan(), (int)m_planes, m_sigma.data(), alpha, x.data(), beta, y.data(), nullptr));
+    }
+};
+
 }  // namespace dgb200

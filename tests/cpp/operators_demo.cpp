@@ -41,5 +41,15 @@ int main(int argc, char** argv) {
     ex.extrapolate(1.0, s);
     printf("extrapolation checksum: %.17g\n", blas2::dot(s, w, s));
     printf("max: %.17g min: %.17g\n", blas1::reduce(s, -1e300, blas1::reduce_op::max), blas1::reduce(s, 1e300, blas1::reduce_op::min));
+    // Elliptic3d in compute-in-2d mode on a cylindrical grid (R, Z, phi)
+    Grid3d g3(3., 5., -1., 1., 0., 2 * M_PI, 3, 12, 10, 5, DIR, NEU, PER, true);
+    Elliptic3d pol3(g3, centered, 0.7);
+    HVec hx(g3.size()), hchi(g3.size());
+    for (size_t i = 0; i < hx.size(); i++) { hx[i] = sin(0.37 * (double)i); hchi[i] = 1.25 + 0.5 * cos(0.11 * (double)i); }
+    DVec x3(hx), y3(g3.size(), 0.25), chi3(hchi);
+    pol3.set_chi(chi3);
+    pol3.symv(-0.5, x3, 0.3, y3);
+    printf("elliptic3d checksum: %.17g\n", blas2::dot(y3, pol3.weights(), y3));
+    printf("elliptic3dprecond checksum: %.17g\n", blas2::dot(pol3.precond(), pol3.weights(), pol3.precond()));
     return 0;
 }

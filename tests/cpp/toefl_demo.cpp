@@ -1,6 +1,6 @@
 // C++ host program against include/dg_b200.hpp: the toefl right-hand side (src/toefl/toefl.h, "global" model with the
 // default input src/toefl/input/default.json) driven by dg::ERKStep and dg::Adaptive exactly like src/toefl/toefl.cpp:79-91.
-//   toefl_demo <N> <fixed steps> <adaptive steps> [initial state: file of 2*size doubles]
+//   toefl_demo <N> <fixed steps> <adaptive steps> [initial state: file of 2*size doubles] [multistep steps]
 // prints exact-dot checksums of the state; tests/test_cpp_host.py compares them with the fixtures of the unmodified reference.
 #include <cmath>
 #include <cstdio>
@@ -143,6 +143,20 @@ int main(int argc, char** argv) {
             printf(" %.17g", dt);
         }
         printf("\nadaptive checksum: %.17g %.17g t %.17g failed %u\n", blas1::dot(y[0], y[0]), blas1::dot(y[1], y[1]), t, adapt.nfailed());
+    }
+    const int msteps = argc > 5 ? atoi(argv[5]) : 0;
+    if (msteps > 0) {  // dg::ExplicitMultistep("TVB-3-3"), dt = 0.3 (BASELINE config 3 names a multistep stepper)
+        Explicit rhs(p);
+        DVec2 y = initial(rhs, file);
+        ExplicitMultistep ms("TVB-3-3", y);
+        double t = 0.;
+        ms.init(rhs, t, y, 0.3);
+        printf("multistep ts:");
+        for (int k = 0; k < msteps; k++) {
+            ms.step(rhs, t, y);
+            printf(" %.17g", t);
+        }
+        printf("\nmultistep checksum: %.17g %.17g calls %u\n", blas1::dot(y[0], y[0]), blas1::dot(y[1], y[1]), rhs.ncalls());
     }
     return 0;
 }

@@ -35,14 +35,14 @@ def test_cpp_toefl_demo_builds():
 def test_cpp_toefl_demo_matches_reference_fixtures(tmp_path):
     """toefl::Explicit + dg::ERKStep + dg::Adaptive written against include/dg_b200.hpp (tests/cpp/toefl_demo.cpp) reproduce
     the fixtures of the unmodified reference bit for bit: exact-dot checksums of the state and both potentials after 3 fixed
-    steps, every adaptive step size, the end time and state of the adaptive run"""
+    steps, every adaptive step size, the end time and state of the adaptive run, and the TVB-3-3 multistep run"""
     from oracle import orc
     if not os.path.exists(EXE3):
         build(EXE3, "toefl_demo")
     gold = np.load(os.path.join(ROOT, "tests", "golden", "toefl_golden.npz"))
     init = tmp_path / "init.bin"
     np.concatenate([gold["global_init0"], gold["global_init1"]]).tofile(init)
-    out = subprocess.run([EXE3, "24", "3", "8", str(init)], capture_output=True, text=True, timeout=600)
+    out = subprocess.run([EXE3, "24", "3", "8", str(init), "5"], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout + out.stderr
     xdot = lambda a: orc.dot2(a, a)[0]
     m = re.search(r"erk checksum: (\S+) (\S+) phi (\S+) (\S+) calls (\d+)", out.stdout)
@@ -54,6 +54,10 @@ def test_cpp_toefl_demo_matches_reference_fixtures(tmp_path):
     m = re.search(r"adaptive checksum: (\S+) (\S+) t (\S+) failed (\d+)", out.stdout)
     assert [float(m.group(1)), float(m.group(2))] == [xdot(gold["adaptA_y0"]), xdot(gold["adaptA_y1"])]
     assert float(m.group(3)) == gold["adaptA_t_nfailed"][0] and int(m.group(4)) == int(gold["adaptA_t_nfailed"][1])
+    ts = [float(v) for v in re.search(r"multistep ts:((?: \S+)+)", out.stdout).group(1).split()]
+    m = re.search(r"multistep checksum: (\S+) (\S+) calls (\d+)", out.stdout)
+    assert ts == list(gold["msTVB_ts"]) and int(m.group(3)) == int(gold["msTVB_ncalls"][0])
+    assert [float(m.group(1)), float(m.group(2))] == [xdot(gold["msTVB_y0"]), xdot(gold["msTVB_y1"])]
     # the initial condition computed in the demo itself agrees with the reference's to rounding of the host exp() argument
     own = subprocess.run([EXE3, "24", "0", "0"], capture_output=True, text=True, timeout=600)
     c = [float(v) for v in re.search(r"init checksum: (\S+) (\S+)", own.stdout).groups()]
@@ -111,6 +115,18 @@ def test_cpp_operators_demo_matches_harness():
     ex.extrapolate(1.0, s)
     assert blas2.dot(s, w, s) == val["extrapolation"]
     assert blas1.reduce(s, -1e300, "max") == mx and blas1.reduce(s, 1e300, "min") == mn
+    # Elliptic3d (compute-in-2d, cylindrical grid): the harness class is bit-identical to the reference (test_gpu_elliptic3d.py)
+    from feltor_b200.elliptic import Elliptic3d
+    g3 = T.Grid([3., -1., 0.], [5., 1., 2 * math.pi], [3, 3, 1], [12, 10, 5], [T.DIR, T.NEU, T.PER])
+    pol3 = Elliptic3d(g3, direction=T.CENTERED, jfactor=0.7, cylindrical=True)
+    i = np.arange(g3.size, dtype=np.float64)
+    hx = np.array([math.sin(0.37 * v) for v in i])
+    hchi = np.array([1.25 + 0.5 * math.cos(0.11 * v) for v in i])
+    pol3.set_chi(G.make(hchi))
+    y3 = torch.full((g3.size,), 0.25, dtype=torch.float64, device="cuda")
+    pol3.symv(-0.5, G.make(hx), 0.3, y3)
+    assert blas2.dot(y3, pol3.weights(), y3) == val["elliptic3d"]
+    assert blas2.dot(pol3.precond(), pol3.weights(), pol3.precond()) == val["elliptic3dprecond"]
 
 
 def test_cpp_host_only():
