@@ -280,6 +280,18 @@ int dgb_elliptic2d_symv_planes(dgb_elliptic2d* h, int nplanes, const double* sig
     const double *sigma0 = p.sigma, *helm0 = p.helm_chi;
     const size_t n = (size_t)p.size;
     int e = 0;
+    // all planes in one launch of the tile kernel when the plan qualifies for it (DGB_ELLIPTIC_PLANES_LOOP=1: per-plane loop)
+    static int env_loop = -1;
+    if (env_loop < 0) { const char* v = getenv("DGB_ELLIPTIC_PLANES_LOOP"); env_loop = (v && atoi(v)) ? 1 : 0; }
+    const bool identity_chi = !p.chi[0] && !p.chi[1] && !p.chi[2] && !p.chi[3];
+    const bool helm_ok = !p.helm || (alpha == 1. && beta == 0. && p.helm_alpha != 0.);
+    if (!env_loop && nplanes > 1 && p.fusable && identity_chi && !p.chi_weight_jump && helm_ok && x != y &&
+        (long long)nplanes * p.Ny * p.n < (1ll << 31)) {
+        p.sigma = sigma3d;
+        e = elliptic2d_fused_launch_planes(p, nplanes, alpha, x, beta, y, as_stream(s));
+        p.sigma = sigma0;
+        return e;
+    }
     for (int k = 0; k < nplanes && !e; k++) {
         p.sigma = sigma3d + k * n;
         if (helm0) p.helm_chi = helm0 + k * n;

@@ -34,5 +34,6 @@ bool elliptic2d_walker_supported(const Elliptic2dPlan& p, bool with_dot = false)
 int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
                     bool force_unfused);
 int elliptic2d_fused_launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st);
+int elliptic2d_fused_launch_planes(Elliptic2dPlan& p, int nplanes, double alpha, const double* x, double beta, double* y, cudaStream_t st);
 
 }  // namespace dgb

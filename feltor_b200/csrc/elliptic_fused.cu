@@ -30,6 +30,10 @@ struct FusedArgs {
     int Nx, Ny, wrapx, wrapy;
     int fx_lo, fx_hi, fy_lo, fy_hi;  // cells [lo, hi) that are interior rows of all three x- resp. y-matrices
     int ntx, ntiles, use_tma;
+    // Elliptic3d in compute-in-2d mode: nplanes consecutive planes of plane_stride doubles in x, y, sigma (and the
+    // Helmholtz chi); tile index = plane * ntiles + tile of the plane.  nplanes == 1: the 2-d operator
+    int nplanes;
+    size_t plane_stride;
     // slab mode (domain decomposition in y): the operands x and sigma carry `ghost` cell rows on either side, row 0
     // of the slab is global cell row `yoff` of `Nyg`; the periodic wrap in y is done by the halo exchange
     int slab, ghost, yoff, Nyg, pery;
@@ -169,7 +173,7 @@ struct Tile {
 template <int N, int DIRK, bool DOT, bool FAST>
 __device__ __forceinline__ void compute_tile(const FusedArgs& A, const EllipticCoef<N, Offs<DIRK>::BPL>& C, double* xs, double* ss,
                                              double* txs, double* tys, int cx0, int cy0, int tid, sa::Fpe& fpe, int& bad,
-                                             long long* dsm) {
+                                             long long* dsm, size_t poff) {
     constexpr int B = Offs<DIRK>::BPL;
     constexpr int RK = DIRK, LK = DIRK == 0 ? 1 : (DIRK == 1 ? 0 : 2);  // stencil kinds of the right / left derivatives
     using TL = Tile<N, B>;
@@ -318,7 +322,7 @@ __device__ __forceinline__ void compute_tile(const FusedArgs& A, const EllipticC
             okv[i][j] = FAST || ((cy0 + warp) < A.Ny && (cx0 + (lane + 32 * j) / N) < A.Nx);
             yin[i][j] = 0.; vin[i][j] = 1.; win[i][j] = 0.;
             if (okv[i][j]) {
-                if (A.beta != 0.) yin[i][j] = A.y[g];
+                if (A.beta != 0.) yin[i][j] = A.y[poff + g];
                 if (A.vol) vin[i][j] = __ldg(A.vol + g);
                 if (DOT) win[i][j] = __ldg(A.dot_w + g);
             }
@@ -333,10 +337,10 @@ __device__ __forceinline__ void compute_tile(const FusedArgs& A, const EllipticC
             const double b = A.beta == 0. ? 0. : __dmul_rn(yin[i][j], A.beta);
             double v = __fma_rn(A.alpha, t, b);
             if (A.helm) {  // pointwiseDot(1., chi, x, -helm_alpha, y): y *= -helm_alpha; y = fma(1*chi, x, y)
-                const double c = A.helm_chi ? __ldg(A.helm_chi + gbase + (size_t)i * LDG + 32 * j) : 1.;
+                const double c = A.helm_chi ? __ldg(A.helm_chi + poff + gbase + (size_t)i * LDG + 32 * j) : 1.;
                 v = __fma_rn(__dmul_rn(1., c), sxr[i * XC + 32 * j], __dmul_rn(v, -A.helm_alpha));
             }
-            A.y[gbase + (size_t)i * LDG + 32 * j] = v;
+            A.y[poff + gbase + (size_t)i * LDG + 32 * j] = v;
             if (DOT) {
                 double pr = __dmul_rn(__dmul_rn(sxr[i * XC + 32 * j], win[i][j]), v);
                 if (!isfinite(pr)) { bad = 1; pr = 0.; }
@@ -373,32 +377,36 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
     __syncthreads();
     unsigned phase = 0;
     // rows/columns of cells that are interior rows of every matrix (host-computed intersection)
-    for (int tile = blockIdx.x; tile < A.ntiles; tile += gridDim.x) {
+    for (int gtile = blockIdx.x; gtile < A.ntiles * A.nplanes; gtile += gridDim.x) {
+        int plane = 0, tile = gtile;
+        if (A.nplanes > 1) { plane = gtile / A.ntiles; tile = gtile - plane * A.ntiles; }
+        const size_t poff = (size_t)plane * A.plane_stride;
         const int tyi = tile / A.ntx, txi = tile - tyi * A.ntx;
         const int cx0 = txi * TX, cy0 = tyi * TY;
-        // ---- phase 0
+        // ---- phase 0  (stacked planes: the rows beyond a plane belong to its neighbours, so tiles at the y boundary
+        //      always take the boundary-aware loader)
         const bool seam = (A.wrapx && (cx0 - H < 0 || cx0 + TX + H > A.Nx)) ||
-                          (!A.slab && A.wrapy && (cy0 - H < 0 || cy0 + TY + H > A.Ny));
+                          (!A.slab && (A.wrapy || A.nplanes > 1) && (cy0 - H < 0 || cy0 + TY + H > A.Ny));
         if (A.use_tma && !seam) {
             if (tid == 0) {
                 mbar_expect_tx(bar, (unsigned)((TL::XR * XC + TL::SR * SC) * sizeof(double)));
                 // in slab mode the maps start at the first ghost row
-                tma_load_2d(smem + TL::XS, &map_x, bar, (cx0 - H) * N - TL::XSH, (cy0 - H + A.ghost) * N);
-                tma_load_2d(smem + TL::SS, &map_s, bar, (cx0 - 1) * N - TL::SSH, (cy0 - 1 + A.ghost) * N);
+                tma_load_2d(smem + TL::XS, &map_x, bar, (cx0 - H) * N - TL::XSH, (cy0 - H + A.ghost + plane * A.Ny) * N);
+                tma_load_2d(smem + TL::SS, &map_s, bar, (cx0 - 1) * N - TL::SSH, (cy0 - 1 + A.ghost + plane * A.Ny) * N);
                 mbar_wait(bar, phase);  // one thread polls, the CTA sleeps on the barrier below
             }
             phase ^= 1;
             __syncthreads();
         } else {
-            load_tile_ldgsts<N, TL::XR, TL::XC, XC>(xs, A.x, cy0 - H, cx0 - H, A, tid);
-            load_tile_ldgsts<N, TL::SR, TL::SC, SC>(ss, A.sigma, cy0 - 1, cx0 - 1, A, tid);
+            load_tile_ldgsts<N, TL::XR, TL::XC, XC>(xs, A.x + poff, cy0 - H, cx0 - H, A, tid);
+            load_tile_ldgsts<N, TL::SR, TL::SC, SC>(ss, A.sigma + poff, cy0 - 1, cx0 - 1, A, tid);
             cp_async_wait_all();
             __syncthreads();
         }
         const bool fast = cx0 - 1 >= A.fx_lo && cx0 + TX + 1 <= A.fx_hi && cy0 + A.yoff - 1 >= A.fy_lo &&
                           cy0 + A.yoff + TY + 1 <= A.fy_hi && cy0 + TY <= A.Ny;
-        if (fast) compute_tile<N, DIRK, DOT, true>(A, C, xs, ss, txs, tys, cx0, cy0, tid, fpe, bad, dsm);
-        else compute_tile<N, DIRK, DOT, false>(A, C, xs, ss, txs, tys, cx0, cy0, tid, fpe, bad, dsm);
+        if (fast) compute_tile<N, DIRK, DOT, true>(A, C, xs, ss, txs, tys, cx0, cy0, tid, fpe, bad, dsm, poff);
+        else compute_tile<N, DIRK, DOT, false>(A, C, xs, ss, txs, tys, cx0, cy0, tid, fpe, bad, dsm, poff);
     }
     if (DOT) {
         fpe.flush_warp(dsm);
@@ -408,7 +416,7 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
 
 template <int N, int DIRK, bool DOT>
 static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
-                  const FusedDot* fd) {
+                  const FusedDot* fd, int nplanes = 1) {
     constexpr int B = Offs<DIRK>::BPL;
     using TL = Tile<N, B>;
     static bool configured = false;
@@ -433,6 +441,8 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
     A.fy_hi = std::min({p.righty.i_hi, p.lefty.i_hi, p.jumpy.i_hi});
     A.ntx = (p.Nx + TX - 1) / TX;
     A.ntiles = A.ntx * ((A.Ny + TY - 1) / TY);
+    A.nplanes = nplanes; A.plane_stride = (size_t)p.size;
+    if (nplanes != 1 && (p.slab || DOT || nplanes < 1)) { set_error("elliptic2d fused kernel: planes need a plain 2-d plan"); return DGB_ERR_UNSUPPORTED; }
     A.sigma = p.sigma; A.vol = p.vol; A.x = x; A.y = y;
     A.alpha = alpha; A.beta = beta; A.jfactor = p.jfactor;
     A.helm = p.helm ? 1 : 0; A.helm_alpha = p.helm_alpha; A.helm_chi = p.helm_chi;
@@ -443,13 +453,13 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
     memset(&mx, 0, sizeof(mx));
     memset(&ms, 0, sizeof(ms));
     const long long gh = (long long)A.ghost * N * p.Nx * N;  // doubles in the ghost rows below the slab
-    A.use_tma = !no_tma && make_map(&mx, x - gh, (A.Ny + 2 * A.ghost) * N, p.Nx * N, TL::XR, TL::XP) &&
-                make_map(&ms, p.sigma - gh, (A.Ny + 2 * A.ghost) * N, p.Nx * N, TL::SR, TL::SP);
+    A.use_tma = !no_tma && make_map(&mx, x - gh, (A.Ny * nplanes + 2 * A.ghost) * N, p.Nx * N, TL::XR, TL::XP) &&
+                make_map(&ms, p.sigma - gh, (A.Ny * nplanes + 2 * A.ghost) * N, p.Nx * N, TL::SR, TL::SP);
     EllipticCoef<N, B> C;
     fill<N, B>(C.rx, p.rightx); fill<N, B>(C.ry, p.righty); fill<N, B>(C.lx, p.leftx); fill<N, B>(C.ly, p.lefty);
     fill<N, 3>(C.jx, p.jumpx); fill<N, 3>(C.jy, p.jumpy);
     int per_sm = std::max(1, std::min(FUSED_MIN_CTAS, (int)(220 * 1024 / (TL::BYTES + 1024))));
-    int grid = std::min(A.ntiles, per_sm * sm_count());
+    int grid = (int)std::min<long long>((long long)A.ntiles * nplanes, (long long)per_sm * sm_count());
     elliptic2d_fused_kernel<N, DIRK, DOT><<<grid, FUSED_THREADS, TL::BYTES, st>>>(A, C, mx, ms);
     DGB_LAUNCHED();
     return 0;
@@ -457,17 +467,17 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
 
 template <bool DOT>
 static int dispatch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st,
-                    const FusedDot* fd) {
+                    const FusedDot* fd, int nplanes = 1) {
     switch (p.n * 10 + p.dirk) {
-        case 20: return launch<2, 0, DOT>(p, alpha, x, beta, y, st, fd);
-        case 21: return launch<2, 1, DOT>(p, alpha, x, beta, y, st, fd);
-        case 22: return launch<2, 2, DOT>(p, alpha, x, beta, y, st, fd);
-        case 30: return launch<3, 0, DOT>(p, alpha, x, beta, y, st, fd);
-        case 31: return launch<3, 1, DOT>(p, alpha, x, beta, y, st, fd);
-        case 32: return launch<3, 2, DOT>(p, alpha, x, beta, y, st, fd);
-        case 40: return launch<4, 0, DOT>(p, alpha, x, beta, y, st, fd);
-        case 41: return launch<4, 1, DOT>(p, alpha, x, beta, y, st, fd);
-        case 42: return launch<4, 2, DOT>(p, alpha, x, beta, y, st, fd);
+        case 20: return launch<2, 0, DOT>(p, alpha, x, beta, y, st, fd, nplanes);
+        case 21: return launch<2, 1, DOT>(p, alpha, x, beta, y, st, fd, nplanes);
+        case 22: return launch<2, 2, DOT>(p, alpha, x, beta, y, st, fd, nplanes);
+        case 30: return launch<3, 0, DOT>(p, alpha, x, beta, y, st, fd, nplanes);
+        case 31: return launch<3, 1, DOT>(p, alpha, x, beta, y, st, fd, nplanes);
+        case 32: return launch<3, 2, DOT>(p, alpha, x, beta, y, st, fd, nplanes);
+        case 40: return launch<4, 0, DOT>(p, alpha, x, beta, y, st, fd, nplanes);
+        case 41: return launch<4, 1, DOT>(p, alpha, x, beta, y, st, fd, nplanes);
+        case 42: return launch<4, 2, DOT>(p, alpha, x, beta, y, st, fd, nplanes);
     }
     set_error("elliptic2d fused kernel: unsupported n=%d direction kind=%d", p.n, p.dirk);
     return DGB_ERR_UNSUPPORTED;
@@ -475,6 +485,10 @@ static int dispatch(Elliptic2dPlan& p, double alpha, const double* x, double bet
 int elliptic2d_fused_launch(Elliptic2dPlan& p, double alpha, const double* x, double beta, double* y, cudaStream_t st) {
     if (elliptic2d_walker_supported(p)) return elliptic2d_walker_launch(p, alpha, x, beta, y, st, nullptr);
     return dispatch<false>(p, alpha, x, beta, y, st, nullptr);
+}
+// the 2-d operator on nplanes stacked planes in ONE launch of the tile kernel (p.sigma points to the 3-d sigma)
+int elliptic2d_fused_launch_planes(Elliptic2dPlan& p, int nplanes, double alpha, const double* x, double beta, double* y, cudaStream_t st) {
+    return dispatch<false>(p, alpha, x, beta, y, st, nullptr, nplanes);
 }
 // y = A x fused with dot(x, w, y) and the PCG alpha update (pcg.h:165-166)
 int elliptic2d_fused_launch_dot(Elliptic2dPlan& p, const double* x, double* y, cudaStream_t st, const FusedDot& fd) {

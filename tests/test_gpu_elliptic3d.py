@@ -17,15 +17,17 @@ def G():
 
 @pytest.mark.parametrize("cyl", [False, True])
 @pytest.mark.parametrize("direction", [0, 2])
-@pytest.mark.parametrize("chi_weight_jump", [False, True])
-def test_elliptic3d_compute_in_2d(G, cyl, direction, chi_weight_jump):
+@pytest.mark.parametrize("chi_weight_jump,N", [(False, [12, 10, 5]), (True, [12, 10, 5]), (False, [70, 66, 4]), (False, [33, 40, 3])])
+def test_elliptic3d_compute_in_2d(G, cyl, direction, chi_weight_jump, N):
+    """chi_weight_jump = False: all planes in one launch of the tile kernel (interior tiles by TMA from the stacked planes,
+    tiles at a plane's y boundary by the boundary-aware loader); True: per-plane unfused path"""
     from oracle import refwrap as R
     if not R.available():
         pytest.skip("oracle/_ref/libdgref.so not present")
     from feltor_b200 import topology as T
     from feltor_b200.elliptic import Elliptic3d
     x0, x1 = ([3., -1., 0.], [5., 1., 2 * np.pi]) if cyl else ([0., 0., 0.], [1., 2., 3.])
-    N, bc = [12, 10, 5], [T.DIR, T.NEU if cyl else T.PER, T.PER]
+    bc = [T.DIR, T.NEU if cyl else T.PER, T.PER]
     g = T.Grid(x0, x1, [3, 3, 1], N, bc)
     rg = R.grid(x0, x1, 3, N, bc)
     r = rng(7 + 2 * cyl + direction)
@@ -52,3 +54,28 @@ def test_elliptic3d_rejects_wrong_size(G):
     op = Elliptic3d(g)
     with pytest.raises(ValueError):
         op.symv(G.make(np.zeros(7)), G.make(np.zeros(g.size)))
+
+
+def test_helmholtz_planes_equal_per_plane_calls(G):
+    """a Helmholtz plan (chi x - alpha Elliptic x, chi and sigma 3-d) on stacked planes == the 2-d calls plane by plane"""
+    import ctypes as C
+    import torch
+    from feltor_b200 import topology as T, lib
+    from feltor_b200._dev import ptr, stream
+    from feltor_b200.elliptic import Elliptic2d
+    g = T.Grid([0., 0.], [1., 2.], 3, [40, 36], [T.DIR, T.PER])
+    nz, n2 = 6, g.size
+    r = rng(77)
+    x, sig, chi = (G.make(r.uniform(0.5, 1.5, n2 * nz)) for _ in range(3))
+    op = Elliptic2d(g, direction=T.CENTERED, jfactor=1.)
+    want = torch.zeros(n2 * nz, dtype=torch.float64, device="cuda")
+    for k in range(nz):
+        lib().elliptic2d_set_sigma(op.h, ptr(sig[k * n2:(k + 1) * n2]))
+        lib().elliptic2d_set_helmholtz(op.h, 1, C.c_double(-0.5), ptr(chi[k * n2:(k + 1) * n2]))
+        lib().elliptic2d_symv(op.h, C.c_double(1.), ptr(x[k * n2:(k + 1) * n2]), C.c_double(0.), ptr(want[k * n2:(k + 1) * n2]), stream())
+    lib().elliptic2d_set_helmholtz(op.h, 1, C.c_double(-0.5), ptr(chi))
+    got = torch.full((n2 * nz,), float("nan"), dtype=torch.float64, device="cuda")
+    lib().elliptic2d_symv_planes(op.h, nz, ptr(sig), C.c_double(1.), ptr(x), C.c_double(0.), ptr(got), stream())
+    assert same_bits(G.get(got), G.get(want))
+    lib().elliptic2d_set_helmholtz(op.h, 0, C.c_double(0.), None)
+    lib().elliptic2d_set_sigma(op.h, ptr(op._sigma))
