@@ -74,6 +74,41 @@ class Elliptic2d:
             pass
 
 
+class Elliptic1d:
+    """dg::Elliptic1d (inc/dg/elliptic.h:65-200): -d/dx(chi d/dx) + jump on a 1-d grid -- three Ell symv and one pointwiseDot,
+    the same calls in the same order as the reference template"""
+
+    def __init__(self, g, bcx=None, direction=T.FORWARD, jfactor=1.0):
+        assert g.ndim == 1
+        bcx = g.bc[0] if bcx is None else bcx
+        self.leftx = T.derivative(0, g, T.inverse_bc(bcx), T.inverse_dir(direction))
+        self.rightx = T.derivative(0, g, bcx, direction)
+        self.jumpx = T.jump(0, g, bcx)
+        self.size, self.jfactor = g.size, jfactor
+        self._weights = dvec(g.weights())
+        self._precond = torch.ones(self.size, dtype=torch.float64, device="cuda")
+        self._sigma = torch.ones_like(self._precond)
+        self._tempx = torch.ones_like(self._precond)
+
+    def weights(self):
+        return self._weights
+
+    def precond(self):
+        return self._precond
+
+    def set_chi(self, sigma):
+        blas1.copy(sigma, self._sigma)
+        blas1.pointwiseDivide(torch.ones_like(sigma), sigma, self._precond)
+
+    def symv(self, *a):
+        alpha, x, beta, y = (1., a[0], 0., a[1]) if len(a) == 2 else a
+        self.rightx.symv(1., x, 0., self._tempx)
+        blas1.pointwiseDot(self._tempx, self._sigma, self._tempx)
+        self.leftx.symv(-alpha, self._tempx, beta, y)
+        if self.jfactor != 0.:
+            self.jumpx.symv(self.jfactor * alpha, x, 1., y)
+
+
 class Elliptic3d:
     """dg::Elliptic3d with set_compute_in_2d(true) (inc/dg/elliptic.h:557-797, the mode src/feltor/feltor.h uses) on a
     CartesianGrid3d or a CylindricalGrid3d (x = R, y = Z, z = phi: vol = R): the 2-d plan applied to every plane."""

@@ -321,6 +321,19 @@ void ref_elliptic2d_variation(void* h, double alpha, const double* lambda, const
 void ref_elliptic2d_weights(void* h, double* out) { copy_out(((Ell2d*)h)->weights(), out); }
 void ref_elliptic2d_precond(void* h, double* out) { copy_out(((Ell2d*)h)->precond(), out); }
 
+// ---------------------------------------------------------------- Elliptic1d (inc/dg/elliptic.h:65-200)
+void ref_elliptic1d_symv(const RefGrid* g, int bcx, int dir, double jfactor, const double* chi, double alpha, const double* x,
+                         double beta, double* y, double* weights, double* precond) {
+    dg::Elliptic1d<dg::Grid1d, DMatrix, DVec> e(g1(g), (dg::bc)bcx, (dg::direction)dir, jfactor);
+    size_t n = e.weights().size();
+    if (chi) { CView s(chi, n); e.set_chi(s); }
+    CView vx(x, n);
+    VView vy(y, n);
+    e.symv(alpha, vx, beta, vy);
+    if (weights) copy_out(e.weights(), weights);
+    if (precond) copy_out(e.precond(), precond);
+}
+
 // ---------------------------------------------------------------- Elliptic3d (inc/dg/elliptic.h:557-797)
 // y = alpha Elliptic3d(x) + beta y with set_compute_in_2d(true) (the mode the feltor application uses, src/feltor/feltor.h)
 // on a CartesianGrid3d (cylindrical = 0) or a CylindricalGrid3d (x = R, y = Z, z = phi; vol = R); chi = scalar field or NULL.

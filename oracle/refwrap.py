@@ -277,3 +277,12 @@ def elliptic3d_symv(g, cylindrical, direction, jfactor, chi_weight_jump, chi, al
                               dp(chi) if chi is not None else None, C.c_double(alpha), dp(np.ascontiguousarray(x)),
                               C.c_double(beta), dp(out), dp(w), dp(p))
     return out, w, p
+
+
+def elliptic1d_symv(g, bcx, direction, jfactor, chi, alpha, x, beta, y):
+    """dg::Elliptic1d (elliptic.h:65-200); g: RefGrid (ndim 1); returns (y, weights, precond)"""
+    n = x.size
+    out, w, p = np.array(y, copy=True), np.empty(n), np.empty(n)
+    lib().ref_elliptic1d_symv(C.byref(g), int(bcx), int(direction), C.c_double(jfactor), dp(chi) if chi is not None else None,
+                              C.c_double(alpha), dp(np.ascontiguousarray(x)), C.c_double(beta), dp(out), dp(w), dp(p))
+    return out, w, p

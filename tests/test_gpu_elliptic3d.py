@@ -1,4 +1,4 @@
-"""GPU: dg::Elliptic3d in its compute-in-2d mode (inc/dg/elliptic.h:557-797, the mode src/feltor/feltor.h runs) through
+"""GPU: dg::Elliptic1d and dg::Elliptic3d in its compute-in-2d mode (inc/dg/elliptic.h:557-797, the mode src/feltor/feltor.h runs) through
 dgb_elliptic2d_symv_planes, against the UNMODIFIED reference class (oracle/_ref/libdgref.so, live) on Cartesian and
 cylindrical 3-d grids.  Tolerance of the north star for symv: 1e-12 relative (measured: bit-identical)."""
 import numpy as np
@@ -79,3 +79,28 @@ def test_helmholtz_planes_equal_per_plane_calls(G):
     assert same_bits(G.get(got), G.get(want))
     lib().elliptic2d_set_helmholtz(op.h, 0, C.c_double(0.), None)
     lib().elliptic2d_set_sigma(op.h, ptr(op._sigma))
+
+
+@pytest.mark.parametrize("bcx", [0, 1, 2, 3, 4])
+@pytest.mark.parametrize("direction", [0, 1, 2])
+def test_elliptic1d(G, bcx, direction):
+    """dg::Elliptic1d (elliptic.h:65-200) against the unmodified reference class, bit for bit"""
+    from oracle import refwrap as R
+    if not R.available():
+        pytest.skip("oracle/_ref/libdgref.so not present")
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic1d
+    g = T.Grid([0.3], [2.1], 3, [37], [bcx])
+    rg = R.grid([0.3], [2.1], 3, [37], [bcx])
+    r = rng(11 + bcx)
+    n = g.size
+    x, y0, chi = r.uniform(-1, 1, n), r.uniform(-1, 1, n), r.uniform(0.5, 2., n)
+    op = Elliptic1d(g, direction=direction, jfactor=0.7)
+    for use_chi, (alpha, beta) in ((False, (1., 0.)), (True, (1., 0.)), (True, (-0.5, 0.3))):
+        want, w, p = R.elliptic1d_symv(rg, bcx, direction, 0.7, chi if use_chi else None, alpha, x, beta, y0)
+        if use_chi:
+            op.set_chi(G.make(chi))
+        y = G.make(y0 if beta != 0. else np.full(n, np.nan))
+        op.symv(alpha, G.make(x), beta, y)
+        assert same_bits(G.get(y), want), (bcx, direction, use_chi, alpha, beta)
+        assert same_bits(G.get(op.weights()), w) and same_bits(G.get(op.precond()), p)
