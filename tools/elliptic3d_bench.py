@@ -1,6 +1,6 @@
 """Elliptic3d (compute-in-2d) at the feltor grid of BASELINE config 5: n=3, 192 x 192 x 64; us per apply and GB/s (24 B/dof)"""
 import sys, os, numpy as np, torch
-ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 from feltor_b200 import topology as T
 from feltor_b200.elliptic import Elliptic3d
