@@ -718,4 +718,73 @@ class Elliptic3d {
     }
 };
 
+// device array of int (CSR row offsets / column indices of stencil and interpolation matrices)
+class IVec {
+    int* m_p = nullptr;
+    size_t m_n = 0;
+  public:
+    IVec() = default;
+    IVec(const std::vector<int>& h) : m_n(h.size()) {
+        if (!m_n) return;
+        check(dgb_malloc((void**)&m_p, m_n * sizeof(int)));
+        check(dgb_memcpy_h2d(m_p, h.data(), m_n * sizeof(int), nullptr));
+        check(dgb_stream_synchronize(nullptr));
+    }
+    IVec(const IVec&) = delete;
+    IVec(IVec&& o) noexcept { std::swap(m_p, o.m_p); std::swap(m_n, o.m_n); }
+    ~IVec() { if (m_p) dgb_free(m_p); }
+    size_t size() const { return m_n; }
+    const int* data() const { return m_p; }
+};
+
+namespace blas2 {
+// dg::blas2::stencil(f, M, x, y) (blas2.h:454) for the library's CSR filters (topology/filter.h:174-266)
+enum class csr_filter { median = DGB_STENCIL_MEDIAN, swm = DGB_STENCIL_SWM, average = DGB_STENCIL_AVERAGE, symv = DGB_STENCIL_SYMV };
+inline void stencil(csr_filter f, const IVec& row_offsets, const IVec& cols, const DVec* vals, const DVec& x, DVec& y, double alpha = 0.) {
+    check(dgb_csr_stencil((int)f, (int)row_offsets.size() - 1, row_offsets.data(), cols.data(), vals ? vals->data() : nullptr, alpha,
+                          x.data(), y.data(), nullptr));
+}
+}  // namespace blas2
+
+namespace tensor {
+// dg::tensor::multiply3d (multiply.h:243): out_i = lambda T_ij in_j + mu out_i; t row major, null entries = identity
+inline void multiply3d(double lambda, const std::array<const DVec*, 9>& t, const std::array<const DVec*, 3>& in, double mu,
+                       const std::array<DVec*, 3>& out) {
+    const double* tp[9];
+    for (int k = 0; k < 9; k++) tp[k] = t[k] ? t[k]->data() : nullptr;
+    const double* ip[3] = {in[0]->data(), in[1]->data(), in[2]->data()};
+    double* op[3] = {out[0]->data(), out[1]->data(), out[2]->data()};
+    check(dgb_tensor_multiply3d(in[0]->size(), nullptr, lambda, tp, ip, mu, op, nullptr));
+}
+}  // namespace tensor
+
+namespace geo {
+// the fields of a dg::geo::Fieldaligned the parallel-derivative formulas read (fieldaligned.h: deltaPhi, sqrtG*, bphi*)
+struct FieldalignedFields {
+    double delta_phi = 0;
+    const DVec *sqrtGm = nullptr, *sqrtG = nullptr, *sqrtGp = nullptr, *bphiM = nullptr, *bphi = nullptr, *bphiP = nullptr;
+};
+namespace detail {
+inline const double* p(const DVec* v) { return v ? v->data() : nullptr; }
+inline void apply(int kind, const FieldalignedFields& fa, double alpha, const DVec& a, const DVec& b, const DVec* c, double beta, DVec& g) {
+    if (kind < 6) check(dgb_ds_apply(kind, g.size(), alpha, a.data(), b.data(), p(c), p(fa.bphiM), p(fa.bphi), p(fa.bphiP), fa.delta_phi, beta, g.data(), nullptr));
+    else check(dgb_ds_apply_vol(kind, g.size(), alpha, a.data(), b.data(), p(c), p(fa.sqrtGm), p(fa.sqrtG), p(fa.sqrtGp), p(fa.bphiM), p(fa.bphi),
+                                p(fa.bphiP), fa.delta_phi, beta, g.data(), nullptr));
+}
+}  // namespace detail
+// free functions of inc/geometries/ds.h:743-1016, same argument order
+inline void ds_forward(const FieldalignedFields& fa, double alpha, const DVec& f, const DVec& fp, double beta, DVec& g) { detail::apply(0, fa, alpha, f, fp, nullptr, beta, g); }
+inline void ds_backward(const FieldalignedFields& fa, double alpha, const DVec& fm, const DVec& f, double beta, DVec& g) { detail::apply(1, fa, alpha, f, fm, nullptr, beta, g); }
+inline void ds_centered(const FieldalignedFields& fa, double alpha, const DVec& fm, const DVec& fp, double beta, DVec& g) { detail::apply(2, fa, alpha, fm, fp, nullptr, beta, g); }
+inline void ds_forward2(const FieldalignedFields& fa, double alpha, const DVec& f, const DVec& fp, const DVec& fpp, double beta, DVec& g) { detail::apply(3, fa, alpha, f, fp, &fpp, beta, g); }
+inline void ds_backward2(const FieldalignedFields& fa, double alpha, const DVec& fmm, const DVec& fm, const DVec& f, double beta, DVec& g) { detail::apply(4, fa, alpha, f, fm, &fmm, beta, g); }
+inline void dss_centered(const FieldalignedFields& fa, double alpha, const DVec& fm, const DVec& f, const DVec& fp, double beta, DVec& g) { detail::apply(5, fa, alpha, fm, f, &fp, beta, g); }
+inline void dssd_centered(const FieldalignedFields& fa, double alpha, const DVec& fm, const DVec& f, const DVec& fp, double beta, DVec& g) { detail::apply(6, fa, alpha, fm, f, &fp, beta, g); }
+inline void ds_divBackward(const FieldalignedFields& fa, double alpha, const DVec& fm, const DVec& f, double beta, DVec& g) { detail::apply(7, fa, alpha, fm, f, nullptr, beta, g); }
+inline void ds_divForward(const FieldalignedFields& fa, double alpha, const DVec& f, const DVec& fp, double beta, DVec& g) { detail::apply(8, fa, alpha, f, fp, nullptr, beta, g); }
+inline void ds_divCentered(const FieldalignedFields& fa, double alpha, const DVec& fm, const DVec& fp, double beta, DVec& g) { detail::apply(9, fa, alpha, fm, fp, nullptr, beta, g); }
+inline void ds_average(const FieldalignedFields& fa, double alpha, const DVec& fm, const DVec& fp, double beta, DVec& g) { detail::apply(10, fa, alpha, fm, fp, nullptr, beta, g); }
+inline void ds_slope(const FieldalignedFields& fa, double alpha, const DVec& fm, const DVec& fp, double beta, DVec& g) { ds_centered(fa, alpha, fm, fp, beta, g); }
+}  // namespace geo
+
 }  // namespace dgb200

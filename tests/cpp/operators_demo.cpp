@@ -51,5 +51,29 @@ int main(int argc, char** argv) {
     pol3.symv(-0.5, x3, 0.3, y3);
     printf("elliptic3d checksum: %.17g\n", blas2::dot(y3, pol3.weights(), y3));
     printf("elliptic3dprecond checksum: %.17g\n", blas2::dot(pol3.precond(), pol3.weights(), pol3.precond()));
+    // blas2::stencil (median over the window i-1, i, i+1), tensor::multiply3d, two ds.h formulas
+    {
+        const int n = (int)grid.size();
+        std::vector<int> pos(n + 1), idx;
+        for (int i = 0; i < n; i++) {
+            pos[i] = (int)idx.size();
+            for (int k = std::max(i - 1, 0); k <= std::min(i + 1, n - 1); k++) idx.push_back(k);
+        }
+        pos[n] = (int)idx.size();
+        IVec dpos(pos), didx(idx);
+        DVec med(grid.size(), 0.);
+        blas2::stencil(blas2::csr_filter::median, dpos, didx, nullptr, f, med);
+        printf("median checksum: %.17g\n", blas2::dot(med, w, med));
+        DVec o0(f), o1(b), o2(vx);
+        tensor::multiply3d(-1.5, {&vx, nullptr, &vy, nullptr, nullptr, &b, &f, nullptr, nullptr}, {&f, &b, &vy}, 0.25, {&o0, &o1, &o2});
+        printf("tensor3d checksum: %.17g\n", blas2::dot(o0, w, o1) + blas2::dot(o2, w, o2));
+        geo::FieldalignedFields fa;
+        DVec G0(grid.size(), 1.5), Gm(grid.size(), 1.25), Gp(grid.size(), 1.75), bphi(grid.size(), 0.5);
+        fa.delta_phi = 0.1; fa.sqrtGm = &Gm; fa.sqrtG = &G0; fa.sqrtGp = &Gp; fa.bphiM = &bphi; fa.bphi = &bphi; fa.bphiP = &bphi;
+        DVec g1(grid.size(), 0.5), g2(grid.size(), 0.5);
+        geo::ds_divCentered(fa, 0.7, f, b, -0.3, g1);
+        geo::dss_centered(fa, 0.7, f, b, vx, -0.3, g2);
+        printf("dsdiv checksum: %.17g\ndss checksum: %.17g\n", blas2::dot(g1, w, g1), blas2::dot(g2, w, g2));
+    }
     return 0;
 }

@@ -127,6 +127,27 @@ def test_cpp_operators_demo_matches_harness():
     pol3.symv(-0.5, G.make(hx), 0.3, y3)
     assert blas2.dot(y3, pol3.weights(), y3) == val["elliptic3d"]
     assert blas2.dot(pol3.precond(), pol3.weights(), pol3.precond()) == val["elliptic3dprecond"]
+    # blas2::stencil, tensor::multiply3d and the ds.h formulas through the header == the same ABI calls from the harness
+    from feltor_b200._dev import dvec
+    n = g.size
+    pos, idx = [0], []
+    for i in range(n):
+        idx += list(range(max(i - 1, 0), min(i + 1, n - 1) + 1))
+        pos.append(len(idx))
+    med = torch.zeros_like(f)
+    blas2.stencil("median", dvec(np.array(pos, dtype=np.int32)), dvec(np.array(idx, dtype=np.int32)), None, f, med)
+    assert blas2.dot(med, w, med) == val["median"]
+    o = [f.clone(), b.clone(), vx.clone()]
+    blas1.tensor_multiply3d(-1.5, [vx, None, vy, None, None, b, f, None, None], [f, b, vy], 0.25, o)
+    assert blas2.dot(o[0], w, o[1]) + blas2.dot(o[2], w, o[2]) == val["tensor3d"]
+    full = lambda v: torch.full_like(f, v)
+    G0, Gm, Gp, bphi = full(1.5), full(1.25), full(1.75), full(0.5)
+    g1, g2 = full(0.5), full(0.5)
+    lib().ds_apply_vol(9, n, C.c_double(0.7), ptr(f), ptr(b), None, ptr(Gm), ptr(G0), ptr(Gp), ptr(bphi), ptr(bphi), ptr(bphi),
+                       C.c_double(0.1), C.c_double(-0.3), ptr(g1), stream())
+    lib().ds_apply(5, n, C.c_double(0.7), ptr(f), ptr(b), ptr(vx), ptr(bphi), ptr(bphi), ptr(bphi), C.c_double(0.1), C.c_double(-0.3),
+                   ptr(g2), stream())
+    assert blas2.dot(g1, w, g1) == val["dsdiv"] and blas2.dot(g2, w, g2) == val["dss"]
 
 
 def test_cpp_host_only():
