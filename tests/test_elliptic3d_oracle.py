@@ -72,3 +72,57 @@ def test_elliptic1d_is_three_symv(R, bcx):
             orc.ell_symv(jump, 0.7 * alpha, x, 1., y)
             assert same_bits(y, want), (bcx, direction, alpha, beta)
             assert same_bits(w, g.weights()) and same_bits(p, 1. / chi)
+
+
+# ------------------------------------------------------------------ the same against committed fixtures (no reference build needed)
+@pytest.fixture(scope="module")
+def gold3():
+    import os
+    return np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "elliptic3d_golden.npz"))
+
+
+@pytest.mark.parametrize("cyl", [0, 1])
+@pytest.mark.parametrize("direction", [0, 2])
+@pytest.mark.parametrize("cwj", [0, 1])
+def test_elliptic3d_fixture(gold3, cyl, direction, cwj):
+    from feltor_b200 import topology as T
+    x0, x1 = ([3., -1., 0.], [5., 1., 2 * np.pi]) if cyl else ([0., 0., 0.], [1., 2., 3.])
+    N, bc = [9, 7, 4], [T.DIR, T.NEU if cyl else T.PER, T.PER]
+    g2 = T.Grid(x0[:2], x1[:2], 3, N[:2], bc[:2])
+    n2, nz = g2.size, N[2]
+    mats = dict(leftx=T.derivative(0, g2, T.inverse_bc(bc[0]), T.inverse_dir(direction)),
+                lefty=T.derivative(1, g2, T.inverse_bc(bc[1]), T.inverse_dir(direction)),
+                rightx=T.derivative(0, g2, bc[0], direction), righty=T.derivative(1, g2, bc[1], direction),
+                jumpx=T.jump(0, g2, bc[0]), jumpy=T.jump(1, g2, bc[1]))
+    vol = None
+    if cyl:
+        Rr = np.ascontiguousarray(np.broadcast_to(g2.abscissas(0), (g2.shape(1), g2.shape(0))).reshape(-1))
+        vol = 1. / np.sqrt((1. / Rr) / Rr)
+    x, y0, chi = gold3["x"], gold3["y0"], gold3["chi"]
+    want = gold3[f"e3d/cyl{cyl}/dir{direction}/cwj{cwj}/y"]
+    for k in range(nz):
+        sl = slice(k * n2, (k + 1) * n2)
+        sigma = chi[sl] * vol if cyl else chi[sl].copy()
+        E = orc.Elliptic2d(mats, sigma=np.ascontiguousarray(sigma), vol=vol, jfactor=0.7, chi_weight_jump=bool(cwj))
+        y = y0[sl].copy()
+        E.symv(-0.5, np.ascontiguousarray(x[sl]), 0.3, y)
+        assert same_bits(y, want[sl]), (cyl, direction, cwj, k)
+    w3 = T.Grid(x0, x1, [3, 3, 1], N, bc).weights()
+    assert same_bits(gold3[f"e3d/cyl{cyl}/weights"], w3 * np.tile(vol, nz) if cyl else w3)
+    assert same_bits(gold3[f"e3d/cyl{cyl}/precond"], 1. / chi)
+
+
+@pytest.mark.parametrize("bcx", [0, 1, 2, 3, 4])
+def test_elliptic1d_fixture(gold3, bcx):
+    from feltor_b200 import topology as T
+    g = T.Grid([0.3], [2.1], 3, [21], [bcx])
+    x, y0, chi = gold3["x1d"], gold3["y1d"], gold3["chi1d"]
+    for direction in (0, 1, 2):
+        left = T.derivative(0, g, T.inverse_bc(bcx), T.inverse_dir(direction))
+        right, jump = T.derivative(0, g, bcx, direction), T.jump(0, g, bcx)
+        t, y = np.zeros(g.size), y0.copy()
+        orc.ell_symv(right, 1., x, 0., t)
+        orc.pointwiseDot(1., t.copy(), chi, 0., t)
+        orc.ell_symv(left, 0.5, t, 0.3, y)
+        orc.ell_symv(jump, 0.7 * -0.5, x, 1., y)
+        assert same_bits(y, gold3[f"e1d/bc{bcx}/dir{direction}/y"]), (bcx, direction)
