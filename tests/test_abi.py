@@ -52,3 +52,19 @@ def test_compute_fails_loudly_without_device():
     p = C.c_void_p()
     with pytest.raises(fb.DgbError):
         fb.lib().malloc(C.byref(p), 1024)
+    # kernels launched on host memory without a device: every entry point reports the CUDA error instead of computing
+    a, b = np.ones(64), np.ones(64)
+    pa, pb = a.ctypes.data, b.ctypes.data
+    d = C.c_double
+    pos, idx = np.arange(65, dtype=np.int32), np.arange(64, dtype=np.int32)
+    calls = [
+        lambda: fb.lib().axpby(64, d(1.), pa, d(1.), pb, None),
+        lambda: fb.lib().adaptive_tolerance(64, d(1.), d(1.), pa, pb, None),
+        lambda: fb.lib().csr_stencil(0, 64, pos.ctypes.data, idx.ctypes.data, None, d(0.), pa, pb, None),
+        lambda: fb.lib().ds_apply_vol(10, 64, d(1.), pa, pa, None, None, None, None, None, None, None, d(1.), d(0.), pb, None),
+        lambda: fb.lib().reduce(64, pa, 0, 0, d(0.), pb, None),
+    ]
+    for k, call in enumerate(calls):
+        with pytest.raises(fb.DgbError):
+            call()
+        assert np.all(b == 1.), k   # nothing was computed on the host
