@@ -58,6 +58,14 @@ class DVec {
     size_t size() const { return m_n; }
     double* data() { return m_p; }
     const double* data() const { return m_p; }
+    // element read from the host like thrust::device_vector's v[i] (blas1_t.cpp:26-38 does this); one blocking 8-byte copy
+    double operator[](size_t i) const {
+        double v;
+        check(dgb_memcpy_d2h(&v, m_p + i, sizeof(double), nullptr));
+        check(dgb_stream_synchronize(nullptr));
+        return v;
+    }
+    void assign(size_t n, double value) { resize(n); if (n) check(dgb_fill(n, value, m_p, nullptr)); }
     HVec to_host() const { HVec h(m_n); if (m_n) { check(dgb_memcpy_d2h(h.data(), m_p, m_n * sizeof(double), nullptr)); check(dgb_stream_synchronize(nullptr)); } return h; }
 };
 
