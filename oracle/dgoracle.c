@@ -149,6 +149,49 @@ ORC_API void orc_ds_apply(int kind, int n, double alpha, const double* a, const 
         g[i] = beta == 0. ? v : v + beta * g[i];
     }
 }
+/* assign_bc_along_field_2nd / _1st (inc/geometries/ds.h:169-296): ghost values fmg, fpg of the minus / plus neighbours where the
+ * field line leaves the domain (bbm, bbo, bbp = masks, hbm / hbp = distances to the wall); order 2 uses (fm, f, fp), order 1
+ * (fm, fp); neu != 0: Neumann values (dbm, dbp) = (bv0, bv1), else Dirichlet values (fbm, fbp).  Left-to-right, separately
+ * rounded (the reference's are user lambdas: parity ~1e-14) */
+ORC_API void orc_assign_bc_along_field(int order, int neu, int n, double delta, const double* fm_, const double* f_,
+                                       const double* fp_, const double* hbm_, const double* hbp_, const double* bbm_,
+                                       const double* bbo_, const double* bbp_, double bv0, double bv1, double* fmg, double* fpg) {
+    for (int i = 0; i < n; i++) {
+        double fm = fm_[i], fp = fp_[i], fo = f_ ? f_[i] : 0., hm = delta, hp = delta;
+        double hbm = hbm_ ? hbm_[i] : 0., hbp = hbp_ ? hbp_[i] : 0., bbm = bbm_[i], bbo = bbo_ ? bbo_[i] : 0., bbp = bbp_[i];
+        double plus, minus, bothP = 0., bothM = 0.;
+        if (order == 2 && neu) {
+            double dbm = bv0, dbp = bv1;
+            plus = dbp * hp * (hm + hp) / (2. * hbp + hm) + fo * (2. * hbp + hm - hp) * (hm + hp) / hm / (2. * hbp + hm) +
+                   fm * hp * (-2. * hbp + hp) / hm / (2. * hbp + hm);
+            minus = fp * hm * (-2. * hbm + hm) / hp / (2. * hbm + hp) - dbm * hm * (hm + hp) / (2. * hbm + hp) +
+                    fo * (2. * hbm - hm + hp) * (hm + hp) / hp / (2. * hbm + hp);
+            bothM = fo + dbp * hm * (-2. * hbm + hm) / 2. / (hbm + hbp) - dbm * hm * (2. * hbp + hm) / 2. / (hbm + hbp);
+            bothP = fo + dbp * hp * (2. * hbm + hp) / 2. / (hbm + hbp) + dbm * hp * (2. * hbp - hp) / 2. / (hbm + hbp);
+        } else if (order == 2) {
+            double fbm = bv0, fbp = bv1;
+            plus = fm * hp * (-hbp + hp) / hm / (hbp + hm) + fo * (hbp - hp) * (hm + hp) / hbp / hm + fbp * hp * (hm + hp) / hbp / (hbp + hm);
+            minus = +fo * (hbm - hm) * (hm + hp) / hbm / hp + fbm * hm * (hm + hp) / hbm / (hbm + hp) + fp * hm * (-hbm + hm) / hp / (hbm + hp);
+            bothM = fbp * hm * (-hbm + hm) / hbp / (hbm + hbp) + fo * (hbm - hm) * (hbp + hm) / hbm / hbp + fbm * hm * (hbp + hm) / hbm / (hbm + hbp);
+            bothP = fo * (hbp - hp) * (hbm + hp) / hbm / hbp + fbp * hp * (hbm + hp) / hbp / (hbm + hbp) + fbm * hp * (-hbp + hp) / hbm / (hbm + hbp);
+        } else if (neu) {
+            double dbm = bv0, dbp = bv1;
+            plus = fm + dbp * (hp + hm);
+            minus = fp - dbm * (hp + hm);
+            fmg[i] = (1. - bbm) * fm + bbm * minus;
+            fpg[i] = (1. - bbp) * fp + bbp * plus;
+            continue;
+        } else {
+            double fbm = bv0, fbp = bv1;
+            plus = fm + (fbp - fm) / (hbp + hm) * (hp + hm);
+            minus = fp - (hp + hm) * (fp - fbm) / (hp + hbm);
+            bothM = fbp + (fbp - fbm) / (hbp + hbm) * (hp + hbm);
+            bothP = fbp - (fbp - fbm) / (hbp + hbm) * (hbp + hm);
+        }
+        fmg[i] = (1. - bbo - bbm) * fm + bbm * minus + bbo * bothM;
+        fpg[i] = (1. - bbo - bbp) * fp + bbp * plus + bbo * bothP;
+    }
+}
 /* dg::blas2::stencil / parallel_for with the library's CSR stencil functors, inc/dg/topology/filter.h:84-266.
  * The (lower) median is an order statistic -- rank (n+1)/2 of the stencil values -- so it is restated here by sorting;
  * kind 0 CSRMedianFilter, 1 CSRSWMFilter(alpha), 2 CSRAverageFilter, 3 CSRSymvFilter */

@@ -101,6 +101,12 @@ def ds_apply(kind, alpha, a, b, c, G, bphi, delta, beta, g):
                        dp(bphi[2]), d(delta), d(beta), dp(g))
 
 
+def assign_bc_along_field(order, neu, delta, fm, f, fp, hbm, hbp, bbm, bbo, bbp, bv, fmg, fpg):
+    """inc/geometries/ds.h:169-296; order 2 (fm, f, fp) or 1 (fm, fp; f None); bv = (boundary value minus, plus)"""
+    lib().orc_assign_bc_along_field(order, int(neu), fm.size, d(delta), dp(fm), dp(f), dp(fp), dp(hbm), dp(hbp), dp(bbm), dp(bbo),
+                                    dp(bbp), d(bv[0]), d(bv[1]), dp(fmg), dp(fpg))
+
+
 def csr_stencil(kind, pos, idx, val, alpha, x, y):
     """blas2::stencil with CSRMedianFilter (0) / CSRSWMFilter(alpha) (1) / CSRAverageFilter (2) / CSRSymvFilter (3)"""
     lib().orc_csr_stencil(kind, len(pos) - 1, ip(pos), ip(idx), dp(val), d(alpha), dp(x), dp(y))

@@ -14,7 +14,13 @@ using Vec = thrust::host_vector<double>;
 struct MockFA {
     double delta;
     Vec gm, g0, gp, bm, b0, bp;
+    Vec v_hbm, v_hbp, v_bbm, v_bbo, v_bbp;
     double deltaPhi() const { return delta; }
+    const Vec& hbm() const { return v_hbm; }
+    const Vec& hbp() const { return v_hbp; }
+    const Vec& bbm() const { return v_bbm; }
+    const Vec& bbo() const { return v_bbo; }
+    const Vec& bbp() const { return v_bbp; }
     const Vec& sqrtGm() const { return gm; }
     const Vec& sqrtG() const { return g0; }
     const Vec& sqrtGp() const { return gp; }
@@ -47,6 +53,17 @@ void ref_ds_apply(int kind, int n, double alpha, const double* a, const double* 
         case 10: dg::geo::ds_average(fa, alpha, va, vb, beta, vg); break;
     }
     for (int i = 0; i < n; i++) g[i] = vg[i];
+}
+// assign_bc_along_field_2nd (order 2: fm, f, fp) / _1st (order 1: fm, fp) of inc/geometries/ds.h:169-296; bound: 4 = NEU else DIR
+void ref_assign_bc_along_field(int order, int bound, int n, double delta, const double* fm, const double* f, const double* fp,
+                               const double* hbm, const double* hbp, const double* bbm, const double* bbo, const double* bbp,
+                               double bv0, double bv1, double* fmg, double* fpg) {
+    MockFA fa{delta, Vec(), Vec(), Vec(), Vec(), Vec(), Vec(), mk(hbm, n), mk(hbp, n), mk(bbm, n), mk(bbo, n), mk(bbp, n)};
+    Vec vfm = mk(fm, n), vf = mk(f, n), vfp = mk(fp, n), g0(n, 0.), g1(n, 0.);
+    dg::bc b = bound == 4 ? dg::NEU : dg::DIR;
+    if (order == 2) dg::geo::assign_bc_along_field_2nd(fa, vfm, vf, vfp, g0, g1, b, {bv0, bv1});
+    else dg::geo::assign_bc_along_field_1st(fa, vfm, vfp, g0, g1, b, {bv0, bv1});
+    for (int i = 0; i < n; i++) { fmg[i] = g0[i]; fpg[i] = g1[i]; }
 }
 // t: 9 arrays (row major), in/out: 3 arrays each
 void ref_tensor_multiply3d(int n, const double* lambda, const double* const* t, const double* const* in, double mu,

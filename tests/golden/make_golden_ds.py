@@ -64,5 +64,21 @@ for kind in range(4):
     y = np.zeros(nr)
     L.ref_csr_stencil(kind, nr, nr, pos.ctypes.data_as(c_ip), idx.ctypes.data_as(c_ip), dp(val), d(1.5), dp(xs), dp(y))
     out[f"stencil/kind{kind}"] = y
+# ---- assign_bc_along_field_2nd / _1st (ds.h:169-296): masks bbm/bbo/bbp in {0,1} (at most one set), wall distances in (0, delta)
+nb = 777
+bc_in = {k: r.uniform(-1, 1, nb) for k in ("fm", "f", "fp")}
+delta = 2 * np.pi / 7
+bc_in["hbm"], bc_in["hbp"] = r.uniform(0.05, 0.95, nb) * delta, r.uniform(0.05, 0.95, nb) * delta
+which = r.integers(0, 4, nb)
+for j, k in enumerate(("bbm", "bbo", "bbp")):
+    bc_in[k] = (which == j + 1).astype(np.float64)
+for k, v in bc_in.items():
+    out["bc/" + k] = v
+for order in (1, 2):
+    for bound in (4, 1):   # NEU, DIR
+        g0, g1 = np.zeros(nb), np.zeros(nb)
+        L.ref_assign_bc_along_field(order, bound, nb, d(delta), dp(bc_in["fm"]), dp(bc_in["f"]), dp(bc_in["fp"]), dp(bc_in["hbm"]),
+                                    dp(bc_in["hbp"]), dp(bc_in["bbm"]), dp(bc_in["bbo"]), dp(bc_in["bbp"]), d(0.3), d(-0.2), dp(g0), dp(g1))
+        out[f"bc/order{order}/bound{bound}/fmg"], out[f"bc/order{order}/bound{bound}/fpg"] = g0, g1
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "ds_golden.npz"), **out)
 print("wrote ds_golden.npz with", len(out), "arrays")

@@ -57,3 +57,17 @@ def test_csr_stencil_fixture(gold, kind):
     y = np.full(gold["stencil/x"].size, np.nan)
     orc.csr_stencil(kind, gold["stencil/pos"], gold["stencil/idx"], gold["stencil/val"], 1.5, gold["stencil/x"], y)
     assert same_bits(y, gold[f"stencil/kind{kind}"])
+
+
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("bound", [4, 1])
+def test_assign_bc_along_field_fixture(gold, order, bound):
+    """assign_bc_along_field_1st / _2nd (ds.h:169-296), NEU (4) and DIR (1): user lambdas, tolerance 1e-13 as above"""
+    k = {n: gold["bc/" + n] for n in ("fm", "f", "fp", "hbm", "hbp", "bbm", "bbo", "bbp")}
+    fmg, fpg = np.full(k["fm"].size, np.nan), np.full(k["fm"].size, np.nan)
+    orc.assign_bc_along_field(order, bound == 4, 2 * np.pi / 7, k["fm"], k["f"] if order == 2 else None, k["fp"], k["hbm"], k["hbp"],
+                              k["bbm"], k["bbo"], k["bbp"], (0.3, -0.2), fmg, fpg)
+    assert ds_close(fmg, gold[f"bc/order{order}/bound{bound}/fmg"]) and ds_close(fpg, gold[f"bc/order{order}/bound{bound}/fpg"])
+    # interior points (no mask set) keep the shifted values exactly
+    inner = (k["bbm"] + k["bbo"] + k["bbp"]) == 0
+    assert np.array_equal(fmg[inner], k["fm"][inner]) and np.array_equal(fpg[inner], k["fp"][inner])
