@@ -68,3 +68,17 @@ def test_compute_fails_loudly_without_device():
         with pytest.raises(fb.DgbError):
             call()
         assert np.all(b == 1.), k   # nothing was computed on the host
+
+
+def test_headers_compile_standalone(tmp_path):
+    """include/dgb200.h is a plain C99 header (the drop-in boundary has no C++ or torch types in it) and
+    include/dg_b200.hpp compiles on its own as pedantic C++17"""
+    import os
+    import subprocess
+    inc = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include")
+    c = tmp_path / "h.c"
+    c.write_text('#include "dgb200.h"\nint main(void) { return sizeof(dgb_dot_result) == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I" + inc, str(c)])
+    cpp = tmp_path / "h.cpp"
+    cpp.write_text('#include "dg_b200.hpp"\n#include "dg_b200.hpp"\nint main() { return 0; }\n')
+    subprocess.check_call(["g++", "-std=c++17", "-Wall", "-Wextra", "-Werror", "-pedantic", "-fsyntax-only", "-I" + inc, str(cpp)])
