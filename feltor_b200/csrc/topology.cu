@@ -4,6 +4,7 @@
 // derivatives,interpolation,projection,fast_interpolation}.h.  The ARITHMETIC (order of the floating point
 // operations, fused multiply-adds in the small dense products) follows the reference so that the coefficients
 // come out bit-identical to what its OpenMP build produces (checked in tests/test_topology.py).
+#include <cstdint>
 #include "common.cuh"
 #include "topology.h"
 #include <cmath>
@@ -359,6 +360,64 @@ int dgb_topo_dlt(int which, int n, double* out) {
     if (n < 1 || n > DLT_NMAX || which < 0 || which > 3) { set_error("dgb_topo_dlt: invalid arguments"); return DGB_ERR_INVALID; }
     std::vector<double> v = which == 0 ? dlt_abscissas(n) : which == 1 ? dlt_weights(n) : which == 2 ? dlt_backward(n).a : dlt_forward(n).a;
     std::copy(v.begin(), v.end(), out);
+    return 0;
+}
+// dg::create::window_stencil (inc/dg/topology/stencil.h:56-88,177-237): the neighbourhood matrix blas2::stencil runs on.
+// 1-d: row k lists the columns k - w/2 ... k - w/2 + w - 1, all values 1; points beyond the boundary are wrapped (PER) or
+// mirrored (value -1 on a Dirichlet side); duplicates are kept and nothing is sorted, as in the reference.  2-d / 3-d: the
+// Kronecker product, last axis outermost.  Caller-allocated outputs: row_offsets[size + 1], cols / vals[size * prod(window)].
+int dgb_topo_window_stencil(const dgb_grid* g, const int* window, int* row_offsets, int* cols, double* vals) {
+    int e = check_grid(g); if (e) return e;
+    if (!window || !row_offsets || !cols || !vals) { set_error("dgb_topo_window_stencil: null argument"); return DGB_ERR_INVALID; }
+    std::vector<std::vector<int>> ax_cols(g->ndim);
+    std::vector<std::vector<double>> ax_vals(g->ndim);
+    std::vector<int> len(g->ndim);
+    size_t per_row = 1;
+    for (int u = 0; u < g->ndim; u++) {
+        const int w = window[u], n = g->n[u] * g->N[u], radius = w / 2, bc = g->bc[u];
+        if (w < 1) { set_error("dgb_topo_window_stencil: window size must be positive"); return DGB_ERR_INVALID; }
+        len[u] = n;
+        per_row *= (size_t)w;
+        for (int k = 0; k < n; k++)
+            for (int l = 0; l < w; l++) {
+                int c = k + l - radius;
+                double v = 1.;
+                if (c < 0) {
+                    if (bc == DGB_PER) c += n;
+                    else { c = -(c + 1); if (bc == DGB_DIR || bc == DGB_DIR_NEU) v = -1.; }
+                } else if (c >= n) {
+                    if (bc == DGB_PER) c -= n;
+                    else { c = 2 * n - 1 - c; if (bc == DGB_DIR || bc == DGB_NEU_DIR) v = -1.; }
+                }
+                ax_cols[u].push_back(c);
+                ax_vals[u].push_back(v);
+            }
+    }
+    const size_t rows = grid_size(g);
+    if (rows * per_row > (size_t)INT32_MAX) { set_error("dgb_topo_window_stencil: matrix too large for int indices"); return DGB_ERR_UNSUPPORTED; }
+    // row index = ((iz) * ny + iy) * nx + ix; entries of a row: outermost axis slowest (tensorproduct(my, mx), xspacelib.h:38-70)
+    size_t counter = 0;
+    row_offsets[0] = 0;
+    std::vector<int> idx(g->ndim, 0), ent(g->ndim, 0);
+    for (size_t r = 0; r < rows; r++) {
+        size_t rr = r;
+        for (int u = 0; u < g->ndim; u++) { idx[u] = (int)(rr % len[u]); rr /= len[u]; }
+        for (size_t q = 0; q < per_row; q++) {
+            size_t qq = q;
+            for (int u = 0; u < g->ndim; u++) { ent[u] = (int)(qq % window[u]); qq /= window[u]; }
+            long long c = 0;
+            double v = 1.;
+            for (int u = g->ndim - 1; u >= 0; u--) {
+                const size_t at = (size_t)idx[u] * window[u] + ent[u];
+                c = c * len[u] + ax_cols[u][at];
+                v = v * ax_vals[u][at];
+            }
+            cols[counter] = (int)c;
+            vals[counter] = v;
+            counter++;
+        }
+        row_offsets[r + 1] = (int)counter;
+    }
     return 0;
 }
 int dgb_topo_size(const dgb_grid* g, size_t* size) {

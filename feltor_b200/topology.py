@@ -163,3 +163,13 @@ def dlt(which, n):
     out = np.empty(n * n if which >= 2 else n)
     lib().topo_dlt(which, n, out.ctypes.data)
     return out
+
+
+def window_stencil(g, window):
+    """dg::create::window_stencil (inc/dg/topology/stencil.h:177-237): CSR arrays (row_offsets, cols int32; vals float64) of the
+    neighbourhood matrix blas2.stencil runs on; window = points per axis"""
+    window = [int(window)] * g.ndim if np.isscalar(window) else [int(w) for w in window]
+    rows, per_row = g.size, int(np.prod(window))
+    pos, idx, val = np.empty(rows + 1, dtype=np.int32), np.empty(rows * per_row, dtype=np.int32), np.empty(rows * per_row)
+    lib().topo_window_stencil(g.ref(), (C.c_int * g.ndim)(*window), pos.ctypes.data, idx.ctypes.data, val.ctypes.data)
+    return pos, idx, val

@@ -226,6 +226,10 @@ typedef struct dgb_grid { /* aRealTopology<double,Nd>, inc/dg/topology/grid.h:92
 } dgb_grid;
 typedef struct dgb_ellh dgb_ellh; /* host EllSparseBlockMat owning its arrays */
 DGB_API int dgb_topo_dlt(int which, int n, double* out_host); /* dlt.h: 0 abscissas, 1 weights, 2 backward, 3 forward */
+/* dg::create::window_stencil (topology/stencil.h:177-237): neighbourhood matrix for dgb_csr_stencil.  window[ndim] = points per
+ * axis; outputs are caller-allocated HOST arrays: row_offsets[size + 1], cols / vals[size * prod(window)] (entries unsorted,
+ * duplicates kept, value -1 for points mirrored at a Dirichlet boundary, exactly as the reference builds it) */
+DGB_API int dgb_topo_window_stencil(const dgb_grid* g, const int* window, int* row_offsets, int* cols, double* vals);
 DGB_API int dgb_topo_size(const dgb_grid* g, size_t* size);
 DGB_API int dgb_topo_abscissas(const dgb_grid* g, int axis, double* out_host); /* grid.h:128 */
 DGB_API int dgb_topo_weights1d(const dgb_grid* g, int axis, double* out_host); /* grid.h:155 */

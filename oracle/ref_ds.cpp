@@ -92,3 +92,15 @@ extern "C" void ref_csr_stencil(int kind, int num_rows, int num_cols, const int*
     }
     for (int i = 0; i < num_rows; i++) y[i] = vy[i];
 }
+
+// dg::create::window_stencil on a 1-d / 2-d grid (inc/dg/topology/stencil.h:177-237); returns nnz, arrays caller-allocated
+extern "C" int ref_window_stencil(int ndim, const double* x0, const double* x1, int n, const int* N, const int* bc, const int* window,
+                                  int* pos, int* idx, double* val) {
+    dg::IHMatrix m;
+    if (ndim == 1) m = dg::create::window_stencil((unsigned)window[0], dg::Grid1d(x0[0], x1[0], n, N[0], (dg::bc)bc[0]), (dg::bc)bc[0]);
+    else m = dg::create::window_stencil(std::array<int, 2>{window[0], window[1]},
+                                        dg::Grid2d(x0[0], x1[0], x0[1], x1[1], n, N[0], N[1], (dg::bc)bc[0], (dg::bc)bc[1]), (dg::bc)bc[0], (dg::bc)bc[1]);
+    for (size_t i = 0; i < m.row_offsets().size(); i++) pos[i] = m.row_offsets()[i];
+    for (size_t i = 0; i < m.column_indices().size(); i++) { idx[i] = m.column_indices()[i]; val[i] = m.values()[i]; }
+    return (int)m.values().size();
+}
