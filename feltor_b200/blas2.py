@@ -48,7 +48,10 @@ def _operand(v):
 def superacc(*ops, ws=None):
     """doDot_superacc: returns (acc[39] normalised int64 numpy, status).  2 or 3 operands."""
     ws = ws or _ws()
-    n = max(o.numel() for o in ops if not isinstance(o, (int, float)))
+    sizes = {o.numel() for o in ops if not isinstance(o, (int, float))}
+    if len(sizes) != 1:
+        raise ValueError("dg::Error: dot: operand sizes differ %s" % sorted(sizes))   # blas1.h: the reference throws as well
+    n = sizes.pop()
     acc = np.zeros(BIN_COUNT, dtype=np.int64)
     val = C.c_double()
     st = C.c_int()

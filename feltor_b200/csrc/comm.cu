@@ -138,36 +138,48 @@ static int comm_p2p_setup(Comm* c) {
     return 0;
 }
 
-int comm_p2p_map(Comm* c, void* basep, void** peers) {
-    if (!c || !c->p2p) return 1;
-    cudaIpcMemHandle_t mine;
-    cudaError_t ce = cudaIpcGetMemHandle(&mine, basep);
-    const size_t HB = sizeof(cudaIpcMemHandle_t) + 8;
-    unsigned char* dev = nullptr;
-    DGB_CUDA(cudaMalloc(&dev, HB * c->size));
-    std::vector<unsigned char> host(HB * c->size, 0);
-    if (ce == cudaSuccess) { memcpy(host.data() + HB * c->rank, &mine, sizeof(mine)); host[HB * c->rank + sizeof(mine)] = 1; }
-    else cudaGetLastError();
-    DGB_CUDA(cudaMemcpy(dev + HB * c->rank, host.data() + HB * c->rank, HB, cudaMemcpyHostToDevice));
-    DGB_NCCL(nccl()->AllGather(dev + HB * c->rank, dev, HB, 0 /* ncclInt8 */, c->comm, nullptr));
-    DGB_CUDA(cudaDeviceSynchronize());
-    DGB_CUDA(cudaMemcpy(host.data(), dev, HB * c->size, cudaMemcpyDeviceToHost));
-    bool ok = true;
-    for (int r = 0; r < c->size; r++) ok = ok && host[HB * r + sizeof(mine)] == 1;
+int comm_p2p_map(Comm* c, void* basep, void** peers, int* mapped) {
+    *mapped = 0;
+    if (!c || !c->p2p) return 0;  // decided collectively at communicator creation: no rank communicates here
     for (int r = 0; r < c->size; r++) peers[r] = nullptr;
+    const size_t HB = sizeof(cudaIpcMemHandle_t) + 8;
+    std::vector<unsigned char> host(HB * c->size, 0);
+    unsigned char* dev = nullptr;
+    bool ok = cudaMalloc(&dev, HB * c->size + 8) == cudaSuccess;  // [handles | agreement flag]
+    int nccl_err = 0;
+    if (ok) {
+        cudaIpcMemHandle_t mine;
+        if (cudaIpcGetMemHandle(&mine, basep) == cudaSuccess) { memcpy(host.data() + HB * c->rank, &mine, sizeof(mine)); host[HB * c->rank + sizeof(mine)] = 1; }
+        ok = cudaMemcpy(dev + HB * c->rank, host.data() + HB * c->rank, HB, cudaMemcpyHostToDevice) == cudaSuccess;
+    }
+    // a rank whose scratch allocation failed cannot take part in the collectives at all: that is the one fatal case
+    if (!dev) { cudaGetLastError(); set_error("comm_p2p_map: cudaMalloc of the handle exchange buffer failed"); return (int)cudaErrorMemoryAllocation; }
+    if (nccl()->AllGather(dev + HB * c->rank, dev, HB, 0 /* ncclInt8 */, c->comm, nullptr) != 0) { ok = false; nccl_err = 1; }
+    ok = (cudaDeviceSynchronize() == cudaSuccess) && ok;
+    ok = (cudaMemcpy(host.data(), dev, HB * c->size, cudaMemcpyDeviceToHost) == cudaSuccess) && ok;
+    for (int r = 0; r < c->size; r++) ok = ok && host[HB * r + sizeof(cudaIpcMemHandle_t)] == 1;
     for (int r = 0; r < c->size && ok; r++) {
         if (r == c->rank) { peers[r] = basep; continue; }
         cudaIpcMemHandle_t h;
         memcpy(&h, host.data() + HB * r, sizeof(h));
-        if (cudaIpcOpenMemHandle(&peers[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { cudaGetLastError(); peers[r] = nullptr; ok = false; }
+        if (cudaIpcOpenMemHandle(&peers[r], h, cudaIpcMemLazyEnablePeerAccess) != cudaSuccess) { peers[r] = nullptr; ok = false; }
     }
+    cudaGetLastError();  // local failures are not sticky errors; they are reported through the flag
     long long hv = ok ? 0 : 1;
-    DGB_CUDA(cudaMemcpy(dev, &hv, 8, cudaMemcpyHostToDevice));
-    DGB_NCCL(nccl()->AllReduce(dev, dev, 1, ncclInt64, ncclSum, c->comm, nullptr));
-    DGB_CUDA(cudaDeviceSynchronize());
-    DGB_CUDA(cudaMemcpy(&hv, dev, 8, cudaMemcpyDeviceToHost));
+    long long* flag = reinterpret_cast<long long*>(dev + HB * c->size);
+    int e = 0;
+    if (cudaMemcpy(flag, &hv, 8, cudaMemcpyHostToDevice) != cudaSuccess) e = (int)cudaErrorUnknown;
+    if (!e && !nccl_err && nccl()->AllReduce(flag, flag, 1, ncclInt64, ncclSum, c->comm, nullptr) != 0) e = DGB_ERR_INVALID;
+    if (!e && cudaDeviceSynchronize() != cudaSuccess) e = (int)cudaErrorUnknown;
+    if (!e && cudaMemcpy(&hv, flag, 8, cudaMemcpyDeviceToHost) != cudaSuccess) e = (int)cudaErrorUnknown;
     cudaFree(dev);
-    if (hv != 0) { comm_p2p_unmap(c, peers); return 1; }
+    if (e || nccl_err) {
+        comm_p2p_unmap(c, peers);
+        set_error("comm_p2p_map: the agreement collective failed (%s)", nccl_err ? "ncclAllGather" : "allreduce / CUDA");
+        return e ? e : DGB_ERR_INVALID;
+    }
+    if (hv != 0) { comm_p2p_unmap(c, peers); return 0; }
+    *mapped = 1;
     return 0;
 }
 void comm_p2p_unmap(Comm* c, void** peers) {

@@ -29,9 +29,11 @@ struct P2pView {
 // the view and the next epoch of `count` consecutive channels starting at `first` (epochs advance by one per call)
 P2pView comm_p2p_view(Comm* c);
 // COLLECTIVE: map the cudaMalloc'ed buffer `base` of every rank into this process; peers[r] = rank r's buffer (own rank:
-// base itself).  Returns 0 and fills peers only if the peer-memory path is enabled, 1 if it is not (no communication),
-// an error code otherwise.  Mapped buffers stay open until comm_p2p_unmap / the communicator is destroyed.
-int comm_p2p_map(Comm* c, void* base, void** peers);
+// base itself).  *mapped = 1 and peers filled if every rank mapped every buffer, *mapped = 0 (peers cleared) if the
+// peer-memory path is disabled or any rank failed -- all ranks take the same decision: local failures (IPC handle, NCCL,
+// CUDA) travel as a flag through the closing allreduce, which every rank reaches.  Returns a DGB_ERR_* code only for
+// failures of that agreement itself.  Mapped buffers stay open until comm_p2p_unmap / the communicator is destroyed.
+int comm_p2p_map(Comm* c, void* base, void** peers, int* mapped);
 void comm_p2p_unmap(Comm* c, void** peers);
 // neighbour barrier of the slab ring/chain on channel 7: returns when `lower` and `upper` (rank ids, -1 = none) have
 // passed the same point of their streams, i.e. their preceding kernels (with their peer stores) are complete

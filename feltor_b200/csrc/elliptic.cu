@@ -89,6 +89,7 @@ int elliptic2d_symv(Elliptic2dPlan& p, double alpha, const double* x, double bet
         set_error("dgb_elliptic2d_symv: a Helmholtz plan supports symv(x, y) only (alpha = 1, beta = 0), as the reference");
         return DGB_ERR_UNSUPPORTED;
     }
+    if (p.kernel_mode == DGB_ELLIPTIC_KERNEL_UNFUSED && !p.slab) force_unfused = true;
     if (!force_unfused && !env_unfused_helm() && p.fusable && p.helm_alpha != 0. && !p.chi[0] && !p.chi[1] && !p.chi[2] && !p.chi[3] &&
         !p.chi_weight_jump && p.sigma && x != y)
         return elliptic2d_fused_launch(p, 1., x, 0., y, st);  // both fused kernels apply the Helmholtz epilogue themselves
@@ -115,6 +116,7 @@ static int elliptic2d_symv_plain(Elliptic2dPlan& p, double alpha, const double* 
         }
         return elliptic2d_fused_launch(p, alpha, x, beta, y, st);
     }
+    if (p.kernel_mode == DGB_ELLIPTIC_KERNEL_UNFUSED) force_unfused = true;
     if (!force_unfused && !env_unfused && p.fusable && identity_chi && !p.chi_weight_jump)
         return elliptic2d_fused_launch(p, alpha, x, beta, y, st);
     return elliptic2d_unfused(p, alpha, x, beta, y, st);
@@ -259,6 +261,30 @@ int dgb_elliptic2d_set_slab(dgb_elliptic2d* h, int yoff, int rows, int ghost) {
     if (!p->fusable) { set_error("dgb_elliptic2d_set_slab: the plan's matrices are not supported by the fused kernel"); return DGB_ERR_UNSUPPORTED; }
     if (yoff < 0 || rows < 1 || yoff + rows > p->Ny || ghost < 0) { set_error("dgb_elliptic2d_set_slab: invalid slab"); return DGB_ERR_INVALID; }
     p->slab = true; p->slab_yoff = yoff; p->slab_rows = rows; p->slab_ghost = ghost;
+    return 0;
+}
+int dgb_elliptic2d_set_kernel(dgb_elliptic2d* h, int kernel) {
+    Elliptic2dPlan* p = reinterpret_cast<Elliptic2dPlan*>(h);
+    if (kernel < DGB_ELLIPTIC_KERNEL_AUTO || kernel > DGB_ELLIPTIC_KERNEL_UNFUSED) { set_error("dgb_elliptic2d_set_kernel: unknown kernel %d", kernel); return DGB_ERR_INVALID; }
+    if ((kernel == DGB_ELLIPTIC_KERNEL_TILE || kernel == DGB_ELLIPTIC_KERNEL_WALKER) && !p->fusable) {
+        set_error("dgb_elliptic2d_set_kernel: the plan's matrices do not have the dx.h structure of the fused kernels"); return DGB_ERR_UNSUPPORTED;
+    }
+    if (kernel == DGB_ELLIPTIC_KERNEL_WALKER && !(p->n == 2 || p->n == 3)) {
+        set_error("dgb_elliptic2d_set_kernel: the walker kernel exists for n = 2, 3 (n = %d)", p->n); return DGB_ERR_UNSUPPORTED;
+    }
+    if (kernel == DGB_ELLIPTIC_KERNEL_WALKER && (p->Nx < 5 || p->Ny < 5)) {
+        set_error("dgb_elliptic2d_set_kernel: the walker kernel needs at least 5 x 5 cells"); return DGB_ERR_UNSUPPORTED;
+    }
+    p->kernel_mode = kernel;
+    return 0;
+}
+int dgb_elliptic2d_get_kernel(const dgb_elliptic2d* h, int with_dot, int* kernel) {
+    const Elliptic2dPlan* p = reinterpret_cast<const Elliptic2dPlan*>(h);
+    const bool identity_chi = !p->chi[0] && !p->chi[1] && !p->chi[2] && !p->chi[3];
+    const bool fused = p->fusable && identity_chi && !p->chi_weight_jump && p->kernel_mode != DGB_ELLIPTIC_KERNEL_UNFUSED &&
+                       (p->slab || !getenv("DGB_ELLIPTIC_UNFUSED"));
+    *kernel = !fused ? DGB_ELLIPTIC_KERNEL_UNFUSED
+                     : (elliptic2d_walker_supported(*p, with_dot != 0) ? DGB_ELLIPTIC_KERNEL_WALKER : DGB_ELLIPTIC_KERNEL_TILE);
     return 0;
 }
 int dgb_elliptic2d_size(const dgb_elliptic2d* h, size_t* size, int* fused) {

@@ -852,18 +852,24 @@ void elliptic2d_walker_release(Elliptic2dPlan& p) {
     }
 }
 
+// structural support only; whether the walker is also the FASTER kernel is decided by elliptic2d_walker_supported
+bool elliptic2d_walker_possible(const Elliptic2dPlan& p) {
+    return p.fusable && (p.n == 2 || p.n == 3) && p.Nx >= 5 && (p.slab ? p.slab_rows : p.Ny) >= 5 && !(p.helm && p.helm_alpha == 0.);
+}
 bool elliptic2d_walker_supported(const Elliptic2dPlan& p, bool with_dot) {
-    static int off = -1;
+    (void)with_dot;  // measured with the budget partition: the walker wins from ~400^2 cells on for every variant
+    if (p.kernel_mode == DGB_ELLIPTIC_KERNEL_WALKER) return elliptic2d_walker_possible(p);
+    if (p.kernel_mode != DGB_ELLIPTIC_KERNEL_AUTO) return false;
+    // process-wide defaults for plans in auto mode (read once); a plan's own mode (dgb_elliptic2d_set_kernel) wins
+    static int off = -1, force = -1;
     if (off < 0) { const char* e = getenv("DGB_ELLIPTIC_TILE"); off = (e && atoi(e)) ? 1 : 0; }
-    static int force = -1;
     if (force < 0) { const char* e = getenv("DGB_ELLIPTIC_WALKER"); force = (e && atoi(e)) ? 1 : 0; }
-    if (off || !p.fusable || !(p.n == 2 || p.n == 3) || p.Nx < 5 || p.Ny < 5 || (p.helm && p.helm_alpha == 0.)) return false;
+    if (off || !elliptic2d_walker_possible(p)) return false;
     if (force) return true;
     // measured on B200 (n = 3): the walker wins for the one-sided discretisations from ~512^2 cells on (87 vs 119 us at
     // 1024^2); below that each warp gets too few rows to amortise its pipeline fill.  The centered stencil (28 useful
     // lanes, 250 registers, 8 warps) gains less: 118 vs 156 us for the plain apply, +3..6 % in PCG with the fused dot
     const long long cells = (long long)p.Nx * (p.slab ? p.slab_rows : p.Ny);
-    (void)with_dot;  // measured again with the budget partition: the walker wins from ~400^2 cells on for every variant
     return cells >= 400 * 400;
 }
 

@@ -297,7 +297,11 @@ int dgb_dot3(dgb_dot_ws* p, size_t n, const double* x, const double* w, const do
     if (e) return e;
     return dot_sync(ws, acc_host, value, status, s);
 }
-int dgb_superacc_normalize_host(int64_t* acc) { return normalize_host(acc); }
+int dgb_superacc_normalize_host(int64_t* acc, int* negative) {
+    const int neg = normalize_host(acc);
+    if (negative) *negative = neg;
+    return 0;
+}
 double dgb_superacc_round_host(const int64_t* acc) { return round_host(acc); }
 int dgb_superacc_combine(const int64_t* parts, int nparts, const int32_t* status_parts, dgb_dot_result* result,
                          dgb_stream_t s) {

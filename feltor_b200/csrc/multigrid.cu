@@ -153,6 +153,7 @@ int dgb_multigrid2d_solve(dgb_multigrid2d* h, dgb_elliptic2d* const* ops, const 
     for (int u = 0; u < S; u++) {
         A[u] = reinterpret_cast<Elliptic2dPlan*>(ops[u]);
         if (!A[u] || A[u]->size != m->sizes[u]) { set_error("dgb_multigrid2d_solve: operator %d does not match the stage size", u); return DGB_ERR_INVALID; }
+        if (!precond[u] || !weights[u]) { set_error("dgb_multigrid2d_solve: preconditioner / weights of stage %d missing", u); return DGB_ERR_INVALID; }
     }
     int e;
     // residual r = b - A x                                                     multigrid.h:205-206

@@ -286,10 +286,17 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
     if (nA != n) { set_error("dgb_pcg_solve: operator size %zu != workspace size %zu", nA, n); return DGB_ERR_INVALID; }
     if (dist != A.slab) { set_error("dgb_pcg_solve: a slab plan needs the distributed solve and vice versa"); return DGB_ERR_INVALID; }
     if (test_frequency < 1) { set_error("dgb_pcg_solve: test_frequency must be >= 1"); return DGB_ERR_INVALID; }
+    // K2 / K3 move every operand with 128-bit accesses.  Device vectors of the reference (thrust::device_vector) and of
+    // cudaMalloc are 256-byte aligned; an offset view is rejected here instead of faulting inside the kernel
+    if (!aligned16(x) || !aligned16(b) || !aligned16(P) || !aligned16(W)) {
+        set_error("dgb_pcg_solve: x, b, P and W must be 16-byte aligned");
+        return DGB_ERR_INVALID;
+    }
     int e;
-    // search direction: in slab mode it carries ghost rows that the halo exchange fills
+    // search direction: in slab mode it carries ghost rows that the halo exchange fills.  The ghost block in front is
+    // padded to an even number of doubles so that s.p itself stays 16-byte aligned for odd n * Nx * ghost
     const size_t row_len = dist ? (size_t)A.Nx * A.n : 0;
-    const size_t ghost_rows = dist ? (size_t)A.slab_ghost * A.n : 0, gh = ghost_rows * row_len;
+    const size_t ghost_rows = dist ? (size_t)A.slab_ghost * A.n : 0, gh_rows = ghost_rows * row_len, gh = gh_rows + (gh_rows & 1);
     if (s.p_cap < n + 2 * gh) {
         if (s.p_mapped) { comm_p2p_unmap(s.p_peers_comm, s.p_peers); s.p_mapped = false; }
         cudaFree(s.p_base);
@@ -307,9 +314,9 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
         if (!s.p_mapped || s.p_peers_comm != comm) {
             if (s.p_mapped) comm_p2p_unmap(s.p_peers_comm, s.p_peers);
             DGB_CUDA(cudaStreamSynchronize(st));
-            const int m = comm_p2p_map(comm, s.p_base, s.p_peers);
-            if (m > 1) return m;
-            s.p_mapped = m == 0;
+            int mapped = 0;
+            if ((e = comm_p2p_map(comm, s.p_base, s.p_peers, &mapped))) return e;
+            s.p_mapped = mapped != 0;
             s.p_peers_comm = comm;
         }
         const int rank = comm_rank(comm), size = comm_size(comm);
@@ -320,7 +327,7 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
         // [gh | n_nb | gh] with ITS n -- its upper ghost starts at gh + n_nb, which we do not know; so only the LOWER ghost
         // of the upper neighbour (offset 0) and, for equal n, the upper ghost of the lower neighbour are addressable.
         // bench/solver slabs are equal-sized whenever Ny divides by the rank count; otherwise NCCL does the exchange.
-        p2p_halo = s.p_mapped && gh > 0 && (n % 2 == 0) && (gh % 2 == 0) && A.Ny % size == 0 && A.slab_rows == A.Ny / size;
+        p2p_halo = s.p_mapped && gh > 0 && (n % 2 == 0) && (gh_rows % 2 == 0) && A.Ny % size == 0 && A.slab_rows == A.Ny / size;
         if (p2p_halo) {
             if (nb_lower >= 0) rem_lo = reinterpret_cast<double*>(s.p_peers[nb_lower]) + gh + n;  // its upper ghost rows
             if (nb_upper >= 0) rem_up = reinterpret_cast<double*>(s.p_peers[nb_upper]);           // its lower ghost rows
@@ -370,6 +377,7 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
     if (std::sqrt(s.results_host[3].value) < tol) { *iterations = 0; return 0; }  // pcg.h:157
     const bool identity_chi = !A.chi[0] && !A.chi[1] && !A.chi[2] && !A.chi[3];
     const bool fused = A.fusable && identity_chi && !A.chi_weight_jump && (dist || !getenv("DGB_ELLIPTIC_UNFUSED")) &&
+                       (dist || A.kernel_mode != DGB_ELLIPTIC_KERNEL_UNFUSED) &&
                        (!A.helm || A.helm_alpha != 0.);
     const P2pView pview = comm_p2p_view(comm);
     // The finishing block of K1/K2 can run the peer-memory exchange itself (one launch less per dot); measured at 2 GPUs this

@@ -40,6 +40,24 @@ class Elliptic2d:
         lib().elliptic2d_size(self.h, None, C.byref(f))
         return bool(f.value)
 
+    KERNELS = {"auto": 0, "tile": 1, "walker": 2, "unfused": 3}
+
+    def set_kernel(self, kernel):
+        """dgb_elliptic2d_set_kernel: "auto" | "tile" | "walker" | "unfused" -- every mode gives bitwise the same result"""
+        lib().elliptic2d_set_kernel(self.h, self.KERNELS[kernel])
+        return self
+
+    def kernel(self, with_dot=False):
+        """the kernel the next symv (or PCG iteration, with_dot=True) on this plan launches"""
+        k = C.c_int()
+        lib().elliptic2d_get_kernel(self.h, int(with_dot), C.byref(k))
+        return {v: n for n, v in self.KERNELS.items()}[k.value]
+
+    def set_vol(self, vol):
+        """curvilinear volume form m_vol (elliptic.h:292-296); the tensor stays borrowed by the plan"""
+        self._vol = vol
+        lib().elliptic2d_set_vol(self.h, ptr(vol) if vol is not None else None)
+
     def weights(self):
         return self._weights
 
@@ -217,6 +235,8 @@ class MultigridCG2d:
     def solve(self, ops, x, b, eps):
         """multigrid.h:617-658: ops = list of Elliptic2d (one per stage); eps scalar or list; returns iteration numbers"""
         eps = [eps] * self.stages if np.isscalar(eps) else list(eps)
+        if len(ops) != self.stages or len(eps) != self.stages:
+            raise ValueError("dg::Error: MultigridCG2d::solve needs one operator and one accuracy per stage (%d)" % self.stages)
         A = (C.c_void_p * self.stages)(*[o.h.value for o in ops])
         P = (C.c_void_p * self.stages)(*[o.precond().data_ptr() for o in ops])
         W = (C.c_void_p * self.stages)(*[o.weights().data_ptr() for o in ops])

@@ -225,7 +225,7 @@ class Explicit:
             blas1.pointwiseDot(self.chi, self.binv, self.chi)
             if not p.boussinesq:
                 self.multi_chi = self.multigrid.project(self.chi)
-                for u in range(3):
+                for u in range(len(self.multi_pol)):
                     self.multi_pol[u].set_chi(self.multi_chi[u])
         if p.tau == 0.:
             blas1.axpby(1., y[1], 0., self.gamma_n)
@@ -373,7 +373,7 @@ def pair_dot(x, y):
         if st != 0:
             raise FloatingPointError("dg::Error: dot product failed since one of the inputs contains NaN or Inf")
         acc += part
-    lib().superacc_normalize_host(acc.ctypes.data_as(C.c_void_p))
+    lib().superacc_normalize_host(acc.ctypes.data_as(C.c_void_p), None)
     lib().superacc_round_host.restype = C.c_double
     return lib().superacc_round_host(acc.ctypes.data_as(C.c_void_p))
 

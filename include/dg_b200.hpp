@@ -407,6 +407,7 @@ class MultigridCG2d {
         std::vector<dgb_elliptic2d*> A;
         std::vector<const double*> P, W;
         for (auto& o : ops) { A.push_back(o.plan()); P.push_back(o.precond().data()); W.push_back(o.weights().data()); }
+        if (ops.size() != m_stages || eps.size() != m_stages) throw Error(DGB_ERR_INVALID, "dg::Error: MultigridCG2d::solve needs one operator and one accuracy per stage");
         std::vector<int> num(m_stages);
         check(dgb_multigrid2d_solve(m_mg, A.data(), P.data(), W.data(), x.data(), b.data(), eps.data(), num.data(), nullptr));
         return std::vector<unsigned>(num.begin(), num.end());
@@ -418,6 +419,7 @@ class MultigridCG2d {
         std::vector<dgb_elliptic2d*> A;
         std::vector<const double*> P, W;
         for (auto& o : ops) { A.push_back(o.plan()); P.push_back(o.precond().data()); W.push_back(o.weights().data()); }
+        if (ops.size() != m_stages || eps.size() != m_stages) throw Error(DGB_ERR_INVALID, "dg::Error: MultigridCG2d::solve needs one operator and one accuracy per stage");
         std::vector<int> num(m_stages);
         check(dgb_multigrid2d_solve(m_mg, A.data(), P.data(), W.data(), x.data(), b.data(), eps.data(), num.data(), nullptr));
         return std::vector<unsigned>(num.begin(), num.end());
@@ -441,7 +443,7 @@ inline double dot(const DVec2& x, const DVec2& y) {
         if (status != 0) throw Error(DGB_ERR_NOTFINITE, "dg::Error: dot product failed since one of the inputs contains NaN or Inf");
         for (int k = 0; k < DGB_BIN_COUNT; k++) acc[k] += part[k];
     }
-    check(dgb_superacc_normalize_host(acc));
+    check(dgb_superacc_normalize_host(acc, nullptr));
     return dgb_superacc_round_host(acc);
 }
 inline double l2norm(const DVec2& x) { return std::sqrt(dot(x, x)); }  // adaptive.h:22

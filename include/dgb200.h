@@ -167,7 +167,8 @@ DGB_API int dgb_dot3(dgb_dot_ws* ws, size_t n, const double* x, const double* w,
                      double* value, int* status, dgb_stream_t s);
 /* host-side helpers with the reference's arithmetic (accumulate.h:267-349), for callers that combine
  * accumulators of std::vector<DVec> / ranks (blas1_dispatch_vector.h:153-176, mpi_accumulate.h:94-125) */
-DGB_API int dgb_superacc_normalize_host(int64_t* acc);
+/* returns 0; *negative (may be NULL) receives what exblas::cpu::Normalize returns: 1 if the accumulator is negative */
+DGB_API int dgb_superacc_normalize_host(int64_t* acc, int* negative);
 DGB_API double dgb_superacc_round_host(const int64_t* acc);
 /* device-side combine for multi-GPU: acc[i] = Normalize(sum_r parts[r][i]) then Round; parts = nparts normalised
  * accumulators (<= 256, mpi_accumulate.h:75-77) contiguous in device memory; result_dev filled like dgb_exdot */
@@ -329,6 +330,17 @@ DGB_API int dgb_elliptic2d_set_vol(dgb_elliptic2d* plan, const double* vol);    
 DGB_API int dgb_elliptic2d_set_chi(dgb_elliptic2d* plan, const double* xx, const double* xy, const double* yx,
                                    const double* yy);                             /* m_chi; NULL = identity entry */
 DGB_API int dgb_elliptic2d_set_jfactor(dgb_elliptic2d* plan, double jfactor);
+/* Which kernel applies the operator (and runs inside dgb_pcg_solve_* / dgb_multigrid2d_solve on this plan).  AUTO picks
+ * by problem size (walker from ~400^2 cells on, tile kernel below, the unfused composition for matrices / chi tensors the
+ * fused kernels do not cover); the explicit modes exist so that every kernel can be parity-tested on any grid and A/B-timed.
+ * All modes give bitwise the same result.  Errors: DGB_ERR_UNSUPPORTED if the plan cannot run on that kernel. */
+#define DGB_ELLIPTIC_KERNEL_AUTO 0
+#define DGB_ELLIPTIC_KERNEL_TILE 1     /* elliptic2d_fused_kernel: persistent CTAs, TMA-staged cell tiles            */
+#define DGB_ELLIPTIC_KERNEL_WALKER 2   /* elliptic2d_walker_kernel: warp-private TMA sliding window (n = 2, 3)       */
+#define DGB_ELLIPTIC_KERNEL_UNFUSED 3  /* the reference's launch sequence elliptic.h:431-458 on dgb_ell_symv / blas1 */
+DGB_API int dgb_elliptic2d_set_kernel(dgb_elliptic2d* plan, int kernel);
+/* *kernel = the DGB_ELLIPTIC_KERNEL_* the next symv (with_dot = 0) / PCG iteration (with_dot = 1) on this plan will launch */
+DGB_API int dgb_elliptic2d_get_kernel(const dgb_elliptic2d* plan, int with_dot, int* kernel);
 /* test hook, host only: the work partition the warp-walker kernel would use (tasks_out: column, first row, end row per piece) */
 DGB_API int dgb_debug_walker_partition(int Nx, int Ny, int centered, int nwarps, int fx_lo, int fx_hi, int wrapx, int tma, int dot,
                                        int* tasks_out, int max_tasks, int* ntasks, int* tbegin_out);

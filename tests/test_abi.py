@@ -37,9 +37,26 @@ def test_host_superacc_helpers_match_oracle():
         raw[3] += 5 << 56  # de-normalise: push carries into a word
         raw[4] -= 5
         a = raw.copy()
-        L.raw["dgb_superacc_normalize_host"](a.ctypes.data)
+        L.raw["dgb_superacc_normalize_host"](a.ctypes.data, None)
         assert np.array_equal(a, acc)
         assert L.raw["dgb_superacc_round_host"](raw.ctypes.data) == orc.round_acc(acc)
+
+
+def test_host_superacc_negative_sum_is_not_an_error():
+    """a negative accumulator (dot(x, -x)) must come back as status 0 with the sign in the out-parameter: the helper used
+    to return exblas::cpu::Normalize's sign flag as if it were an error code"""
+    L = fb.lib()
+    x = rng(2).uniform(-1, 1, 257)
+    acc, _ = orc.exdot2(x, -x)
+    raw = acc.copy()
+    raw[20] -= 3 << 56
+    raw[21] += 3
+    neg = C.c_int(-1)
+    assert L.superacc_normalize_host(raw.ctypes.data_as(C.c_void_p), C.byref(neg)) == 0   # the CHECKED wrapper: no DgbError
+    assert neg.value == 1 and np.array_equal(raw, orc.normalize(acc))
+    assert L.raw["dgb_superacc_round_host"](raw.ctypes.data) == orc.round_acc(acc) < 0
+    acc, _ = orc.exdot2(x, x)
+    assert L.superacc_normalize_host(acc.ctypes.data_as(C.c_void_p), C.byref(neg)) == 0 and neg.value == 0
 
 
 def test_compute_fails_loudly_without_device():
