@@ -11,7 +11,9 @@
 #include <vector>
 #include <array>
 #include <chrono>
+#ifdef _OPENMP
 #include <omp.h>
+#endif
 #include "dg/algorithm.h"
 #include "dg/file/json_utilities.h"
 #include "toefl.h"
@@ -34,8 +36,8 @@ static void in2(const double* a, const double* b, size_t n, Vec2& y) {
     y[1].assign(b, b + n);
 }
 static void out2(const Vec2& y, double* a, double* b) {
-    std::copy(y[0].begin(), y[0].end(), a);
-    std::copy(y[1].begin(), y[1].end(), b);
+    thrust::copy(y[0].begin(), y[0].end(), a);
+    thrust::copy(y[1].begin(), y[1].end(), b);
 }
 
 extern "C" {
@@ -73,7 +75,7 @@ double ref_toefl_rhs(void* hh, double t, const double* y0, const double* y1, dou
 }
 void ref_toefl_phi(void* hh, int i, double* out) {
     const DVec& v = ((RefToefl*)hh)->rhs.phi(i);
-    std::copy(v.begin(), v.end(), out);
+    thrust::copy(v.begin(), v.end(), out);
 }
 // nsteps fixed steps of size dt with dg::ERKStep (runge_kutta.h:163-400); returns the seconds spent
 double ref_toefl_erk(void* hh, const char* tableau, double t0, double dt, int nsteps, double* y0, double* y1) {
@@ -130,6 +132,17 @@ void ref_toefl_multistep(void* hh, const char* tableau, double t0, double dt, in
     }
     out2(y, y0, y1);
 }
+// how many dispatches of this library went to libdgb200.so entry points / to generic kernel templates (device backend only)
+void ref_dispatch_counters(long long* library, long long* generic) {
+#if THRUST_DEVICE_SYSTEM == THRUST_DEVICE_SYSTEM_CUDA
+    *library = dgb::shim::counters().library;
+    *generic = dgb::shim::counters().generic;
+#else
+    *library = 0;
+    *generic = 0;
+#endif
+}
+int ref_toefl_backend_is_device() { return THRUST_DEVICE_SYSTEM == THRUST_DEVICE_SYSTEM_CUDA ? 1 : 0; }
 int ref_toefl_ncalls(void* hh) { return (int)((RefToefl*)hh)->rhs.ncalls(); }
 
 // ---- the building blocks of toefl::Explicit one by one (the class keeps them private), constructed as toefl.h:60-83 does
@@ -143,7 +156,7 @@ void ref_toefl_helmholtz_solve(void* hh, double* x, const double* b, int* number
     DVec xv(x, x + n), bv(b, b + n);
     std::vector<unsigned> num = mg.solve(ops, xv, bv, p.eps_gamma);
     for (unsigned u = 0; u < p.num_stages; u++) numbers[u] = (int)num[u];
-    std::copy(xv.begin(), xv.end(), x);
+    thrust::copy(xv.begin(), xv.end(), x);
 }
 void ref_toefl_pol_solve(void* hh, const double* chi, double* x, const double* b, int* numbers) {
     RefToefl* h = (RefToefl*)hh;
@@ -157,7 +170,7 @@ void ref_toefl_pol_solve(void* hh, const double* chi, double* x, const double* b
     for (unsigned u = 0; u < p.num_stages; u++) ops[u].set_chi(mc[u]);
     std::vector<unsigned> num = mg.solve(ops, xv, bv, p.eps_pol);
     for (unsigned u = 0; u < p.num_stages; u++) numbers[u] = (int)num[u];
-    std::copy(xv.begin(), xv.end(), x);
+    thrust::copy(xv.begin(), xv.end(), x);
 }
 void ref_toefl_upwind(void* hh, double alpha, const double* vx, const double* vy, const double* f, double beta, double* result) {
     RefToefl* h = (RefToefl*)hh;
@@ -165,7 +178,7 @@ void ref_toefl_upwind(void* hh, double alpha, const double* vx, const double* vy
     dg::Advection<dg::CartesianGrid2d, dg::DMatrix, DVec> adv(h->grid);
     DVec a(vx, vx + n), b(vy, vy + n), c(f, f + n), r(result, result + n);
     adv.upwind(alpha, a, b, c, beta, r);
-    std::copy(r.begin(), r.end(), result);
+    thrust::copy(r.begin(), r.end(), result);
 }
 void ref_toefl_arakawa(void* hh, double alpha, const double* lhs, const double* rhs, double beta, double* result) {
     RefToefl* h = (RefToefl*)hh;
@@ -173,7 +186,7 @@ void ref_toefl_arakawa(void* hh, double alpha, const double* lhs, const double* 
     dg::ArakawaX<dg::CartesianGrid2d, dg::DMatrix, DVec> ar(h->grid);
     DVec a(lhs, lhs + n), b(rhs, rhs + n), r(result, result + n);
     ar(alpha, a, b, beta, r);
-    std::copy(r.begin(), r.end(), result);
+    thrust::copy(r.begin(), r.end(), result);
 }
 void ref_toefl_variation(void* hh, const double* phi, double* out) {
     RefToefl* h = (RefToefl*)hh;
@@ -181,12 +194,12 @@ void ref_toefl_variation(void* hh, const double* phi, double* out) {
     dg::Elliptic<dg::CartesianGrid2d, dg::DMatrix, DVec> pol(h->grid, h->p.pol_dir, 1.);
     DVec a(phi, phi + n), r(n);
     pol.variation(a, r);
-    std::copy(r.begin(), r.end(), out);
+    thrust::copy(r.begin(), r.end(), out);
 }
 void ref_toefl_binv(void* hh, double* out) {
     RefToefl* h = (RefToefl*)hh;
     const toefl::Parameters& p = h->p;
     DVec b = dg::evaluate(dg::LinearX(p.kappa, 1. - p.kappa * p.posX * p.lx), h->grid);
-    std::copy(b.begin(), b.end(), out);
+    thrust::copy(b.begin(), b.end(), out);
 }
 }

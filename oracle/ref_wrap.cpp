@@ -18,15 +18,39 @@
 #include <vector>
 #include <array>
 #include <chrono>
+#ifdef _OPENMP
 #include <omp.h>
+#endif
 #include "dg/algorithm.h"
 
 using DVec = dg::DVec;
 using HVec = dg::HVec;
 using DMatrix = dg::DMatrix;
 using HMatrix = dg::HMatrix;
+#if THRUST_DEVICE_SYSTEM == THRUST_DEVICE_SYSTEM_CUDA
+// The same wrapper compiled on a DEVICE backend (integration/Makefile builds it against the libdgb200 binding): the
+// caller's host arrays are staged through device vectors; the views below are what the host-backend build gets for free.
+struct CStage : dg::View<const DVec> {
+    DVec buf;
+    CStage(const double* p, size_t n) : buf(p, p + n) { this->construct(thrust::raw_pointer_cast(buf.data()), n); }
+    CStage(const CStage&) = delete;
+};
+using CView = const CStage;
+struct VView : dg::View<DVec> {
+    DVec buf;
+    double* host;
+    VView(double* p, size_t n) : buf(p, p + n), host(p) { this->construct(thrust::raw_pointer_cast(buf.data()), n); }
+    VView(const VView&) = delete;
+    ~VView() { thrust::copy(buf.begin(), buf.end(), host); }
+};
+namespace dg {
+template <> struct TensorTraits<CStage> : TensorTraits<View<const DVec>> {};
+template <> struct TensorTraits<VView> : TensorTraits<View<DVec>> {};
+}  // namespace dg
+#else
 using VView = dg::View<DVec>;
 using CView = const dg::View<const DVec>;
+#endif
 
 extern "C" {
 
@@ -37,8 +61,25 @@ struct RefGrid {
 };
 
 int ref_version() { return 1; }
+#ifdef _OPENMP
 void ref_set_num_threads(int t) { omp_set_num_threads(t); }
 int ref_get_max_threads() { return omp_get_max_threads(); }
+#else
+void ref_set_num_threads(int) {}
+int ref_get_max_threads() { return 1; }
+#endif
+// how many dispatches of this library went to libdgb200.so entry points / to generic kernel templates (device backend only)
+void ref_dispatch_counters(long long* library, long long* generic) {
+#if THRUST_DEVICE_SYSTEM == THRUST_DEVICE_SYSTEM_CUDA
+    *library = dgb::shim::counters().library;
+    *generic = dgb::shim::counters().generic;
+#else
+    *library = 0;
+    *generic = 0;
+#endif
+}
+// 0: the reference's OpenMP backend; 1: a device backend (the libdgb200 binding of integration/)
+int ref_backend_is_device() { return THRUST_DEVICE_SYSTEM == THRUST_DEVICE_SYSTEM_CUDA ? 1 : 0; }
 
 } // extern C
 
@@ -57,7 +98,7 @@ dg::CartesianGrid3d g3(const RefGrid* g) {
 }
 template <class V>
 void copy_out(const V& v, double* out) {
-    for (size_t i = 0; i < v.size(); i++) out[i] = v[i];
+    thrust::copy(v.begin(), v.end(), out);
 }
 double now() {
     return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count();
@@ -267,12 +308,24 @@ void ref_tensor_multiply2d(int n, const double* lambda, const double* t00, const
 // returns status; acc = un-normalised superaccumulator as doDot_superacc returns it
 int ref_dot2(int n, const double* x, const double* y, int64_t* acc) {
     int status = 0;
+#if THRUST_DEVICE_SYSTEM == THRUST_DEVICE_SYSTEM_CUDA
+    CView a(x, n), b(y, n);
+    std::vector<int64_t> v = dg::blas1::detail::doDot_superacc(&status, a, b);  // what blas1::dot rounds (blas1.h:159)
+    std::copy(v.begin(), v.end(), acc);
+#else
     dg::exblas::exdot_omp((unsigned)n, x, y, acc, &status);
+#endif
     return status;
 }
 int ref_dot3(int n, const double* x, const double* w, const double* y, int64_t* acc) {
     int status = 0;
+#if THRUST_DEVICE_SYSTEM == THRUST_DEVICE_SYSTEM_CUDA
+    CView a(x, n), b(w, n), c(y, n);
+    std::vector<int64_t> v = dg::blas2::detail::doDot_superacc(&status, a, b, c);  // what blas2::dot rounds (blas2.h:94)
+    std::copy(v.begin(), v.end(), acc);
+#else
     dg::exblas::exdot_omp((unsigned)n, x, w, y, acc, &status);
+#endif
     return status;
 }
 double ref_round(const int64_t* acc) {

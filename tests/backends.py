@@ -84,8 +84,8 @@ class OracleBlas1:
 class RefBlas1:
     """the unmodified reference's dg::blas1 through oracle/_ref/libdgref.so"""
 
-    def __init__(self):
-        self.l = refwrap.lib()
+    def __init__(self, lib=None):
+        self.l = lib if lib is not None else refwrap.lib()
         self.d, self.p = C.c_double, refwrap.dp
 
     def copy(self, x, y): self.l.ref_copy(x.size, self.p(x), self.p(y))
