@@ -10,15 +10,20 @@ size).  metric = PCG iterations per second (whole job).
   value   device-resident inputs, timed with CUDA events on the launching stream
   e2e     the same solve through the C-ABI entry point with HOST buffers: b and x0 copied host->device from
           pinned memory and x copied back inside the timed region, every step
-  roofline  dominant kernel = the fused Elliptic apply + dot(p,W,Ap) kernel (K1): algorithmic 32 B/dof
-          (read p, sigma, W; write Ap) / its live CUDA-event duration, against MEASURED_PEAKS.json
+  roofline  the kernel the north star names = the fused Elliptic apply + dot(p,W,Ap) kernel (K1): algorithmic 32 B/dof
+          (read p, sigma, W; write Ap) / its live CUDA-event duration, against MEASURED_PEAKS.json; the streaming update
+          kernel K2 (72 B/dof, the larger time share) is listed beside it under roofline_other_kernels
+  micro     config 1 (and the same kernels at the benchmark size): axpby, pointwiseDot, dot, dx/dy, Elliptic apply in GB/s
+  toefl     config 3 on one GPU: steps/s of the toefl right-hand side + Bogacki-Shampine step (N = 1 only)
   cpu_baseline  the reference's own OpenMP implementation (oracle/_ref/libdgref.so) on the host cores, bounded sample
 
   python bench.py [--gpus N] [--steps K] [--warmup W] [--iters M] [--cells 1024] [--impl reference]
 N > 1 (torchrun): weak scaling of ONE global problem n=3, Nx=1024, Ny=1024*N cut into N slabs of cell rows (one per
-GPU): NCCL halo exchange of the search direction and an integer allreduce of the three exact dots per iteration
-(bit-identical to the single-GPU arithmetic).  value = N * iterations / max-over-ranks time (dof-iterations are
-what scales; every rank performs the same iteration count).
+GPU): the halo rows of the search direction and the three exact dots per iteration travel through CUDA-IPC peer memory
+over NVLink (NCCL if peer memory is unavailable), bit-identical to the single-GPU arithmetic.  value = N * iterations /
+max-over-ranks time (dof-iterations are what scales; every rank performs the same iteration count).  A "strong_scaling"
+record (the FIXED 1024^2 grid of config 2 cut into N slabs) is measured after the timed region and attached to the line.
+The reference arm at N > 1 runs the SAME global problem on all host cores (rank 0 only) and reports N * iterations / s.
 """
 import argparse
 import ctypes as C
@@ -95,12 +100,17 @@ def reference_arm(args, rank, world):
     """the reference's own CPU implementation of the path (oracle/_ref) on the host cores; rank 0 only"""
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its children: the CPU arm uses every host core, set explicitly and stated
+    ncores = os.cpu_count() or 1
+    os.environ["OMP_NUM_THREADS"] = str(ncores)
     from oracle import refwrap as R
     cells = args.cells
     kind = "reference"
     m = args.ref_iters
+    ny = cells * world  # N > 1: the same global problem our arm cuts into N slabs
     if R.available():
-        g = R.grid([0, 0], [np.pi, 2 * np.pi], 3, [cells, cells], [R.DIR, R.PER])
+        R.lib().ref_set_num_threads(ncores)
+        g = R.grid([0, 0], [np.pi, 2 * np.pi * world], 3, [cells, ny], [R.DIR, R.PER])
         E = R.Elliptic2d(g, R.DIR, R.PER, R.FORWARD, 1.0)
         chi = R.evaluate(g, "pol")
         E.set_chi(chi)
@@ -116,7 +126,7 @@ def reference_arm(args, rank, world):
         from oracle import orc
         from feltor_b200 import topology as T
         kind, cores = "port", 1
-        g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, [cells, cells], [T.DIR, T.PER])
+        g = T.Grid([0, 0], [np.pi, 2 * np.pi * world], 3, [cells, ny], [T.DIR, T.PER])
         fchi, frhs = problem_functions()
         chi, b, W = g.evaluate(fchi), g.evaluate(frhs), g.weights()
         mats = dict(leftx=T.derivative(0, g, T.NEU, T.BACKWARD), lefty=T.derivative(1, g, T.PER, T.BACKWARD),
@@ -130,20 +140,21 @@ def reference_arm(args, rank, world):
             t0 = time.time()
             it = E.pcg_solve(x, b, P, W, 1e-8, 1.0, 1, max_iter=m + 1)
             return min(it, m), time.time() - t0
-    for _ in range(args.warmup if args.warmup < 2 else 1):
+    nwarm = min(args.warmup, 1)  # every step re-solves from x = 0: one untimed step warms caches and the thread pool
+    for _ in range(nwarm):
         step()
     its, secs = 0, 0.
     for _ in range(args.steps):
         i, s = step()
         its += i
         secs += s
-    v = its / secs
-    sample = "%d PCG iterations per step of the n=3 %dx%d problem, %d steps" % (m, cells, cells, args.steps)
+    v = world * its / secs  # in units of the per-GPU (1024^2) problem, like our arm's weak-scaling value
+    sample = "%d PCG iterations per step of the n=3 %dx%d problem, %d steps, %d OpenMP threads" % (m, cells, ny, args.steps, cores)
     out = {"metric": "pcg_iterations_per_second", "value": v, "unit": "iterations/s", "n_gpus": args.gpus,
-           "steps": args.steps, "warmup": args.warmup, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
+           "steps": args.steps, "warmup": nwarm, "ms_per_step": secs / args.steps * 1e3, "higher_is_better": True,
            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "impl": "reference",
            "config": {"workload": "2D dg::Elliptic+dg::PCG Poisson n=3 Nx=Ny=%d eps=1e-8 DIRxPER (config 2)" % cells,
-                      "iterations_per_step": m},
+                      "iterations_per_step": m, "global_grid_cells": [cells, ny]},
            "cpu_baseline": {"value": v, "unit": "iterations/s", "cores": cores, "kind": kind, "sample": sample},
            "e2e": {"value": v, "unit": "iterations/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
            "gpu_launches": 0}
@@ -221,6 +232,11 @@ def main():
                     help="pcg: the headline (config 2); toefl: config 3; ds: config 4 -- the two secondary workloads print their own "
                          "JSON line (single GPU) with the reference's CPU path timed beside them")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--scaling", default="weak", choices=["weak", "strong"],
+                    help="N > 1: weak = 1024 x 1024*N cells (default), strong = the fixed 1024^2 grid cut into N slabs")
+    ap.add_argument("--no-strong", action="store_true", help="N > 1: skip the attached strong-scaling record")
+    ap.add_argument("--no-micro", action="store_true", help="skip the config-1 kernel table")
+    ap.add_argument("--no-toefl", action="store_true", help="skip the config-3 (toefl) record")
     args = ap.parse_args()
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -235,7 +251,6 @@ def main():
     import feltor_b200 as fb
     from feltor_b200 import topology as T
     from feltor_b200.elliptic import Elliptic2d, PCG
-    from feltor_b200._dev import ptr, stream
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the product has no CPU path")
     torch.cuda.set_device(local)
@@ -244,48 +259,57 @@ def main():
     L = fb.lib()
     cells, M = args.cells, args.iters
     fchi, frhs = problem_functions()
-    if world == 1:
-        g = T.Grid([0., 0.], [np.pi, 2 * np.pi], 3, [cells, cells], [T.DIR, T.PER])
-        E = Elliptic2d(g, T.DIR, T.PER, T.FORWARD, 1.0)
-        E.set_chi(torch.from_numpy(g.evaluate(fchi).copy()).cuda())
-        ndof = g.size
-        b_np = g.evaluate(frhs).copy()
-        pcg = PCG(ndof, M + 1)
-        pcg.set_throw_on_fail(False)
-    else:
+    comm = None
+    if world > 1:
         from feltor_b200.dist import Comm, SlabElliptic2d, DistPCG
         comm = Comm.from_torch_distributed()
-        g = T.Grid([0., 0.], [np.pi, 2 * np.pi * world], 3, [cells, cells * world], [T.DIR, T.PER])
-        E = SlabElliptic2d(comm, g, T.DIR, T.PER, T.FORWARD, 1.0)
-        E.set_chi(torch.from_numpy(E.evaluate(fchi)).cuda())
-        ndof = E.size
-        b_np = E.evaluate(frhs)
-        pcg = DistPCG(comm, ndof, M + 1)
-        pcg.throw_on_fail = False
-    b_host = torch.from_numpy(b_np).pin_memory()
-    x0_host = torch.zeros(ndof, dtype=torch.float64).pin_memory()
-    xout_host = torch.empty(ndof, dtype=torch.float64).pin_memory()
-    b = b_host.cuda()
-    x = torch.zeros(ndof, dtype=torch.float64, device="cuda")
-    P, W = E.precond(), E.weights()
-
-    def solve_device():
-        x.zero_()
-        return min(pcg.solve(E, x, b, P, W, 1e-8, 1.0, 1), M)
-
-    def solve_e2e():
-        b.copy_(b_host, non_blocking=True)
-        x.copy_(x0_host, non_blocking=True)
-        it = min(pcg.solve(E, x, b, P, W, 1e-8, 1.0, 1), M)
-        xout_host.copy_(x, non_blocking=True)
-        torch.cuda.current_stream().synchronize()
-        return it
 
     def barrier():
         torch.cuda.synchronize()
         if world > 1:
             dist.barrier()
             torch.cuda.synchronize()
+
+    class Problem:
+        """config 2 on `world` GPUs: a global grid of cells x ny_global cells, cut into slabs of cell rows when world > 1"""
+
+        def __init__(self, ny_global):
+            self.ny = ny_global
+            ly = 2 * np.pi * ny_global / cells
+            if world == 1:
+                g = T.Grid([0., 0.], [np.pi, ly], 3, [cells, ny_global], [T.DIR, T.PER])
+                self.E = Elliptic2d(g, T.DIR, T.PER, T.FORWARD, 1.0)
+                self.E.set_chi(torch.from_numpy(g.evaluate(fchi).copy()).cuda())
+                self.ndof = g.size
+                b_np = g.evaluate(frhs).copy()
+                self.pcg = PCG(self.ndof, M + 1)
+                self.pcg.set_throw_on_fail(False)
+            else:
+                g = T.Grid([0., 0.], [np.pi, ly], 3, [cells, ny_global], [T.DIR, T.PER])
+                self.E = SlabElliptic2d(comm, g, T.DIR, T.PER, T.FORWARD, 1.0)
+                self.E.set_chi(torch.from_numpy(self.E.evaluate(fchi)).cuda())
+                self.ndof = self.E.size
+                b_np = self.E.evaluate(frhs)
+                self.pcg = DistPCG(comm, self.ndof, M + 1)
+                self.pcg.throw_on_fail = False
+            self.b_host = torch.from_numpy(b_np).pin_memory()
+            self.x0_host = torch.zeros(self.ndof, dtype=torch.float64).pin_memory()
+            self.xout_host = torch.empty(self.ndof, dtype=torch.float64).pin_memory()
+            self.b = self.b_host.cuda()
+            self.x = torch.zeros(self.ndof, dtype=torch.float64, device="cuda")
+            self.P, self.W = self.E.precond(), self.E.weights()
+
+        def solve_device(self):
+            self.x.zero_()
+            return min(self.pcg.solve(self.E, self.x, self.b, self.P, self.W, 1e-8, 1.0, 1), M)
+
+        def solve_e2e(self):
+            self.b.copy_(self.b_host, non_blocking=True)
+            self.x.copy_(self.x0_host, non_blocking=True)
+            it = min(self.pcg.solve(self.E, self.x, self.b, self.P, self.W, 1e-8, 1.0, 1), M)
+            self.xout_host.copy_(self.x, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+            return it
 
     def timed(fn, steps):
         barrier()
@@ -305,26 +329,46 @@ def main():
             return tmax[0].item(), int(t[1].item())
         return ms, its
 
-    for _ in range(max(args.warmup, 3)):
-        solve_device()
+    strong = args.scaling == "strong"
+    if strong and cells % world:
+        raise SystemExit("bench.py: --scaling strong needs --cells divisible by the GPU count")
+    pr = Problem(cells if strong else cells * world)
+    nwarm = max(args.warmup, 3)
+    for _ in range(nwarm):
+        pr.solve_device()
     # timed region: exactly K steps, no instrumentation inside
     sampler = ClockSampler(local)
     if rank == 0:
         sampler.start()
     launches0 = L.raw["dgb_launch_count"]()
-    ms, its = timed(solve_device, args.steps)
+    ms, its = timed(pr.solve_device, args.steps)
     launches = L.raw["dgb_launch_count"]() - launches0
     clocks = sampler.stop() if rank == 0 else None
     # per-kernel durations for the roofline: a separate pass with CUDA events on the launching stream around K1/K2/K3
     # (the events cost a few percent, so they stay out of the timed region above)
-    L.pcg_set_profile(pcg.h, 1)
-    timed(solve_device, min(args.steps, 2))
+    L.pcg_set_profile(pr.pcg.h, 1)
+    timed(pr.solve_device, min(args.steps, 2))
     prof = [C.c_double(), C.c_double(), C.c_double()]
     pn = C.c_longlong()
-    L.pcg_get_profile(pcg.h, C.byref(prof[0]), C.byref(prof[1]), C.byref(prof[2]), C.byref(pn))
-    L.pcg_set_profile(pcg.h, 0)
-    solve_e2e()
-    ms_e2e, its_e2e = timed(solve_e2e, args.steps)
+    L.pcg_get_profile(pr.pcg.h, C.byref(prof[0]), C.byref(prof[1]), C.byref(prof[2]), C.byref(pn))
+    L.pcg_set_profile(pr.pcg.h, 0)
+    pr.solve_e2e()
+    ms_e2e, its_e2e = timed(pr.solve_e2e, args.steps)
+    ndof = pr.ndof
+    # strong scaling of the named 1024^2 grid (N > 1, default weak run): the same solver on cells x cells cells cut into N slabs
+    strong_rec = None
+    if world > 1 and not strong and cells % world == 0 and not args.no_strong:
+        del pr
+        torch.cuda.empty_cache()
+        ps = Problem(cells)
+        for _ in range(3):
+            ps.solve_device()
+        ms_s, its_s = timed(ps.solve_device, args.steps)
+        strong_rec = {"metric": "pcg_iterations_per_second", "value": (its_s / world) / (ms_s * 1e-3), "unit": "iterations/s",
+                      "scaling": "strong", "n_gpus": world, "global_grid_cells": [cells, cells], "dof_per_gpu": ps.ndof,
+                      "ms_per_step": ms_s / args.steps, "steps": args.steps, "warmup": 3,
+                      "note": "iterations/s of the FIXED n=3 %dx%d problem; divide by the N=1 value for the strong-scaling speed-up" % (cells, cells)}
+        del ps
 
     if rank != 0:
         if world > 1:
@@ -348,33 +392,58 @@ def main():
     for k in kernels:
         k["achieved"] = k["bytes_per_launch"] / (k["ms_per_launch"] * 1e-3) / 1e9 if k["ms_per_launch"] > 0 else None
         k["frac"] = k["achieved"] / peak if k["achieved"] else None
-    dom = max(kernels, key=lambda k: k["ms_per_launch"])  # the dominant kernel of the step = the one with the largest share of it
-    value = its / (ms * 1e-3)
+        k["share_of_iteration"] = k["ms_per_launch"] / max(prof[0].value + prof[1].value + prof[2].value, 1e-30) * max(pn.value, 1)
+    named = kernels[0]  # the kernel the north star names (the fused Elliptic apply); K2 has the larger time share and is listed beside it
+    value = (its / world if strong else its) / (ms * 1e-3)
+    if world == 1:
+        par = "single GPU"
+    else:
+        plane = ("CUDA-IPC peer memory over NVLink: K3 stores the halo rows into the neighbours' ghost rows, the 39-word int64 dot "
+                 "records are exchanged by peer stores + polling (NCCL only ships the IPC handles)") if comm.peer_memory else \
+                "NCCL: grouped ncclSend/ncclRecv of the ghost rows, ncclAllReduce(int64) of the dot records"
+        par = "y-slabs x%d of a global grid of %dx%d cells; %s" % (world, cells, cells if strong else cells * world, plane)
     out = {
         "metric": "pcg_iterations_per_second", "value": value, "unit": "iterations/s", "n_gpus": world,
-        "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms / args.steps, "higher_is_better": True,
-        "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "steps": args.steps, "warmup": nwarm, "ms_per_step": ms / args.steps, "higher_is_better": True,
+        "scaling": "strong" if strong else "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": "2D dg::Elliptic+dg::PCG Poisson n=3 Nx=Ny=%d eps=1e-8 DIRxPER (config 2)" % cells,
                    "dof_per_gpu": ndof, "iterations_per_step": M, "l2": "working set 8 vectors x %.0f MB > 126 MB L2"
-                   % (ndof * 8 / 1e6), "parallelism": ("y-slabs x%d, NCCL halo + int64 superacc allreduce, global grid %dx%d cells" % (world, cells, cells * world))
-                   if world > 1 else "single"},
-        "e2e": {"value": its_e2e / (ms_e2e * 1e-3), "unit": "iterations/s", "h2d_bytes_per_step": 2 * ndof * 8,
+                   % (ndof * 8 / 1e6), "parallelism": par},
+        "e2e": {"value": (its_e2e / world if strong else its_e2e) / (ms_e2e * 1e-3), "unit": "iterations/s", "h2d_bytes_per_step": 2 * ndof * 8,
                 "d2h_bytes_per_step": ndof * 8},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved"], "peak": peak, "peak_kind": peak_kind,
-                     "unit": "GB/s", "frac": dom["frac"], "traffic": dom["traffic"], "bytes_per_launch": dom["bytes_per_launch"],
-                     "ms_per_launch": dom["ms_per_launch"]},
-        "roofline_other_kernels": [{kk: k[kk] for kk in ("kernel", "achieved", "frac", "traffic", "bytes_per_launch", "ms_per_launch")}
-                                   for k in kernels if k is not dom],
+        "roofline": {"bound": "hbm", "kernel": named["kernel"], "achieved": named["achieved"], "peak": peak, "peak_kind": peak_kind,
+                     "unit": "GB/s", "frac": named["frac"], "traffic": named["traffic"], "bytes_per_launch": named["bytes_per_launch"],
+                     "ms_per_launch": named["ms_per_launch"], "share_of_iteration": named["share_of_iteration"]},
+        "roofline_other_kernels": [{kk: k[kk] for kk in ("kernel", "achieved", "frac", "traffic", "bytes_per_launch", "ms_per_launch",
+                                                         "share_of_iteration")} for k in kernels if k is not named],
         "kernels_ms_per_iteration": {"apply_dot": k1_ms, "update_dots": prof[1].value / max(pn.value, 1),
                                      "direction": prof[2].value / max(pn.value, 1)},
-        "pcg_gbs_at_128B_per_dof": 128 * ndof * value / world / 1e9,
+        "pcg_gbs_at_128B_per_dof": 128 * ndof * (its / (ms * 1e-3)) / world / 1e9,
     }
+    if strong_rec is not None:
+        out["strong_scaling"] = strong_rec
+    if world == 1 and not args.no_micro:
+        try:
+            out["micro"] = micro_table(cells, peak)
+        except Exception as e:
+            out["micro"] = {"failed": repr(e)}
+    if world == 1 and not args.no_toefl:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import toefl_bench
+            t_out, _ = toefl_bench.run(cells, 4, 2, 0.5)
+            out["toefl"] = {"metric": "toefl_steps_per_second", "value": t_out["steps_per_s"], "unit": "steps/s", "rhs_per_s": t_out["rhs_per_s"],
+                            "config": t_out["workload"], "kernel_launches_per_step": t_out["kernel_launches"] / t_out["steps"],
+                            "mean_pcg_iterations_per_solve": t_out["mean_pcg_iterations_per_solve(stage0,1,2)"]}
+        except Exception as e:
+            out["toefl"] = {"failed": repr(e)}
     if not args.no_cpu_baseline and world == 1:
         try:
             from oracle import refwrap as R
             if R.available():
+                R.lib().ref_set_num_threads(os.cpu_count() or 1)
                 m = args.ref_iters * 4
                 gr = R.grid([0, 0], [np.pi, 2 * np.pi], 3, [cells, cells], [R.DIR, R.PER])
                 Er = R.Elliptic2d(gr, R.DIR, R.PER, R.FORWARD, 1.0)
@@ -395,6 +464,65 @@ def main():
     print(json.dumps(out), flush=True)
     if world > 1:
         dist.destroy_process_group()
+
+
+def micro_table(cells, peak):
+    """config 1 of BASELINE.json (n=3, 128^2: 1.2 MB vectors, launch/latency bound) and the same kernels at the benchmark
+    size: algorithmic GB/s from CUDA events, median of 20, L2 flushed between calls"""
+    import torch
+    import feltor_b200 as fb
+    from feltor_b200 import blas1, blas2, topology as T
+    from feltor_b200.elliptic import Elliptic2d
+    from feltor_b200._dev import ptr, stream
+    L = fb.lib()
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    ws = blas2.DotWorkspace()
+    res = torch.zeros(41, dtype=torch.int64, device="cuda")
+    table = {"unit": "GB/s algorithmic (us per call)", "peak_gbs": peak, "method": "CUDA events, median of 20, 256 MB written between calls (L2 flush)"}
+
+    def timeit(f):
+        for _ in range(3):
+            f()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(20):
+            flush.zero_()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            f()
+            e1.record()
+            torch.cuda.synchronize()
+            ts.append(e0.elapsed_time(e1) * 1e-3)
+        return float(np.median(ts))
+
+    for N in sorted({128, cells}):
+        g = T.Grid([0., 0.], [2 * np.pi] * 2, 3, [N, N], [T.PER, T.PER])
+        n = g.size
+        gen = torch.Generator(device="cuda").manual_seed(0)
+        v = [torch.rand(n, dtype=torch.float64, device="cuda", generator=gen) + 0.5 for _ in range(4)]
+        B = 8 * n
+        rows = {}
+
+        def rec(name, nbytes, f):
+            t = timeit(f)
+            rows[name] = {"gbs": nbytes / t / 1e9, "us": t * 1e6, "frac": nbytes / t / 1e9 / peak}
+        rec("axpby", 3 * B, lambda: blas1.axpby(1.0000001, v[0], 0.9999999, v[1]))
+        rec("pointwiseDot", 4 * B, lambda: blas1.pointwiseDot(1.0000001, v[0], v[1], 0.5, v[2]))
+        rec("dot2", 2 * B, lambda: L.exdot2(ws.h, n, ptr(v[0]), C.c_double(0), ptr(v[1]), C.c_double(0), ptr(res), stream()))
+        rec("dot3", 3 * B, lambda: L.exdot3(ws.h, n, ptr(v[0]), C.c_double(0), ptr(v[1]), C.c_double(0), ptr(v[2]), C.c_double(0),
+                                            ptr(res), stream()))
+        for name, m in (("dx_forward", T.derivative(0, g, T.PER, T.FORWARD)), ("dy_forward", T.derivative(1, g, T.PER, T.FORWARD)),
+                        ("dx_centered", T.derivative(0, g, T.PER, T.CENTERED)), ("dy_centered", T.derivative(1, g, T.PER, T.CENTERED))):
+            m.handle
+            rec(name, 2 * B, lambda: m.symv(1.0, v[0], 0.0, v[1]))
+        ge = T.Grid([0., 0.], [np.pi, 2 * np.pi], 3, [N, N], [T.DIR, T.PER])
+        for dname, dd in (("elliptic_forward", T.FORWARD), ("elliptic_centered", T.CENTERED)):
+            E = Elliptic2d(ge, T.DIR, T.PER, dd, 1.0)
+            E.set_chi(v[2])
+            rec(dname, 3 * B, lambda: E.symv(v[0], v[1]))
+            rows[dname]["kernel"] = E.kernel()
+        table["n3_%dx%d" % (N, N)] = rows
+    return table
 
 
 if __name__ == "__main__":

@@ -300,6 +300,14 @@ int dgb_comm_create(dgb_comm** out, const char* id128, int rank, int nranks) {
     *out = reinterpret_cast<dgb_comm*>(c);
     return 0;
 }
+int dgb_comm_info(const dgb_comm* h, int* rank, int* size, int* peer_memory) {
+    const Comm* c = reinterpret_cast<const Comm*>(h);
+    if (!c) { set_error("dgb_comm_info: communicator is NULL"); return DGB_ERR_INVALID; }
+    if (rank) *rank = c->rank;
+    if (size) *size = c->size;
+    if (peer_memory) *peer_memory = c->p2p ? 1 : 0;
+    return 0;
+}
 int dgb_comm_destroy(dgb_comm* h) {
     Comm* c = reinterpret_cast<Comm*>(h);
     if (!c) return 0;

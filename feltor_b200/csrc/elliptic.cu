@@ -278,6 +278,12 @@ int dgb_elliptic2d_set_kernel(dgb_elliptic2d* h, int kernel) {
     p->kernel_mode = kernel;
     return 0;
 }
+int dgb_elliptic2d_set_ordering(dgb_elliptic2d* h, int ordering) {
+    Elliptic2dPlan* p = reinterpret_cast<Elliptic2dPlan*>(h);
+    if (ordering != DGB_ORDER_REFERENCE && ordering != DGB_ORDER_RELAXED) { set_error("dgb_elliptic2d_set_ordering: unknown ordering %d", ordering); return DGB_ERR_INVALID; }
+    p->relaxed = ordering == DGB_ORDER_RELAXED;
+    return 0;
+}
 int dgb_elliptic2d_get_kernel(const dgb_elliptic2d* h, int with_dot, int* kernel) {
     const Elliptic2dPlan* p = reinterpret_cast<const Elliptic2dPlan*>(h);
     const bool identity_chi = !p->chi[0] && !p->chi[1] && !p->chi[2] && !p->chi[3];

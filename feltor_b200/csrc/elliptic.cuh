@@ -26,6 +26,7 @@ struct Elliptic2dPlan {
     bool helm = false;
     double helm_alpha = 0.;
     const double* helm_chi = nullptr;  // borrowed, nullptr = 1
+    bool relaxed = false;  // dgb_elliptic2d_set_ordering: interior rows of the walker kernel in the relaxed operation order
     int kernel_mode = 0;  // dgb_elliptic2d_set_kernel: 0 auto, 1 tile kernel, 2 walker kernel, 3 unfused (reference launch sequence)
     void* walk_part[2] = {nullptr, nullptr};  // work partitions of the walker kernel (plain / fused-dot variant)
 };

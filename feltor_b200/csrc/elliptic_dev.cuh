@@ -1,6 +1,7 @@
 // Internal: device helpers shared by the two fused Elliptic2d kernels (elliptic_fused.cu: CTA tiles,
 // elliptic_walker.cu: warp-private sliding window).
 #pragma once
+#include "async_copy.cuh"
 #include "elliptic.cuh"
 #include "superacc.cuh"
 #include "pcg.cuh"
@@ -25,24 +26,7 @@ struct EllipticCoef {
 };
 
 // ------------------------------------------------------------------------------------------------ TMA / LDGSTS
-__device__ __forceinline__ unsigned smem_u32(const void* p) { return (unsigned)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void mbar_init(unsigned long long* bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-    asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(unsigned long long* bar, unsigned bytes) {
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long* bar, unsigned phase) {
-    unsigned ok;
-    do {
-        asm volatile(
-            "{\n .reg .pred p;\n mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n selp.u32 %0, 1, 0, p;\n}\n"
-            : "=r"(ok)
-            : "r"(smem_u32(bar)), "r"(phase)
-            : "memory");
-    } while (!ok);
-}
+// (mbarrier helpers: async_copy.cuh)
 // 2-d tile load global -> shared through the tensor map; completion is signalled on the mbarrier in bytes
 __device__ __forceinline__ void tma_load_2d(void* dst, const CUtensorMap* map, unsigned long long* bar, int c0, int c1) {
     asm volatile(

@@ -3,6 +3,7 @@
 // blocking D2H of 39 words and a host-side Round) by ONE persistent kernel sized to the SM count whose last block
 // normalises, rounds and publishes {acc[39], value, status} in device memory.
 #include "superacc.cuh"
+#include "async_copy.cuh"
 #include <cmath>
 #include <cstring>
 #include <cstdlib>
@@ -73,8 +74,8 @@ exdot_kernel(const double* __restrict__ x, double xs, const double* __restrict__
             spill = spill || res[2 * u] != 0.0 || res[2 * u + 1] != 0.0;
         }
         if (spill) {  // rare: a residue the expansions cannot hold goes to the shared accumulator (exact)
-#pragma unroll 1
-            for (int u = 0; u < 2 * U; u++) sa::accumulate(my, res[u], 1);
+#pragma unroll
+            for (int u = 0; u < 2 * U; u++) sa::accumulate(my, res[u], 1);  // unrolled: res[] stays in registers
         }
 #pragma unroll
         for (int u = 0; u < U; u++) { a[u] = an[u]; b[u] = bn[u]; c[u] = cn[u]; }
@@ -86,6 +87,110 @@ exdot_kernel(const double* __restrict__ x, double xs, const double* __restrict__
     for (int u = 1; u < NE; u++) fpe[0].merge(fpe[u], my);
     fpe[0].flush_warp(my);
     sa::block_finish<1>(smem, bad, slot);
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// Streaming variant for large vectors: the operands reach the SM through the TMA engine.
+// The register-prefetch kernel above keeps one trip of loads per thread in flight (~49 KB per SM), which at the loaded
+// HBM latency of B200 (> 1 us) caps it near 4.6 TB/s.  Here one producer lane per CTA keeps a ring of STAGES chunks per
+// operand in flight with 1-d bulk copies (cp.async.bulk, SASS UBLKCP; completion counted in bytes on an mbarrier), i.e.
+// up to 192 KB per SM, independent of the register budget; 16 consumer warps take the chunks out of shared memory with
+// conflict-free 128-bit loads and run them through four independent floating-point expansions each.  Chunks are dealt
+// round robin to one persistent CTA per SM; the exact arithmetic, the accumulator and the finish are those of the kernel
+// above, so the result words are identical (integer accumulation is order independent).
+constexpr int TDOT_CONSUMERS = 512, TDOT_THREADS = TDOT_CONSUMERS + 32, TDOT_CHUNK = 2048;  // doubles per operand and stage
+template <int NOPS>
+struct TDot {
+    static constexpr int STAGES = NOPS == 3 ? 4 : 6;
+    static constexpr unsigned STAGE_BYTES = NOPS * TDOT_CHUNK * 8;
+    static constexpr size_t SMEM = (size_t)STAGES * STAGE_BYTES + 2 * STAGES * 8 + 16;
+};
+template <int NOPS, bool PLAIN = false>
+__global__ void __launch_bounds__(TDOT_THREADS, 1)
+exdot_tma_kernel(const double* __restrict__ x, const double* __restrict__ w, const double* __restrict__ y, size_t n, sa::DotSlot slot) {
+    using P = TDot<NOPS>;
+    constexpr int STAGES = P::STAGES;
+    __shared__ long long acc_sm[sa::BINS];
+    extern __shared__ __align__(128) unsigned char ring_raw[];
+    double* ring = reinterpret_cast<double*>(ring_raw);
+    unsigned long long* full = reinterpret_cast<unsigned long long*>(ring_raw + (size_t)STAGES * P::STAGE_BYTES);
+    unsigned long long* empty = full + STAGES;
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    for (int i = tid; i < sa::BINS; i += blockDim.x) acc_sm[i] = 0;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(full + s, 1); mbar_init(empty + s, TDOT_CONSUMERS / 32); }
+    }
+    __syncthreads();
+    const size_t nchunks = n / TDOT_CHUNK;
+    // chunks of this CTA: blockIdx.x, blockIdx.x + gridDim.x, ...
+    const int mine = nchunks > blockIdx.x ? (int)((nchunks - blockIdx.x + gridDim.x - 1) / gridDim.x) : 0;
+    int bad = 0;
+    sa::Fpe fpe[4];
+#pragma unroll
+    for (int u = 0; u < 4; u++) fpe[u].clear();
+    if (warp == TDOT_CONSUMERS / 32) {
+        // ---- producer: one lane issues every copy of this CTA
+        if (lane == 0) {
+            int s = 0;
+            unsigned ph = 1;  // parity of the PREVIOUS use of slot s (first round: nothing to wait for)
+            for (int it = 0; it < mine; it++) {
+                if (it >= STAGES) mbar_wait(empty + s, ph);
+                const size_t base = ((size_t)blockIdx.x + (size_t)it * gridDim.x) * (size_t)TDOT_CHUNK;
+                double* dst = ring + (size_t)s * NOPS * TDOT_CHUNK;
+                mbar_expect_tx(full + s, P::STAGE_BYTES);
+                bulk_load_1d(dst, x + base, TDOT_CHUNK * 8, full + s);
+                if (NOPS == 3) bulk_load_1d(dst + TDOT_CHUNK, w + base, TDOT_CHUNK * 8, full + s);
+                bulk_load_1d(dst + (NOPS - 1) * TDOT_CHUNK, y + base, TDOT_CHUNK * 8, full + s);
+                if (++s == STAGES) { s = 0; ph ^= 1u; }
+            }
+        }
+    } else {
+        // ---- consumers
+        int s = 0;
+        unsigned ph = 0;
+        for (int it = 0; it < mine; it++) {
+            mbar_wait(full + s, ph);
+            const double* src = ring + (size_t)s * NOPS * TDOT_CHUNK;
+            double2 a[2], b[2], c[2];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                const int e = 2 * (tid + u * TDOT_CONSUMERS);
+                a[u] = *reinterpret_cast<const double2*>(src + e);
+                if (NOPS == 3) b[u] = *reinterpret_cast<const double2*>(src + TDOT_CHUNK + e);
+                c[u] = *reinterpret_cast<const double2*>(src + (NOPS - 1) * TDOT_CHUNK + e);
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(empty + s);  // the operands are in registers: the slot may be refilled
+            if (++s == STAGES) { s = 0; ph ^= 1u; }
+            if (PLAIN) {  // timing experiment only (DGB_DOT_DEBUG_PLAIN): the memory pipeline without the exact arithmetic
+#pragma unroll
+                for (int u = 0; u < 2; u++) {
+                    fpe[2 * u].a[0] += dot_product<NOPS>(a[u].x, b[u].x, c[u].x, bad);
+                    fpe[2 * u + 1].a[0] += dot_product<NOPS>(a[u].y, b[u].y, c[u].y, bad);
+                }
+                continue;
+            }
+            double res[4];
+#pragma unroll
+            for (int u = 0; u < 2; u++) {
+                res[2 * u] = fpe[2 * u].add_lazy(dot_product<NOPS>(a[u].x, b[u].x, c[u].x, bad));
+                res[2 * u + 1] = fpe[2 * u + 1].add_lazy(dot_product<NOPS>(a[u].y, b[u].y, c[u].y, bad));
+            }
+            if (res[0] != 0.0 || res[1] != 0.0 || res[2] != 0.0 || res[3] != 0.0) {  // rare: exact spill to the shared accumulator
+#pragma unroll
+                for (int u = 0; u < 4; u++) sa::accumulate(acc_sm, res[u], 1);
+            }
+        }
+        // elements behind the last full chunk: block 0, straight from global memory
+        if (blockIdx.x == 0) {
+            for (size_t i = nchunks * TDOT_CHUNK + tid; i < n; i += TDOT_CONSUMERS)
+                fpe[0].add(dot_product<NOPS>(x[i], NOPS == 3 ? w[i] : 0., y[i], bad), acc_sm);
+        }
+#pragma unroll
+        for (int u = 1; u < 4; u++) fpe[0].merge(fpe[u], acc_sm);
+    }
+    fpe[0].flush_warp(acc_sm);  // the producer warp carries empty expansions: adds nothing
+    sa::block_finish<1>(acc_sm, bad, slot);
 }
 
 // operands that are not 16-byte aligned: scalar loads, same arithmetic
@@ -170,7 +275,28 @@ int exdot_launch(DotWs* ws, int nops, size_t n, const double* x, double xs, cons
     slot.result = result ? result : ws->result;
     bool vec = (!x || aligned16(x)) && (!w || aligned16(w)) && (!y || aligned16(y));
     cudaStream_t st = as_stream(s);
-    if (vec) {
+    static int tma_min = -1;  // vectors at least this long take the TMA-pipelined kernel (DGB_DOT_TMA_MIN; 0 disables it)
+    if (tma_min < 0) { const char* e = getenv("DGB_DOT_TMA_MIN"); tma_min = e ? atoi(e) : 1 << 20; }
+    const bool all_vectors = x && y && (nops == 2 || w);
+    if (vec && all_vectors && tma_min > 0 && n >= (size_t)tma_min) {
+        const size_t nchunks = n / TDOT_CHUNK;
+        const unsigned grid = (unsigned)(nchunks < (size_t)sm_count() ? (nchunks ? nchunks : 1) : (size_t)sm_count());
+        static bool configured = false;
+        if (!configured) {
+            DGB_CUDA(cudaFuncSetAttribute(exdot_tma_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TDot<2>::SMEM));
+            DGB_CUDA(cudaFuncSetAttribute(exdot_tma_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TDot<3>::SMEM));
+            configured = true;
+        }
+        static int plain = -1;
+        if (plain < 0) {
+            const char* e = getenv("DGB_DOT_DEBUG_PLAIN");
+            plain = (e && atoi(e)) ? 1 : 0;
+            if (plain) DGB_CUDA(cudaFuncSetAttribute(exdot_tma_kernel<2, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TDot<2>::SMEM));
+        }
+        if (plain && nops == 2) exdot_tma_kernel<2, true><<<grid, TDOT_THREADS, TDot<2>::SMEM, st>>>(x, nullptr, y, n, slot);
+        else if (nops == 3) exdot_tma_kernel<3><<<grid, TDOT_THREADS, TDot<3>::SMEM, st>>>(x, w, y, n, slot);
+        else exdot_tma_kernel<2><<<grid, TDOT_THREADS, TDot<2>::SMEM, st>>>(x, nullptr, y, n, slot);
+    } else if (vec) {
         if (nops == 3) exdot_pick<3>(ws->max_blocks, n, x, xs, w, wsc, y, ys, slot, st);
         else exdot_pick<2>(ws->max_blocks, n, x, xs, nullptr, 0., y, ys, slot, st);
     } else {

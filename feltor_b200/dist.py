@@ -49,6 +49,13 @@ class Comm:
         dist.broadcast(t, 0)
         return cls(rank, size, bytes(t.cpu().numpy().tobytes()))
 
+    @property
+    def peer_memory(self):
+        """True if dots and halos travel by CUDA-IPC peer stores over NVLink, False if by NCCL"""
+        pm = C.c_int()
+        lib().comm_info(self.h, None, None, C.byref(pm))
+        return bool(pm.value)
+
     def halo_rows(self, padded, row_len, nrows, ghost_rows, periodic):
         interior = C.c_void_p(padded.data_ptr() + ghost_rows * row_len * 8)
         lib().comm_halo_rows(self.h, interior, row_len, nrows, ghost_rows, int(periodic), stream())

@@ -53,6 +53,12 @@ class Elliptic2d:
         lib().elliptic2d_get_kernel(self.h, int(with_dot), C.byref(k))
         return {v: n for n, v in self.KERNELS.items()}[k.value]
 
+    def set_ordering(self, ordering):
+        """dgb_elliptic2d_set_ordering: "reference" (default, bitwise the reference's rounding sequence) | "relaxed" (one FMA
+        chain per output in the interior rows of the walker kernel: faster, equal to <= 1e-13 relative)"""
+        lib().elliptic2d_set_ordering(self.h, {"reference": 0, "relaxed": 1}[ordering])
+        return self
+
     def set_vol(self, vol):
         """curvilinear volume form m_vol (elliptic.h:292-296); the tensor stays borrowed by the plan"""
         self._vol = vol

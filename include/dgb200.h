@@ -339,6 +339,13 @@ DGB_API int dgb_elliptic2d_set_jfactor(dgb_elliptic2d* plan, double jfactor);
 #define DGB_ELLIPTIC_KERNEL_WALKER 2   /* elliptic2d_walker_kernel: warp-private TMA sliding window (n = 2, 3)       */
 #define DGB_ELLIPTIC_KERNEL_UNFUSED 3  /* the reference's launch sequence elliptic.h:431-458 on dgb_ell_symv / blas1 */
 DGB_API int dgb_elliptic2d_set_kernel(dgb_elliptic2d* plan, int kernel);
+/* Operation order of the fused kernels.  REFERENCE (default): the rounding sequence of the reference's OpenMP backend, result
+ * bitwise equal to it.  RELAXED (opt-in): interior rows of the walker kernel accumulate every output in one fused-multiply-add
+ * chain (27 % fewer FP64 operations; the kernel is FP64-pipe bound); results agree with the reference to <= 1e-13 relative,
+ * inside the 1e-12 the reference's own tests allow for symv, but NOT bit for bit -- PCG iteration counts may differ by a few. */
+#define DGB_ORDER_REFERENCE 0
+#define DGB_ORDER_RELAXED 1
+DGB_API int dgb_elliptic2d_set_ordering(dgb_elliptic2d* plan, int ordering);
 /* *kernel = the DGB_ELLIPTIC_KERNEL_* the next symv (with_dot = 0) / PCG iteration (with_dot = 1) on this plan will launch */
 DGB_API int dgb_elliptic2d_get_kernel(const dgb_elliptic2d* plan, int with_dot, int* kernel);
 /* test hook, host only: the work partition the warp-walker kernel would use (tasks_out: column, first row, end row per piece) */
@@ -408,6 +415,9 @@ typedef struct dgb_comm dgb_comm;
 DGB_API int dgb_comm_unique_id(char* id128);                 /* ncclGetUniqueId on rank 0; ship the 128 bytes to the others */
 DGB_API int dgb_comm_create(dgb_comm** comm, const char* id128, int rank, int nranks);
 DGB_API int dgb_comm_destroy(dgb_comm* comm);
+/* *peer_memory = 1 if the data plane of this communicator is CUDA-IPC peer memory (dot records and halo rows stored straight
+ * into the peers' buffers over NVLink), 0 if it is NCCL (ncclSend/Recv halo, ncclAllReduce of the int64 records) */
+DGB_API int dgb_comm_info(const dgb_comm* comm, int* rank, int* size, int* peer_memory);
 /* halo exchange of `ghost_rows` rows with the lower/upper neighbour; buffer layout [ghost | nrows | ghost], `interior`
  * points to the first interior row; periodic closes the ring (mpi_gather_kron.h global_gather_init/wait) */
 DGB_API int dgb_comm_halo_rows(dgb_comm* comm, double* interior, size_t row_len, size_t nrows, size_t ghost_rows,

@@ -371,3 +371,42 @@ def test_vdot_is_the_exact_dot_with_a_scalar_operand(G):
     got = blas2.dot(1., G.make(x))
     import math
     assert got == math.fsum(x)
+
+
+# ------------------------------------------------------------------------------------------------ CooSparseBlockMat
+class _Coo(__import__("ctypes").Structure):
+    import ctypes as _C
+    _fields_ = [("num_rows", _C.c_int), ("num_cols", _C.c_int), ("num_entries", _C.c_int), ("n", _C.c_int),
+                ("left_size", _C.c_int), ("right_size", _C.c_int), ("data", _C.c_void_p), ("rows_idx", _C.c_void_p),
+                ("cols_idx", _C.c_void_p), ("data_idx", _C.c_void_p)]
+
+
+@pytest.mark.parametrize("n,left,right,rows,chunks,entries", [(3, 1, 1, 7, 2, 5), (3, 4, 24, 12, 3, 9), (2, 5, 1, 9, 1, 4),
+                                                              (4, 1, 30, 6, 4, 11), (5, 3, 7, 5, 2, 6), (3, 64, 9, 20, 2, 0)])
+def test_coo_symv_vs_oracle(G, n, left, right, rows, chunks, entries):
+    """dgb_coo_symv == CooSparseBlockMat::symv (sparseblockmat_omp_kernels.h:354-380): the outer (communicating) part of
+    MPISparseBlockMat -- entries hit the same row repeatedly, x is a table of chunk pointers laid out [q][s][j]; bit-exact"""
+    import ctypes as C
+    import torch
+    import feltor_b200 as fb
+    from feltor_b200._dev import ptr, stream
+    r = rng(n * 100 + left + entries)
+    nblocks = 3
+    data = r.uniform(-1, 1, nblocks * n * n)
+    rows_idx = r.integers(0, rows, entries).astype(np.int32)
+    cols_idx = r.integers(0, chunks, entries).astype(np.int32)
+    data_idx = r.integers(0, nblocks, entries).astype(np.int32)
+    xs = [r.uniform(-1, 1, n * left * right) for _ in range(chunks)]
+    y0 = r.uniform(-1, 1, left * rows * n * right)
+    yo = y0.copy()
+    orc.coo_symv([rows, chunks, entries, n, left, right], data, rows_idx, cols_idx, data_idx, -0.7, xs, yo)
+    d_data, d_y = G.make(data), G.make(y0)
+    d_rows, d_cols, d_didx = (torch.from_numpy(a).cuda() for a in (rows_idx, cols_idx, data_idx))
+    d_xs = [G.make(x) for x in xs]
+    table = torch.tensor([t.data_ptr() for t in d_xs], dtype=torch.int64, device="cuda")
+    m = _Coo(rows, chunks, entries, n, left, right, d_data.data_ptr(), d_rows.data_ptr(), d_cols.data_ptr(), d_didx.data_ptr())
+    fb.lib().coo_symv(C.byref(m), C.c_double(-0.7), ptr(table), C.c_double(1.), ptr(d_y), stream())
+    assert same_bits(G.get(d_y), yo)
+    if entries:
+        with pytest.raises(fb.DgbError):     # beta != 1 is rejected like the reference's assert (sparseblockmat.h:324)
+            fb.lib().coo_symv(C.byref(m), C.c_double(1.), ptr(table), C.c_double(0.), ptr(d_y), stream())
