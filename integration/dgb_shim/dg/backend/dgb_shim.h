@@ -45,6 +45,13 @@ inline void note_generic( const char* what)
     if( trace_enabled()) std::fprintf( stderr, "[dgb shim] generic %s <%s>\n", what, typeid(F).name());
 }
 inline void note_library() { counters().library++; }
+// run-time switch of the second binding level (dgb_fused.h): 1 = Elliptic2d / PCG use the fused kernels (default),
+// 0 = only the backend dispatch is bound (DGB_SHIM_NO_FUSION=1 or fusion_flag() = 0) -- for A/B tests
+inline int& fusion_flag()
+{
+    static int f = [](){ const char* e = std::getenv( "DGB_SHIM_NO_FUSION"); return (e && std::atoi( e)) ? 0 : 1; }();
+    return f;
+}
 
 // persistent-style launch geometry for the generic templates: enough CTAs to fill the machine, never more than needed
 inline unsigned generic_grid( size_t size, unsigned threads = 256)

@@ -32,10 +32,98 @@ def edit(path, old, new, count=1):
     open(path, "w").write(s)
 
 
+def fusion_hooks(out):
+    """4. second level (integration/dgb_shim/dg/backend/dgb_fused.h): dg::Elliptic2d::symv and dg::PCG::solve reach the fused
+    kernels.  Each hook is a prologue of a few lines guarded by `if constexpr` on device double vectors; when the operator is
+    outside the fused kernels' scope the hook returns false and the reference's own code runs, so every other instantiation
+    (host vectors, MPI vectors, other value types, curvilinear grids) compiles and behaves as before."""
+    ell = os.path.join(out, "dg", "elliptic.h")
+    edit(ell, '#include "topology/geometry.h"', '#include "topology/geometry.h"\n#include "backend/dgb_fused.h" // libdgb200 binding: fused Elliptic2d')
+    # (a) Elliptic2d: plan cache member + accessor (the FIRST "m_chi_weight_jump;\n};" after "class Elliptic2d" closes that class)
+    s = open(ell).read()
+    k = s.index("class Elliptic2d")
+    member = "    value_type m_jfactor;\n    bool m_chi_weight_jump;\n};"
+    j = s.index(member, k)
+    s = (s[:j] + "    value_type m_jfactor;\n    bool m_chi_weight_jump;\n"
+         "    mutable dgb::shim::EllipticPlanCache m_dgb; //!< libdgb200 fused-kernel plan (built on first use, dropped on copy)\n"
+         "    public:\n"
+         "    /// libdgb200 binding: the fused-kernel plan of this operator or nullptr if it is outside the kernels' scope\n"
+         "    dgb_elliptic2d* dgb_plan() const {\n"
+         "        if constexpr( dgb::shim::is_device_dvec<Container>::value && std::is_same_v<dg::get_value_type<Matrix>, double>)\n"
+         "            return dgb::shim::elliptic2d_plan( m_dgb, m_leftx, m_lefty, m_rightx, m_righty, m_jumpX, m_jumpY, m_sigma, m_vol, m_chi, m_jfactor, m_chi_weight_jump);\n"
+         "        else return nullptr;\n"
+         "    }\n"
+         "};" + s[j + len(member):])
+    # (b) symv prologue of Elliptic2d (first occurrence of the 4-argument symv after the class head)
+    head = ("    void symv( value_type alpha, const ContainerType0& x, value_type beta, ContainerType1& y)\n    {\n"
+            "        //compute gradient\n        dg::blas2::gemv( m_rightx, x, m_tempx); //R_x*f\n        dg::blas2::gemv( m_righty, x, m_tempy); //R_y*f\n")
+    j = s.index(head, k)
+    hook = ("    void symv( value_type alpha, const ContainerType0& x, value_type beta, ContainerType1& y)\n    {\n"
+            "        if constexpr( dgb::shim::all_device_dvec<Container, ContainerType0, ContainerType1>::value)\n"
+            "        {   // libdgb200 binding: the whole operator in one kernel\n"
+            "            if( dgb_elliptic2d* plan = dgb_plan())\n"
+            "            {\n"
+            "                dgb::shim::check( dgb_elliptic2d_symv( plan, alpha, dgb::shim::cptr(x), beta, dgb::shim::mptr(y), nullptr), \"dg::Elliptic2d::symv\");\n"
+            "                dgb::shim::note_library();\n"
+            "                return;\n"
+            "            }\n"
+            "        }\n"
+            "        //compute gradient\n        dg::blas2::gemv( m_rightx, x, m_tempx); //R_x*f\n        dg::blas2::gemv( m_righty, x, m_tempy); //R_y*f\n")
+    s = s[:j] + hook + s[j + len(head):]
+    # (c) a new tensor invalidates the plan (the assignment may reuse the old storage)
+    old = "        m_chi = SparseTensor<Container>(tau);\n"
+    j = s.index(old, k)
+    s = s[:j] + old + "        m_dgb.forget();\n" + s[j + len(old):]
+    open(ell, "w").write(s)
+    # (d) GeneralHelmholtz: the plan of the wrapped operator in Helmholtz mode (chi x - alpha A x in the kernel epilogue)
+    hh = os.path.join(out, "dg", "helmholtz.h")
+    edit(hh, "    const Container& chi() const{return m_chi;}\n    private:\n    value_type m_alpha;\n    Matrix m_matrix;\n    Container m_chi;\n",
+         "    const Container& chi() const{return m_chi;}\n"
+         "    /// libdgb200 binding: plan of the wrapped operator switched to y = chi x - alpha A x, or nullptr\n"
+         "    dgb_elliptic2d* dgb_plan() const {\n"
+         "        if constexpr( dgb::shim::has_dgb_plan<const Matrix>::value && dgb::shim::is_device_dvec<Container>::value) {\n"
+         "            if( m_alpha == 0) return nullptr;\n"
+         "            dgb_elliptic2d* plan = m_matrix.dgb_plan();\n"
+         "            if( plan) dgb::shim::check( dgb_elliptic2d_set_helmholtz( plan, 1, m_alpha, dgb::shim::cptr( m_chi)), \"dgb_elliptic2d_set_helmholtz\");\n"
+         "            return plan;\n"
+         "        }\n"
+         "        else return nullptr;\n"
+         "    }\n"
+         "    private:\n    value_type m_alpha;\n    Matrix m_matrix;\n    Container m_chi;\n")
+    edit(hh, "        if( m_alpha != 0)\n            blas2::symv( m_matrix, x, y);\n",
+         "        if constexpr( dgb::shim::all_device_dvec<Container, ContainerType0, ContainerType1>::value)\n"
+         "        {   // libdgb200 binding: operator and chi x - alpha y epilogue in one kernel\n"
+         "            if( dgb::shim::cptr(x) != dgb::shim::cptr(y))\n"
+         "            if( dgb_elliptic2d* plan = dgb_plan())\n"
+         "            {\n"
+         "                dgb::shim::check( dgb_elliptic2d_symv( plan, 1., dgb::shim::cptr(x), 0., dgb::shim::mptr(y), nullptr), \"dg::GeneralHelmholtz::symv\");\n"
+         "                dgb::shim::note_library();\n"
+         "                return;\n"
+         "            }\n"
+         "        }\n"
+         "        if( m_alpha != 0)\n            blas2::symv( m_matrix, x, y);\n")
+    # (e) PCG::solve
+    pcg = os.path.join(out, "dg", "pcg.h")
+    edit(pcg, '#include "blas.h"', '#include "blas.h"\n#include "backend/dgb_fused.h" // libdgb200 binding: fused PCG')
+    edit(pcg, "    unsigned max_iter;\n    bool m_verbose = false, m_throw_on_fail = true;\n};",
+         "    unsigned max_iter;\n    bool m_verbose = false, m_throw_on_fail = true;\n"
+         "    dgb::shim::PcgCache m_dgb; //!< libdgb200 solver workspace (created on first fused solve)\n};")
+    edit(pcg, "    // self-adjoint: apply PCG algorithm to (P 1/W) (W A) x = (P 1/W) (W b) : P' A' x = P' b'\n",
+         "    if constexpr( dgb::shim::has_dgb_plan<std::remove_reference_t<Matrix>>::value &&\n"
+         "                  dgb::shim::all_device_dvec<ContainerType, ContainerType0, ContainerType1, std::remove_reference_t<Preconditioner>, ContainerType2>::value)\n"
+         "    {   // libdgb200 binding: the whole solve in the library (3 kernels per iteration, scalars on the device)\n"
+         "        unsigned its = 0;\n"
+         "        if( !m_verbose && dgb::shim::pcg_solve( m_dgb, A, x, b, P, W, eps, nrmb_correction, save_on_dots, max_iter, m_throw_on_fail, its))\n"
+         "            return its;\n"
+         "    }\n"
+         "    // self-adjoint: apply PCG algorithm to (P 1/W) (W A) x = (P 1/W) (W b) : P' A' x = P' b'\n")
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--reference", default="/root/reference")
     ap.add_argument("--out", default=os.path.join(HERE, "_build", "inc"))
+    ap.add_argument("--no-fusion", action="store_true", help="backend files only: leave elliptic.h / helmholtz.h / pcg.h untouched")
     a = ap.parse_args()
     src = os.path.join(a.reference, "inc")
     if not os.path.isdir(src):
@@ -70,6 +158,8 @@ def main():
     s = (s[:beg] + "#if THRUST_DEVICE_SYSTEM==THRUST_DEVICE_SYSTEM_CUDA\n" + ns_close +
          '#include "dgb_parallel_for.cuh" // libdgb200 binding: doParallelFor_dispatch( CudaTag, ...)\n' + ns_open + s[end:])
     open(st, "w").write(s)
+    if not a.no_fusion:
+        fusion_hooks(a.out)
     print("make_tree.py: wrote", a.out)
 
 

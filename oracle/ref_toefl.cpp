@@ -31,6 +31,12 @@ struct RefToefl {
         : p(pp), grid(0, pp.lx, 0., pp.ly, pp.n, pp.Nx, pp.Ny, pp.bcx, pp.bcy), rhs(grid, pp), flr(f) {}
 };
 
+// device backend: the timed regions end when the device has finished
+static void device_sync() {
+#if THRUST_DEVICE_SYSTEM == THRUST_DEVICE_SYSTEM_CUDA
+    cudaDeviceSynchronize();
+#endif
+}
 static void in2(const double* a, const double* b, size_t n, Vec2& y) {
     y[0].assign(a, a + n);
     y[1].assign(b, b + n);
@@ -69,6 +75,7 @@ double ref_toefl_rhs(void* hh, double t, const double* y0, const double* y1, dou
     yp = y;
     auto t0 = std::chrono::steady_clock::now();
     h->rhs(t, y, yp);
+    device_sync();
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     out2(yp, yp0, yp1);
     return sec;
@@ -92,6 +99,7 @@ double ref_toefl_erk(void* hh, const char* tableau, double t0, double dt, int ns
         t = t1;
         y.swap(y1v);
     }
+    device_sync();
     double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - c0).count();
     out2(y, y0, y1);
     return sec;
@@ -131,6 +139,14 @@ void ref_toefl_multistep(void* hh, const char* tableau, double t0, double dt, in
         if (ts) ts[k] = t;
     }
     out2(y, y0, y1);
+}
+// device backend: switch the fused Elliptic2d / PCG hooks of the binding on or off (integration/dgb_shim/dg/backend/dgb_fused.h)
+void ref_set_fusion(int on) {
+#if THRUST_DEVICE_SYSTEM == THRUST_DEVICE_SYSTEM_CUDA
+    dgb::shim::fusion_flag() = on ? 1 : 0;
+#else
+    (void)on;
+#endif
 }
 // how many dispatches of this library went to libdgb200.so entry points / to generic kernel templates (device backend only)
 void ref_dispatch_counters(long long* library, long long* generic) {

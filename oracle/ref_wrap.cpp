@@ -68,6 +68,14 @@ int ref_get_max_threads() { return omp_get_max_threads(); }
 void ref_set_num_threads(int) {}
 int ref_get_max_threads() { return 1; }
 #endif
+// device backend: switch the fused Elliptic2d / PCG hooks of the binding on or off (integration/dgb_shim/dg/backend/dgb_fused.h)
+void ref_set_fusion(int on) {
+#if THRUST_DEVICE_SYSTEM == THRUST_DEVICE_SYSTEM_CUDA
+    dgb::shim::fusion_flag() = on ? 1 : 0;
+#else
+    (void)on;
+#endif
+}
 // how many dispatches of this library went to libdgb200.so entry points / to generic kernel templates (device backend only)
 void ref_dispatch_counters(long long* library, long long* generic) {
 #if THRUST_DEVICE_SYSTEM == THRUST_DEVICE_SYSTEM_CUDA
