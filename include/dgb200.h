@@ -310,6 +310,25 @@ DGB_API int dgb_gather_ds_centered(const dgb_gather_plan* plus, const dgb_gather
                                    const double* f, const double* bphi, double delta_phi, double beta, double* g,
                                    dgb_stream_t s);
 
+/* Cell-tiled layout for the matrices dg::geo::Fieldaligned actually builds (inc/geometries/fieldaligned.h:631-657, projection *
+ * interpolation): the n^2 rows of one target cell share ONE column list (the nodes of the 2..6 source cells its field lines end
+ * in), i.e. the matrix is a dense n^2 x U block per target cell.  The plan keeps that block and 16-bit indices into a
+ * shared-memory staging buffer; a thread owns one target cell and two planes, so every gathered operand feeds 2 n^2 FMAs
+ * instead of one (feltor_b200/csrc/celltile.cu).  n, Nx, Ny: polynomial order and cells of the perpendicular grid
+ * (num_rows = n^2 Nx Ny, x fastest).  A CSR matrix without that structure -> DGB_ERR_UNSUPPORTED (use dgb_gather_plan_*).
+ * Results are bitwise those of dgb_csr_spmv_planes / dgb_gather_* (column order of the CSR rows). */
+typedef struct dgb_celltile_plan dgb_celltile_plan;
+DGB_API int dgb_celltile_plan_create(dgb_celltile_plan** plan, int n, int Nx, int Ny, const int* row_offsets_dev, const int* cols_dev,
+                                     const double* vals_dev, dgb_stream_t s);
+DGB_API int dgb_celltile_plan_destroy(dgb_celltile_plan* plan);
+DGB_API int dgb_celltile_plan_info(const dgb_celltile_plan* plan, int* ntiles, int* max_source_cells, int* planes_per_cta, long long* nnz);
+/* y[pl] = alpha M x[(pl + shift) mod nplanes] + beta y[pl]; alpha = +-1, beta != 1 (the cases Fieldaligned::ePlus/eMinus use) */
+DGB_API int dgb_celltile_spmv_planes(const dgb_celltile_plan* plan, double alpha, const double* x, double beta, double* y, int nplanes,
+                                     int shift, dgb_stream_t s);
+/* DS::centered(alpha, f, beta, g) (ds.h:481-485), periodic z, ONE launch: both gathers and the formula */
+DGB_API int dgb_celltile_ds_centered(const dgb_celltile_plan* plus, const dgb_celltile_plan* minus, int nplanes, double alpha,
+                                     const double* f, const double* bphi, double delta_phi, double beta, double* g, dgb_stream_t s);
+
 /* ---------------------------------------------------------------------------------------------------
  * Fused Elliptic2d: replaces the 8-kernel composition of Elliptic2d::symv inc/dg/elliptic.h:428-458
  *   y = alpha/vol * [ -Lx sigma (chi_xx Rx + chi_xy Ry) x - Ly sigma (chi_yx Rx + chi_yy Ry) x

@@ -201,3 +201,109 @@ def test_gather_plan_equals_csr_kernels(G, n, nz, maxlen):
         assert same_bits(G.get(a), G.get(b)), beta
     lib().gather_plan_destroy(hp)
     lib().gather_plan_destroy(hm)
+
+
+# ------------------------------------------------------------------------------------------------ cell-tiled layout
+def _fieldaligned_like_matrix(r, n, Nx, Ny, max_shift=3):
+    """CSR matrix with the structure of Fieldaligned's I+ / I-: all n^2 rows of a target cell couple to all nodes of the same
+    2..5 source cells (smoothly displaced, clipped at the boundary), columns ascending"""
+    rowlen = Nx * n
+    pos, idx, val = [0], [], []
+    rows = {}
+    for cy in range(Ny):
+        for cx in range(Nx):
+            sx = int(np.clip(cx + round(max_shift * np.sin(0.3 * cy + 0.1 * cx)), 0, Nx - 2))
+            sy = int(np.clip(cy + round(max_shift * np.cos(0.2 * cx)), 0, Ny - 2))
+            cells = {(sy, sx), (sy, sx + 1), (sy + 1, sx), (sy + 1, sx + 1)}
+            k = r.integers(0, 3)
+            if k == 1 and sx + 2 < Nx:
+                cells.add((sy, sx + 2))
+            if k == 2:
+                cells = {(sy, sx), (sy, sx + 1)}
+            cols = sorted((py * n + ky) * rowlen + px * n + kx for (py, px) in cells for ky in range(n) for kx in range(n))
+            for ky in range(n):
+                for kx in range(n):
+                    rows[(cy * n + ky) * rowlen + cx * n + kx] = (cols, r.uniform(-1, 1, len(cols)))
+    for i in range(n * n * Nx * Ny):
+        c, v = rows[i]
+        idx.extend(c)
+        val.extend(v.tolist())
+        pos.append(len(idx))
+    return np.array(pos, dtype=np.int32), np.array(idx, dtype=np.int32), np.array(val)
+
+
+@pytest.mark.parametrize("n,Nx,Ny,nz", [(3, 40, 12, 20), (2, 33, 9, 5), (3, 96, 7, 16), (4, 20, 6, 3)])
+def test_celltile_plan_equals_csr_kernels(G, n, Nx, Ny, nz):
+    """the cell-tiled layout (dgb_celltile_*) == the CSR kernels bit for bit: all-planes SpMV and the fused DS::centered; ragged
+    strips (Nx not a multiple of 32), plane counts that are not multiples of the planes per CTA, n = 2, 3, 4"""
+    import ctypes as C
+    import torch
+    from feltor_b200._lib import lib
+    from feltor_b200._dev import ptr, stream
+    r = rng(n * 10 + Nx)
+    P, M = _fieldaligned_like_matrix(r, n, Nx, Ny), _fieldaligned_like_matrix(r, n, Nx, Ny, 2)
+    rows = n * n * Nx * Ny
+    f = r.uniform(-1, 1, rows * nz)
+    df, bphi = G.make(f), G.make(r.uniform(0.5, 1.5, rows * nz))
+    dP = [torch.from_numpy(a).cuda() for a in P]
+    dM = [torch.from_numpy(a).cuda() for a in M]
+    hp, hm = C.c_void_p(), C.c_void_p()
+    lib().celltile_plan_create(C.byref(hp), n, Nx, Ny, ptr(dP[0]), ptr(dP[1]), ptr(dP[2]), stream())
+    lib().celltile_plan_create(C.byref(hm), n, Nx, Ny, ptr(dM[0]), ptr(dM[1]), ptr(dM[2]), stream())
+    for alpha, beta, shift in ((1., 0., 1), (-1., 0., -1), (1., 0.5, 0), (1., 0., nz + 2)):
+        y0 = r.uniform(-1, 1, rows * nz)
+        a, b = G.make(y0), G.make(y0)
+        lib().csr_spmv_planes(rows, rows, ptr(dP[0]), ptr(dP[1]), ptr(dP[2]), C.c_double(alpha), ptr(df), C.c_double(beta), ptr(a), nz, shift, stream())
+        lib().celltile_spmv_planes(hp, C.c_double(alpha), ptr(df), C.c_double(beta), ptr(b), nz, shift, stream())
+        assert same_bits(G.get(a), G.get(b)), (alpha, beta, shift)
+    for beta in (0., 2.):
+        y0 = r.uniform(-1, 1, rows * nz)
+        a, b = G.make(y0), G.make(y0)
+        lib().ds_centered_fused(rows, nz, ptr(dP[0]), ptr(dP[1]), ptr(dP[2]), ptr(dM[0]), ptr(dM[1]), ptr(dM[2]), C.c_double(0.7), ptr(df),
+                                ptr(bphi), C.c_double(0.1), C.c_double(beta), ptr(a), stream())
+        lib().celltile_ds_centered(hp, hm, nz, C.c_double(0.7), ptr(df), ptr(bphi), C.c_double(0.1), C.c_double(beta), ptr(b), stream())
+        assert same_bits(G.get(a), G.get(b)), beta
+    lib().celltile_plan_destroy(hp)
+    lib().celltile_plan_destroy(hm)
+    # a matrix without the cell structure is refused (the gather plan takes it)
+    import feltor_b200 as fb
+    bad = P[1].copy()
+    bad[0] = (bad[0] + 1) % rows
+    dbad = torch.from_numpy(bad).cuda()
+    with pytest.raises(fb.DgbError):
+        lib().celltile_plan_create(C.byref(hp), n, Nx, Ny, ptr(dP[0]), ptr(dbad), ptr(dP[2]), stream())
+
+
+def test_celltile_ds_centered_on_reference_fieldaligned(G):
+    """REAL field-line matrices: the unmodified dg::geo::Fieldaligned (circular field of inc/geometries/ds_b.cpp, built live in
+    oracle/_ref/libdgref_fa.so) hands out I+ / I- and bphi; DS::centered on the cell-tiled plan == the gather plan bitwise and ==
+    the reference's ds.centered to 1e-13 (the reference's compiler contracts the formula, tests/test_ds_oracle.py)"""
+    import ctypes as C
+    import torch
+    from feltor_b200._lib import lib
+    from feltor_b200._dev import ptr, stream
+    from oracle import reffa
+    if not reffa.available():
+        pytest.skip("oracle/_ref/libdgref_fa.so not present")
+    n, Nx, Ny, Nz = 3, 24, 20, 12
+    F = reffa.RefFieldaligned(n, Nx, Ny, Nz, 6, 6, "dg")
+    f = F.testfunction()
+    gref, _ = F.ds("centered", 0.8, f, 0., np.zeros(F.size))
+    P, M = F.csr("plus"), F.csr("minus")
+    dP = [torch.from_numpy(a).cuda() for a in P]
+    dM = [torch.from_numpy(a).cuda() for a in M]
+    df, bphi = G.make(f), G.make(F.field("bphi"))
+    hp, hm, gp, gm = C.c_void_p(), C.c_void_p(), C.c_void_p(), C.c_void_p()
+    lib().celltile_plan_create(C.byref(hp), n, Nx, Ny, ptr(dP[0]), ptr(dP[1]), ptr(dP[2]), stream())
+    lib().celltile_plan_create(C.byref(hm), n, Nx, Ny, ptr(dM[0]), ptr(dM[1]), ptr(dM[2]), stream())
+    lib().gather_plan_create(C.byref(gp), F.plane, F.plane, ptr(dP[0]), ptr(dP[1]), ptr(dP[2]), stream())
+    lib().gather_plan_create(C.byref(gm), F.plane, F.plane, ptr(dM[0]), ptr(dM[1]), ptr(dM[2]), stream())
+    a, b = G.make(np.zeros(F.size)), G.make(np.zeros(F.size))
+    lib().celltile_ds_centered(hp, hm, Nz, C.c_double(0.8), ptr(df), ptr(bphi), C.c_double(F.delta_phi), C.c_double(0.), ptr(a), stream())
+    lib().gather_ds_centered(gp, gm, Nz, C.c_double(0.8), ptr(df), ptr(bphi), C.c_double(F.delta_phi), C.c_double(0.), ptr(b), stream())
+    assert same_bits(G.get(a), G.get(b))
+    assert np.abs(G.get(a) - gref).max() <= 1e-13 * np.abs(gref).max()
+    for h in (hp, hm):
+        lib().celltile_plan_destroy(h)
+    for h in (gp, gm):
+        lib().gather_plan_destroy(h)

@@ -104,12 +104,71 @@ def run(cells=96, planes=64, reps=30, kinds=(("dg", 2), ("cubic", 3))):
     return out
 
 
+def run_real(cells=96, planes=64, reps=30, methods=("dg",), mx=10, my=10, cpu_reps=2):
+    """config 4 on the REAL matrices: dg::geo::Fieldaligned of the unmodified reference (circular field of ds_b.cpp:70-84) is
+    built on the host through oracle/_ref/libdgref_fa.so (test infrastructure; about a minute at 96 x 96), its I+ / I- and bphi
+    feed the library's three layouts; the reference's own ds.centered (OpenMP) is timed beside them and checks the result."""
+    from oracle import reffa
+    if not reffa.available():
+        return None
+    L = fb.lib()
+    out = []
+    for method in methods:
+        F = reffa.RefFieldaligned(n, cells, cells, planes, mx, my, method)
+        rows, size, Nz = F.plane, F.size, planes
+        fh = F.testfunction()
+        gref, cpu_sec = F.ds("centered", 1., fh, 0., np.zeros(size), reps=cpu_reps)
+        P = [torch.from_numpy(a).cuda() for a in F.csr("plus")]
+        M = [torch.from_numpy(a).cuda() for a in F.csr("minus")]
+        f, bphi = dvec(fh), dvec(F.field("bphi"))
+        g, g2, g3 = (torch.zeros(size, dtype=torch.float64, device="cuda") for _ in range(3))
+        nnz = P[1].numel()
+        alg = 24 * size + 2 * nnz * 12
+        dphi = F.delta_phi
+        t_csr = timeit(lambda: L.ds_centered_fused(rows, Nz, ptr(P[0]), ptr(P[1]), ptr(P[2]), ptr(M[0]), ptr(M[1]), ptr(M[2]), C.c_double(1.),
+                                                   ptr(f), ptr(bphi), C.c_double(dphi), C.c_double(0.), ptr(g), stream()), reps)
+        hp, hm = C.c_void_p(), C.c_void_p()
+        L.gather_plan_create(C.byref(hp), rows, rows, ptr(P[0]), ptr(P[1]), ptr(P[2]), stream())
+        L.gather_plan_create(C.byref(hm), rows, rows, ptr(M[0]), ptr(M[1]), ptr(M[2]), stream())
+        t_plan = timeit(lambda: L.gather_ds_centered(hp, hm, Nz, C.c_double(1.), ptr(f), ptr(bphi), C.c_double(dphi), C.c_double(0.), ptr(g2), stream()), reps)
+        L.gather_plan_destroy(hp); L.gather_plan_destroy(hm)
+        rec = {"method": method, "matrices": "dg::geo::Fieldaligned of the reference, circular field R0=10 I0=20 (ds_b.cpp:70-84), mx=my=%d" % mx,
+               "entries_per_row": nnz / rows, "elements": size, "algorithmic_bytes": alg, "cells": cells, "planes": Nz,
+               "csr_fused_us": t_csr * 1e6, "gather_plan_us": t_plan * 1e6, "gather_plan_gbs": alg / t_plan / 1e9,
+               "bitwise_plan_equals_csr": bool((g.view(torch.int64) == g2.view(torch.int64)).all()),
+               "reference_openmp_ms": cpu_sec * 1e3, "reference_threads": F.threads()}
+        cp, cm = C.c_void_p(), C.c_void_p()
+        try:
+            L.celltile_plan_create(C.byref(cp), n, cells, cells, ptr(P[0]), ptr(P[1]), ptr(P[2]), stream())
+            L.celltile_plan_create(C.byref(cm), n, cells, cells, ptr(M[0]), ptr(M[1]), ptr(M[2]), stream())
+            t_ct = timeit(lambda: L.celltile_ds_centered(cp, cm, Nz, C.c_double(1.), ptr(f), ptr(bphi), C.c_double(dphi), C.c_double(0.), ptr(g3), stream()), reps)
+            info = [C.c_int(), C.c_int(), C.c_int(), C.c_longlong()]
+            L.celltile_plan_info(cp, *[C.byref(v) for v in info])
+            rec.update({"celltile_us": t_ct * 1e6, "celltile_gbs": alg / t_ct / 1e9, "celltile_frac_of_peak": alg / t_ct / 1e9 / peak(),
+                        "bitwise_celltile_equals_csr": bool((g.view(torch.int64) == g3.view(torch.int64)).all()),
+                        "celltile_tiles": info[0].value, "celltile_max_source_cells": info[1].value, "celltile_planes_per_cta": info[2].value})
+            L.celltile_plan_destroy(cp); L.celltile_plan_destroy(cm)
+        except fb.DgbError as e:
+            rec["celltile"] = "unsupported: %s" % e
+        gh = g2.cpu().numpy()
+        rec["max_rel_diff_vs_reference_ds_centered"] = float(np.abs(gh - gref).max() / np.abs(gref).max())
+        out.append(rec)
+        del F
+    return out
+
+
 if __name__ == "__main__":
     ap = argparse.ArgumentParser()
     ap.add_argument("--cells", type=int, default=96)
     ap.add_argument("--planes", type=int, default=64)
     ap.add_argument("--reps", type=int, default=30)
+    ap.add_argument("--real", action="store_true", help="the reference's own Fieldaligned matrices (oracle/_ref/libdgref_fa.so)")
+    ap.add_argument("--methods", default="dg")
     a = ap.parse_args()
+    if a.real:
+        for rec in run_real(a.cells, a.planes, a.reps, tuple(a.methods.split(","))) or [{"real": "oracle/_ref/libdgref_fa.so not present"}]:
+            print(json.dumps(rec), flush=True)
+        sys.exit(0)
     PEAK = peak()
     rows = run(a.cells, a.planes, a.reps)
     print(f"# DS centered, n=3 {a.cells}x{a.cells}x{a.planes}: {rows[0]['elements']} elements, L2 flushed between calls")
