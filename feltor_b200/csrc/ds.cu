@@ -137,6 +137,63 @@ static unsigned ew_grid(size_t n) {
     return (unsigned)(want < cap ? want : cap);
 }
 
+// assign_bc_along_field_2nd / _1st and swap_bc_perp (ds.h:169-330): ghost values of the minus / plus neighbours where the field
+// line leaves the domain.  The reference's functors are user lambdas; the expressions below are theirs, evaluated left to
+// right with separately rounded operations (the library is compiled with -fmad=false).  fmg may alias fm, fpg may alias fp.
+template <int ORDER, bool NEU>
+__global__ void __launch_bounds__(256)
+assign_bc_kernel(size_t n, double delta, const double* fm_, const double* __restrict__ f_, const double* fp_,
+                 const double* __restrict__ hbm_, const double* __restrict__ hbp_, const double* __restrict__ bbm_,
+                 const double* __restrict__ bbo_, const double* __restrict__ bbp_, double bv0, double bv1, double* fmg, double* fpg) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double fm = fm_[i], fp = fp_[i], fo = ORDER == 2 ? f_[i] : 0., hm = delta, hp = delta;
+        const double bbm = bbm_[i], bbp = bbp_[i];
+        double plus, minus, bothP = 0., bothM = 0.;
+        if (ORDER == 1 && NEU) {  // ds.h:247-258
+            const double dbm = bv0, dbp = bv1;
+            plus = fm + dbp * (hp + hm);
+            minus = fp - dbm * (hp + hm);
+            fmg[i] = (1. - bbm) * fm + bbm * minus;
+            fpg[i] = (1. - bbp) * fp + bbp * plus;
+            continue;
+        }
+        const double hbm = hbm_[i], hbp = hbp_[i], bbo = bbo_[i];
+        if (ORDER == 2 && NEU) {  // ds.h:178-200
+            const double dbm = bv0, dbp = bv1;
+            plus = dbp * hp * (hm + hp) / (2. * hbp + hm) + fo * (2. * hbp + hm - hp) * (hm + hp) / hm / (2. * hbp + hm) +
+                   fm * hp * (-2. * hbp + hp) / hm / (2. * hbp + hm);
+            minus = fp * hm * (-2. * hbm + hm) / hp / (2. * hbm + hp) - dbm * hm * (hm + hp) / (2. * hbm + hp) +
+                    fo * (2. * hbm - hm + hp) * (hm + hp) / hp / (2. * hbm + hp);
+            bothM = fo + dbp * hm * (-2. * hbm + hm) / 2. / (hbm + hbp) - dbm * hm * (2. * hbp + hm) / 2. / (hbm + hbp);
+            bothP = fo + dbp * hp * (2. * hbm + hp) / 2. / (hbm + hbp) + dbm * hp * (2. * hbp - hp) / 2. / (hbm + hbp);
+        } else if (ORDER == 2) {  // ds.h:204-225
+            const double fbm = bv0, fbp = bv1;
+            plus = fm * hp * (-hbp + hp) / hm / (hbp + hm) + fo * (hbp - hp) * (hm + hp) / hbp / hm + fbp * hp * (hm + hp) / hbp / (hbp + hm);
+            minus = +fo * (hbm - hm) * (hm + hp) / hbm / hp + fbm * hm * (hm + hp) / hbm / (hbm + hp) + fp * hm * (-hbm + hm) / hp / (hbm + hp);
+            bothM = fbp * hm * (-hbm + hm) / hbp / (hbm + hbp) + fo * (hbm - hm) * (hbp + hm) / hbm / hbp + fbm * hm * (hbp + hm) / hbm / (hbm + hbp);
+            bothP = fo * (hbp - hp) * (hbm + hp) / hbm / hbp + fbp * hp * (hbm + hp) / hbp / (hbm + hbp) + fbm * hp * (-hbp + hp) / hbm / (hbm + hbp);
+        } else {  // ORDER == 1, DIR: ds.h:262-277
+            const double fbm = bv0, fbp = bv1;
+            plus = fm + (fbp - fm) / (hbp + hm) * (hp + hm);
+            minus = fp - (hp + hm) * (fp - fbm) / (hp + hbm);
+            bothM = fbp + (fbp - fbm) / (hbp + hbm) * (hp + hbm);
+            bothP = fbp - (fbp - fbm) / (hbp + hbm) * (hbp + hm);
+        }
+        fmg[i] = (1. - bbo - bbm) * fm + bbm * minus + bbo * bothM;
+        fpg[i] = (1. - bbo - bbp) * fp + bbp * plus + bbo * bothP;
+    }
+}
+// swap_bc_perp (ds.h:307-318): the values outside the box change sign
+__global__ void __launch_bounds__(256)
+swap_bc_perp_kernel(size_t n, const double* fm_, const double* fp_, const double* __restrict__ bbm_, const double* __restrict__ bbo_,
+                    const double* __restrict__ bbp_, double* fmg, double* fpg) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const double fm = fm_[i], fp = fp_[i], bbm = bbm_[i], bbo = bbo_[i], bbp = bbp_[i];
+        fmg[i] = (1. - bbo - bbm) * fm + (bbm + bbo) * (-fm);
+        fpg[i] = (1. - bbo - bbp) * fp + (bbp + bbo) * (-fp);
+    }
+}
+
 }  // namespace dgb
 
 using namespace dgb;
@@ -206,6 +263,36 @@ int dgb_fa_shift(int plus, int num_rows, int nplanes, const int* pos, const int*
     if (e) return e;
     if ((e = dgb_axpby(n, -1., ti, 1., ghost, s))) return e;       // ghost = 1*ghost - 1*temp  (axpby(1,ghost,-1,temp,ghost))
     return dgb_pointwise_dot(n, 1., limiter, ghost, 1., ti, s);    // temp += limiter * ghost
+}
+
+int dgb_assign_bc_along_field(int order, int bc, size_t n, double delta_phi, const double* fm, const double* f, const double* fp,
+                              const double* hbm, const double* hbp, const double* bbm, const double* bbo, const double* bbp, double bv_minus,
+                              double bv_plus, double* fmg, double* fpg, dgb_stream_t s) {
+    if (order != 1 && order != 2) { set_error("dgb_assign_bc_along_field: order must be 1 or 2"); return DGB_ERR_INVALID; }
+    if (bc != DGB_NEU && bc != DGB_DIR) { set_error("dgb_assign_bc_along_field: only dg::NEU and dg::DIR exist (ds.h:173,201)"); return DGB_ERR_UNSUPPORTED; }
+    const bool neu = bc == DGB_NEU;
+    if (!fm || !fp || !fmg || !fpg || !bbm || !bbp || (order == 2 && !f) || (!(order == 1 && neu) && (!hbm || !hbp || !bbo))) {
+        set_error("dgb_assign_bc_along_field: missing operand");
+        return DGB_ERR_INVALID;
+    }
+    if (n == 0) return 0;
+    size_t want = (n + 255) / 256, cap = (size_t)sm_count() * 8;
+    const unsigned grid = (unsigned)(want < cap ? want : cap);
+    cudaStream_t st = as_stream(s);
+    if (order == 2 && neu) assign_bc_kernel<2, true><<<grid, 256, 0, st>>>(n, delta_phi, fm, f, fp, hbm, hbp, bbm, bbo, bbp, bv_minus, bv_plus, fmg, fpg);
+    else if (order == 2) assign_bc_kernel<2, false><<<grid, 256, 0, st>>>(n, delta_phi, fm, f, fp, hbm, hbp, bbm, bbo, bbp, bv_minus, bv_plus, fmg, fpg);
+    else if (neu) assign_bc_kernel<1, true><<<grid, 256, 0, st>>>(n, delta_phi, fm, f, fp, hbm, hbp, bbm, bbo, bbp, bv_minus, bv_plus, fmg, fpg);
+    else assign_bc_kernel<1, false><<<grid, 256, 0, st>>>(n, delta_phi, fm, f, fp, hbm, hbp, bbm, bbo, bbp, bv_minus, bv_plus, fmg, fpg);
+    DGB_LAUNCHED();
+    return 0;
+}
+int dgb_swap_bc_perp(size_t n, const double* fm, const double* fp, const double* bbm, const double* bbo, const double* bbp, double* fmg,
+                     double* fpg, dgb_stream_t s) {
+    if (n == 0) return 0;
+    size_t want = (n + 255) / 256, cap = (size_t)sm_count() * 8;
+    swap_bc_perp_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(s)>>>(n, fm, fp, bbm, bbo, bbp, fmg, fpg);
+    DGB_LAUNCHED();
+    return 0;
 }
 
 // DS::centered(alpha, f, beta, g) for periodic z in one launch (ds.h:481-485)

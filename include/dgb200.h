@@ -289,6 +289,15 @@ DGB_API int dgb_ds_apply_vol(int kind, size_t n, double alpha, const double* a, 
                              const double* sqrtG_m, const double* sqrtG, const double* sqrtG_p, const double* bphi_m,
                              const double* bphi, const double* bphi_p, double delta_phi, double beta, double* g,
                              dgb_stream_t s);
+/* assign_bc_along_field_2nd (order = 2; fm, f, fp) / _1st (order = 1; fm, fp, f unused) (ds.h:169-296): ghost values fmg / fpg of
+ * the shifted fields where the field line leaves the domain.  bc = DGB_NEU (boundary values = derivatives) or DGB_DIR (values);
+ * bv_minus / bv_plus = boundary_value[0] / [1]; hbm, hbp, bbm, bbo, bbp = the fields of the Fieldaligned object (the first-order
+ * Neumann form needs only bbm, bbp).  fmg may alias fm, fpg may alias fp.  dgb_swap_bc_perp: swap_bc_perp (ds.h:307-318). */
+DGB_API int dgb_assign_bc_along_field(int order, int bc, size_t n, double delta_phi, const double* fm, const double* f, const double* fp,
+                                      const double* hbm, const double* hbp, const double* bbm, const double* bbo, const double* bbp,
+                                      double bv_minus, double bv_plus, double* fmg, double* fpg, dgb_stream_t s);
+DGB_API int dgb_swap_bc_perp(size_t n, const double* fm, const double* fp, const double* bbm, const double* bbo, const double* bbp,
+                             double* fmg, double* fpg, dgb_stream_t s);
 /* DS::centered(alpha, f, beta, g) (ds.h:481-485) for periodic z fused into one kernel (gather f+, f-, formula) */
 DGB_API int dgb_ds_centered_fused(int num_rows, int nplanes, const int* plus_pos, const int* plus_idx,
                                   const double* plus_val, const int* minus_pos, const int* minus_idx,

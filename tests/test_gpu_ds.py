@@ -2,6 +2,7 @@
 numpy/oracle restatement of inc/geometries/fieldaligned.h:850-912 and ds.h:744-852 (the CSR part bitwise, the
 user-lambda formulas to 1e-14 relative), plus fused DS::centered == its composition bit for bit."""
 import ctypes as C
+import os
 import numpy as np
 import pytest
 from oracle import orc
@@ -307,3 +308,35 @@ def test_celltile_ds_centered_on_reference_fieldaligned(G):
         lib().celltile_plan_destroy(h)
     for h in (gp, gm):
         lib().gather_plan_destroy(h)
+
+
+# ------------------------------------------------------------------------------------------------ boundary conditions along the field
+@pytest.mark.parametrize("order", [1, 2])
+@pytest.mark.parametrize("bound", [4, 1])
+def test_assign_bc_along_field_vs_oracle_and_fixture(G, order, bound):
+    """dgb_assign_bc_along_field == the oracle restatement bitwise (same left-to-right arithmetic) and == the fixtures of the
+    unmodified reference functions (ds.h:169-296, user lambdas) to 1e-13; aliasing fmg = fm, fpg = fp as DS uses it"""
+    import ctypes as C
+    from feltor_b200._lib import lib
+    from feltor_b200._dev import ptr, stream
+    gold = np.load(os.path.join(os.path.dirname(__file__), "golden", "ds_golden.npz"))
+    k = {n: gold["bc/" + n] for n in ("fm", "f", "fp", "hbm", "hbp", "bbm", "bbo", "bbp")}
+    n = k["fm"].size
+    delta = 2 * np.pi / 7
+    fmo, fpo = np.full(n, np.nan), np.full(n, np.nan)
+    orc.assign_bc_along_field(order, bound == 4, delta, k["fm"], k["f"] if order == 2 else None, k["fp"], k["hbm"], k["hbp"], k["bbm"],
+                              k["bbo"], k["bbp"], (0.3, -0.2), fmo, fpo)
+    d = {key: G.make(v) for key, v in k.items()}
+    fmg, fpg = G.make(k["fm"]), G.make(k["fp"])   # in place
+    lib().assign_bc_along_field(order, bound, n, C.c_double(delta), ptr(fmg), ptr(d["f"]), ptr(fpg), ptr(d["hbm"]), ptr(d["hbp"]),
+                                ptr(d["bbm"]), ptr(d["bbo"]), ptr(d["bbp"]), C.c_double(0.3), C.c_double(-0.2), ptr(fmg), ptr(fpg), stream())
+    assert same_bits(G.get(fmg), fmo) and same_bits(G.get(fpg), fpo)
+    for got, name in ((G.get(fmg), "fmg"), (G.get(fpg), "fpg")):
+        ref = gold[f"bc/order{order}/bound{bound}/{name}"]
+        assert np.abs(got - ref).max() <= 1e-13 * max(np.abs(ref).max(), 1.)
+    # swap_bc_perp: values outside the box change sign
+    sm, sp = G.make(np.zeros(n)), G.make(np.zeros(n))
+    lib().swap_bc_perp(n, ptr(d["fm"]), ptr(d["fp"]), ptr(d["bbm"]), ptr(d["bbo"]), ptr(d["bbp"]), ptr(sm), ptr(sp), stream())
+    em = (1. - k["bbo"] - k["bbm"]) * k["fm"] + (k["bbm"] + k["bbo"]) * (-k["fm"])
+    ep = (1. - k["bbo"] - k["bbp"]) * k["fp"] + (k["bbp"] + k["bbo"]) * (-k["fp"])
+    assert same_bits(G.get(sm), em) and same_bits(G.get(sp), ep)
