@@ -10,8 +10,9 @@
  *    is what the reference uses everywhere) and returns asynchronously, except the functions documented
  *    as synchronous (they return host data, like the reference's dot).
  *  - Return value: 0 = success, otherwise a DGB_ERR_* code or a cudaError_t value (>0);
- *    dgb_last_error() returns a thread-local message.  Nothing throws across the boundary; the C++ shim
- *    (include/dg/backend/b200_dispatch.h) converts non-zero codes into dg::Error like blas1_cuda.cuh:39-41.
+ *    dgb_last_error() returns a thread-local message.  Nothing throws across the boundary; the reference-side binding
+ *    (integration/dgb_shim/dg/backend/dgb_shim.h, dgb::shim::check) converts non-zero codes into dg::Error like
+ *    blas1_cuda.cuh:39-41 does, and DGB_ERR_NOCONVERGE into dg::Fail.
  *  - Like the reference (static scratch buffers in blas1_cuda.cuh:18,33,50) the library is host-thread-affine:
  *    one host thread per device context.  Workspaces are explicit handles so several may coexist.
  *  - There is NO CPU fallback: every compute entry point fails with a CUDA error when no sm_100 device is present.
