@@ -10,9 +10,11 @@ size).  metric = PCG iterations per second (whole job).
   value   device-resident inputs, timed with CUDA events on the launching stream
   e2e     the same solve through the C-ABI entry point with HOST buffers: b and x0 copied host->device from
           pinned memory and x copied back inside the timed region, every step
-  roofline  the kernel the north star names = the fused Elliptic apply + dot(p,W,Ap) kernel (K1): algorithmic 32 B/dof
-          (read p, sigma, W; write Ap) / its live CUDA-event duration, against MEASURED_PEAKS.json; the streaming update
-          kernel K2 (72 B/dof, the larger time share) is listed beside it under roofline_other_kernels
+  roofline  the kernel the north star names = the fused Elliptic apply + dot(p,W,Ap) kernel (K1).  With the PCG direction
+          update folded into its loader (the default on the walker kernel, dgb_pcg_last_folded) it reads z, the old
+          direction, sigma, W and writes the new direction and Ap: algorithmic 48 B/dof (32 B/dof for the classic
+          three-kernel iteration) / its live CUDA-event duration, against MEASURED_PEAKS.json; the streaming update
+          kernel K2 (72 B/dof) is listed beside it under roofline_other_kernels
   micro     config 1 (and the same kernels at the benchmark size): axpby, pointwiseDot, dot, dx/dy, Elliptic apply in GB/s
   toefl     config 3 on one GPU: steps/s of the toefl right-hand side + Bogacki-Shampine step (N = 1 only)
   cpu_baseline  the reference's own OpenMP implementation (oracle/_ref/libdgref.so) on the host cores, bounded sample
@@ -349,6 +351,9 @@ def main():
     pn = C.c_longlong()
     L.pcg_get_profile(pr.pcg.h, C.byref(prof[0]), C.byref(prof[1]), C.byref(prof[2]), C.byref(pn))
     L.pcg_set_profile(pr.pcg.h, 0)
+    folded = C.c_int(0)
+    L.pcg_last_folded(pr.pcg.h, C.byref(folded))
+    folded = bool(folded.value)
     pr.solve_e2e()
     ms_e2e, its_e2e = timed(pr.solve_e2e, args.steps)
     ndof = pr.ndof
@@ -374,15 +379,18 @@ def main():
     peak, peak_kind = peaks()
     k1_ms = prof[0].value / max(pn.value, 1)
     k2_ms = prof[1].value / max(pn.value, 1)
-    # algorithmic bytes per launch: K1 = fused Elliptic apply + dot: read p, sigma, W, write Ap = 32 B/dof;
-    # K2 = update + two dots: read p, Ap, x, r, P, W, write x, r, z = 72 B/dof
+    # algorithmic bytes per launch: K1 = fused Elliptic apply + dot: read p, sigma, W, write Ap = 32 B/dof,
+    # with the folded direction update read z, p_old, sigma, W, write p_new, Ap = 48 B/dof;
+    # K2 = update + two dots: read p, Ap, x, r, P, W, write x, r, z = 72 B/dof; K3 (classic iteration only) 24 B/dof
     try:
         tr = json.load(open(os.path.join(ROOT, "profiles", "roofline_traffic.json")))
     except Exception:
         tr = {}
     kernels = [
-        {"kernel": "elliptic2d_walker_kernel<3,fwd,dot> (Elliptic apply + dot(p,W,Ap))", "bytes_per_launch": 32 * ndof, "ms_per_launch": k1_ms,
-         "traffic": tr.get("elliptic2d_fused_dot_bytes_per_launch")},
+        {"kernel": ("elliptic2d_walker_kernel<3,fwd,dot,fold> (p = z + beta p in the loader, Elliptic apply, dot(p,W,Ap))" if folded else
+                    "elliptic2d_walker_kernel<3,fwd,dot> (Elliptic apply + dot(p,W,Ap))"),
+         "bytes_per_launch": (48 if folded else 32) * ndof, "ms_per_launch": k1_ms,
+         "traffic": tr.get("elliptic2d_fold_dot_bytes_per_launch" if folded else "elliptic2d_fused_dot_bytes_per_launch")},
         {"kernel": "pcg_update_kernel (x, r, z = P r updates + dot(r,W,r), dot(z,W,r))", "bytes_per_launch": 72 * ndof, "ms_per_launch": k2_ms,
          "traffic": tr.get("pcg_update_bytes_per_launch")},
     ]
@@ -395,7 +403,7 @@ def main():
     if world == 1:
         par = "single GPU"
     else:
-        plane = ("CUDA-IPC peer memory over NVLink: K3 stores the halo rows into the neighbours' ghost rows, the 39-word int64 dot "
+        plane = ("CUDA-IPC peer memory over NVLink: the update kernel stores the boundary rows of z = P r into the neighbours' ghost rows, the 39-word int64 dot "
                  "records are exchanged by peer stores + polling (NCCL only ships the IPC handles)") if comm.peer_memory else \
                 "NCCL: grouped ncclSend/ncclRecv of the ghost rows, ncclAllReduce(int64) of the dot records"
         par = "y-slabs x%d of a global grid of %dx%d cells; %s" % (world, cells, cells if strong else cells * world, plane)
@@ -417,7 +425,8 @@ def main():
                                                          "share_of_iteration")} for k in kernels if k is not named],
         "kernels_ms_per_iteration": {"apply_dot": k1_ms, "update_dots": prof[1].value / max(pn.value, 1),
                                      "direction": prof[2].value / max(pn.value, 1)},
-        "pcg_gbs_at_128B_per_dof": 128 * ndof * (its / (ms * 1e-3)) / world / 1e9,
+        "pcg_iteration": {"launches": 2 if folded else 3, "algorithmic_bytes_per_dof": 120 if folded else 128,
+                          "gbs": (120 if folded else 128) * ndof * (its / (ms * 1e-3)) / world / 1e9},
     }
     if strong_rec is not None:
         out["strong_scaling"] = strong_rec

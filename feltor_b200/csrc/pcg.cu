@@ -5,6 +5,9 @@
 //   K2  x += alpha p; r -= alpha ap; z = P r -> ap; dot(r,W,r) and dot(z,W,r) in the same pass;
 //       its last blocks test ||r||_W < tol and compute beta = nrmzr_new / nrmzr_old               (pcg.h:167-181)
 //   K3  p = z + beta p                                                                             (pcg.h:182)
+// When the operator runs on the walker kernel with TMA operands, K3 disappears: from the second iteration on K1 reads z and
+// the old direction, forms the new direction in its shared-memory ring (same Axpby arithmetic), applies the operator to it
+// and writes it to the other direction buffer -- two launches and 120 B/dof per iteration (DGB_PCG_NO_FOLD=1 switches back).
 // All scalars live in a PcgState record on the device.  The host enqueues batches of iterations and reads the
 // record once per batch; after convergence the remaining launches of a batch exit at their first instruction, so
 // x, r and the iteration count are exactly those of the reference's loop exit.
@@ -29,6 +32,14 @@ struct Pcg {
     void* p_peers[P2P_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
     Comm* p_peers_comm = nullptr;
     bool p_mapped = false;
+    // folded direction update (K3 inside K1's loader, elliptic_walker.cuh FOLD): the direction ping-pongs between p and p2,
+    // z = P r gets its own buffer (K1 overwrites ap while neighbouring strips still read z); both laid out like p
+    double *p2_base = nullptr, *p2 = nullptr, *z_base = nullptr, *z = nullptr;
+    size_t fold_cap = 0;
+    void* z_peers[P2P_MAX_RANKS] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+    Comm* z_peers_comm = nullptr;
+    bool z_mapped = false;
+    bool last_folded = false;
     PcgState* st = nullptr;       // device
     PcgState* st_host = nullptr;  // pinned
     sa::DotSlot slot;             // 4 slots: 0 pAp, 1 rWr, 2 zWr, 3 setup dots
@@ -79,9 +90,12 @@ pcg_dot3_kernel(size_t n, const double* __restrict__ x, const double* __restrict
 // per SM); otherwise the kernel relies on occupancy (BPS CTAs per SM).
 template <bool CHECK, bool PREFETCH, int BPS, bool P2P>  // P2P: the finishing block exchanges the dots over peer memory
 __global__ void __launch_bounds__(PCG_THREADS, BPS)
-pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ ap, double* __restrict__ x,
+pcg_update_kernel(size_t n, const double* __restrict__ p, const double* ap, double* __restrict__ x,
                   double* __restrict__ r, const double* __restrict__ P, const double* __restrict__ W, PcgState* st,
-                  sa::DotSlot slot, int iter, P2pView peer, unsigned long long epoch) {
+                  sa::DotSlot slot, int iter, P2pView peer, unsigned long long epoch, double* zout, double* rem_lo,
+                  double* rem_up, size_t gcnt) {
+    // zout: where z = P r goes -- the ap buffer itself (classic three-kernel iteration) or the z buffer of the folded
+    // iteration, whose bottom / top rows are ALSO stored into the neighbours' ghost rows (rem_lo / rem_up, peer memory)
     __shared__ long long smem[2 * sa::BINS];  // one accumulator per dot and block: [0] rr (slot 1), [1] zr (slot 2)
     if (st->done) return;
     const double alpha = st->alpha, malpha = -alpha;
@@ -115,7 +129,9 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
         double2 z = make_double2(__dmul_rn(Pv.x, rv.x), __dmul_rn(Pv.y, rv.y));  // symv(P, r, ap) == P*r
         st2(x + 2 * i, xv);
         st2(r + 2 * i, rv);
-        st2(ap + 2 * i, z);
+        st2(zout + 2 * i, z);
+        if (rem_lo && 2 * i < gcnt) st2(rem_lo + 2 * i, z);
+        if (rem_up && 2 * i >= n - gcnt) st2(rem_up + (2 * i - (n - gcnt)), z);
         double ra0 = 0., ra1 = 0.;
         if (CHECK) {
             double a0 = __dmul_rn(__dmul_rn(rv.x, Wv.x), rv.x), a1 = __dmul_rn(__dmul_rn(rv.y, Wv.y), rv.y);
@@ -140,7 +156,7 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, double* __restrict__ a
         double xs = __fma_rn(alpha, p[i], __dmul_rn(x[i], 1.));
         double rs = __fma_rn(malpha, ap[i], __dmul_rn(r[i], 1.));
         double z = __dmul_rn(P[i], rs);
-        x[i] = xs; r[i] = rs; ap[i] = z;
+        x[i] = xs; r[i] = rs; zout[i] = z;
         if (CHECK) {
             double a0 = __dmul_rn(__dmul_rn(rs, W[i]), rs);
             if (!isfinite(a0)) { bad = 1; a0 = 0.; }
@@ -379,6 +395,41 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
     const bool fused = A.fusable && identity_chi && !A.chi_weight_jump && (dist || !getenv("DGB_ELLIPTIC_UNFUSED")) &&
                        (dist || A.kernel_mode != DGB_ELLIPTIC_KERNEL_UNFUSED) &&
                        (!A.helm || A.helm_alpha != 0.);
+    // ---- folded direction update: buffers (and, multi-GPU, the peer mapping of z)
+    bool fold = fused && !getenv("DGB_PCG_NO_FOLD") && elliptic2d_walker_fold_possible(A, W) && n % 2 == 0 &&
+                true;
+    double *zrem_lo = nullptr, *zrem_up = nullptr;
+    if (fold) {
+        if (s.fold_cap < n + 2 * gh) {
+            if (s.z_mapped) { comm_p2p_unmap(s.z_peers_comm, s.z_peers); s.z_mapped = false; }
+            cudaFree(s.p2_base); cudaFree(s.z_base);
+            s.p2_base = s.z_base = nullptr;
+            s.fold_cap = 0;
+            DGB_CUDA(cudaMalloc(&s.p2_base, (n + 2 * gh) * sizeof(double)));
+            DGB_CUDA(cudaMalloc(&s.z_base, (n + 2 * gh) * sizeof(double)));
+            DGB_CUDA(cudaMemsetAsync(s.p2_base, 0, (n + 2 * gh) * sizeof(double), st));
+            DGB_CUDA(cudaMemsetAsync(s.z_base, 0, (n + 2 * gh) * sizeof(double), st));
+            s.fold_cap = n + 2 * gh;
+        }
+        s.p2 = s.p2_base + gh;
+        s.z = s.z_base + gh;
+        if (p2p_halo) {  // the same collective decision on every rank: p2p_halo is derived from agreed quantities
+            if (!s.z_mapped || s.z_peers_comm != comm) {
+                if (s.z_mapped) comm_p2p_unmap(s.z_peers_comm, s.z_peers);
+                DGB_CUDA(cudaStreamSynchronize(st));
+                int mapped = 0;
+                if ((e = comm_p2p_map(comm, s.z_base, s.z_peers, &mapped))) return e;
+                s.z_mapped = mapped != 0;
+                s.z_peers_comm = comm;
+            }
+            if (s.z_mapped) {
+                if (nb_lower >= 0) zrem_lo = reinterpret_cast<double*>(s.z_peers[nb_lower]) + gh + n;
+                if (nb_upper >= 0) zrem_up = reinterpret_cast<double*>(s.z_peers[nb_upper]);
+            }
+        }
+    }
+    s.last_folded = fold;
+    const bool z_by_peer = fold && p2p_halo && s.z_mapped;
     const P2pView pview = comm_p2p_view(comm);
     // The finishing block of K1/K2 can run the peer-memory exchange itself (one launch less per dot); measured at 2 GPUs this
     // is 3 % SLOWER than the separate 64-thread exchange kernel (the serial tail of a 300-CTA kernel gets longer), so it is
@@ -397,6 +448,7 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
         if (want == 0) want = 1;
         g3 = (unsigned)(want < cap ? want : cap);
     }
+    double *pcur = s.p, *palt = s.p2;  // folded iteration: direction of this / the next iteration
     int i = 1;
     while (i < max_iter) {
         // a batch ends where the host looks at the device state.  Convergence can only be raised by an iteration that
@@ -415,7 +467,10 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
             if (prof) cudaEventRecord(s.ev[s.prof_n][0], st);
             if (fused) {
                 if (p2p_dots) fd.epoch = comm_p2p_next_epoch(comm, 0, 1);
-                if ((e = elliptic2d_fused_launch_dot(A, s.p, s.ap, st, fd))) return e;
+                if (fold && i > 1) {
+                    if ((e = elliptic2d_walker_launch_fold(A, s.z, pcur, palt, s.ap, st, fd))) return e;
+                    std::swap(pcur, palt);
+                } else if ((e = elliptic2d_fused_launch_dot(A, pcur, s.ap, st, fd))) return e;
             } else {
                 if ((e = elliptic2d_symv(A, 1., s.p, 0., s.ap, st, false))) return e;
                 pcg_dot3_kernel<2><<<g1, PCG_THREADS, 0, st>>>(n, s.p, W, s.ap, s.slot, 0, s.st);
@@ -428,23 +483,28 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
             k2v.enabled = p2p_dots ? 1 : 0;
             const unsigned long long k2e = p2p_dots ? comm_p2p_next_epoch(comm, check ? 1 : 2, check ? 2 : 1) : 0ull;
             if (k2_variant == 0) {
-                if (check) DGB_K2(true, true, 2)<<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
-                else DGB_K2(false, true, 2)<<<g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
+                if (check) DGB_K2(true, true, 2)<<<g2, PCG_THREADS, 0, st>>>(n, pcur, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e, fold ? s.z : s.ap, z_by_peer ? zrem_lo : nullptr, z_by_peer ? zrem_up : nullptr, gh);
+                else DGB_K2(false, true, 2)<<<g2, PCG_THREADS, 0, st>>>(n, pcur, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e, fold ? s.z : s.ap, z_by_peer ? zrem_lo : nullptr, z_by_peer ? zrem_up : nullptr, gh);
             } else if (k2_variant == 1) {
-                if (check) DGB_K2(true, false, 4)<<<2 * g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
-                else DGB_K2(false, false, 4)<<<2 * g2, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
+                if (check) DGB_K2(true, false, 4)<<<2 * g2, PCG_THREADS, 0, st>>>(n, pcur, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e, fold ? s.z : s.ap, z_by_peer ? zrem_lo : nullptr, z_by_peer ? zrem_up : nullptr, gh);
+                else DGB_K2(false, false, 4)<<<2 * g2, PCG_THREADS, 0, st>>>(n, pcur, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e, fold ? s.z : s.ap, z_by_peer ? zrem_lo : nullptr, z_by_peer ? zrem_up : nullptr, gh);
             } else {
-                if (check) DGB_K2(true, false, 3)<<<g2 / 2 * 3, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
-                else DGB_K2(false, false, 3)<<<g2 / 2 * 3, PCG_THREADS, 0, st>>>(n, s.p, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e);
+                if (check) DGB_K2(true, false, 3)<<<g2 / 2 * 3, PCG_THREADS, 0, st>>>(n, pcur, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e, fold ? s.z : s.ap, z_by_peer ? zrem_lo : nullptr, z_by_peer ? zrem_up : nullptr, gh);
+                else DGB_K2(false, false, 3)<<<g2 / 2 * 3, PCG_THREADS, 0, st>>>(n, pcur, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e, fold ? s.z : s.ap, z_by_peer ? zrem_lo : nullptr, z_by_peer ? zrem_up : nullptr, gh);
             }
 #undef DGB_K2
             DGB_LAUNCHED();
             if (dist && !p2p_dots && (e = dist_finish<3>(s, comm, check ? 1 : 2, check ? 2 : 1, i, check, st))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n][2], st);
-            pcg_direction_kernel<<<g3, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st, rem_lo, rem_up, gh);
-            DGB_LAUNCHED();
-            if (p2p_halo) { if ((e = comm_p2p_neighbour_barrier(comm, nb_lower, nb_upper, st))) return e; }
-            else if ((e = halo(s.p))) return e;
+            if (fold) {  // the next K1 forms the direction itself; it needs the neighbours' boundary rows of z
+                if (z_by_peer) { if ((e = comm_p2p_neighbour_barrier(comm, nb_lower, nb_upper, st))) return e; }
+                else if ((e = halo(s.z))) return e;
+            } else {
+                pcg_direction_kernel<<<g3, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st, rem_lo, rem_up, gh);
+                DGB_LAUNCHED();
+                if (p2p_halo) { if ((e = comm_p2p_neighbour_barrier(comm, nb_lower, nb_upper, st))) return e; }
+                else if ((e = halo(s.p))) return e;
+            }
             if (prof) cudaEventRecord(s.ev[s.prof_n++][3], st);
         }
         if ((e = fetch_state(s, st))) return e;
@@ -512,6 +572,8 @@ void pcg_delete(Pcg* s) {
         for (int k = 0; k < Pcg::PROF_MAX; k++)
             for (int j = 0; j < 4; j++) cudaEventDestroy(s->ev[k][j]);
     if (s->p_mapped) comm_p2p_unmap(s->p_peers_comm, s->p_peers);
+    if (s->z_mapped) comm_p2p_unmap(s->z_peers_comm, s->z_peers);
+    cudaFree(s->p2_base); cudaFree(s->z_base);
     cudaFree(s->r); cudaFree(s->p_base); cudaFree(s->ap); cudaFree(s->st); cudaFreeHost(s->st_host);
     cudaFree(s->slot.gacc); cudaFree(s->slot.gstatus); cudaFree(s->slot.ticket);
     cudaFree(s->results); cudaFreeHost(s->results_host);
@@ -549,6 +611,11 @@ int dgb_pcg_get_profile(dgb_pcg* h, double* ms_apply_dot, double* ms_update, dou
     if (ms_update) *ms_update = s->prof_ms[1];
     if (ms_direction) *ms_direction = s->prof_ms[2];
     if (iterations) *iterations = s->prof_count;
+    return 0;
+}
+int dgb_pcg_last_folded(dgb_pcg* h, int* folded) {
+    if (!h || !folded) { set_error("dgb_pcg_last_folded: NULL argument"); return DGB_ERR_INVALID; }
+    *folded = reinterpret_cast<Pcg*>(h)->last_folded ? 1 : 0;
     return 0;
 }
 int dgb_pcg_destroy(dgb_pcg* h) {

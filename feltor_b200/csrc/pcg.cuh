@@ -70,5 +70,10 @@ __device__ inline void fused_dot_finish(bool last, PcgState* st, dgb_dot_result*
 
 struct Elliptic2dPlan;
 int elliptic2d_fused_launch_dot(Elliptic2dPlan& p, const double* x, double* y, cudaStream_t st, const FusedDot& fd);
+// PCG iteration with the direction update folded into the operator kernel (elliptic_walker_fold.cu): possible when the plan
+// runs on the walker kernel and every operand is TMA-describable (no periodic seam in x, 16-byte aligned rows)
+bool elliptic2d_walker_fold_possible(const Elliptic2dPlan& p, const double* w);
+int elliptic2d_walker_launch_fold(Elliptic2dPlan& p, const double* z, const double* p_old, double* p_new, double* ap, cudaStream_t st,
+                                  const FusedDot& fd);
 
 }  // namespace dgb

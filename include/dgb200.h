@@ -468,6 +468,10 @@ DGB_API int dgb_pcg_solve_elliptic2d_dist(dgb_pcg* pcg, dgb_comm* comm, dgb_elli
 DGB_API int dgb_pcg_set_profile(dgb_pcg* pcg, int on);
 DGB_API int dgb_pcg_get_profile(dgb_pcg* pcg, double* ms_apply_dot, double* ms_update, double* ms_direction,
                                 long long* iterations);
+/* *folded = 1 if the last solve on this workspace ran the two-kernel iteration: the direction update p = z + beta p
+ * (pcg.h:182) formed inside the operator kernel's loader (walker kernel, TMA operands) instead of a third launch;
+ * the arithmetic and the results are the same either way.  DGB_PCG_NO_FOLD=1 in the environment forces three kernels. */
+DGB_API int dgb_pcg_last_folded(dgb_pcg* pcg, int* folded);
 
 #ifdef __cplusplus
 }

@@ -281,3 +281,73 @@ def test_walker_relaxed_ordering_within_tolerance(G, n, N, bcx, bcy, d):
     it = pcg.solve(E, xs, G.make(b), E.precond(), E.weights(), 1e-7, 1.0, 1)
     assert 0 < ito < 5000 and abs(it - ito) <= max(5, ito // 20)
     assert np.linalg.norm(G.get(xs) - xo) <= 1e-5 * np.linalg.norm(xo)
+
+
+FOLD_CASES = [(3, [40, 24], 1, 0, 0, 1, False), (3, [40, 33], 4, 1, 2, 1, False), (2, [61, 33], 2, 3, 1, 3, False),
+              (3, [62, 45], 3, 2, 2, 1, True), (2, [36, 30], 1, 0, 0, 1, True), (3, [34, 70], 1, 4, 1, 10, False)]
+
+
+@pytest.mark.parametrize("n,N,bcx,bcy,d,tf,helm", FOLD_CASES)
+def test_walker_pcg_folded_direction_update(G, monkeypatch, n, N, bcx, bcy, d, tf, helm):
+    """PCG with the direction update p = z + beta p folded into the loader of the walker kernel (two launches per iteration)
+    against the three-kernel iteration (DGB_PCG_NO_FOLD=1) and the oracle: same iteration count, same bits, fewer launches"""
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic2d, PCG
+    from feltor_b200.toefl import Helmholtz
+    from feltor_b200._lib import lib
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], n, N, [bcx, bcy])
+    chi = g.evaluate(lambda x, y: 1. + 0.9 * np.sin(x) * np.sin(y))
+    b = g.evaluate(lambda x, y: np.sin(x) * np.sin(y) * (1 + np.cos(3 * y)))
+    if bcx == 4 and bcy in (0, 4):
+        b = g.evaluate(lambda x, y: np.cos(x) * np.sin(y))
+    res = {}
+    for mode in ("fold", "nofold"):
+        if mode == "nofold":
+            monkeypatch.setenv("DGB_PCG_NO_FOLD", "1")
+        else:
+            monkeypatch.delenv("DGB_PCG_NO_FOLD", raising=False)
+        E = walker(Elliptic2d(g, bcx, bcy, d, 1.0), with_dot=True)
+        E.set_chi(G.make(chi))
+        A = Helmholtz(-0.5, E) if helm else E
+        x = G.make(np.zeros(g.size))
+        pcg = PCG(g.size, 300)
+        pcg.set_throw_on_fail(False)
+        l0 = lib().raw["dgb_launch_count"]()
+        it = pcg.solve(A, x, G.make(b), A.precond(), A.weights(), 1e-9, 1.0, tf)
+        res[mode] = (it, G.get(x), lib().raw["dgb_launch_count"]() - l0)
+    assert res["fold"][0] == res["nofold"][0] and res["fold"][0] > 3
+    assert same_bits(res["fold"][1], res["nofold"][1])
+    assert res["fold"][2] < res["nofold"][2] - (res["fold"][0] - 3), "the folded iteration did not run"
+    if not helm:
+        O = oracle_elliptic(T, g, bcx, bcy, d, 1.0, chi)
+        xo = np.zeros(g.size)
+        ito = O.pcg_solve(xo, b, 1. / chi, g.weights(), 1e-9, 1.0, tf, max_iter=300)
+        assert ito == res["fold"][0] and same_bits(res["fold"][1], xo)
+
+
+@pytest.mark.parametrize("N,bcy,d", [([40, 24], 0, 0), ([38, 31], 1, 2), ([44, 26], 0, 1)])
+def test_walker_slab_pcg_folded(G, N, bcy, d):
+    """the folded iteration in slab mode (communicator of size 1: ghost rows of z and of both direction buffers, ring-closing
+    halo copy of z) against the plain single-GPU solve"""
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import Elliptic2d, PCG
+    from feltor_b200.dist import Comm, SlabElliptic2d, DistPCG
+    from feltor_b200._lib import lib
+    g = T.Grid([0, 0], [np.pi, 2 * np.pi], 3, N, [T.DIR, bcy])
+    chi = g.evaluate(lambda x, y: 1. + 0.9 * np.sin(x) * np.sin(y))
+    b = g.evaluate(lambda x, y: np.sin(x) * np.sin(y) * (1 + np.cos(3 * y)))
+    E = Elliptic2d(g, T.DIR, bcy, d, 1.0).set_kernel("tile")
+    E.set_chi(G.make(chi))
+    x = G.make(np.zeros(g.size))
+    it = PCG(g.size, g.size).solve(E, x, G.make(b), E.precond(), E.weights(), 1e-9, 1.0, 1)
+    comm = Comm(0, 1)
+    S = SlabElliptic2d(comm, g, T.DIR, bcy, d, 1.0)
+    lib().elliptic2d_set_kernel(S.h, 2)
+    S.set_chi(G.make(chi))
+    xs = G.make(np.zeros(g.size))
+    l0 = lib().raw["dgb_launch_count"]()
+    its = DistPCG(comm, g.size, g.size).solve(S, xs, G.make(b), S.precond(), S.weights(), 1e-9, 1.0, 1)
+    launches = lib().raw["dgb_launch_count"]() - l0
+    assert its == it and it > 5
+    assert same_bits(G.get(xs), G.get(x))
+    assert launches < 5 * its + 30, "expected K1 + scalar + K2 + scalar per iteration (no direction kernel)"
