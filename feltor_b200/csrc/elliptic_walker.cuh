@@ -43,6 +43,12 @@ constexpr bool WALK_WRING = DGB_WALK_WRING != 0;
 constexpr int WNOROW = -(1 << 30);
 // keeps the compiler from hoisting the next phase's shared-memory loads above this point (register pressure)
 #define DGB_PHASE_FENCE() asm volatile("" ::: "memory")
+#ifndef DGB_WALK_NOFENCE_DOT
+#define DGB_WALK_NOFENCE_DOT 0  // 1: the fused-dot variants (8 warps, 255 registers available) drop the phase fences
+#endif
+#ifndef DGB_WALK_FPE_PER_CELL
+#define DGB_WALK_FPE_PER_CELL 0  // 1: one expansion per nodal value of the cell instead of one per column (one-sided stencils)
+#endif
 
 struct WalkArgs {
     MatView rx, ry, lx, ly, jx, jy;
@@ -403,13 +409,15 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
     unsigned long long* bar = reinterpret_cast<unsigned long long*>(wb + L::BOFF);
     // N independent two-term expansions per lane: the fused dot rides in the FP64 pipe this kernel is bound by, so it
     // uses the short expansion and keeps the add cascades of one cell row independent of each other
-    sa::FpeT<2> fpe[N];
+    constexpr int NE = (DGB_WALK_FPE_PER_CELL && DIRK != 2) ? N * N : N;
+    sa::FpeT<2> fpe[NE];
+#define WPHASE() do { if (!(DGB_WALK_NOFENCE_DOT && DOT)) DGB_PHASE_FENCE(); } while (0)
     int bad = 0;
     if (DOT) {
         if (A.pcg->done) return;  // solver already converged: the remaining launches of the batch are no-ops
         sa::block_init<1>(dsm);
 #pragma unroll
-        for (int k = 0; k < N; k++) fpe[k].clear();
+        for (int k = 0; k < NE; k++) fpe[k].clear();
     }
     const double fbeta = FOLD ? A.pcg->beta : 0.;
     if (lane == 0) {
@@ -592,7 +600,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
 #pragma unroll
                     for (int b = 0; b < N; b++) gy[NGY - 1][a][b] = g[a][b];
             }
-            DGB_PHASE_FENCE();
+            WPHASE();
             if (emit) {
                 const double* x0 = xrow(iy);
                 // beta != 0 / curvilinear volume: the epilogue reads y / vol with lane-strided loads; pull the lines into L1
@@ -639,7 +647,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                             gxp[a][b] = LK != 1 ? shfl_down_d(gxv[a][b]) : 0.;
                         }
                 }
-                DGB_PHASE_FENCE();
+                WPHASE();
                 // ---- the cell's n x n outputs
 #pragma unroll
                 for (int a = 0; a < N; a++)
@@ -649,7 +657,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                     // acc = -(Ly GY) - (Lx GX) + jfactor ((Jx + Jy) x): one chain per output for the fluxes, one for the jumps
                     stencil_lines_relaxed<N, LK, true, -1>(C.ly, gy[LK == 0 ? 0 : -1 - LLO], gy[-LLO], gy[LK == 1 ? -LLO : 1 - LLO], acc);
                     stencil_lines_relaxed<N, LK, false, -1>(C.lx, gxm, gxv, gxp, acc);
-                    DGB_PHASE_FENCE();
+                    WPHASE();
                     if (A.jfactor != 0.) {
                         double accj[N][N];
 #pragma unroll
@@ -657,7 +665,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
 #pragma unroll
                             for (int b = 0; b < N; b++) accj[a][b] = 0.;
                         stencil_mem_relaxed<N, 2, RP, 1, false, 1>(C.jx, x0 + el, x0 + eo, x0 + er, accj);
-                        DGB_PHASE_FENCE();
+                        WPHASE();
                         stencil_mem_relaxed<N, 2, 1, RP, true, 1>(C.jy, xrow(iy - 1) + eo, x0 + eo, xrow(iy + 1) + eo, accj);
 #pragma unroll
                         for (int a = 0; a < N; a++)
@@ -675,18 +683,18 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                         for (int b = 0; b < N; b++) acc[a][b] = __dmul_rn(acc[a][b], -1.);
                     if (FAST) stencil_lines<N, LK, true, false>(A.lx, C.lx, 0, gxm, gxv, gxp, -1., acc);
                         else stencil_lines<N, LK, false, false>(A.lx, C.lx, gx, gxm, gxv, gxp, -1., acc);
-                    DGB_PHASE_FENCE();
+                    WPHASE();
                     if (A.jfactor != 0.) {
                         if (FAST) stencil_mem<N, 2, true, RP, 1, false>(A.jx, C.jx, 0, x0 + el, x0 + eo, x0 + er, A.jfactor, acc);
                         else stencil_mem<N, 2, false, RP, 1, false>(A.jx, C.jx, gx, x0 + el, x0 + eo, x0 + er, A.jfactor, acc);
-                        DGB_PHASE_FENCE();
+                        WPHASE();
                         const double* xd = xrow(iy - 1) + eo;
                         const double* xu = xrow(iy + 1) + eo;
                         if (FAST) stencil_mem<N, 2, true, 1, RP, true>(A.jy, C.jy, 0, xd, x0 + eo, xu, A.jfactor, acc);
                         else stencil_mem<N, 2, false, 1, RP, true>(A.jy, C.jy, ym, xd, x0 + eo, xu, A.jfactor, acc);
                     }
                 }
-                DGB_PHASE_FENCE();
+                WPHASE();
                 }
             };
             if (fast) stencils(std::true_type{});
@@ -765,7 +773,7 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
                             for (int kx = 0; kx < N; kx++) {
                                 double pr = __dmul_rn(__dmul_rn(XC[ky][kx], WV[ky][kx]), acc[ky][kx]);
                                 if (!isfinite(pr)) { bad = 1; pr = 0.; }
-                                res[ky][kx] = fpe[kx].add_lazy(pr);
+                                res[ky][kx] = fpe[NE == N ? kx : ky * N + kx].add_lazy(pr);
                                 spill = spill || res[ky][kx] != 0.;
                             }
                         if (spill) {  // rare: residues the expansions cannot hold go to the shared accumulator (exact)
@@ -808,7 +816,8 @@ elliptic2d_walker_kernel(const __grid_constant__ WalkArgs A, const __grid_consta
     if ((ALLTMA || A.tma_store) && lane == 0) bulk_wait<0>();
     if (DOT) {
 #pragma unroll
-        for (int k = 1; k < N; k++) fpe[0].merge(fpe[k], dsm);
+        for (int k = 1; k < NE; k++) fpe[0].merge(fpe[k], dsm);
+#undef WPHASE
         fpe[0].flush_warp(dsm);
         fused_dot_finish(sa::block_finish<1>(dsm, bad, A.slot, 0), A.pcg, A.slot.result, A.p2p, A.epoch);
     }

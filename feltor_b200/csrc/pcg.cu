@@ -497,7 +497,11 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
             if (dist && !p2p_dots && (e = dist_finish<3>(s, comm, check ? 1 : 2, check ? 2 : 1, i, check, st))) return e;
             if (prof) cudaEventRecord(s.ev[s.prof_n][2], st);
             if (fold) {  // the next K1 forms the direction itself; it needs the neighbours' boundary rows of z
-                if (z_by_peer) { if ((e = comm_p2p_neighbour_barrier(comm, nb_lower, nb_upper, st))) return e; }
+                // peer-memory dots: the all-to-all record exchange of pcg_scalar_kernel<3> (enqueued after K2 on every rank,
+                // returns only when every rank's record has arrived) already orders the neighbours' K2 -- and with it their
+                // stores into our ghost rows -- before our next K1: no separate neighbour barrier
+                if (z_by_peer && pview.enabled && !p2p_dots) {}
+                else if (z_by_peer) { if ((e = comm_p2p_neighbour_barrier(comm, nb_lower, nb_upper, st))) return e; }
                 else if ((e = halo(s.z))) return e;
             } else {
                 pcg_direction_kernel<<<g3, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st, rem_lo, rem_up, gh);

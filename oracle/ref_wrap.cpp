@@ -423,6 +423,32 @@ void ref_elliptic3d_symv(const RefGrid* g, int cylindrical, int dir, double jfac
     }
 }
 
+// The same class in its FULL 3-d mode (compute_in_2d = 0: the z derivative, the 3-d tensor product elliptic.h:693 and the
+// z jump term elliptic.h:730,743 take part) or restricted to the planes (compute_in_2d = 1).  variation != NULL additionally
+// returns Elliptic3d::variation(x) (elliptic.h:758-766).
+void ref_elliptic3d_symv_mode(const RefGrid* g, int cylindrical, int dir, double jfactor, int chi_weight_jump, int compute_in_2d,
+                              const double* chi, double alpha, const double* x, double beta, double* y, double* variation) {
+    auto run = [&](auto& e) {
+        size_t n = e.weights().size();
+        e.set_compute_in_2d(compute_in_2d != 0);
+        if (chi) { CView s(chi, n); e.set_chi(s); }
+        CView vx(x, n);
+        VView vy(y, n);
+        e.symv(alpha, vx, beta, vy);
+        if (variation) { DVec v(n); e.variation(vx, v); copy_out(v, variation); }
+    };
+    if (cylindrical) {
+        dg::CylindricalGrid3d grid(g->x0[0], g->x1[0], g->x0[1], g->x1[1], g->x0[2], g->x1[2], g->n[0], g->N[0], g->N[1], g->N[2],
+                                   (dg::bc)g->bc[0], (dg::bc)g->bc[1], (dg::bc)g->bc[2]);
+        dg::Elliptic3d<dg::CylindricalGrid3d, DMatrix, DVec> e(grid, (dg::direction)dir, jfactor, (bool)chi_weight_jump);
+        run(e);
+    } else {
+        dg::CartesianGrid3d grid = g3(g);
+        dg::Elliptic3d<dg::CartesianGrid3d, DMatrix, DVec> e(grid, (dg::direction)dir, jfactor, (bool)chi_weight_jump);
+        run(e);
+    }
+}
+
 // ---------------------------------------------------------------- PCG (inc/dg/pcg.h:136-195)
 // returns number of iterations (max_iter if not converged; throw_on_fail is disabled).
 // seconds (optional) receives the wall time of solve() only.

@@ -279,6 +279,18 @@ def elliptic3d_symv(g, cylindrical, direction, jfactor, chi_weight_jump, chi, al
     return out, w, p
 
 
+def elliptic3d_symv_mode(g, cylindrical, direction, jfactor, chi_weight_jump, compute_in_2d, chi, alpha, x, beta, y, variation=False):
+    """dg::Elliptic3d in its full 3-d mode (compute_in_2d False: elliptic.h:688-697,727-746) or restricted to the planes;
+    returns y, or (y, variation(x)) with variation=True"""
+    n = x.size
+    out = np.array(y, copy=True)
+    var = np.empty(n) if variation else None
+    lib().ref_elliptic3d_symv_mode(C.byref(g), int(cylindrical), int(direction), C.c_double(jfactor), int(chi_weight_jump),
+                                   int(compute_in_2d), dp(chi) if chi is not None else None, C.c_double(alpha),
+                                   dp(np.ascontiguousarray(x)), C.c_double(beta), dp(out), dp(var) if variation else None)
+    return (out, var) if variation else out
+
+
 def elliptic1d_symv(g, bcx, direction, jfactor, chi, alpha, x, beta, y):
     """dg::Elliptic1d (elliptic.h:65-200); g: RefGrid (ndim 1); returns (y, weights, precond)"""
     n = x.size

@@ -30,5 +30,13 @@ for bcx in range(5):
     for direction in (0, 1, 2):
         y, w, p = R.elliptic1d_symv(rg, bcx, direction, 0.7, out["chi1d"], -0.5, out["x1d"], 0.3, out["y1d"])
         out[f"e1d/bc{bcx}/dir{direction}/y"] = y
+# full 3-d mode (compute_in_2d = 0: z derivative + 3-d tensor product, elliptic.h:688-697) and the restricted one, same call
+Nf, nf = [9, 7, 5], 9 * 7 * 5 * 9
+out["x_full"], out["y0_full"], out["chi_full"] = r.uniform(-1, 1, nf), r.uniform(-1, 1, nf), r.uniform(0.5, 2., nf)
+for (cyl, direction, cwj, in2d) in [(0, 0, 0, 0), (1, 2, 0, 0), (0, 1, 1, 0), (1, 0, 1, 0), (1, 2, 1, 1), (0, 2, 0, 1)]:
+    x0, x1 = ([3., -1., 0.], [5., 1., 2 * np.pi]) if cyl else ([0., 0., 0.], [1., 2., 3.])
+    rg = R.grid(x0, x1, 3, Nf, [1, 4 if cyl else 0, 0])
+    out[f"e3dfull/cyl{cyl}/dir{direction}/cwj{cwj}/in2d{in2d}/y"] = R.elliptic3d_symv_mode(
+        rg, cyl, direction, 0.7, cwj, in2d, out["chi_full"], -0.5, out["x_full"], 0.3, out["y0_full"])
 np.savez_compressed(os.path.join(ROOT, "tests", "golden", "elliptic3d_golden.npz"), **out)
 print("wrote", len(out), "arrays")

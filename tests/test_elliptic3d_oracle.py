@@ -126,3 +126,59 @@ def test_elliptic1d_fixture(gold3, bcx):
         orc.ell_symv(left, 0.5, t, 0.3, y)
         orc.ell_symv(jump, 0.7 * -0.5, x, 1., y)
         assert same_bits(y, gold3[f"e1d/bc{bcx}/dir{direction}/y"]), (bcx, direction)
+
+
+# ------------------------------------------------------------------ full 3-d mode (z derivative, 3-d tensor product: elliptic.h:688-697)
+class _OrcBackend:
+    """dg-shaped primitives of the C oracle on numpy arrays (the GPU twin lives in tests/test_gpu_elliptic3d.py)"""
+
+    def __init__(self):
+        from backends import OracleBlas1
+        self.b = OracleBlas1()
+
+    def make(self, a): return np.array(a, dtype=np.float64, copy=True)
+    def symv(self, m, a, x, b, y): orc.ell_symv(m, a, x, b, y)
+    def tensor_multiply3d(self, lam, t, ins, mu, outs): orc.tensor_multiply3d(lam, t, list(ins), mu, list(outs))
+    def tensor_multiply2d(self, lam, t, i0, i1, mu, o0, o1): orc.tensor_multiply2d(lam, t, i0, i1, mu, o0, o1)
+    def pointwiseDot(self, *a): self.b.pointwiseDot(*a)
+    def pointwiseDivide(self, *a): self.b.pointwiseDivide(*a)
+    def axpbypgz(self, *a): self.b.axpbypgz(*a)
+    def scal(self, x, a): self.b.scal(x, a)
+
+
+E3_CASES = [(0, 0, 0, 0), (1, 2, 0, 0), (0, 1, 1, 0), (1, 0, 1, 0), (1, 2, 1, 1), (0, 2, 0, 1)]   # cyl, direction, cwj, compute_in_2d
+
+
+def _e3_setup(cyl):
+    x0, x1 = ([3., -1., 0.], [5., 1., 2 * np.pi]) if cyl else ([0., 0., 0.], [1., 2., 3.])
+    return x0, x1, [9, 7, 5], [1, 4 if cyl else 0, 0]
+
+
+@pytest.mark.parametrize("cyl,direction,cwj,in2d", E3_CASES)
+def test_elliptic3d_full_mode_composition_vs_reference(R, cyl, direction, cwj, in2d):
+    """the call-by-call restatement of Elliptic3d::symv (tests/util.elliptic3d_full_symv) on the C oracle equals the live
+    reference class in its full 3-d mode bit for bit: pins the harness the GPU test runs on the C ABI"""
+    from feltor_b200 import topology as T
+    from util import elliptic3d_full_symv
+    x0, x1, N, bc = _e3_setup(cyl)
+    rg = R.grid(x0, x1, 3, N, bc)
+    n = 9 * N[0] * N[1] * N[2]
+    r = rng(11 + direction + 2 * cyl)
+    x, y0, chi = r.uniform(-1, 1, n), r.uniform(-1, 1, n), r.uniform(0.5, 2., n)
+    for alpha, beta in ((1., 0.), (-0.5, 0.3)):
+        want = R.elliptic3d_symv_mode(rg, cyl, direction, 0.7, cwj, in2d, chi, alpha, x, beta, y0)
+        y = y0.copy()
+        elliptic3d_full_symv(_OrcBackend(), T, x0, x1, N, bc, direction, 0.7, bool(cwj), bool(cyl), chi, alpha, x, beta, y, bool(in2d))
+        assert same_bits(y, want), (cyl, direction, cwj, in2d, alpha, beta)
+
+
+@pytest.mark.parametrize("cyl,direction,cwj,in2d", E3_CASES)
+def test_elliptic3d_full_mode_fixture(gold3, cyl, direction, cwj, in2d):
+    """the same against committed outputs of the reference (tests/golden/make_golden_elliptic3d.py): no reference build needed"""
+    from feltor_b200 import topology as T
+    from util import elliptic3d_full_symv
+    x0, x1, N, bc = _e3_setup(cyl)
+    x, y0, chi = gold3["x_full"], gold3["y0_full"], gold3["chi_full"]
+    y = y0.copy()
+    elliptic3d_full_symv(_OrcBackend(), T, x0, x1, N, bc, direction, 0.7, bool(cwj), bool(cyl), chi, -0.5, x, 0.3, y, bool(in2d))
+    assert same_bits(y, gold3[f"e3dfull/cyl{cyl}/dir{direction}/cwj{cwj}/in2d{in2d}/y"])

@@ -104,3 +104,37 @@ def test_elliptic1d(G, bcx, direction):
         op.symv(alpha, G.make(x), beta, y)
         assert same_bits(G.get(y), want), (bcx, direction, use_chi, alpha, beta)
         assert same_bits(G.get(op.weights()), w) and same_bits(G.get(op.precond()), p)
+
+
+class _GpuBackend:
+    """dg-shaped primitives of the C ABI on device vectors: the twin of tests/test_elliptic3d_oracle._OrcBackend"""
+
+    def __init__(self, G):
+        from feltor_b200 import blas1
+        self.G, self.b = G, blas1
+
+    def make(self, a): return self.G.make(a)
+    def symv(self, m, a, x, b, y): self.G.symv(m, a, x, b, y)
+    def tensor_multiply3d(self, lam, t, ins, mu, outs): self.b.tensor_multiply3d(lam, t, list(ins), mu, list(outs))
+    def tensor_multiply2d(self, lam, t, i0, i1, mu, o0, o1): self.b.tensor_multiply2d(lam, t, i0, i1, mu, o0, o1)
+    def pointwiseDot(self, *a): self.b.pointwiseDot(*a)
+    def pointwiseDivide(self, *a): self.b.pointwiseDivide(*a)
+    def axpbypgz(self, *a): self.b.axpbypgz(*a)
+    def scal(self, x, a): self.b.scal(x, a)
+
+
+@pytest.mark.parametrize("cyl,direction,cwj,in2d", [(0, 0, 0, 0), (1, 2, 0, 0), (0, 1, 1, 0), (1, 0, 1, 0), (1, 2, 1, 1), (0, 2, 0, 1)])
+def test_elliptic3d_full_3d_mode(G, cyl, direction, cwj, in2d):
+    """dg::Elliptic3d::symv in its FULL 3-d mode (z derivative through the 3-d Ell matrices, TensorMultiply3d, elliptic.h:688-697)
+    composed call by call from the C ABI (dgb_ell_symv in x / y / z, dgb_tensor_multiply3d, blas1): bitwise equal to the
+    reference's outputs committed in tests/golden/elliptic3d_golden.npz (and to the oracle composition the CPU suite pins)"""
+    import os
+    from feltor_b200 import topology as T
+    from util import elliptic3d_full_symv
+    gold3 = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "elliptic3d_golden.npz"))
+    x0, x1 = ([3., -1., 0.], [5., 1., 2 * np.pi]) if cyl else ([0., 0., 0.], [1., 2., 3.])
+    N, bc = [9, 7, 5], [1, 4 if cyl else 0, 0]
+    x, y0, chi = gold3["x_full"], gold3["y0_full"], gold3["chi_full"]
+    y = G.make(y0)
+    elliptic3d_full_symv(_GpuBackend(G), T, x0, x1, N, bc, direction, 0.7, bool(cwj), bool(cyl), G.make(chi), -0.5, G.make(x), 0.3, y, bool(in2d))
+    assert same_bits(G.get(y), gold3[f"e3dfull/cyl{cyl}/dir{direction}/cwj{cwj}/in2d{in2d}/y"])

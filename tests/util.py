@@ -73,3 +73,53 @@ def blas1_sequence(B, make, get, n=500):
     B.transform(v1, v3, "exp")
     out["exp"] = bits(get(v3))
     return out
+
+
+def elliptic3d_full_symv(B, T, x0, x1, N, bc, direction, jfactor, cwj, cyl, chi, alpha, x, beta, y, compute_in_2d=False):
+    """dg::Elliptic3d::symv of the reference (inc/dg/elliptic.h:680-749) in its FULL 3-d mode, restated call by
+    call on a backend B of dg-shaped primitives -- the C oracle on numpy arrays (tests/test_elliptic3d_oracle.py, pinned against
+    the live reference and committed fixtures) or the C ABI of libdgb200.so on device vectors (tests/test_gpu_elliptic3d.py).
+    B: make(np) -> vector, symv(m, a, x, b, y), tensor_multiply3d / tensor_multiply2d, pointwiseDot, pointwiseDivide, axpby,
+    axpbypgz.  Grids: n = 3 in x and y, 1 in z => g.nz() == 1: centered dz on both sides and NO jump term in z (elliptic.h:606-611)."""
+    g = T.Grid(x0, x1, [3, 3, 1], N, bc)
+    n = g.size
+    inv_d = T.inverse_dir(direction)
+    leftx, lefty = T.derivative(0, g, T.inverse_bc(bc[0]), inv_d), T.derivative(1, g, T.inverse_bc(bc[1]), inv_d)
+    rightx, righty = T.derivative(0, g, bc[0], direction), T.derivative(1, g, bc[1], direction)
+    jumpx, jumpy = T.jump(0, g, bc[0]), T.jump(1, g, bc[1])
+    rightz, leftz = T.derivative(2, g, bc[2], T.CENTERED), T.derivative(2, g, T.inverse_bc(bc[2]), T.CENTERED)
+    ones, zeros = np.ones(n), np.zeros(n)
+    if cyl:   # CylindricalGrid3d: g^pp = 1/R/R (base_geometry.h:336-344), vol = 1/sqrt(det) (multiply.h:389)
+        R = np.ascontiguousarray(np.broadcast_to(g.abscissas(0), (g.shape(2), g.shape(1), g.shape(0))).reshape(-1))
+        gpp = (1. / R) / R
+        vol = 1. / np.sqrt(gpp)
+    else:
+        gpp, vol = ones, ones.copy()
+    # the metric as SparseTensor: value 0 = zeros, 1 = ones (tensor.h): every entry is a vector, the arithmetic is carried out
+    t9 = [B.make(v) for v in (ones, zeros, zeros, zeros, ones, zeros, zeros, zeros, gpp)]
+    t4 = [t9[0], t9[1], t9[3], t9[4]]
+    vold = B.make(vol)
+    sigma = B.make(np.zeros(n))
+    B.pointwiseDot(chi, vold, sigma)                                  # set_chi: elliptic.h:638
+    tx, ty, tz, temp = (B.make(np.zeros(n)) for _ in range(4))
+    B.symv(rightx, 1., x, 0., tx)
+    B.symv(righty, 1., x, 0., ty)
+    if not compute_in_2d:
+        B.symv(rightz, 1., x, 0., tz)
+        B.tensor_multiply3d(sigma, t9, (tx, ty, tz), 0., (tx, ty, tz))
+        B.symv(leftz, -1., tz, 0., temp)
+        B.symv(lefty, -1., ty, 1., temp)
+    else:
+        B.tensor_multiply2d(sigma, t4, tx, ty, 0., tx, ty)
+        B.symv(lefty, -1., ty, 0., temp)
+    B.symv(leftx, -1., tx, 1., temp)
+    if jfactor != 0:
+        if cwj:
+            B.symv(jumpx, jfactor, x, 0., tx)
+            B.symv(jumpy, jfactor, x, 0., ty)
+            B.tensor_multiply2d(sigma, t4, tx, ty, 0., tx, ty)
+            B.axpbypgz(1., tx, 1., ty, 1., temp)
+        else:
+            B.symv(jumpx, jfactor, x, 1., temp)
+            B.symv(jumpy, jfactor, x, 1., temp)
+    B.pointwiseDivide(alpha, temp, vold, beta, y)
