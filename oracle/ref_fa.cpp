@@ -24,8 +24,20 @@
 #undef private
 #include "geometries/ds.h"
 
-using FA = dg::geo::Fieldaligned<dg::aProductGeometry3d, dg::IHMatrix, dg::HVec>;
-using DSop = dg::geo::DS<dg::aProductGeometry3d, dg::IHMatrix, dg::HVec>;
+// The same file is compiled a second time by integration/Makefile with nvcc on the libdgb200 binding (-DREF_FA_DEVICE): the
+// reference's Fieldaligned / DS templates instantiated on DEVICE containers (dg::IDMatrix, dg::DVec), i.e. what a Feltor
+// application on a GPU runs; tests/test_gpu_shim.py compares the two builds call by call.
+#ifdef REF_FA_DEVICE
+using FaMatrix = dg::IDMatrix;
+using FaVec = dg::DVec;
+#else
+using FaMatrix = dg::IHMatrix;
+using FaVec = dg::HVec;
+#endif
+using FA = dg::geo::Fieldaligned<dg::aProductGeometry3d, FaMatrix, FaVec>;
+using DSop = dg::geo::DS<dg::aProductGeometry3d, FaMatrix, FaVec>;
+template <class V>
+static void to_host(const V& v, double* out) { thrust::copy(v.begin(), v.end(), out); }
 
 struct RefFA {
     dg::CylindricalGrid3d g3d;
@@ -54,15 +66,15 @@ int ref_fa_nnz(void* h, int which) {
 }
 void ref_fa_csr(void* h, int which, int* pos, int* idx, double* val) {
     auto& m = which == 0 ? ((RefFA*)h)->fa.m_plus : ((RefFA*)h)->fa.m_minus;
-    std::copy(m.row_offsets().begin(), m.row_offsets().end(), pos);
-    std::copy(m.column_indices().begin(), m.column_indices().end(), idx);
-    std::copy(m.values().begin(), m.values().end(), val);
+    thrust::copy(m.row_offsets().begin(), m.row_offsets().end(), pos);
+    thrust::copy(m.column_indices().begin(), m.column_indices().end(), idx);
+    thrust::copy(m.values().begin(), m.values().end(), val);
 }
 // 3-d fields of the Fieldaligned object: 0 bphi, 1 bphiM, 2 bphiP, 3 sqrtG, 4 sqrtGm, 5 sqrtGp, 6 hbm, 7 hbp
 void ref_fa_field(void* h, int which, double* out) {
     FA& fa = ((RefFA*)h)->fa;
-    const dg::HVec* v[8] = {&fa.bphi(), &fa.bphiM(), &fa.bphiP(), &fa.sqrtG(), &fa.sqrtGm(), &fa.sqrtGp(), &fa.hbm(), &fa.hbp()};
-    std::copy(v[which]->begin(), v[which]->end(), out);
+    const FaVec* v[8] = {&fa.bphi(), &fa.bphiM(), &fa.bphiP(), &fa.sqrtG(), &fa.sqrtGm(), &fa.sqrtGp(), &fa.hbm(), &fa.hbp()};
+    to_host(*v[which], out);
 }
 // the test function of ds_b.cpp:86-87 pulled back to the grid
 void ref_fa_testfunction(void* h, double* out) {
@@ -74,16 +86,16 @@ void ref_fa_testfunction(void* h, double* out) {
 void ref_fa_shift(void* h, int which, const double* f, double* fe) {
     RefFA* r = (RefFA*)h;
     const size_t n = r->g3d.size();
-    dg::HVec in(f, f + n), out(n);
+    FaVec in(f, f + n), out(n);
     r->fa(which == 0 ? dg::geo::einsPlus : dg::geo::einsMinus, in, out);
-    std::copy(out.begin(), out.end(), fe);
+    to_host(out, fe);
 }
 // kind: 0 centered(alpha, f, beta, g)  1 forward  2 backward  3 dss  4 divCentered  5 symv (-DS^dagger DS, not used yet)
 // returns the seconds of ONE application (mean over reps), result of the last one in g
 double ref_fa_ds(void* h, int kind, double alpha, const double* f, double beta, double* g, int reps) {
     RefFA* r = (RefFA*)h;
     const size_t n = r->g3d.size();
-    dg::HVec in(f, f + n), out(g, g + n), out0(out);
+    FaVec in(f, f + n), out(g, g + n), out0(out);
     double sec = 0.;
     for (int k = 0; k < reps; k++) {
         out = out0;
@@ -95,8 +107,18 @@ double ref_fa_ds(void* h, int kind, double alpha, const double* f, double beta, 
         else r->ds.divCentered(alpha, in, beta, out);
         sec += std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
     }
-    std::copy(out.begin(), out.end(), g);
+#ifdef REF_FA_DEVICE
+    cudaDeviceSynchronize();
+#endif
+    to_host(out, g);
     return sec / reps;
+}
+int ref_fa_is_device() {
+#ifdef REF_FA_DEVICE
+    return 1;
+#else
+    return 0;
+#endif
 }
 int ref_fa_threads() {
 #ifdef _OPENMP

@@ -354,3 +354,41 @@ def test_shim_toefl_operators(toefl_pair):
     xd, nd = D.pol_solve(chi, np.zeros(n), f)
     xo, no = O.pol_solve(chi, np.zeros(n), f)
     assert nd == no and same_bits(xd, xo)
+
+
+SHIM_FA = os.path.join(ROOT, "integration", "_build", "libdgshim_fa.so")
+
+
+def test_shim_fieldaligned_and_ds_vs_openmp():
+    """the reference's dg::geo::Fieldaligned and dg::geo::DS templates instantiated on DEVICE containers (dg::IDMatrix, dg::DVec)
+    and compiled on the binding -- ePlus / eMinus through dgb_csr_spmv, DS::centered / forward / backward / dss / divCentered
+    through the class's own device lambdas -- against the same wrapper on the OpenMP backend: identical matrices and fields
+    (host construction), bitwise field-line shifts (row-ordered CSR kernel), DS members within 1e-12"""
+    from oracle import reffa
+    if not os.path.exists(SHIM_FA) or not reffa.available():
+        pytest.skip("integration/_build/libdgshim_fa.so or oracle/_ref/libdgref_fa.so not built")
+    import gpu_backend
+    gpu_backend.require_library_loaded()
+    dev = _clone("shimfa", "reffa.py", "_PATH", SHIM_FA)
+    assert dev.lib().ref_fa_is_device() == 1 and reffa.lib().ref_fa_is_device() == 0
+    l0 = launches()
+    objs = [m.RefFieldaligned(3, 14, 12, 8, 5, 5, "dg") for m in (dev, reffa)]
+    D, H = objs
+    for which in ("plus", "minus"):
+        for a, b in zip(D.csr(which), H.csr(which)):
+            assert np.array_equal(a, b)
+    for name in ("bphi", "bphiM", "bphiP", "sqrtG", "hbm", "hbp"):
+        assert same_bits(D.field(name), H.field(name))
+    f = H.testfunction()
+    assert same_bits(D.testfunction(), f)
+    r = rng(3)
+    g0 = r.uniform(-1, 1, f.size)
+    for which in ("plus", "minus"):
+        assert same_bits(D.shift(which, f), H.shift(which, f)), which
+    for kind in ("centered", "forward", "backward", "dss", "divCentered"):
+        for alpha, beta in ((1., 0.), (-0.5, 0.3)):
+            gd, _ = D.ds(kind, alpha, f, beta, g0)
+            gh, _ = H.ds(kind, alpha, f, beta, g0)
+            scale = np.max(np.abs(gh))
+            assert np.max(np.abs(gd - gh)) <= 1e-12 * scale, (kind, alpha, beta, np.max(np.abs(gd - gh)) / scale)
+    assert launches() > l0, "the device build did not reach libdgb200.so"
