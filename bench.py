@@ -415,6 +415,19 @@ def main():
                       "note": "iterations/s of the FIXED n=3 %dx%d problem; divide by the N=1 value for the strong-scaling speed-up" % (cells, cells)}
         del ps
 
+    # toefl (config 3) on the fixed grid cut into N slabs: strong scaling of the step rate (N > 1; N = 1 runs further down)
+    toefl_dist = None
+    if world > 1 and not args.no_toefl and cells % (4 * world) == 0:
+        try:
+            sys.path.insert(0, os.path.join(ROOT, "tools"))
+            import toefl_bench
+            torch.cuda.empty_cache()
+            t_out, _ = toefl_bench.run(cells, 4, 2, 0.5, comm=comm)
+            toefl_dist = {"metric": "toefl_steps_per_second", "value": t_out["steps_per_s"], "unit": "steps/s", "n_gpus": world,
+                          "scaling": "strong", "rhs_per_s": t_out["rhs_per_s"], "config": t_out["workload"],
+                          "mean_pcg_iterations_per_solve": t_out["mean_pcg_iterations_per_solve(stage0,1,2)"]}
+        except Exception as e:
+            toefl_dist = {"failed": repr(e)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -477,6 +490,8 @@ def main():
     }
     if strong_rec is not None:
         out["strong_scaling"] = strong_rec
+    if toefl_dist is not None:
+        out["toefl"] = toefl_dist
     if world == 1 and not args.no_micro:
         try:
             out["micro"] = micro_table(cells, peak)

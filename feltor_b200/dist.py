@@ -103,6 +103,7 @@ class SlabElliptic2d:
         wx, wy = g.weights1d(0), g.weights1d(1)[self.yoff * n:(self.yoff + self.rows) * n]
         self._weights = dvec((wy[:, None] * wx[None, :]).reshape(-1))  # = rows of create::weights (w_x[i] * w_y[j])
         self._precond = torch.ones(self.size, dtype=torch.float64, device="cuda")
+        self._pad = None
 
     def local(self, global_host_vector):
         """this rank's rows of a global host vector"""
@@ -130,13 +131,17 @@ class SlabElliptic2d:
         self.comm.halo_rows(self._sigma_pad, self.row_len, self.nrows, self.ghost_rows, self.periodic_y)
         blas1.pointwiseDivide(torch.ones_like(sigma_local), sigma_local, self._precond)
 
-    def symv(self, x_local, y_local):
-        """y = A x; x is staged in a padded buffer and its halo exchanged (MPISparseBlockMat::symv, mpi_matrix.h:183-217)"""
-        pad = torch.zeros((self.nrows + 2 * self.ghost_rows) * self.row_len, dtype=torch.float64, device="cuda")
+    def symv(self, *a):
+        """y = A x or y = alpha A x + beta y; x is staged in a padded buffer and its halo exchanged (MPISparseBlockMat::symv,
+        mpi_matrix.h:183-217)"""
+        alpha, x_local, beta, y_local = (1., a[0], 0., a[1]) if len(a) == 2 else a
+        if self._pad is None:
+            self._pad = torch.zeros((self.nrows + 2 * self.ghost_rows) * self.row_len, dtype=torch.float64, device="cuda")
+        pad = self._pad
         interior = pad[self.ghost_rows * self.row_len:][:self.size]
         interior.copy_(x_local)
         self.comm.halo_rows(pad, self.row_len, self.nrows, self.ghost_rows, self.periodic_y)
-        lib().elliptic2d_symv(self.h, d(1.), ptr(interior), d(0.), ptr(y_local), stream())
+        lib().elliptic2d_symv(self.h, d(alpha), ptr(interior), d(beta), ptr(y_local), stream())
 
     def __del__(self):
         try:

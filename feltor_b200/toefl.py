@@ -210,10 +210,14 @@ class Explicit:
             self.old_psi.extrapolate(t, self.phi[1])
             self.numbers["gammaPhi"] = self.multigrid.solve(self.multi_gamma1, self.phi[1], self.phi[0], p.eps_gamma)
             self.old_psi.update(t, self.phi[1])
-        lib().elliptic2d_variation(self.multi_pol[0].h, d(1.), None, ptr(self.phi[0]), d(0.), ptr(self.uE2), stream())
+        self._variation(self.phi[0], self.uE2)
         if p.model == "global":
             blas1.pointwiseDot(1., self.binv, self.binv, self.uE2, 0., self.uE2)
             blas1.axpby(-0.5, self.uE2, 1., self.phi[1])
+
+    def _variation(self, phi, out):
+        """Elliptic::variation of the finest polarisation operator (elliptic.h:497-502)"""
+        lib().elliptic2d_variation(self.multi_pol[0].h, d(1.), None, ptr(phi), d(0.), ptr(out), stream())
 
     def polarisation(self, t, y):
         p = self.p

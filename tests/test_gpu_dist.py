@@ -55,3 +55,41 @@ def test_slab_pcg_equals_global(G):
     its = DistPCG(comm, g.size, g.size).solve(S, xs, G.make(b), S.precond(), S.weights(), 1e-9, 1.0, 1)
     assert its == it
     assert same_bits(G.get(xs), G.get(x))
+
+
+def _toefl_params(N, model="global"):
+    return {"grid": {"n": 3, "Nx": N, "Ny": N, "lx": 200, "ly": 200},
+            "init": {"amplitude": 1.0, "sigma": 10, "posX": 0.3, "posY": 0.5, "flr": "gamma_inv"},
+            "bc": ["DIR", "PER"],
+            "elliptic": {"stages": 3, "eps_pol": [1e-6, 1, 1], "eps_gamma": [1e-7, 1, 1], "direction": "centered"},
+            "model": {"type": model, "boussinesq": False, "curvature": 0.00015, "tau": 1, "nu": 1e-6}}
+
+
+@pytest.mark.parametrize("N,model", [(32, "global"), (40, "local")])
+def test_dist_toefl_equals_single_gpu(G, N, model):
+    """toefl::Explicit + Bogacki-Shampine steps on the slab harness (feltor_b200/dist_toefl.py: row-sliced block matrices with
+    remapped columns, ghost-row exchanges, slab Helmholtz / polarisation plans, distributed PCG inside the restated nested
+    iteration) with a communicator of size 1 against the plain single-GPU harness: state, potentials and every per-stage
+    iteration count bit for bit (tools/dist_check.py repeats it on N GPUs)"""
+    import torch
+    from feltor_b200 import toefl as TF
+    from feltor_b200.dist import Comm
+    from feltor_b200.dist_toefl import DistExplicit
+    js = _toefl_params(N, model)
+    results = []
+    for dist in (False, True):
+        ex = DistExplicit(Comm(0, 1), TF.Parameters(js)) if dist else TF.Explicit(TF.Parameters(js))
+        u0 = ex.initial_condition()
+        u1 = [torch.zeros_like(u0[0]), torch.zeros_like(u0[0])]
+        delta = [torch.zeros_like(u0[0]), torch.zeros_like(u0[0])]
+        erk = TF.ERKStep("Bogacki-Shampine-4-2-3", u0)
+        t, nums = 0., []
+        for _ in range(2):
+            t = erk.step(ex, t, u0, u1, 0.5, delta)
+            u0, u1 = u1, u0
+            nums.append(dict(ex.numbers))
+        results.append((G.get(u0[0]), G.get(u0[1]), G.get(ex.phi[0]), G.get(ex.phi[1]), nums))
+    a, b = results
+    assert a[4] == b[4], (a[4], b[4])
+    for k in range(4):
+        assert same_bits(a[k], b[k]), k

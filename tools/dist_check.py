@@ -81,6 +81,30 @@ its = p2.solve(S, xs, dvec(S.local(b)), S.precond(), S.weights(), 1e-30, 1.0, 1)
 same_pcg = its == it1 and np.array_equal(hvec(xs).view(np.int64), S.local(hvec(xs1)).view(np.int64))
 print(f"rank {rank}/{size} N={N} (walker slabs): symv {same_symv} pcg-40-iterations {same_pcg}", flush=True)
 ok = ok and same_symv and same_pcg
+# toefl (config 3) on slabs: two Bogacki-Shampine steps of the right-hand side on N ranks against the single-GPU harness on every
+# rank: state rows, potentials and every per-stage PCG iteration count bit for bit
+from feltor_b200 import toefl as TF  # noqa: E402
+from feltor_b200.dist_toefl import DistExplicit  # noqa: E402
+Nt = 32 * size if size <= 4 else 16 * size
+js = {"grid": {"n": 3, "Nx": 48, "Ny": Nt, "lx": 200, "ly": 200}, "init": {"amplitude": 1.0, "sigma": 10, "posX": 0.3, "posY": 0.5, "flr": "gamma_inv"},
+      "bc": ["DIR", "PER"], "elliptic": {"stages": 3, "eps_pol": [1e-6, 1, 1], "eps_gamma": [1e-7, 1, 1], "direction": "centered"},
+      "model": {"type": "global", "boussinesq": False, "curvature": 0.00015, "tau": 1, "nu": 1e-6}}
+res = []
+for exd in (TF.Explicit(TF.Parameters(js)), DistExplicit(comm, TF.Parameters(js))):
+    u0 = exd.initial_condition()
+    u1 = [torch.zeros_like(u0[0]), torch.zeros_like(u0[0])]
+    delta = [torch.zeros_like(u0[0]), torch.zeros_like(u0[0])]
+    erk = TF.ERKStep("Bogacki-Shampine-4-2-3", u0)
+    tt, nums = 0., []
+    for _ in range(2):
+        tt = erk.step(exd, tt, u0, u1, 0.5, delta)
+        u0, u1 = u1, u0
+        nums.append(dict(exd.numbers))
+    res.append((hvec(u0[0]), hvec(u0[1]), hvec(exd.phi[0]), nums, exd))
+slab = res[1][4].slab
+same_toefl = res[0][3] == res[1][3] and all(np.array_equal(slab.local(res[0][k]).view(np.int64), res[1][k].view(np.int64)) for k in range(3))
+print(f"rank {rank}/{size} toefl 48x{Nt} on slabs: {same_toefl} (iterations {res[1][3][-1]})", flush=True)
+ok = ok and same_toefl
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:

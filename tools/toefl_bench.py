@@ -25,10 +25,16 @@ def params(N):
             "model": {"type": "global", "boussinesq": False, "curvature": 0.00015, "tau": 1, "nu": 1e-6}}
 
 
-def run(cells=1024, steps=6, warmup=2, dt=0.5):
-    """returns (result dict, initial state as two numpy arrays)"""
+def run(cells=1024, steps=6, warmup=2, dt=0.5, comm=None):
+    """returns (result dict, initial state as two numpy arrays); comm: feltor_b200.dist.Comm -> the grid is cut into y-slabs
+    (one per rank, feltor_b200/dist_toefl.py) and the time is the maximum over the ranks"""
     N = cells
-    ex = TF.Explicit(TF.Parameters(params(N)))
+    if comm is not None and comm.size > 1:
+        from feltor_b200.dist_toefl import DistExplicit
+        ex = DistExplicit(comm, TF.Parameters(params(N)))
+    else:
+        comm = None
+        ex = TF.Explicit(TF.Parameters(params(N)))
     u0 = ex.initial_condition()
     y_init = [hvec(u0[0]).copy(), hvec(u0[1]).copy()]
     u1 = [torch.zeros_like(u0[0]), torch.zeros_like(u0[0])]
@@ -43,9 +49,16 @@ def run(cells=1024, steps=6, warmup=2, dt=0.5):
         for k in its:
             its[k].append(ex.numbers[k])
 
+    def sync():
+        torch.cuda.synchronize()
+        if comm is not None:
+            import torch.distributed as dist
+            dist.barrier()
+            torch.cuda.synchronize()
+
     for _ in range(warmup):
         step()
-    torch.cuda.synchronize()
+    sync()
     for k in its:
         its[k].clear()
     calls0, launches0 = ex.ncalls, fb.lib().raw["dgb_launch_count"]()
@@ -54,14 +67,21 @@ def run(cells=1024, steps=6, warmup=2, dt=0.5):
     for _ in range(steps):
         step()
     e1.record()
-    torch.cuda.synchronize()
+    sync()
     sec = e0.elapsed_time(e1) * 1e-3
+    if comm is not None:
+        import torch.distributed as dist
+        tmax = torch.tensor([sec], dtype=torch.float64, device="cuda")
+        dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+        sec = tmax.item()
     calls = ex.ncalls - calls0
     out = {"workload": "toefl global n=3 %dx%d, 3-stage MultigridCG2d, Bogacki-Shampine-4-2-3 fixed dt=%g" % (N, N, dt),
            "steps_per_s": steps / sec, "rhs_per_s": calls / sec, "ms_per_step": sec / steps * 1e3, "steps": steps,
            "rhs_calls": calls, "kernel_launches": int(fb.lib().raw["dgb_launch_count"]() - launches0),
            "mean_pcg_iterations_per_solve(stage0,1,2)": {k: [float(np.mean([v[s] for v in vals])) for s in range(3)] for k, vals in its.items()},
-           "dof": ex.grid.size}
+           "dof": ex.grid.size, "n_gpus": 1 if comm is None else comm.size}
+    if comm is not None:
+        out["workload"] += "; y-slabs x%d (strong scaling of the fixed grid), ghost rows by dgb_comm_halo_rows, distributed PCG" % comm.size
     return out, y_init
 
 
