@@ -312,6 +312,30 @@ void ref_tensor_multiply2d(int n, const double* lambda, const double* t00, const
     dg::blas1::subroutine(dg::TensorMultiply2d(), l, a, b, c, d, i0, i1, mu, o0, o1);
 }
 
+// ---------------------------------------------------------------- vdot / reduce (inc/dg/blas1.h:90-130, 215-222)
+// dg::blas1::vdot( f, x, y): extended-precision (FPE) sum of f(x_i, y_i); kind 0: dg::Product  1: a user functor
+// dg::blas1::reduce( x, zero, op, unary): kind 0: sum of squares  1: maximum of |x|  2: minimum
+struct RefUserBinary {
+    DG_DEVICE double operator()(double a, double b) const { return a * b + 0.25 * a; }
+};
+struct RefSquare {
+    DG_DEVICE double operator()(double a) const { return a * a; }
+};
+struct RefAbs {
+    DG_DEVICE double operator()(double a) const { return a < 0 ? -a : a; }
+};
+double ref_vdot(int kind, int n, const double* x, const double* y) {
+    CView a(x, n), b(y, n);
+    if (kind == 0) return dg::blas1::vdot(dg::Product(), a, b);
+    return dg::blas1::vdot(RefUserBinary(), a, b);
+}
+double ref_reduce(int kind, int n, const double* x) {
+    CView a(x, n);
+    if (kind == 0) return dg::blas1::reduce(a, 0., thrust::plus<double>(), RefSquare());
+    if (kind == 1) return dg::blas1::reduce(a, 0., thrust::maximum<double>(), RefAbs());
+    return dg::blas1::reduce(a, 1e300, thrust::minimum<double>());
+}
+
 // ---------------------------------------------------------------- exblas dot (inc/dg/blas1.h:152, blas2.h:94)
 // returns status; acc = un-normalised superaccumulator as doDot_superacc returns it
 int ref_dot2(int n, const double* x, const double* y, int64_t* acc) {

@@ -191,6 +191,18 @@ def dot3(x, w, y):
     return acc, st
 
 
+def vdot(kind, x, y):
+    """dg::blas1::vdot (blas1.h:90): kind 0 dg::Product, 1 a user functor a*b + a/4"""
+    lib().ref_vdot.restype = C.c_double
+    return float(lib().ref_vdot(int(kind), x.size, dp(np.ascontiguousarray(x)), dp(np.ascontiguousarray(y))))
+
+
+def reduce(kind, x):
+    """dg::blas1::reduce (blas1.h:215): kind 0 sum of squares, 1 max |x|, 2 min"""
+    lib().ref_reduce.restype = C.c_double
+    return float(lib().ref_reduce(int(kind), x.size, dp(np.ascontiguousarray(x))))
+
+
 def round_acc(acc):
     return float(lib().ref_round(lp(np.ascontiguousarray(acc, dtype=np.int64))))
 

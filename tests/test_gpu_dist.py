@@ -93,3 +93,34 @@ def test_dist_toefl_equals_single_gpu(G, N, model):
     assert a[4] == b[4], (a[4], b[4])
     for k in range(4):
         assert same_bits(a[k], b[k]), k
+
+
+def test_dist_ds_centered_z_slab_equals_global(G):
+    """DS::centered with the planes owned in blocks (z decomposition, ghost planes by dgb_comm_halo_rows) on a size-1
+    communicator against the global cell-tiled call: bit for bit (tools/dist_check.py repeats it on N GPUs)"""
+    import ctypes as C
+    import torch
+    from feltor_b200._lib import lib
+    from feltor_b200._dev import ptr, stream
+    from feltor_b200.dist import Comm
+    from feltor_b200.dist_ds import DistDSCentered
+    from test_gpu_ds import _fieldaligned_like_matrix
+    n, Nx, Ny, Nz = 3, 40, 12, 10
+    r = rng(4)
+    P, M = _fieldaligned_like_matrix(r, n, Nx, Ny), _fieldaligned_like_matrix(r, n, Nx, Ny, 2)
+    rows = n * n * Nx * Ny
+    f, bphi, g0 = r.uniform(-1, 1, rows * Nz), r.uniform(0.5, 1.5, rows * Nz), r.uniform(-1, 1, rows * Nz)
+    dP = [torch.from_numpy(a).cuda() for a in P]
+    dM = [torch.from_numpy(a).cuda() for a in M]
+    hp, hm = C.c_void_p(), C.c_void_p()
+    lib().celltile_plan_create(C.byref(hp), n, Nx, Ny, ptr(dP[0]), ptr(dP[1]), ptr(dP[2]), stream())
+    lib().celltile_plan_create(C.byref(hm), n, Nx, Ny, ptr(dM[0]), ptr(dM[1]), ptr(dM[2]), stream())
+    D = DistDSCentered(Comm(0, 1), n, Nx, Ny, Nz, dP, dM, G.make(bphi), 0.1)
+    df, dbphi = G.make(f), G.make(bphi)
+    for alpha, beta in ((0.7, 0.), (-1.3, 0.5)):
+        a, b = G.make(g0), G.make(g0)
+        lib().celltile_ds_centered(hp, hm, Nz, C.c_double(alpha), ptr(df), ptr(dbphi), C.c_double(0.1), C.c_double(beta), ptr(a), stream())
+        D.centered(alpha, df, beta, b)
+        assert same_bits(G.get(a), G.get(b)), (alpha, beta)
+    lib().celltile_plan_destroy(hp)
+    lib().celltile_plan_destroy(hm)

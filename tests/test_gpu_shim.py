@@ -226,6 +226,26 @@ def test_shim_elliptic3d_full_3d_vs_openmp(shim, ref, cyl, d, cwj, in2d):
     assert launches() > l0 and g1[0] > g0[0]
 
 
+def test_shim_vdot_and_reduce_vs_openmp(shim, ref):
+    """dg::blas1::vdot (FPE accumulation, exblas/fpedot_cuda.cuh:66-183 seam) and dg::blas1::reduce (blas1_cuda.cuh:96-102 seam)
+    through the binding's single-launch kernel templates, library functor and user functors, against the OpenMP backend:
+    vdot is an extended-precision sum rounded at the end (not binary reproducible by the reference's own contract, blas1.h:74)
+    -> within 2 ulp; max / min are order independent -> equal; the sum of squares is an ordinary floating-point reduction
+    (different association) -> 1e-14"""
+    if ref is None:
+        pytest.skip("oracle/_ref/libdgref.so not present")
+    r = rng(21)
+    for n in (1, 7, 1000, 40000, 300001):
+        x, y = r.uniform(-1, 1, n), r.uniform(-1, 1, n) * 10. ** r.integers(-3, 4, n)
+        for kind in (0, 1):
+            a, b = shim.vdot(kind, x, y), ref.vdot(kind, x, y)
+            assert abs(a - b) <= 4e-16 * abs(b), (n, kind, a, b)   # blas1.h:74: extended precision, "does not guarantee binary reproducible results"
+        for kind in (1, 2):
+            assert shim.reduce(kind, x) == ref.reduce(kind, x), (n, kind)
+        a, b = shim.reduce(0, x), ref.reduce(0, x)
+        assert abs(a - b) <= 1e-14 * abs(b), (n, a, b)
+
+
 @pytest.mark.parametrize("fusion", [1, 0], ids=["fused", "backend-only"])
 def test_shim_multigrid_vs_openmp(shim, ref, fusion):
     """dg::MultigridCG2d (nested iterations, fast projection / interpolation = MultiMatrix of Ell matrices) on the binding"""

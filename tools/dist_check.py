@@ -105,6 +105,28 @@ slab = res[1][4].slab
 same_toefl = res[0][3] == res[1][3] and all(np.array_equal(slab.local(res[0][k]).view(np.int64), res[1][k].view(np.int64)) for k in range(3))
 print(f"rank {rank}/{size} toefl 48x{Nt} on slabs: {same_toefl} (iterations {res[1][3][-1]})", flush=True)
 ok = ok and same_toefl
+# DS::centered on a z-decomposition (ghost planes by the halo exchange): every rank's planes against the global call
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from test_gpu_ds import _fieldaligned_like_matrix  # noqa: E402
+from feltor_b200.dist_ds import DistDSCentered  # noqa: E402
+nd, Nxd, Nyd, Nzd = 3, 40, 12, 4 * size
+rd = np.random.default_rng(4)
+Pm, Mm = _fieldaligned_like_matrix(rd, nd, Nxd, Nyd), _fieldaligned_like_matrix(rd, nd, Nxd, Nyd, 2)
+rowsd = nd * nd * Nxd * Nyd
+fd, bd, gd0 = rd.uniform(-1, 1, rowsd * Nzd), rd.uniform(0.5, 1.5, rowsd * Nzd), rd.uniform(-1, 1, rowsd * Nzd)
+dPm = [torch.from_numpy(a).cuda() for a in Pm]
+dMm = [torch.from_numpy(a).cuda() for a in Mm]
+hp, hm = C.c_void_p(), C.c_void_p()
+fb.lib().celltile_plan_create(C.byref(hp), nd, Nxd, Nyd, ptr(dPm[0]), ptr(dPm[1]), ptr(dPm[2]), stream())
+fb.lib().celltile_plan_create(C.byref(hm), nd, Nxd, Nyd, ptr(dMm[0]), ptr(dMm[1]), ptr(dMm[2]), stream())
+ga, dfd, dbd = dvec(gd0), dvec(fd), dvec(bd)
+fb.lib().celltile_ds_centered(hp, hm, Nzd, C.c_double(-1.3), ptr(dfd), ptr(dbd), C.c_double(0.1), C.c_double(0.5), ptr(ga), stream())
+DD = DistDSCentered(comm, nd, Nxd, Nyd, Nzd, dPm, dMm, dvec(bd[(Nzd // size) * rank * rowsd:(Nzd // size) * (rank + 1) * rowsd]), 0.1)
+gb = dvec(DD.local(gd0).copy())
+DD.centered(-1.3, dvec(DD.local(fd).copy()), 0.5, gb)
+same_ds = np.array_equal(hvec(gb).view(np.int64), DD.local(hvec(ga)).view(np.int64))
+print(f"rank {rank}/{size} DS::centered on z-slabs ({Nzd} planes): {same_ds}", flush=True)
+ok = ok and same_ds
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
