@@ -154,8 +154,11 @@ def test_toefl_building_blocks_vs_live_reference(G, reft):
     assert num == numr and same_bits(G.get(x), xr)
 
 
-@pytest.mark.parametrize("N,steps", [(48, 4), (64, 2)])
+@pytest.mark.parametrize("N,steps", [(48, 4), (64, 2), (416, 1)])
 def test_toefl_steps_vs_live_reference(G, reft, N, steps):
+    """N = 416: the finest multigrid stage is large enough for the automatic choice of the WALKER kernel, so its Helmholtz and
+    centered polarisation solves run the folded two-kernel PCG iteration (direction update in the TMA loader) inside the
+    nested iteration -- still bit for bit the unmodified reference"""
     if reft is None:
         pytest.skip("oracle/_ref/libdgref_toefl.so not present")
     js = params(3, N, "global")
@@ -167,7 +170,8 @@ def test_toefl_steps_vs_live_reference(G, reft, N, steps):
     assert same_bits(G.get(ex.phi[0]), ref.phi(0)) and same_bits(G.get(ex.phi[1]), ref.phi(1))
     # the initial condition built on the device agrees to rounding (host exp / contraction differ in the last bit)
     yi = ex.initial_condition()
-    assert np.abs(G.get(yi[0]) - y0).max() <= 4e-16 and np.abs(G.get(yi[1]) - y1).max() <= 2e-15
+    # (the gamma_inv image of that last bit grows with the resolution: the discrete Laplacian scales like (n N / lx)^2)
+    assert np.abs(G.get(yi[0]) - y0).max() <= 4e-16 and np.abs(G.get(yi[1]) - y1).max() <= (2e-15 if N <= 64 else 1e-12)
 
 
 def test_helmholtz_symv_fused_equals_composition(G):
