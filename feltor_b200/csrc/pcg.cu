@@ -439,7 +439,9 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
     const bool p2p_dots = dist && pview.enabled && in_kernel;
     FusedDot fd{W, s.slot, s.st, pview, 0ull};
     if (!p2p_dots) fd.p2p.enabled = 0;
-    const unsigned g2 = grid_for(n, 2);
+    static int k2_elems = -1;  // experiment knob: elements per thread that size K2's grid
+    if (k2_elems < 0) { const char* ev = getenv("DGB_PCG_K2_ELEMS"); k2_elems = ev ? atoi(ev) : 2; if (k2_elems < 2) k2_elems = 2; }
+    const unsigned g2 = grid_for(n, k2_elems);
     static int k2_variant = -1;  // experiment knob: 0 register prefetch, 2 CTAs/SM   1 no prefetch, 4 CTAs/SM   2 no prefetch, 3 CTAs/SM
     if (k2_variant < 0) { const char* ev = getenv("DGB_PCG_K2_VARIANT"); k2_variant = ev ? atoi(ev) : 0; }
     unsigned g3;

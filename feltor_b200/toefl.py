@@ -10,7 +10,7 @@ import ctypes as C
 import math
 import numpy as np
 import torch
-from ._lib import lib
+from ._lib import lib, DgbError
 from ._dev import ptr, stream, dvec
 from . import blas1, blas2, topology as T
 from .elliptic import Elliptic2d, MultigridCG2d
@@ -58,9 +58,21 @@ class Advection:
         self.dxb = T.derivative(0, g, bcx, T.BACKWARD)
         self.dyb = T.derivative(1, g, bcy, T.BACKWARD)
         self.t0, self.t1 = _zeros(g.size), _zeros(g.size)
+        self._fused = None
 
-    def upwind(self, alpha, vx, vy, f, beta, result):
+    def upwind(self, alpha, vx, vy, f, beta, result, fused=True):
+        """one kernel (dgb_advection_upwind) when the library recognises the four matrices, else the reference's sequence"""
         n = f.numel()
+        if fused and self._fused is not False:
+            try:
+                lib().advection_upwind(self.dxb.handle, self.dxf.handle, self.dyb.handle, self.dyf.handle, d(alpha), ptr(vx), ptr(vy),
+                                       ptr(f), d(beta), ptr(result), stream())
+                self._fused = True
+                return
+            except DgbError as e:
+                if e.code != -2 or self._fused:   # DGB_ERR_UNSUPPORTED: fall back for good
+                    raise
+                self._fused = False
         self.dxb.symv(1., f, 0., self.t0)
         self.dxf.symv(1., f, 0., self.t1)
         lib().upwind_axpby(n, d(alpha), ptr(vx), ptr(self.t0), ptr(self.t1), d(beta), ptr(result), stream())

@@ -205,6 +205,12 @@ DGB_API int dgb_ell_symv(const dgb_ell* m, double alpha, const double* x, double
 /* same arithmetic through the fully general one-thread-per-element kernel (any n, any pattern); A/B testing */
 DGB_API int dgb_ell_symv_generic(const dgb_ell* m, double alpha, const double* x, double beta, double* y,
                                  dgb_stream_t s);
+/* dg::Advection::upwind( alpha, vx, vy, f, beta, result) (inc/dg/advection.h:112-120) in ONE kernel: the four block matrices are
+ * the backward / forward derivatives in x and y of one 2-d grid (dg::create::dx / dy, n = 2..4, two blocks per row); bitwise the
+ * result of the reference's sequence of four symv and two evaluate( Axpby, UpwindProduct) calls.  DGB_ERR_UNSUPPORTED for
+ * other matrices (compose dgb_ell_symv + dgb_upwind_axpby then).  f must not alias result. */
+DGB_API int dgb_advection_upwind(const dgb_ell* dxb, const dgb_ell* dxf, const dgb_ell* dyb, const dgb_ell* dyf, double alpha,
+                                 const double* vx, const double* vy, const double* f, double beta, double* result, dgb_stream_t s);
 
 typedef struct dgb_coo {
     int num_rows, num_cols, num_entries, n, left_size, right_size;

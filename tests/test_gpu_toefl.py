@@ -198,3 +198,27 @@ def test_helmholtz_symv_fused_equals_composition(G):
         expect = ref_y.clone()
         blas1.pointwiseDot(1., chi, x, 0.37, expect)
         assert same_bits(G.get(y), G.get(expect))
+
+
+@pytest.mark.parametrize("n,N,bcx,bcy", [(3, [37, 19], 1, 0), (2, [24, 40], 0, 1), (3, [33, 17], 4, 2), (4, [12, 15], 3, 0), (3, [5, 6], 1, 1),
+                                         (3, [400, 300], 1, 0)])
+def test_advection_upwind_fused(G, n, N, bcx, bcy):
+    """dgb_advection_upwind (one kernel) == the reference's sequence of four Ell symv and two evaluate( Axpby, UpwindProduct)
+    (advection.h:112-120) bit for bit: interior cells (constant-bank blocks), boundary block rows of every boundary condition,
+    the periodic wrap, alpha / beta variants, velocities of both signs and exact zeros"""
+    import torch
+    from feltor_b200 import topology as T
+    from feltor_b200 import toefl as TF
+    g = T.Grid([0, 0], [3., 2.], n, N, [bcx, bcy])
+    r = rng(n + N[0] + bcx)
+    f, vx, vy, r0 = (r.uniform(-1, 1, g.size) for _ in range(4))
+    vx[::7] = 0.
+    vy[3::11] = 0.
+    adv = TF.Advection(g)
+    for alpha, beta in ((-1., 0.), (0.7, 1.), (1.3, -0.5)):
+        a, b = G.make(r0), G.make(r0)
+        adv.upwind(alpha, G.make(vx), G.make(vy), G.make(f), beta, a, fused=False)
+        df, dvx, dvy = G.make(f), G.make(vx), G.make(vy)
+        adv.upwind(alpha, dvx, dvy, df, beta, b, fused=True)
+        assert adv._fused is True
+        assert same_bits(G.get(a), G.get(b)), (alpha, beta)
