@@ -21,6 +21,8 @@ struct MultiMat {  // Y o X with a temporary (MultiMatrix of dimension 2)
     EllDev mx, my;
     double* temp = nullptr;
     size_t temp_size = 0;
+    int fused = 0;  // 1: factor-2 projection, 2: factor-2 interpolation (one-pass kernels below), 0: two Ell symv through temp
+    int Nxc = 0, Nyc = 0;
 };
 
 struct Multigrid2d {
@@ -37,6 +39,7 @@ static int upload(EllDev& d, const EllHost& h) {
     ell_view(h, &v);
     return ell_upload(d, &v);
 }
+static void analyse(MultiMat& M, bool projection);
 static int build_multimat(MultiMat& M, const dgb_grid& g, bool projection) {
     // X first on grid g, then Y on the grid whose x axis already has the new resolution (fast_interpolation.h:380-398)
     EllHost hx, hy;
@@ -57,10 +60,161 @@ static int build_multimat(MultiMat& M, const dgb_grid& g, bool projection) {
     if ((e = upload(M.my, hy))) return e;
     M.temp_size = M.mx.total_rows();
     DGB_CUDA(cudaMalloc(&M.temp, M.temp_size * sizeof(double)));
+    analyse(M, projection);
     return 0;
 }
-// MultiMatrix::symv (fast_interpolation.h:71-84)
+// ---- MultiMatrix::symv (fast_interpolation.h:71-84) of the factor-2 projection / interpolation in ONE pass ----------------
+// The reference applies the x-matrix into a temporary and the y-matrix from there: 4 vector passes over the fine grid.  A thread
+// here owns one COARSE cell: it reads the 2 x 2 fine cells (projection) resp. its own n x n values (interpolation), forms the
+// rows of the temporary it needs in registers and applies the y-blocks to them -- 10 B per fine element (8 + 2), the
+// algorithmic minimum.  Arithmetic per output element is the reference's: t = FMA chain over q per block, out = fma(1, t, 0) for
+// the x-matrix (alpha = 1, beta = 0), out = fma(alpha, t, beta == 0 ? 0 : y beta) per block in slot order for the y-matrix
+// (sparseblockmat_omp_kernels.h:36-50): bitwise the two-pass result (tests/test_gpu_multigrid.py::test_multimatrix_fused).
+template <int N>
+struct HalfCoef {
+    double x[2][N][N], y[2][N][N];
+};
+template <int N>
+__global__ void __launch_bounds__(128)
+project_half_kernel(const __grid_constant__ HalfCoef<N> C, int Nxc, int Nyc, double alpha, double beta, const double* __restrict__ x,
+                    double* __restrict__ y) {
+    const size_t LDf = (size_t)2 * Nxc * N, LDc = (size_t)Nxc * N;
+    const long long ncells = (long long)Nxc * Nyc;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (long long)gridDim.x * blockDim.x) {
+        const int cy = (int)(c / Nxc), cx = (int)(c - (long long)cy * Nxc);
+        double T[2 * N][N];
+#pragma unroll
+        for (int r = 0; r < 2 * N; r++) {
+            const double* xr = x + ((size_t)2 * cy * N + r) * LDf + (size_t)2 * cx * N;
+            double v[2 * N];
+#pragma unroll
+            for (int q = 0; q < 2 * N; q++) v[q] = xr[q];
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                double out = 0.;
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    double t = 0.;
+#pragma unroll
+                    for (int q = 0; q < N; q++) t = __fma_rn(C.x[d][k][q], v[d * N + q], t);
+                    out = __fma_rn(1., t, out);
+                }
+                T[r][k] = out;
+            }
+        }
+#pragma unroll
+        for (int k = 0; k < N; k++) {
+            double* yr = y + ((size_t)cy * N + k) * LDc + (size_t)cx * N;
+#pragma unroll
+            for (int col = 0; col < N; col++) {
+                double out = beta == 0. ? 0. : __dmul_rn(yr[col], beta);
+#pragma unroll
+                for (int d = 0; d < 2; d++) {
+                    double t = 0.;
+#pragma unroll
+                    for (int q = 0; q < N; q++) t = __fma_rn(C.y[d][k][q], T[d * N + q][col], t);
+                    out = __fma_rn(alpha, t, out);
+                }
+                yr[col] = out;
+            }
+        }
+    }
+}
+template <int N>
+__global__ void __launch_bounds__(128)
+interpolate_double_kernel(const __grid_constant__ HalfCoef<N> C, int Nxc, int Nyc, double alpha, double beta, const double* __restrict__ x,
+                          double* __restrict__ y) {
+    const size_t LDf = (size_t)2 * Nxc * N, LDc = (size_t)Nxc * N;
+    const long long ncells = (long long)Nxc * Nyc;
+    for (long long c = (long long)blockIdx.x * blockDim.x + threadIdx.x; c < ncells; c += (long long)gridDim.x * blockDim.x) {
+        const int cy = (int)(c / Nxc), cx = (int)(c - (long long)cy * Nxc);
+        double T[N][2 * N];  // the temporary: coarse rows of the cell, fine columns
+#pragma unroll
+        for (int r = 0; r < N; r++) {
+            const double* xr = x + ((size_t)cy * N + r) * LDc + (size_t)cx * N;
+            double v[N];
+#pragma unroll
+            for (int q = 0; q < N; q++) v[q] = xr[q];
+#pragma unroll
+            for (int p = 0; p < 2; p++)
+#pragma unroll
+                for (int k = 0; k < N; k++) {
+                    double t = 0.;
+#pragma unroll
+                    for (int q = 0; q < N; q++) t = __fma_rn(C.x[p][k][q], v[q], t);
+                    T[r][p * N + k] = __fma_rn(1., t, 0.);
+                }
+        }
+#pragma unroll
+        for (int p = 0; p < 2; p++)
+#pragma unroll
+            for (int k = 0; k < N; k++) {
+                double* yr = y + ((size_t)(2 * cy + p) * N + k) * LDf + (size_t)2 * cx * N;
+#pragma unroll
+                for (int col = 0; col < 2 * N; col++) {
+                    double out = beta == 0. ? 0. : __dmul_rn(yr[col], beta);
+                    double t = 0.;
+#pragma unroll
+                    for (int q = 0; q < N; q++) t = __fma_rn(C.y[p][k][q], T[q][col], t);
+                    yr[col] = __fma_rn(alpha, t, out);
+                }
+            }
+    }
+}
+
+// does the pair have the structure the one-pass kernels assume?  projection: rows i, two blocks at columns 2i, 2i+1 with data
+// indices (a, b) for every row; interpolation: rows i, one block at column i/2 with data index alternating with the parity of i
+static bool half_pattern(const EllDev& m, bool projection) {
+    if (projection) {
+        if (m.bpl != 2 || m.num_cols != 2 * m.num_rows) return false;
+        for (int i = 0; i < m.num_rows; i++)
+            for (int d = 0; d < 2; d++)
+                if (m.h_cols[(size_t)i * 2 + d] != 2 * i + d || m.h_didx[(size_t)i * 2 + d] != m.h_didx[d]) return false;
+    } else {
+        if (m.bpl != 1 || m.num_rows != 2 * m.num_cols) return false;
+        for (int i = 0; i < m.num_rows; i++)
+            if (m.h_cols[i] != i / 2 || m.h_didx[i] != m.h_didx[i % 2]) return false;
+    }
+    return m.rr0 == 0 && m.rr1 == m.right;
+}
+static void analyse(MultiMat& M, bool projection) {
+    const EllDev &X = M.mx, &Y = M.my;
+    M.fused = 0;
+    if (X.n != Y.n || X.n < 2 || X.n > 4 || !half_pattern(X, projection) || !half_pattern(Y, projection)) return;
+    const int n = X.n;
+    const int Nxc = projection ? X.num_rows : X.num_cols, Nyc = projection ? Y.num_rows : Y.num_cols;
+    const int rows_in = (projection ? 2 : 1) * Nyc * n, cols_out = (projection ? 1 : 2) * Nxc * n;
+    if (X.right != 1 || X.left != rows_in || Y.left != 1 || Y.right != cols_out) return;
+    M.fused = projection ? 1 : 2;
+    M.Nxc = Nxc; M.Nyc = Nyc;
+}
+template <int N>
+static int half_launch(const MultiMat& M, double alpha, double beta, const double* x, double* y, cudaStream_t st) {
+    HalfCoef<N> C;
+    const bool projection = M.fused == 1;
+    for (int d = 0; d < 2; d++)
+        for (int k = 0; k < N; k++)
+            for (int q = 0; q < N; q++) {
+                C.x[d][k][q] = M.mx.h_data[((size_t)M.mx.h_didx[d] * N + k) * N + q];
+                C.y[d][k][q] = M.my.h_data[((size_t)M.my.h_didx[d] * N + k) * N + q];
+            }
+    const long long ncells = (long long)M.Nxc * M.Nyc;
+    long long want = (ncells + 127) / 128, cap = (long long)sm_count() * 16;
+    const unsigned grid = (unsigned)std::max(1ll, std::min(want, cap));
+    if (projection) project_half_kernel<N><<<grid, 128, 0, st>>>(C, M.Nxc, M.Nyc, alpha, beta, x, y);
+    else interpolate_double_kernel<N><<<grid, 128, 0, st>>>(C, M.Nxc, M.Nyc, alpha, beta, x, y);
+    DGB_LAUNCHED();
+    return 0;
+}
+static int g_multimat_two_pass = 0;  // A/B switch of the tests (dgb_multigrid2d_set_two_pass)
 static int multimat_symv(const MultiMat& M, double alpha, const double* x, double beta, double* y, cudaStream_t st) {
+    if (M.fused && !g_multimat_two_pass && x != y) {
+        switch (M.mx.n) {
+            case 2: return half_launch<2>(M, alpha, beta, x, y, st);
+            case 3: return half_launch<3>(M, alpha, beta, x, y, st);
+            default: return half_launch<4>(M, alpha, beta, x, y, st);
+        }
+    }
     int e;
     if ((e = ell_symv(M.mx, 1., x, 0., M.temp, st, false))) return e;
     return ell_symv(M.my, alpha, M.temp, beta, y, st, false);
@@ -119,6 +273,7 @@ int dgb_multigrid2d_create(dgb_multigrid2d** out, const dgb_grid* grid, int stag
     return 0;
 }
 int dgb_multigrid2d_destroy(dgb_multigrid2d* h) { destroy(reinterpret_cast<Multigrid2d*>(h)); return 0; }
+int dgb_multigrid2d_set_two_pass(int on) { g_multimat_two_pass = on ? 1 : 0; return 0; }
 int dgb_multigrid2d_stages(const dgb_multigrid2d* h) { return reinterpret_cast<const Multigrid2d*>(h)->stages; }
 int dgb_multigrid2d_grid(const dgb_multigrid2d* h, int stage, dgb_grid* grid, size_t* size) {
     const Multigrid2d* m = reinterpret_cast<const Multigrid2d*>(h);

@@ -88,14 +88,28 @@ class ArakawaX:
         bcx = g.bc[0] if bcx is None else bcx
         bcy = g.bc[1] if bcy is None else bcy
         n = g.size
-        self.dxlhs, self.dxrhs, self.dylhs, self.dyrhs = (_zeros(n) for _ in range(4))
+        self.work = _zeros(3 * n)   # m_dylhs, m_dxrhs, m_dyrhs of the class, contiguous for dgb_arakawa
+        self.dylhs, self.dxrhs, self.dyrhs = self.work[:n], self.work[n:2 * n], self.work[2 * n:]
+        self.dxlhs = _zeros(n)
         self.bdxf = T.derivative(0, g, bcx, T.CENTERED)
         self.bdyf = T.derivative(1, g, bcy, T.CENTERED)
         self.chi = torch.ones(n, dtype=torch.float64, device="cuda")  # 1 / perp_vol
+        self._fused = None
 
-    def __call__(self, *a):
-        """(lhs, rhs, result) | (alpha, lhs, rhs, beta, result)"""
+    def __call__(self, *a, fused=True):
+        """(lhs, rhs, result) | (alpha, lhs, rhs, beta, result): two kernels (dgb_arakawa) when the library recognises the
+        matrices, else the reference's sequence of eight launches"""
         alpha, lhs, rhs, beta, result = (1., a[0], a[1], 0., a[2]) if len(a) == 3 else a
+        if fused and self._fused is not False:
+            try:
+                lib().arakawa(self.bdxf.handle, self.bdyf.handle, d(alpha), ptr(lhs), ptr(rhs), ptr(self.chi), d(beta), ptr(result),
+                              ptr(self.work), stream())
+                self._fused = True
+                return
+            except DgbError as e:
+                if e.code != -2 or self._fused:   # DGB_ERR_UNSUPPORTED: fall back for good
+                    raise
+                self._fused = False
         self.bdxf.symv(1., lhs, 0., self.dxlhs)
         self.bdyf.symv(1., lhs, 0., self.dylhs)
         self.bdxf.symv(1., rhs, 0., self.dxrhs)

@@ -211,6 +211,14 @@ DGB_API int dgb_ell_symv_generic(const dgb_ell* m, double alpha, const double* x
  * other matrices (compose dgb_ell_symv + dgb_upwind_axpby then).  f must not alias result. */
 DGB_API int dgb_advection_upwind(const dgb_ell* dxb, const dgb_ell* dxf, const dgb_ell* dyb, const dgb_ell* dyf, double alpha,
                                  const double* vx, const double* vy, const double* f, double beta, double* result, dgb_stream_t s);
+/* dg::ArakawaX::operator()( alpha, lhs, rhs, beta, result) (inc/dg/arakawa.h:147-162) in TWO kernels instead of eight launches:
+ * bdx / bdy are the centered derivatives of one 2-d grid (n = 2..4, three blocks per row), chi = 1 / perp_vol (the class'
+ * m_chi), work3 = 3 N doubles of scratch (the class' m_dylhs, m_dxrhs, m_dyrhs).  Bitwise the result of the reference's sequence
+ * (six symv, ArakawaFunctor, pointwiseDot).  DGB_ERR_UNSUPPORTED for other matrices (compose dgb_ell_symv +
+ * dgb_arakawa_functor + dgb_pointwise_dot then).  result must not alias work3; it may alias lhs or rhs (neither is read any
+ * more when result is written). */
+DGB_API int dgb_arakawa(const dgb_ell* bdx, const dgb_ell* bdy, double alpha, const double* lhs, const double* rhs, const double* chi,
+                        double beta, double* result, double* work3, dgb_stream_t s);
 
 typedef struct dgb_coo {
     int num_rows, num_cols, num_entries, n, left_size, right_size;

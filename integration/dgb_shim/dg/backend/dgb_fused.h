@@ -7,6 +7,8 @@
 //   dg::Elliptic2d<Geometry, DMatrix, DVec>::symv( alpha, x, beta, y)  ->  dgb_elliptic2d_symv   (ONE kernel, 24 B/dof)
 //   dg::PCG<DVec>::solve( A, x, b, P, W, eps, ...) with A an Elliptic2d or a Helmholtz of one, P and W vectors
 //                                                                    ->  dgb_pcg_solve_elliptic2d (3 kernels / iteration)
+//   dg::Advection<Geometry, DMatrix, DVec>::upwind( alpha, vx, vy, f, beta, result)   ->  dgb_advection_upwind  (ONE kernel)
+//   dg::ArakawaX<Geometry, DMatrix, DVec>::operator()( alpha, lhs, rhs, beta, result) ->  dgb_arakawa           (TWO kernels)
 // dg::MultigridCG2d::solve reaches the second hook through the dg::PCG objects it owns.  Results are bitwise those of the
 // un-hooked classes (tests/test_gpu_shim.py compares both builds with the OpenMP backend).
 // The plan of an operator lives in the operator (EllipticPlanCache member); it is dropped when the operator is copied or its
@@ -34,6 +36,14 @@ struct is_device_dvec<V, std::enable_if_t<
     std::is_same<std::remove_cv_t<dg::get_value_type<V>>, double>::value>> : std::true_type {};
 template<class... Vs>
 struct all_device_dvec : std::conjunction<is_device_dvec<std::decay_t<Vs>>...> {};
+
+// a double EllSparseBlockMat on the device that carries the launch-plan cache make_tree.py adds (dg::DMatrix)
+template<class M, class = void>
+struct is_device_ell : std::false_type {};
+template<class M>
+struct is_device_ell<M, std::void_t<decltype( std::declval<const M&>().m_dgb_cache)>> : std::bool_constant<
+    std::is_same<dg::get_execution_policy<M>, dg::CudaTag>::value && std::is_same<dg::get_value_type<M>, double>::value> {};
+template<class Mat> inline dgb_ell* ell_plan( const Mat& m);  // sparseblockmat_gpu_kernels.cuh
 
 template<class V> inline const double* cptr( const V& v) { return thrust::raw_pointer_cast( v.data()); }
 template<class V> inline double* mptr( V& v) { return thrust::raw_pointer_cast( v.data()); }
@@ -182,6 +192,41 @@ inline bool pcg_solve( PcgCache& cache, Operator& A, X& x, const B& b, const P& 
         return true;
     }
     check( code, "dg::PCG::solve");
+    return true;
+}
+
+// scratch owned by an operator object; copies of the operator start with their own (empty) scratch
+struct ScratchHolder
+{
+    ScratchHolder() = default;
+    ScratchHolder( const ScratchHolder&) {}
+    ScratchHolder& operator=( const ScratchHolder&) { return *this; }
+    DeviceScratch<double> work;
+};
+// dg::Advection::upwind in one kernel; false if the four matrices are not the derivatives the kernel covers (the caller then
+// runs the reference's sequence)
+template<class Matrix>
+inline bool advection_upwind( const Matrix& dxb, const Matrix& dxf, const Matrix& dyb, const Matrix& dyf, double alpha,
+    const double* vx, const double* vy, const double* f, double beta, double* result)
+{
+    if( !fusion_flag() || f == result) return false;
+    const int code = dgb_advection_upwind( ell_plan( dxb), ell_plan( dxf), ell_plan( dyb), ell_plan( dyf), alpha, vx, vy, f, beta, result, nullptr);
+    if( code == DGB_ERR_UNSUPPORTED) return false;
+    check( code, "dg::Advection::upwind");
+    note_library();
+    return true;
+}
+// dg::ArakawaX::operator() in two kernels; `work` holds the three mixed fields (the class' own temporaries are separate
+// vectors, the kernels want one allocation); false if the matrices are not the centered derivatives the kernels cover
+template<class Matrix>
+inline bool arakawa( DeviceScratch<double>& work, const Matrix& bdx, const Matrix& bdy, double alpha, const double* lhs, const double* rhs,
+    const double* chi, size_t size, double beta, double* result)
+{
+    if( !fusion_flag()) return false;
+    const int code = dgb_arakawa( ell_plan( bdx), ell_plan( bdy), alpha, lhs, rhs, chi, beta, result, work.get( 3 * size), nullptr);
+    if( code == DGB_ERR_UNSUPPORTED) return false;
+    check( code, "dg::ArakawaX::operator()");
+    note_library();
     return true;
 }
 

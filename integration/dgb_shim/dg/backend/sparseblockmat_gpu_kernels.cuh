@@ -74,6 +74,35 @@ inline std::vector<T> to_host( const T* dev, size_t count)
     check( dgb_stream_synchronize( nullptr), "dgb_stream_synchronize");
     return h;
 }
+// The library's launch plan of a double EllSparseBlockMat on the device: built on first use from a host copy of the arrays,
+// kept in the matrix (m_dgb_cache), rebuilt when the arrays or the Kronecker sizes changed.
+template<class Mat>
+inline dgb_ell* ell_plan( const Mat& m)
+{
+    const double* data_ptr = thrust::raw_pointer_cast( m.data.data());
+    const int* cols_ptr = thrust::raw_pointer_cast( m.cols_idx.data());
+    const int* block_ptr = thrust::raw_pointer_cast( m.data_idx.data());
+    const int* range_ptr = thrust::raw_pointer_cast( m.right_range.data());
+    EllCache& c = m.m_dgb_cache;
+    if( !c.plan || c.data != data_ptr || c.cols != cols_ptr || c.didx != block_ptr || c.left != m.left_size || c.right != m.right_size)
+    {
+        c.forget();
+        const std::vector<double> h_data = to_host( data_ptr, m.data.size());
+        const std::vector<int> h_cols = to_host( cols_ptr, m.cols_idx.size());
+        const std::vector<int> h_didx = to_host( block_ptr, m.data_idx.size());
+        const std::vector<int> h_range = to_host( range_ptr, 2);
+        dgb_ell_host h;
+        h.num_rows = m.num_rows; h.num_cols = m.num_cols; h.blocks_per_line = m.blocks_per_line; h.n = m.n;
+        h.left_size = m.left_size; h.right_size = m.right_size;
+        h.num_blocks = (int)(m.data.size() / ((size_t)m.n * m.n));
+        h.right_range[0] = h_range[0]; h.right_range[1] = h_range[1];
+        h.data = h_data.data(); h.cols_idx = h_cols.data(); h.data_idx = h_didx.data();
+        check( dgb_ell_create( &c.plan, &h), "dgb_ell_create");
+        c.data = data_ptr; c.cols = cols_ptr; c.didx = block_ptr;
+        c.left = m.left_size; c.right = m.right_size; c.r0 = h_range[0]; c.r1 = h_range[1];
+    }
+    return c.plan;
+}
 }//namespace shim
 }//namespace dgb
 
@@ -91,25 +120,8 @@ void EllSparseBlockMat<real_type, Vector>::launch_multiply_kernel( CudaTag, valu
     if( num_rows == 0 || left_size == 0 || right_size == 0) return;
     if constexpr( std::is_same_v<real_type, double> && std::is_same_v<value_type, double>)
     {
-        dgb::shim::EllCache& c = m_dgb_cache;
-        if( !c.plan || c.data != data_ptr || c.cols != cols_ptr || c.didx != block_ptr || c.left != left_size || c.right != right_size)
-        {
-            c.forget();
-            const std::vector<double> h_data = dgb::shim::to_host( data_ptr, data.size());
-            const std::vector<int> h_cols = dgb::shim::to_host( cols_ptr, cols_idx.size());
-            const std::vector<int> h_didx = dgb::shim::to_host( block_ptr, data_idx.size());
-            const std::vector<int> h_range = dgb::shim::to_host( range_ptr, 2);
-            dgb_ell_host h;
-            h.num_rows = num_rows; h.num_cols = num_cols; h.blocks_per_line = blocks_per_line; h.n = n;
-            h.left_size = left_size; h.right_size = right_size;
-            h.num_blocks = (int)(data.size() / ((size_t)n * n));
-            h.right_range[0] = h_range[0]; h.right_range[1] = h_range[1];
-            h.data = h_data.data(); h.cols_idx = h_cols.data(); h.data_idx = h_didx.data();
-            dgb::shim::check( dgb_ell_create( &c.plan, &h), "dgb_ell_create");
-            c.data = data_ptr; c.cols = cols_ptr; c.didx = block_ptr;
-            c.left = left_size; c.right = right_size; c.r0 = h_range[0]; c.r1 = h_range[1];
-        }
-        dgb::shim::check( dgb_ell_symv( c.plan, alpha, x_ptr, beta, y_ptr, nullptr), "dg::blas2::symv (EllSparseBlockMat)");
+        dgb_ell* plan = dgb::shim::ell_plan( *this);
+        dgb::shim::check( dgb_ell_symv( plan, alpha, x_ptr, beta, y_ptr, nullptr), "dg::blas2::symv (EllSparseBlockMat)");
         dgb::shim::note_library();
     }
     else

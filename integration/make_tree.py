@@ -118,6 +118,30 @@ def fusion_hooks(out):
          "    }\n"
          "    // self-adjoint: apply PCG algorithm to (P 1/W) (W A) x = (P 1/W) (W b) : P' A' x = P' b'\n")
 
+    # (f) Advection::upwind and ArakawaX::operator(): one / two kernels instead of six / eight launches
+    adv = os.path.join(out, "dg", "advection.h")
+    edit(adv, '#include "topology/derivativesA.h"', '#include "topology/derivativesA.h"\n#include "backend/dgb_fused.h" // libdgb200 binding: fused upwind')
+    edit(adv, "    blas2::symv( m_dxb, f, m_temp0);\n    blas2::symv( m_dxf, f, m_temp1);\n",
+         "    if constexpr( dgb::shim::is_device_ell<Matrix>::value &&\n"
+         "                  dgb::shim::all_device_dvec<Container, ContainerType0, ContainerType1, ContainerType2, ContainerType3>::value)\n"
+         "    {   // libdgb200 binding: the four derivatives and both upwind updates in one kernel\n"
+         "        if( dgb::shim::advection_upwind( m_dxb, m_dxf, m_dyb, m_dyf, alpha, dgb::shim::cptr(vx), dgb::shim::cptr(vy), dgb::shim::cptr(f), beta, dgb::shim::mptr(result)))\n"
+         "            return;\n"
+         "    }\n"
+         "    blas2::symv( m_dxb, f, m_temp0);\n    blas2::symv( m_dxf, f, m_temp1);\n")
+    ara = os.path.join(out, "dg", "arakawa.h")
+    edit(ara, '#include "topology/derivativesA.h"', '#include "topology/derivativesA.h"\n#include "backend/dgb_fused.h" // libdgb200 binding: fused bracket')
+    edit(ara, "    Container m_chi, m_perp_vol;\n};", "    Container m_chi, m_perp_vol;\n"
+         "    dgb::shim::ScratchHolder m_dgb; //!< libdgb200 scratch of the fused bracket (3 vectors, allocated on first use)\n};")
+    edit(ara, "    //compute derivatives in x-space\n    blas2::symv( m_bdxf, lhs, m_dxlhs);\n",
+         "    if constexpr( dgb::shim::is_device_ell<Matrix>::value &&\n"
+         "                  dgb::shim::all_device_dvec<Container, ContainerType0, ContainerType1, ContainerType2>::value)\n"
+         "    {   // libdgb200 binding: derivatives + ArakawaFunctor in one kernel, the two outer derivatives + chi in a second\n"
+         "        if( dgb::shim::arakawa( m_dgb.work, m_bdxf, m_bdyf, alpha, dgb::shim::cptr(lhs), dgb::shim::cptr(rhs), dgb::shim::cptr(m_chi), m_chi.size(), beta, dgb::shim::mptr(result)))\n"
+         "            return;\n"
+         "    }\n"
+         "    //compute derivatives in x-space\n    blas2::symv( m_bdxf, lhs, m_dxlhs);\n")
+
 
 def main():
     ap = argparse.ArgumentParser()
