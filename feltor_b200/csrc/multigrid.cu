@@ -273,6 +273,45 @@ int dgb_multigrid2d_create(dgb_multigrid2d** out, const dgb_grid* grid, int stag
     return 0;
 }
 int dgb_multigrid2d_destroy(dgb_multigrid2d* h) { destroy(reinterpret_cast<Multigrid2d*>(h)); return 0; }
+// dg::MultiMatrix::symv of dimension 2 for any two block matrices (fast_interpolation.h:71-84): the one-pass kernels when the
+// pair is a factor-2 projection / interpolation, else the reference's two products through `temp` (may be NULL in the former case
+// only when the caller has checked with dgb_multimatrix2_fused)
+int dgb_multimatrix2_fused(const dgb_ell* hx, const dgb_ell* hy, int* kind) {
+    if (!hx || !hy || !kind) { set_error("dgb_multimatrix2_fused: NULL argument"); return DGB_ERR_INVALID; }
+    MultiMat M;
+    M.mx = *reinterpret_cast<const EllDev*>(hx);
+    M.my = *reinterpret_cast<const EllDev*>(hy);
+    analyse(M, true);
+    if (!M.fused) analyse(M, false);
+    *kind = M.fused;
+    return 0;
+}
+int dgb_multimatrix2_symv(const dgb_ell* hx, const dgb_ell* hy, int kind, double alpha, const double* x, double beta, double* y, double* temp,
+                          dgb_stream_t s) {
+    if (!hx || !hy || !x || !y) { set_error("dgb_multimatrix2_symv: NULL argument"); return DGB_ERR_INVALID; }
+    const EllDev& X = *reinterpret_cast<const EllDev*>(hx);
+    const EllDev& Y = *reinterpret_cast<const EllDev*>(hy);
+    cudaStream_t st = as_stream(s);
+    if ((kind == 1 || kind == 2) && !g_multimat_two_pass && x != y) {
+        const bool projection = kind == 1;
+        const int Nxc = projection ? X.num_rows : X.num_cols, Nyc = projection ? Y.num_rows : Y.num_cols;
+        if (X.n != Y.n || X.n < 2 || X.n > 4 || X.bpl != (projection ? 2 : 1) || Y.bpl != X.bpl) { set_error("dgb_multimatrix2_symv: kind does not match the matrices"); return DGB_ERR_INVALID; }
+        MultiMat M;
+        M.fused = kind; M.Nxc = Nxc; M.Nyc = Nyc;
+        // coefficient blocks only (no ownership): half_launch reads h_data / h_didx / n
+        M.mx.n = X.n; M.mx.h_data = X.h_data; M.mx.h_didx.assign(X.h_didx.begin(), X.h_didx.begin() + 2);
+        M.my.n = Y.n; M.my.h_data = Y.h_data; M.my.h_didx.assign(Y.h_didx.begin(), Y.h_didx.begin() + 2);
+        switch (X.n) {
+            case 2: return half_launch<2>(M, alpha, beta, x, y, st);
+            case 3: return half_launch<3>(M, alpha, beta, x, y, st);
+            default: return half_launch<4>(M, alpha, beta, x, y, st);
+        }
+    }
+    if (!temp) { set_error("dgb_multimatrix2_symv: the two-pass path needs the temporary"); return DGB_ERR_INVALID; }
+    int e;
+    if ((e = ell_symv(X, 1., x, 0., temp, st, false))) return e;
+    return ell_symv(Y, alpha, temp, beta, y, st, false);
+}
 int dgb_multigrid2d_set_two_pass(int on) { g_multimat_two_pass = on ? 1 : 0; return 0; }
 int dgb_multigrid2d_stages(const dgb_multigrid2d* h) { return reinterpret_cast<const Multigrid2d*>(h)->stages; }
 int dgb_multigrid2d_grid(const dgb_multigrid2d* h, int stage, dgb_grid* grid, size_t* size) {

@@ -238,6 +238,10 @@ class MultigridCG2d:
         lib().multigrid2d_project(self.h, ptr(src), arr, stream())
         return out
 
+    def interpolate(self, coarse_stage, alpha, xc, beta, xf):
+        """multigrid.h:232: xf = alpha * interpolation(coarse_stage - 1) xc + beta xf"""
+        lib().multigrid2d_interpolate(self.h, coarse_stage, d(alpha), ptr(xc), d(beta), ptr(xf), stream())
+
     def solve(self, ops, x, b, eps):
         """multigrid.h:617-658: ops = list of Elliptic2d (one per stage); eps scalar or list; returns iteration numbers"""
         eps = [eps] * self.stages if np.isscalar(eps) else list(eps)

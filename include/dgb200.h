@@ -220,6 +220,15 @@ DGB_API int dgb_advection_upwind(const dgb_ell* dxb, const dgb_ell* dxf, const d
 DGB_API int dgb_arakawa(const dgb_ell* bdx, const dgb_ell* bdy, double alpha, const double* lhs, const double* rhs, const double* chi,
                         double beta, double* result, double* work3, dgb_stream_t s);
 
+/* dg::MultiMatrix::symv of two block matrices, x-matrix first (fast_interpolation.h:71-84): y = alpha my (mx x) + beta y.
+ * dgb_multimatrix2_fused reports in *kind whether the pair is a factor-2 projection (1) or interpolation (2) of
+ * dg::create::fast_projection / fast_interpolation (n = 2..4) -- those run as ONE kernel without the temporary (10 B per fine
+ * element instead of four vector passes), bitwise equal to the two products; kind 0 runs the two products through `temp`
+ * (mx.total_num_rows() doubles). */
+DGB_API int dgb_multimatrix2_fused(const dgb_ell* mx, const dgb_ell* my, int* kind);
+DGB_API int dgb_multimatrix2_symv(const dgb_ell* mx, const dgb_ell* my, int kind, double alpha, const double* x, double beta, double* y,
+                                  double* temp, dgb_stream_t s);
+
 typedef struct dgb_coo {
     int num_rows, num_cols, num_entries, n, left_size, right_size;
     const double* data;  /* device */
@@ -437,6 +446,9 @@ typedef struct dgb_multigrid2d dgb_multigrid2d;
 DGB_API int dgb_multigrid2d_create(dgb_multigrid2d** mg, const dgb_grid* grid, int stages);
 DGB_API int dgb_multigrid2d_destroy(dgb_multigrid2d* mg);
 DGB_API int dgb_multigrid2d_stages(const dgb_multigrid2d* mg);
+/* A/B switch for tests: 1 = projections / interpolations (dg::MultiMatrix::symv, fast_interpolation.h:71-84) run as the
+ * reference's two block-matrix products through a temporary, 0 (default) = the one-pass factor-2 kernels (bitwise equal) */
+DGB_API int dgb_multigrid2d_set_two_pass(int on);
 DGB_API int dgb_multigrid2d_grid(const dgb_multigrid2d* mg, int stage, dgb_grid* grid, size_t* size); /* multigrid.h:128 */
 /* project(src, out): out = HOST array of `stages` device vectors (multigrid.h:94-99) */
 DGB_API int dgb_multigrid2d_project(dgb_multigrid2d* mg, const double* src, double* const* out, dgb_stream_t s);

@@ -9,6 +9,7 @@
 //                                                                    ->  dgb_pcg_solve_elliptic2d (3 kernels / iteration)
 //   dg::Advection<Geometry, DMatrix, DVec>::upwind( alpha, vx, vy, f, beta, result)   ->  dgb_advection_upwind  (ONE kernel)
 //   dg::ArakawaX<Geometry, DMatrix, DVec>::operator()( alpha, lhs, rhs, beta, result) ->  dgb_arakawa           (TWO kernels)
+//   dg::MultiMatrix<DMatrix, DVec>::symv( alpha, x, beta, y) of a factor-2 projection / interpolation -> dgb_multimatrix2_symv (ONE kernel)
 // dg::MultigridCG2d::solve reaches the second hook through the dg::PCG objects it owns.  Results are bitwise those of the
 // un-hooked classes (tests/test_gpu_shim.py compares both builds with the OpenMP backend).
 // The plan of an operator lives in the operator (EllipticPlanCache member); it is dropped when the operator is copied or its
@@ -195,6 +196,29 @@ inline bool pcg_solve( PcgCache& cache, Operator& A, X& x, const B& b, const P& 
     return true;
 }
 
+// dg::MultiMatrix::symv of dimension 2: one kernel for the factor-2 projections / interpolations of dg::create::fast_projection /
+// fast_interpolation (what dg::NestedGrids builds); false for every other pair (the caller runs its two products)
+struct MultiCache
+{
+    const void *px = nullptr, *py = nullptr;  // launch plans the classification belongs to
+    int kind = 0;
+};
+template<class Matrix>
+inline bool multimatrix2_symv( MultiCache& c, const Matrix& mx, const Matrix& my, double alpha, const double* x, double beta, double* y)
+{
+    if( !fusion_flag() || x == y) return false;
+    dgb_ell* px = ell_plan( mx);
+    dgb_ell* py = ell_plan( my);
+    if( c.px != px || c.py != py)
+    {
+        check( dgb_multimatrix2_fused( px, py, &c.kind), "dgb_multimatrix2_fused");
+        c.px = px; c.py = py;
+    }
+    if( c.kind == 0) return false;
+    check( dgb_multimatrix2_symv( px, py, c.kind, alpha, x, beta, y, nullptr, nullptr), "dg::MultiMatrix::symv");
+    note_library();
+    return true;
+}
 // scratch owned by an operator object; copies of the operator start with their own (empty) scratch
 struct ScratchHolder
 {

@@ -142,6 +142,20 @@ def fusion_hooks(out):
          "    }\n"
          "    //compute derivatives in x-space\n    blas2::symv( m_bdxf, lhs, m_dxlhs);\n")
 
+    # (g) MultiMatrix::symv of two block matrices: the factor-2 projection / interpolation of NestedGrids in one kernel
+    fi = os.path.join(out, "dg", "topology", "fast_interpolation.h")
+    edit(fi, '#include "dg/blas.h"', '#include "dg/blas.h"\n#include "dg/backend/dgb_fused.h" // libdgb200 binding: one-pass projection / interpolation')
+    edit(fi, "        dg::blas2::symv( m_inter[0], x,m_temp[0]);\n",
+         "        if constexpr( dgb::shim::is_device_ell<MatrixType>::value && dgb::shim::all_device_dvec<ContainerType, ContainerType0, ContainerType1>::value)\n"
+         "        {   // libdgb200 binding: x- and y-matrix in one kernel, no temporary\n"
+         "            if( dims == 2 && dgb::shim::multimatrix2_symv( m_dgb, m_inter[0], m_inter[1], alpha, dgb::shim::cptr(x), beta, dgb::shim::mptr(y)))\n"
+         "                return;\n"
+         "        }\n"
+         "        dg::blas2::symv( m_inter[0], x,m_temp[0]);\n")
+    edit(fi, "    mutable std::vector<ContainerType > m_temp; // OMG mutable exits !? write even in const\n",
+         "    mutable std::vector<ContainerType > m_temp; // OMG mutable exits !? write even in const\n"
+         "    mutable dgb::shim::MultiCache m_dgb; //!< libdgb200 binding: classification of the matrix pair\n")
+
 
 def main():
     ap = argparse.ArgumentParser()

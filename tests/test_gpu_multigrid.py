@@ -84,3 +84,35 @@ def test_multigrid_full_size(G):
     res = np.sqrt(blas2.dot(r, ops[0].weights(), r))
     nrmb = np.sqrt(blas2.dot(b, ops[0].weights(), b))
     assert res < 1e-8 * (nrmb + 1.0) * 5
+
+
+@pytest.mark.parametrize("n,N,stages", [(3, [16, 24], 3), (2, [20, 12], 3), (4, [8, 12], 2), (3, [2, 2], 2), (3, [256, 192], 3)])
+def test_multimatrix_fused(G, n, N, stages):
+    """the one-pass factor-2 projection / interpolation kernels == dg::MultiMatrix::symv as the reference runs it (x-matrix into a
+    temporary, y-matrix from there, fast_interpolation.h:71-84) bit for bit, for alpha / beta variants"""
+    from feltor_b200 import topology as T
+    from feltor_b200.elliptic import MultigridCG2d
+    from feltor_b200._lib import lib
+    g = T.Grid([0, 0], [1., 2.], n, N, [T.DIR, T.PER])
+    mg = MultigridCG2d(g, stages)
+    r = np.random.default_rng(n + N[0])
+    src = r.uniform(-1, 1, g.size)
+    try:
+        lib().multigrid2d_set_two_pass(1)
+        two = [G.get(v) for v in mg.project(G.make(src))]
+        lib().multigrid2d_set_two_pass(0)
+        one = [G.get(v) for v in mg.project(G.make(src))]
+        for u in range(stages):
+            assert same_bits(one[u], two[u]), u
+        for u in range(1, stages):
+            xc, xf0 = r.uniform(-1, 1, mg.sizes[u]), r.uniform(-1, 1, mg.sizes[u - 1])
+            for alpha, beta in ((1., 1.), (1., 0.), (-0.6, 0.3)):
+                out = []
+                for two_pass in (1, 0):
+                    lib().multigrid2d_set_two_pass(two_pass)
+                    xf = G.make(xf0 if beta != 0. else np.full(mg.sizes[u - 1], np.nan))
+                    mg.interpolate(u, alpha, G.make(xc), beta, xf)
+                    out.append(G.get(xf))
+                assert same_bits(out[0], out[1]), (u, alpha, beta)
+    finally:
+        lib().multigrid2d_set_two_pass(0)
