@@ -187,10 +187,10 @@ def symv(*a):
     return M.symv(alpha, x, beta, y)
 
 
-STENCILS = {"median": 0, "swm": 1, "average": 2, "symv": 3}
+STENCILS = {"median": 0, "swm": 1, "average": 2, "symv": 3, "slope": 4}
 
 
 def stencil(kind, pos, idx, val, x, y, alpha=0.0):
     """blas2::stencil(f, M, x, y) (blas2.h:454) with f = CSRMedianFilter / CSRSWMFilter(alpha) / CSRAverageFilter /
-    CSRSymvFilter (topology/filter.h:174-266); pos, idx int32 device tensors, val float64 or None."""
+    CSRSymvFilter / CSRSlopeLimiter(alpha) (topology/filter.h:174-336); pos, idx int32 device tensors, val float64 or None."""
     lib().csr_stencil(STENCILS[kind], pos.numel() - 1, ptr(pos), ptr(idx), ptr(val), d(alpha), ptr(x), ptr(y), stream())

@@ -420,6 +420,54 @@ int dgb_topo_window_stencil(const dgb_grid* g, const int* window, int* row_offse
     }
     return 0;
 }
+// dg::create::limiter_stencil (inc/dg/topology/stencil.h:89-137,199-256): the matrix dg::CSRSlopeLimiter runs on.  Along the
+// limited axis the first row of every cell holds 3 n entries -- columns of the left neighbour cell with forward(0, j), of the cell
+// with forward(1, j), of the right neighbour with backward(j, 1) -- and the cell's other n - 1 rows are empty; columns beyond
+// the boundary are wrapped or mirrored (sign flip on a Dirichlet side) as in detail::set_boundary (stencil.h:19-53).  In 2-d the
+// Kronecker product with the identity of the other axis (tensorproduct, xspacelib.h:38-70).  Outputs caller-allocated:
+// row_offsets[size + 1], cols / vals[3 size].
+int dgb_topo_limiter_stencil(const dgb_grid* g, int direction, int bound, int* row_offsets, int* cols, double* vals) {
+    int e = check_grid(g); if (e) return e;
+    if (!row_offsets || !cols || !vals) { set_error("dgb_topo_limiter_stencil: null argument"); return DGB_ERR_INVALID; }
+    if (g->ndim > 2 || direction < 0 || direction >= g->ndim) { set_error("dgb_topo_limiter_stencil: 1-d and 2-d grids, direction < ndim"); return DGB_ERR_INVALID; }
+    const int n = g->n[direction], N = g->N[direction], len = n * N;
+    if (n == 1) { set_error("Limiter stencil not possible for n==1!"); return DGB_ERR_INVALID; }
+    Mat fw = dlt_forward(n), bw = dlt_backward(n);
+    std::vector<int> c1((size_t)3 * n * N);
+    std::vector<double> v1((size_t)3 * n * N);
+    for (int k = 0; k < N; k++)
+        for (int part = 0; part < 3; part++)
+            for (int j = 0; j < n; j++) {
+                int c = (k - 1 + part) * n + j;
+                double v = part == 0 ? fw(0, j) : (part == 1 ? fw(1, j) : bw(j, 1));
+                if (c < 0) {
+                    if (bound == DGB_PER) c += len;
+                    else { c = -(c + 1); if (bound == DGB_DIR || bound == DGB_DIR_NEU) v *= -1; }
+                } else if (c >= len) {
+                    if (bound == DGB_PER) c -= len;
+                    else { c = 2 * len - 1 - c; if (bound == DGB_DIR || bound == DGB_NEU_DIR) v *= -1; }
+                }
+                c1[((size_t)k * 3 + part) * n + j] = c;
+                v1[((size_t)k * 3 + part) * n + j] = v;
+            }
+    const int nx = g->n[0] * g->N[0], ny = g->ndim == 2 ? g->n[1] * g->N[1] : 1;
+    size_t counter = 0;
+    row_offsets[0] = 0;
+    for (int iy = 0; iy < ny; iy++)
+        for (int ix = 0; ix < nx; ix++) {
+            const int along = direction == 0 ? ix : iy;
+            if (along % n == 0) {
+                const size_t at = (size_t)(along / n) * 3 * n;
+                for (int q = 0; q < 3 * n; q++) {
+                    cols[counter] = direction == 0 ? iy * nx + c1[at + q] : c1[at + q] * nx + ix;
+                    vals[counter] = v1[at + q] * 1.;
+                    counter++;
+                }
+            }
+            row_offsets[(size_t)iy * nx + ix + 1] = (int)counter;
+        }
+    return 0;
+}
 int dgb_topo_size(const dgb_grid* g, size_t* size) {
     int e = check_grid(g); if (e) return e;
     *size = grid_size(g);

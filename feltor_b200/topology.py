@@ -173,3 +173,14 @@ def window_stencil(g, window):
     pos, idx, val = np.empty(rows + 1, dtype=np.int32), np.empty(rows * per_row, dtype=np.int32), np.empty(rows * per_row)
     lib().topo_window_stencil(g.ref(), (C.c_int * g.ndim)(*window), pos.ctypes.data, idx.ctypes.data, val.ctypes.data)
     return pos, idx, val
+
+
+def limiter_stencil(g, direction=0, bound=None):
+    """dg::create::limiter_stencil (inc/dg/topology/stencil.h:89-137,199-256): CSR arrays of the matrix blas2.stencil("slope", ...)
+    = dg::CSRSlopeLimiter runs on; 1-d grid, or along `direction` (0 x, 1 y) of a 2-d grid; bound defaults to the grid's"""
+    bound = g.bc[direction] if bound is None else bound
+    rows = g.size
+    pos, idx, val = np.empty(rows + 1, dtype=np.int32), np.empty(3 * rows, dtype=np.int32), np.empty(3 * rows)
+    lib().topo_limiter_stencil(g.ref(), int(direction), int(bound), pos.ctypes.data, idx.ctypes.data, val.ctypes.data)
+    return pos, idx, val
+

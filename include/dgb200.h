@@ -255,6 +255,9 @@ DGB_API int dgb_topo_dlt(int which, int n, double* out_host); /* dlt.h: 0 abscis
  * axis; outputs are caller-allocated HOST arrays: row_offsets[size + 1], cols / vals[size * prod(window)] (entries unsorted,
  * duplicates kept, value -1 for points mirrored at a Dirichlet boundary, exactly as the reference builds it) */
 DGB_API int dgb_topo_window_stencil(const dgb_grid* g, const int* window, int* row_offsets, int* cols, double* vals);
+/* dg::create::limiter_stencil (topology/stencil.h:89-137,199-256): the matrix of dg::CSRSlopeLimiter (DGB_STENCIL_SLOPE) for a 1-d
+ * grid or along `direction` (0 x, 1 y) of a 2-d grid with boundary condition `bound`; row_offsets[size + 1], cols / vals[3 size] */
+DGB_API int dgb_topo_limiter_stencil(const dgb_grid* g, int direction, int bound, int* row_offsets, int* cols, double* vals);
 DGB_API int dgb_topo_size(const dgb_grid* g, size_t* size);
 DGB_API int dgb_topo_abscissas(const dgb_grid* g, int axis, double* out_host); /* grid.h:128 */
 DGB_API int dgb_topo_weights1d(const dgb_grid* g, int axis, double* out_host); /* grid.h:155 */
@@ -286,8 +289,10 @@ DGB_API int dgb_csr_spmv_planes(int num_rows, int num_cols, const int* row_offse
 /* dg::blas2::stencil(f, M, x, y) / parallel_for (blas2.h:413-454, blas2_stencil.h:13-70) for the library's CSR stencil
  * functors (topology/filter.h:174-266): the matrix only encodes the neighbourhood of each row (create::window_stencil).
  * y[i] = lower median / switching median (alpha) / average of x over the stencil, or sum x*vals (test filter).
- * x must not alias y. */
-enum { DGB_STENCIL_MEDIAN = 0, DGB_STENCIL_SWM = 1, DGB_STENCIL_AVERAGE = 2, DGB_STENCIL_SYMV = 3 };
+ * DGB_STENCIL_SLOPE = dg::CSRSlopeLimiter( alpha) (filter.h:288-336) on the matrix of create::limiter_stencil: the generalised
+ * minmod slope limiter of every cell along one axis; it writes exactly the entries of y the reference writes (all of them for
+ * a limiter stencil).  x must not alias y. */
+enum { DGB_STENCIL_MEDIAN = 0, DGB_STENCIL_SWM = 1, DGB_STENCIL_AVERAGE = 2, DGB_STENCIL_SYMV = 3, DGB_STENCIL_SLOPE = 4 };
 DGB_API int dgb_csr_stencil(int kind, int num_rows, const int* row_offsets, const int* cols, const double* vals,
                             double alpha, const double* x, double* y, dgb_stream_t s);
 

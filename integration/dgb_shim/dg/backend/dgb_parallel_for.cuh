@@ -1,8 +1,8 @@
 // dg::CudaTag overload of doParallelFor_dispatch (inc/dg/backend/blas2_stencil.h:20-36), spliced into blas2_stencil.h by
 // integration/make_tree.py in place of the reference's CUDA section.  dg::blas2::parallel_for / dg::blas2::stencil call
 //     f( i, x, xs...)   for i in [0, size)
-// with a user functor.  The CSR stencil functors of the library (inc/dg/topology/filter.h:174-266: CSRMedianFilter,
-// CSRSWMFilter, CSRAverageFilter, CSRSymvFilter applied through blas2::stencil( f, M, x, y)) go to dgb_csr_stencil;
+// with a user functor.  The CSR stencil functors of the library (inc/dg/topology/filter.h:174-336: CSRMedianFilter,
+// CSRSWMFilter, CSRAverageFilter, CSRSymvFilter, CSRSlopeLimiter applied through blas2::stencil( f, M, x, y)) go to dgb_csr_stencil;
 // every other functor runs through the indexed kernel template of dgb_shim.h.
 #pragma once
 #include "dgb_shim.h"
@@ -14,6 +14,7 @@ struct CSRMedianFilter;
 struct CSRAverageFilter;
 struct CSRSymvFilter;
 template<class T> struct CSRSWMFilter;
+template<class T> struct CSRSlopeLimiter;
 }//namespace dg
 namespace dgb
 {
@@ -24,8 +25,10 @@ template<> struct stencil_code<dg::CSRMedianFilter> { static constexpr int value
 template<> struct stencil_code<dg::CSRAverageFilter> { static constexpr int value = DGB_STENCIL_AVERAGE; };
 template<> struct stencil_code<dg::CSRSymvFilter> { static constexpr int value = DGB_STENCIL_SYMV; };
 template<> struct stencil_code<dg::CSRSWMFilter<double>> { static constexpr int value = DGB_STENCIL_SWM; };
+template<> struct stencil_code<dg::CSRSlopeLimiter<double>> { static constexpr int value = DGB_STENCIL_SLOPE; };
 template<class F> inline double stencil_alpha( const F&) { return 0.; }
 inline double stencil_alpha( const dg::CSRSWMFilter<double>& f) { return coefficients<dg::CSRSWMFilter<double>, double>( f).a; }
+inline double stencil_alpha( const dg::CSRSlopeLimiter<double>& f) { return coefficients<dg::CSRSlopeLimiter<double>, double>( f).a; }
 // the argument pack blas2::stencil( f, SparseMatrix, x, y) produces: row offsets, columns, values, x, y
 template<class... Ps> struct is_csr_pack : std::false_type {};
 template<> struct is_csr_pack<const int*, const int*, const double*, const double*, double*> : std::true_type {};

@@ -194,7 +194,38 @@ ORC_API void orc_assign_bc_along_field(int order, int neu, int n, double delta, 
 }
 /* dg::blas2::stencil / parallel_for with the library's CSR stencil functors, inc/dg/topology/filter.h:84-266.
  * The (lower) median is an order statistic -- rank (n+1)/2 of the stencil values -- so it is restated here by sorting;
- * kind 0 CSRMedianFilter, 1 CSRSWMFilter(alpha), 2 CSRAverageFilter, 3 CSRSymvFilter */
+ * kind 0 CSRMedianFilter, 1 CSRSWMFilter(alpha), 2 CSRAverageFilter, 3 CSRSymvFilter, 4 CSRSlopeLimiter(alpha) */
+static double orc_minmod2(double a, double b) {   /* dg::MinMod, functors.h:255-285 */
+    if (a > 0 && b > 0) return a < b ? a : b;
+    if (a < 0 && b < 0) return a > b ? a : b;
+    return 0.;
+}
+/* CSRSlopeLimiter::operator() (filter.h:291-333) on row i: rows with 3 n entries (one per cell) limit the cell's n values, the
+ * others do nothing.  The sums are written as `a += b*c` in the reference; both of its compilers (gcc -mfma with the default
+ * -ffp-contract=fast, nvcc with -fmad=true) contract them, so they are FMAs here. */
+static void orc_slope_limiter_row(int i, const int* pos, const int* idx, const double* val, double mod, const double* x, double* y) {
+    int k = pos[i], n = (pos[i + 1] - pos[i]) / 3;
+    if (n == 0) return;
+    for (int u = 0; u < n; u++) y[idx[k + n + u]] = x[idx[k + n + u]];
+    double uM = 0, u0 = 0, uP = 0, u1 = 0;
+    for (int u = 0; u < n; u++) {
+        uM = fma(x[idx[k + u]], fabs(val[k + u]), uM);
+        u0 = fma(x[idx[k + n + u]], fabs(val[k + u]), u0);
+        u1 = fma(x[idx[k + n + u]], val[k + n + u], u1);
+        uP = fma(x[idx[k + 2 * n + u]], fabs(val[k + u]), uP);
+    }
+    if (val[k] < 0) uM *= -1;
+    if (val[k + 2 * n] > 0) uP *= -1;
+    if (fabs(u1) <= mod) return;
+    double m = orc_minmod2(orc_minmod2(u1, uP - u0), u0 - uM);
+    if (m == u1) return;
+    for (int u = 0; u < n; u++)
+    {   /* gcc shares the product m*v between the two arms of the conditional, so it is rounded on its own (pinned on the
+         * golden vectors of the reference's OpenMP build, tests/test_limiter.py) */
+        double t = m * val[k + 2 * n + u];
+        y[idx[k + n + u]] = val[k + 2 * n] > 0 ? u0 - t : u0 + t;
+    }
+}
 static int orc_cmp_double(const void* a, const void* b) {
     double x = *(const double*)a, y = *(const double*)b;
     return x < y ? -1 : x > y;
@@ -212,6 +243,7 @@ ORC_API void orc_csr_stencil(int kind, int num_rows, const int* pos, const int* 
     double* scratch = (double*)malloc(sizeof(double) * maxn);
     for (int i = 0; i < num_rows; i++) {
         int b = pos[i], e = pos[i + 1], n = e - b;
+        if (kind == 4) { orc_slope_limiter_row(i, pos, idx, val, alpha, x, y); continue; }
         if (kind == 0) y[i] = orc_row_median(b, e, idx, x, 0, 0., scratch);
         else if (kind == 1) {
             double med = orc_row_median(b, e, idx, x, 0, 0., scratch);

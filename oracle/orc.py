@@ -108,7 +108,8 @@ def assign_bc_along_field(order, neu, delta, fm, f, fp, hbm, hbp, bbm, bbo, bbp,
 
 
 def csr_stencil(kind, pos, idx, val, alpha, x, y):
-    """blas2::stencil with CSRMedianFilter (0) / CSRSWMFilter(alpha) (1) / CSRAverageFilter (2) / CSRSymvFilter (3)"""
+    """blas2::stencil with CSRMedianFilter (0) / CSRSWMFilter(alpha) (1) / CSRAverageFilter (2) / CSRSymvFilter (3) /
+    CSRSlopeLimiter(alpha) (4; writes only the rows of y the limiter touches)"""
     lib().orc_csr_stencil(kind, len(pos) - 1, ip(pos), ip(idx), dp(val), d(alpha), dp(x), dp(y))
 
 

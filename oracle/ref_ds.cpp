@@ -79,7 +79,7 @@ void ref_tensor_multiply3d(int n, const double* lambda, const double* const* t, 
 }
 
 // dg::blas2::parallel_for with the library's CSR stencil functors (inc/dg/topology/filter.h:174-266, blas2.h:413-454):
-// kind 0 CSRMedianFilter, 1 CSRSWMFilter(alpha), 2 CSRAverageFilter, 3 CSRSymvFilter
+// kind 0 CSRMedianFilter, 1 CSRSWMFilter(alpha), 2 CSRAverageFilter, 3 CSRSymvFilter, 4 CSRSlopeLimiter(alpha) (filter.h:288-336)
 extern "C" void ref_csr_stencil(int kind, int num_rows, int num_cols, const int* pos, const int* idx, const double* val,
                                 double alpha, const double* x, double* y) {
     thrust::host_vector<int> p(pos, pos + num_rows + 1), c(idx, idx + pos[num_rows]);
@@ -89,8 +89,23 @@ extern "C" void ref_csr_stencil(int kind, int num_rows, int num_cols, const int*
         case 1: dg::blas2::parallel_for(dg::CSRSWMFilter<double>(alpha), num_rows, p, c, v, vx, vy); break;
         case 2: dg::blas2::parallel_for(dg::CSRAverageFilter(), num_rows, p, c, v, vx, vy); break;
         case 3: dg::blas2::parallel_for(dg::CSRSymvFilter(), num_rows, p, c, v, vx, vy); break;
+        case 4: dg::blas2::parallel_for(dg::CSRSlopeLimiter<double>(alpha), num_rows, p, c, v, vx, vy); break;
     }
     for (int i = 0; i < num_rows; i++) y[i] = vy[i];
+}
+
+// dg::create::limiter_stencil on a 1-d grid / along `direction` (0 x, 1 y) of a 2-d grid (inc/dg/topology/stencil.h:199-256)
+extern "C" int ref_limiter_stencil(int ndim, const double* x0, const double* x1, int n, const int* N, const int* bc, int direction, int bound,
+                                   int* pos, int* idx, double* val) {
+    dg::IHMatrix m;
+    if (ndim == 1) m = dg::create::limiter_stencil(dg::Grid1d(x0[0], x1[0], n, N[0], (dg::bc)bc[0]), (dg::bc)bound);
+    else m = dg::create::limiter_stencil(direction == 0 ? dg::coo3d::x : dg::coo3d::y,
+                                         dg::Grid2d(x0[0], x1[0], x0[1], x1[1], n, N[0], N[1], (dg::bc)bc[0], (dg::bc)bc[1]), (dg::bc)bound);
+    if (pos)
+        for (size_t i = 0; i < m.row_offsets().size(); i++) pos[i] = m.row_offsets()[i];
+    if (idx)
+        for (size_t i = 0; i < m.column_indices().size(); i++) { idx[i] = m.column_indices()[i]; val[i] = m.values()[i]; }
+    return (int)m.values().size();
 }
 
 // dg::create::window_stencil on a 1-d / 2-d grid (inc/dg/topology/stencil.h:177-237); returns nnz, arrays caller-allocated

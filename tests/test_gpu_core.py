@@ -88,6 +88,36 @@ def test_csr_stencil(G, kind):
         blas2.stencil(kind, dp_, di_, dv_, dx, dx, alpha=0.8)
 
 
+def test_slope_limiter(G):
+    """blas2::stencil( CSRSlopeLimiter( mod), limiter_stencil, x, y) (filter.h:288-336, stencil.h:89-256): golden vectors of the
+    unmodified reference for every boundary condition, 1-d and 2-d, both directions; larger random cases against the oracle"""
+    import os
+    from feltor_b200 import blas2, topology as T
+    from feltor_b200._dev import dvec
+    gold = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "limiter_golden.npz"))
+    names = sorted({k.split("/")[0] for k in gold.files})
+    assert len(names) == 10
+    for name in names:
+        pos, idx, val, x = (gold[name + "/" + k] for k in ("pos", "idx", "val", "x"))
+        for mod in (0., 0.3):
+            y = G.make(np.full(x.size, np.nan))
+            blas2.stencil("slope", dvec(pos), dvec(idx), dvec(val), G.make(x), y, alpha=mod)
+            assert same_bits(G.get(y), gold[name + "/y_mod%g" % mod]), (name, mod)
+    r = rng(77)
+    for n, N, bc, direction in ((3, [200, 150], [1, 0], 0), (3, [200, 150], [1, 0], 1), (4, [64, 33], [2, 3], 1), (2, [31, 17], [4, 1], 0)):
+        g = T.Grid([0., 0.], [1., 2.], n, N, bc)
+        pos, idx, val = T.limiter_stencil(g, direction)
+        t = np.linspace(0, 1, g.size)
+        x = np.sin(40 * t) + (t > 0.3) * 1.1 + 0.2 * r.uniform(-1, 1, g.size)
+        for mod in (0., 0.05):
+            want = np.full(g.size, np.nan)
+            orc.csr_stencil(4, pos, idx, val, mod, x, want)
+            y = G.make(np.full(g.size, np.nan))
+            blas2.stencil("slope", dvec(pos), dvec(idx), dvec(val), G.make(x), y, alpha=mod)
+            assert same_bits(G.get(y), want), (n, N, bc, direction, mod)
+            assert not np.isnan(want).any()
+
+
 def test_tensor_multiply3d(G):
     """TensorMultiply3d (multiply.h:34-58): fixture of the unmodified reference, oracle, aliasing, identity, odd/unaligned"""
     import os
