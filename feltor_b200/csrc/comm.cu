@@ -242,6 +242,29 @@ int comm_halo_rows(Comm* c, double* interior, size_t row_len, size_t nrows, size
     return 0;
 }
 
+// MPIGather::global_gather_init / _wait (inc/dg/backend/mpi_gather.h:454-705) for packed buffers: rank r receives recv_counts[p]
+// doubles from every rank p (in rank order) and sends send_counts[p] doubles to it -- one grouped ncclSend / ncclRecv round, the
+// part a rank sends to itself is a device copy.  Counts live on the host (they are fixed when the gather map is built).
+int comm_gather_packed(Comm* c, const double* send, const int* send_counts, double* recv, const int* recv_counts, cudaStream_t st) {
+    const int rank = comm_rank(c), size = comm_size(c);
+    size_t so = 0, ro = 0;
+    NcclApi* n = size > 1 ? nccl() : nullptr;
+    if (n) DGB_NCCL(n->GroupStart());
+    for (int p = 0; p < size; p++) {
+        const size_t sc = (size_t)send_counts[p], rc = (size_t)recv_counts[p];
+        if (p == rank) {
+            if (sc != rc) { if (n) n->GroupEnd(); set_error("dgb_comm_gather: a rank's message to itself must have equal counts"); return DGB_ERR_INVALID; }
+            if (sc) DGB_CUDA(cudaMemcpyAsync(recv + ro, send + so, sc * sizeof(double), cudaMemcpyDeviceToDevice, st));
+        } else {
+            if (sc) DGB_NCCL(n->Send(send + so, sc, ncclFloat64, p, c->comm, st));
+            if (rc) DGB_NCCL(n->Recv(recv + ro, rc, ncclFloat64, p, c->comm, st));
+        }
+        so += sc; ro += rc;
+    }
+    if (n) DGB_NCCL(n->GroupEnd());
+    return 0;
+}
+
 // normalise + round a summed superaccumulator record in place (status = number of ranks that met NaN/Inf)
 __global__ void superacc_finalize_kernel(dgb_dot_result* r, int nrec) {
     int k = blockIdx.x * blockDim.x + threadIdx.x;
@@ -320,6 +343,10 @@ int dgb_comm_destroy(dgb_comm* h) {
 }
 int dgb_comm_halo_rows(dgb_comm* h, double* interior, size_t row_len, size_t nrows, size_t ghost_rows, int periodic, dgb_stream_t s) {
     return comm_halo_rows(reinterpret_cast<Comm*>(h), interior, row_len, nrows, ghost_rows, periodic, as_stream(s));
+}
+int dgb_comm_gather(dgb_comm* h, const double* send, const int* send_counts, double* recv, const int* recv_counts, dgb_stream_t s) {
+    if (!send_counts || !recv_counts) { set_error("dgb_comm_gather: NULL counts"); return DGB_ERR_INVALID; }
+    return comm_gather_packed(reinterpret_cast<Comm*>(h), send, send_counts, recv, recv_counts, as_stream(s));
 }
 // global exact dot: every rank passes the record its local dgb_exdot2/3 produced; on return all ranks hold the
 // normalised global accumulator, the correctly rounded value and the OR of the status flags

@@ -47,6 +47,24 @@ csr_planes_kernel(int num_rows, int num_cols, const int* __restrict__ pos, const
     }
 }
 
+// pack of a gather: out[i] = x[idx[i]] (the send buffer of MPIGather, mpi_gather.h:454-705)
+__global__ void __launch_bounds__(256) gather_indexed_kernel(size_t n, const int* __restrict__ idx, const double* __restrict__ x, double* __restrict__ out) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) out[i] = __ldg(x + __ldg(idx + i));
+}
+// the outer part of MPIDistMat::symv (mpi_matrix.h:505-521) in one kernel: comp[i] = (outer matrix row i) . buffer with the
+// CSR order of sparsematrix_omp.h:39-48 (alpha = 1, beta = 0), then y[scatter[i]] += comp[i].  Rows of the outer matrix map to
+// distinct rows of y, so no atomics.
+__global__ void __launch_bounds__(128)
+csr_scatter_add_kernel(int num_rows, const int* __restrict__ pos, const int* __restrict__ idx, const double* __restrict__ val,
+                       const double* __restrict__ buffer, const int* __restrict__ scatter, double* __restrict__ y) {
+    const int row = blockIdx.x * blockDim.x + threadIdx.x;
+    if (row >= num_rows) return;
+    double t = 0.;
+    for (int jj = __ldg(pos + row); jj < __ldg(pos + row + 1); jj++) t = __fma_rn(__dmul_rn(1., __ldg(val + jj)), __ldg(buffer + __ldg(idx + jj)), t);
+    const int dst = __ldg(scatter + row);
+    y[dst] = __dadd_rn(y[dst], t);
+}
+
 static int csr_launch(int num_rows, int num_cols, const int* pos, const int* idx, const double* val, double alpha,
                       const double* x, double beta, double* y, int nplanes, int shift, cudaStream_t st) {
     if (num_rows < 0 || num_cols < 0 || nplanes < 0) { set_error("dgb_csr_spmv: negative size"); return DGB_ERR_INVALID; }
@@ -76,5 +94,21 @@ int dgb_csr_spmv(int num_rows, int num_cols, const int* pos, const int* idx, con
 int dgb_csr_spmv_planes(int num_rows, int num_cols, const int* pos, const int* idx, const double* val, double alpha,
                         const double* x, double beta, double* y, int nplanes, int shift, dgb_stream_t s) {
     return csr_launch(num_rows, num_cols, pos, idx, val, alpha, x, beta, y, nplanes, shift, as_stream(s));
+}
+int dgb_gather_indexed(size_t n, const int* idx, const double* x, double* out, dgb_stream_t s) {
+    if (n == 0) return 0;
+    if (!idx || !x || !out) { set_error("dgb_gather_indexed: NULL argument"); return DGB_ERR_INVALID; }
+    size_t want = (n + 255) / 256, cap = (size_t)sm_count() * 16;
+    gather_indexed_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(s)>>>(n, idx, x, out);
+    DGB_LAUNCHED();
+    return 0;
+}
+int dgb_csr_spmv_scatter_add(int num_rows, const int* pos, const int* idx, const double* val, const double* buffer, const int* scatter,
+                             double* y, dgb_stream_t s) {
+    if (num_rows == 0) return 0;
+    if (num_rows < 0 || !pos || !idx || !val || !buffer || !scatter || !y) { set_error("dgb_csr_spmv_scatter_add: invalid argument"); return DGB_ERR_INVALID; }
+    csr_scatter_add_kernel<<<(num_rows + 127) / 128, 128, 0, as_stream(s)>>>(num_rows, pos, idx, val, buffer, scatter, y);
+    DGB_LAUNCHED();
+    return 0;
 }
 }

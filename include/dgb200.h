@@ -286,6 +286,15 @@ DGB_API int dgb_csr_spmv_planes(int num_rows, int num_cols, const int* row_offse
                                 const double* vals, double alpha, const double* x, double beta, double* y,
                                 int nplanes, int shift, dgb_stream_t s);
 
+/* The pieces of dg::MPIDistMat::symv (inc/dg/backend/mpi_matrix.h:478-523) a row-distributed CSR matrix needs besides
+ * dgb_csr_spmv for its inner part and dgb_comm_gather for the exchange (feltor_b200/dist_csr.py puts them together):
+ *   dgb_gather_indexed        out[i] = x[idx[i]]: packs the values other ranks asked for (MPIGather, mpi_gather.h:454-705)
+ *   dgb_csr_spmv_scatter_add  y[scatter[i]] += (outer row i) . buffer -- the outer matrix product and the scatter of its rows in
+ *                             one kernel (the fusion mpi_matrix.h:513-520 asks for), CSR order of sparsematrix_omp.h:39-48 */
+DGB_API int dgb_gather_indexed(size_t n, const int* idx, const double* x, double* out, dgb_stream_t s);
+DGB_API int dgb_csr_spmv_scatter_add(int num_rows, const int* row_offsets, const int* cols, const double* vals, const double* buffer,
+                                     const int* scatter, double* y, dgb_stream_t s);
+
 /* dg::blas2::stencil(f, M, x, y) / parallel_for (blas2.h:413-454, blas2_stencil.h:13-70) for the library's CSR stencil
  * functors (topology/filter.h:174-266): the matrix only encodes the neighbourhood of each row (create::window_stencil).
  * y[i] = lower median / switching median (alpha) / average of x over the stencil, or sum x*vals (test filter).
@@ -482,6 +491,11 @@ DGB_API int dgb_comm_info(const dgb_comm* comm, int* rank, int* size, int* peer_
  * points to the first interior row; periodic closes the ring (mpi_gather_kron.h global_gather_init/wait) */
 DGB_API int dgb_comm_halo_rows(dgb_comm* comm, double* interior, size_t row_len, size_t nrows, size_t ghost_rows,
                                int periodic, dgb_stream_t s);
+/* MPIGather exchange of packed buffers (mpi_gather.h:454-705): this rank sends send_counts[p] doubles to rank p and receives
+ * recv_counts[p] from it, both buffers ordered by rank; the counts are HOST arrays of `size` ints.  One grouped
+ * ncclSend / ncclRecv round on stream s (the message to itself is a device copy; a size-1 communicator needs no NCCL). */
+DGB_API int dgb_comm_gather(dgb_comm* comm, const double* send, const int* send_counts, double* recv, const int* recv_counts,
+                            dgb_stream_t s);
 /* exact global dot: sums the normalised superaccumulators of `nrecords` device records over all ranks (integer
  * allreduce), renormalises and rounds on the device (blas1_dispatch_mpi.h:91-109) */
 DGB_API int dgb_comm_allreduce_dot(dgb_comm* comm, dgb_dot_result* result_dev, int nrecords, dgb_stream_t s);

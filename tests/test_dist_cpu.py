@@ -78,3 +78,117 @@ def test_world2_gloo():
     for p in procs:
         p.join(timeout=30)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+# ---------------------------------------------------------------------------------------------------------------------------
+# dg::make_mpi_matrix / dg::MPIGather host logic of feltor_b200/dist_csr.py (mpi_projection.h:50-124, mpi_gather.h:476-520)
+def random_csr(r, nrows, ncols, max_per_row, band=None):
+    """unsorted columns with duplicates, empty rows -- everything a CSR stencil / interpolation matrix may contain"""
+    counts = r.integers(0, max_per_row + 1, nrows)
+    pos = np.concatenate([[0], np.cumsum(counts)]).astype(np.int32)
+    if band is None:
+        idx = r.integers(0, ncols, pos[-1])
+    else:
+        centre = np.repeat((np.arange(nrows) * ncols) // max(nrows, 1), counts)
+        idx = (centre + r.integers(-band, band + 1, pos[-1])) % ncols
+    return pos, idx.astype(np.int32), r.uniform(-1, 1, pos[-1])
+
+
+def check_plan(plan, pos, idx, val, col_part, rank):
+    """every row of the plan lists exactly the (global column, value) pairs of the original row, in the original order; a row is
+    in the outer matrix iff it touches another rank"""
+    recv_pid = np.repeat(np.arange(plan.size), plan.recv_counts)
+    recv_lidx = np.concatenate(plan.requests) if plan.buffer_size else np.zeros(0, dtype=np.int64)
+    offs = np.array([o for o, _ in col_part])
+    buffer_global = offs[recv_pid] + recv_lidx
+    assert np.all(np.diff(recv_pid * 10 ** 9 + recv_lidx) > 0)              # unique, ascending (rank, index)
+    outer_of = {int(row): k for k, row in enumerate(plan.scatter)}
+    for i in range(plan.num_rows):
+        cols, vals = idx[pos[i]:pos[i + 1]], val[pos[i]:pos[i + 1]]
+        lo, hi = col_part[rank]
+        remote = np.any((cols < lo) | (cols >= lo + hi))
+        a, b = plan.inner_pos[i], plan.inner_pos[i + 1]
+        if remote:
+            assert a == b and i in outer_of
+            k = outer_of[i]
+            c, d = plan.outer_pos[k], plan.outer_pos[k + 1]
+            assert np.array_equal(buffer_global[plan.outer_idx[c:d]], cols) and np.array_equal(plan.outer_val[c:d], vals)
+        else:
+            assert i not in outer_of
+            assert np.array_equal(plan.inner_idx[a:b] + lo, cols) and np.array_equal(plan.inner_val[a:b], vals)
+
+
+@pytest.mark.parametrize("size,band", [(1, None), (3, None), (4, 6), (2, 3)])
+def test_dist_csr_plan(size, band):
+    import sys
+    sys.path.insert(0, ROOT)
+    from feltor_b200.dist import partition
+    from feltor_b200.dist_csr import DistCsrPlan, contiguous_owner
+    r = np.random.default_rng(size)
+    nrows, ncols = 57, 64
+    pos, idx, val = random_csr(r, nrows, ncols, 9, band)
+    row_part, col_part = partition(nrows, size), partition(ncols, size)
+    g2l = contiguous_owner(col_part)
+    plans = []
+    for rank in range(size):
+        r0, nr = row_part[rank]
+        lp = pos[r0:r0 + nr + 1] - pos[r0]
+        li, lv = idx[pos[r0]:pos[r0 + nr]], val[pos[r0]:pos[r0 + nr]]
+        plan = DistCsrPlan(rank, size, lp, li, lv, g2l, col_part[rank][1])
+        check_plan(plan, lp, li, lv, col_part, rank)
+        plans.append(plan)
+    x = r.uniform(-1, 1, ncols)
+    for rank in range(size):                                                  # the exchange, emulated: pack -> route -> buffer
+        plans[rank].set_sends([plans[p].requests[rank] for p in range(size)])
+    for rank in range(size):
+        segs = []
+        for p in range(size):
+            o = plans[p].send_counts[:rank].sum()
+            xp = x[col_part[p][0]:col_part[p][0] + col_part[p][1]]
+            segs.append(xp[plans[p].send_idx[o:o + plans[p].send_counts[rank]]])
+        buf = np.concatenate(segs) if segs else np.zeros(0)
+        offs = np.array([o for o, _ in col_part])
+        want = x[(offs[np.repeat(np.arange(size), plans[rank].recv_counts)] + np.concatenate(plans[rank].requests)).astype(int)] \
+            if plans[rank].buffer_size else np.zeros(0)
+        assert np.array_equal(buf, want)
+    with pytest.raises(ValueError):
+        contiguous_owner(col_part)(np.array([ncols]))
+
+
+def _csr_worker(rank, world, port, q):
+    import sys
+    sys.path.insert(0, ROOT)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from feltor_b200.dist import partition
+    from feltor_b200.dist_csr import DistCsrPlan, contiguous_owner, exchange_requests
+    r = np.random.default_rng(5)                                             # same matrix on both ranks
+    nrows, ncols = 40, 33
+    pos, idx, val = random_csr(r, nrows, ncols, 7)
+    row_part, col_part = partition(nrows, world), partition(ncols, world)
+    r0, nr = row_part[rank]
+    plan = DistCsrPlan(rank, world, pos[r0:r0 + nr + 1] - pos[r0], idx[pos[r0]:pos[r0 + nr]], val[pos[r0]:pos[r0 + nr]],
+                       contiguous_owner(col_part), col_part[rank][1])
+    asked = exchange_requests(plan.requests, rank, world)
+    plan.set_sends(asked)
+    everyone = [None] * world
+    dist.all_gather_object(everyone, [q_.tolist() for q_ in plan.requests])
+    ok = all(np.array_equal(asked[p], np.asarray(everyone[p][rank], dtype=np.int32)) for p in range(world))
+    ok = ok and int(plan.send_counts.sum()) == sum(len(everyone[p][rank]) for p in range(world))
+    q.put((rank, bool(ok)))
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_dist_csr_requests_world2_gloo():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31000 + os.getpid() % 2000
+    procs = [ctx.Process(target=_csr_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = [q.get(timeout=100) for _ in range(2)]
+    for p in procs:
+        p.join(timeout=30)
+    assert sorted(res) == [(0, True), (1, True)]

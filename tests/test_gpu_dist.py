@@ -124,3 +124,108 @@ def test_dist_ds_centered_z_slab_equals_global(G):
         assert same_bits(G.get(a), G.get(b)), (alpha, beta)
     lib().celltile_plan_destroy(hp)
     lib().celltile_plan_destroy(hm)
+
+
+@pytest.mark.parametrize("size,band,nrows,ncols", [(1, None, 500, 640), (3, None, 3001, 2500), (4, 40, 5000, 5000), (2, 5, 64, 64)])
+def test_dist_csr_equals_global(G, size, band, nrows, ncols):
+    """dg::MPIDistMat::symv (feltor_b200/dist_csr.py: pack, exchange, inner product, fused outer product + scatter) on `size`
+    ranks emulated in this process -- the kernels are the ones N processes run, the exchange between the emulated ranks is a
+    copy -- equals dgb_csr_spmv of the global matrix bit for bit; with one rank the exchange is the library's dgb_comm_gather"""
+    import ctypes as C
+    import torch
+    from feltor_b200 import blas2
+    from feltor_b200._lib import lib
+    from feltor_b200._dev import dvec, ptr, stream
+    from feltor_b200.dist import Comm, partition
+    from feltor_b200.dist_csr import DistCsr, DistCsrPlan, contiguous_owner
+    from test_dist_cpu import random_csr
+    r = rng(size + nrows)
+    pos, idx, val = random_csr(r, nrows, ncols, 30, band)
+    x = r.uniform(-1, 1, ncols)
+    want = G.make(np.full(nrows, np.nan))
+    keep = [dvec(pos), dvec(idx), dvec(val), G.make(x)]   # alive until the call is enqueued
+    lib().csr_spmv(nrows, ncols, *[ptr(a) for a in keep[:3]], C.c_double(1.), ptr(keep[3]), C.c_double(0.), ptr(want), stream())
+    want = G.get(want)
+    row_part, col_part = partition(nrows, size), partition(ncols, size)
+    g2l = contiguous_owner(col_part)
+    local = lambda rank: (pos[row_part[rank][0]:row_part[rank][0] + row_part[rank][1] + 1] - pos[row_part[rank][0]],
+                          idx[pos[row_part[rank][0]]:pos[row_part[rank][0] + row_part[rank][1]]],
+                          val[pos[row_part[rank][0]]:pos[row_part[rank][0] + row_part[rank][1]]])
+    plans = [DistCsrPlan(rank, size, *local(rank), g2l, col_part[rank][1]) for rank in range(size)]
+    comm = Comm(0, 1)
+    mats = []
+    for rank in range(size):
+        m = DistCsr.__new__(DistCsr)
+        comm_r = comm if size == 1 else type("EmulatedRank", (), {"rank": rank, "size": size, "h": None})()
+        DistCsr.__init__(m, comm_r, *local(rank), g2l, col_part[rank][1], asked=[plans[p].requests[rank] for p in range(size)])
+        mats.append(m)
+    xs = [G.make(x[o:o + c]) for o, c in col_part]
+    ys = [G.make(np.full(c, np.nan)) for _, c in row_part]
+    if size == 1:
+        mats[0].symv(xs[0], ys[0])
+        assert mats[0].plan.buffer_size == 0
+    else:
+        for rank in range(size):
+            mats[rank].pack(xs[rank])
+        for rank in range(size):                        # the exchange: segment of p's send buffer meant for `rank` -> rank's buffer
+            ro = 0
+            for p in range(size):
+                so, cnt = int(mats[p].plan.send_counts[:rank].sum()), int(mats[p].plan.send_counts[rank])
+                assert cnt == int(mats[rank].plan.recv_counts[p])
+                mats[rank].recv_buf[ro:ro + cnt].copy_(mats[p].send_buf[so:so + cnt])
+                ro += cnt
+        for rank in range(size):
+            mats[rank].apply_inner(xs[rank], ys[rank])
+            mats[rank].apply_outer(ys[rank])
+        assert sum(m.plan.scatter.size for m in mats) > 0
+    got = np.concatenate([G.get(y) for y in ys])
+    assert same_bits(got, want)
+
+
+def test_dist_csr_self_exchange(G):
+    """a size-1 communicator whose column map sends every second element through the gather buffer: exercises dgb_comm_gather's
+    self message, the side stream and the fused outer kernel inside DistCsr.symv itself"""
+    import ctypes as C
+    from feltor_b200._lib import lib
+    from feltor_b200._dev import dvec, ptr, stream
+    from feltor_b200.dist import Comm
+    from feltor_b200.dist_csr import DistCsr
+    from test_dist_cpu import random_csr
+    r = rng(91)
+    nrows = ncols = 4000
+    pos, idx, val = random_csr(r, nrows, ncols, 25, 30)
+    x = r.uniform(-1, 1, ncols)
+    want = G.make(np.full(nrows, np.nan))
+    keep = [dvec(pos), dvec(idx), dvec(val), G.make(x)]   # alive until the call is enqueued
+    lib().csr_spmv(nrows, ncols, *[ptr(a) for a in keep[:3]], C.c_double(1.), ptr(keep[3]), C.c_double(0.), ptr(want), stream())
+
+    comm = Comm(0, 1)
+    g2l_true = lambda gi: (np.zeros(len(gi), dtype=np.int64), np.asarray(gi, dtype=np.int64))
+    from feltor_b200.dist_csr import DistCsrPlan as plan_cls
+    # build the matrix normally (everything inner), then move every row that has an odd column into the outer matrix by hand and
+    # let the rank ask itself for those columns
+    p = plan_cls(0, 1, pos, idx, val, g2l_true, ncols)
+    assert p.buffer_size == 0
+    counts = np.diff(pos)
+    row_of = np.repeat(np.arange(nrows), counts)
+    outer_row = np.zeros(nrows, dtype=bool)
+    outer_row[row_of[idx % 2 == 1]] = True
+    eo = outer_row[row_of]
+    m = DistCsr(comm, pos, idx, val, g2l_true, ncols)
+    uniq, inv = np.unique(idx[eo], return_inverse=True)
+    m.plan.inner_pos = np.concatenate([[0], np.cumsum(np.where(outer_row, 0, counts))]).astype(np.int32)
+    m.plan.scatter = np.nonzero(outer_row)[0].astype(np.int32)
+    m.plan.buffer_size = int(uniq.size)
+    m.plan.send_idx = uniq.astype(np.int32)
+    m.inner = tuple(dvec(a) for a in (m.plan.inner_pos, idx[~eo].astype(np.int32), val[~eo]))
+    m.outer = tuple(dvec(a) for a in (np.concatenate([[0], np.cumsum(counts[m.plan.scatter])]).astype(np.int32), inv.astype(np.int32), val[eo]))
+    m.scatter, m.send_idx = dvec(m.plan.scatter), dvec(m.plan.send_idx)
+    import torch
+    m.send_buf = torch.empty(uniq.size, dtype=torch.float64, device="cuda")
+    m.recv_buf = torch.full((uniq.size,), float("nan"), dtype=torch.float64, device="cuda")
+    m._sc = (C.c_int * 1)(int(uniq.size))
+    m._rc = (C.c_int * 1)(int(uniq.size))
+    y = G.make(np.full(nrows, np.nan))
+    for _ in range(3):
+        m.symv(G.make(x), y)
+    assert same_bits(G.get(y), G.get(want))

@@ -127,6 +127,28 @@ DD.centered(-1.3, dvec(DD.local(fd).copy()), 0.5, gb)
 same_ds = np.array_equal(hvec(gb).view(np.int64), DD.local(hvec(ga)).view(np.int64))
 print(f"rank {rank}/{size} DS::centered on z-slabs ({Nzd} planes): {same_ds}", flush=True)
 ok = ok and same_ds
+# row-distributed CSR product (dg::MPIDistMat, feltor_b200/dist_csr.py) on N ranks: every rank's rows against the global product
+from test_dist_cpu import random_csr  # noqa: E402
+from feltor_b200.dist import partition  # noqa: E402
+from feltor_b200.dist_csr import DistCsr, contiguous_owner  # noqa: E402
+for band in (None, 60):
+    rc = np.random.default_rng(21)
+    nr_, nc_ = 20000, 18000
+    cpos, cidx, cval = random_csr(rc, nr_, nc_, 40, band)
+    cx = rc.uniform(-1, 1, nc_)
+    cy = torch.full((nr_,), float("nan"), dtype=torch.float64, device="cuda")
+    keep = [dvec(cpos), dvec(cidx), dvec(cval), dvec(cx)]
+    fb.lib().csr_spmv(nr_, nc_, *[ptr(a) for a in keep[:3]], C.c_double(1.), ptr(keep[3]), C.c_double(0.), ptr(cy), stream())
+    rp, cp = partition(nr_, size), partition(nc_, size)
+    r0, nrl = rp[rank]
+    M = DistCsr(comm, cpos[r0:r0 + nrl + 1] - cpos[r0], cidx[cpos[r0]:cpos[r0 + nrl]], cval[cpos[r0]:cpos[r0 + nrl]], contiguous_owner(cp), cp[rank][1])
+    yl = torch.full((nrl,), float("nan"), dtype=torch.float64, device="cuda")
+    xl = dvec(cx[cp[rank][0]:cp[rank][0] + cp[rank][1]].copy())
+    for _ in range(3):
+        M.symv(xl, yl)
+    same_csr = np.array_equal(hvec(yl).view(np.int64), hvec(cy)[r0:r0 + nrl].view(np.int64))
+    print(f"rank {rank}/{size} DistCsr band={band}: {same_csr} (outer rows {M.plan.scatter.size}, buffer {M.plan.buffer_size}, sends {M.plan.send_idx.size})", flush=True)
+    ok = ok and same_csr
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
