@@ -194,3 +194,33 @@ def stencil(kind, pos, idx, val, x, y, alpha=0.0):
     """blas2::stencil(f, M, x, y) (blas2.h:454) with f = CSRMedianFilter / CSRSWMFilter(alpha) / CSRAverageFilter /
     CSRSymvFilter / CSRSlopeLimiter(alpha) (topology/filter.h:174-336); pos, idx int32 device tensors, val float64 or None."""
     lib().csr_stencil(STENCILS[kind], pos.numel() - 1, ptr(pos), ptr(idx), ptr(val), d(alpha), ptr(x), ptr(y), stream())
+
+
+def spgemm(B_rows, B_cols, C_cols, B, Cm):
+    """A = B Cm for CSR matrices on the device (pos, idx int32; val float64), bitwise the reference's host product
+    dg::SparseMatrix::operator* (sparsematrix.h:549-566, sparsematrix_cpu.h:19-95): returns (pos, idx, val) device tensors"""
+    import torch
+    h, nnz = C.c_void_p(), C.c_longlong()
+    lib().csr_spgemm_symbolic(C.byref(h), B_rows, B_cols, C_cols, ptr(B[0]), ptr(B[1]), ptr(Cm[0]), ptr(Cm[1]), C.byref(nnz), stream())
+    try:
+        pos = torch.empty(B_rows + 1, dtype=torch.int32, device="cuda")
+        idx = torch.empty(max(nnz.value, 1), dtype=torch.int32, device="cuda")
+        val = torch.empty(max(nnz.value, 1), dtype=torch.float64, device="cuda")
+        lib().csr_spgemm_numeric(h, ptr(B[0]), ptr(B[1]), ptr(B[2]), ptr(Cm[0]), ptr(Cm[1]), ptr(Cm[2]), ptr(pos), ptr(idx), ptr(val), stream())
+    finally:
+        lib().csr_spgemm_destroy(h)
+    return pos, idx[:nnz.value], val[:nnz.value]
+
+
+def spgemm_host(B_rows, B_cols, C_cols, B, Cm):
+    """the same for host (numpy) arrays, as the binding of SparseMatrix::operator* uses it"""
+    import numpy as np
+    B = (np.ascontiguousarray(B[0], dtype=np.int32), np.ascontiguousarray(B[1], dtype=np.int32), np.ascontiguousarray(B[2], dtype=np.float64))
+    Cm = (np.ascontiguousarray(Cm[0], dtype=np.int32), np.ascontiguousarray(Cm[1], dtype=np.int32), np.ascontiguousarray(Cm[2], dtype=np.float64))
+    h, nnz = C.c_void_p(), C.c_longlong()
+    a = lambda x: C.c_void_p(x.ctypes.data)
+    lib().csr_spgemm_host_begin(C.byref(h), B_rows, B_cols, C_cols, a(B[0]), a(B[1]), a(B[2]), a(Cm[0]), a(Cm[1]), a(Cm[2]), C.byref(nnz))
+    pos, idx, val = np.empty(B_rows + 1, dtype=np.int32), np.empty(max(nnz.value, 1), dtype=np.int32), np.empty(max(nnz.value, 1))
+    lib().csr_spgemm_host_finish(h, a(pos), a(idx), a(val))
+    return pos, idx[:nnz.value], val[:nnz.value]
+

@@ -286,6 +286,24 @@ DGB_API int dgb_csr_spmv_planes(int num_rows, int num_cols, const int* row_offse
                                 const double* vals, double alpha, const double* x, double beta, double* y,
                                 int nplanes, int shift, dgb_stream_t s);
 
+/* A = B C for CSR matrices ON THE DEVICE, bit-identical to the reference's host kernel dg::detail::spgemm_cpu_kernel
+ * (inc/dg/backend/sparsematrix_cpu.h:19-95, called by SparseMatrix::operator*, sparsematrix.h:549-566): rows of A sorted by
+ * column, duplicates and unsorted input allowed, every entry accumulated as w = fma(b, c, w) in the serial loop's candidate order.
+ * The reference has no device version; dg::geo::Fieldaligned spends seconds to minutes in it (fieldaligned.h:549-735).
+ *   symbolic  counts the distinct columns of every row, returns the plan and the number of entries of A (synchronises);
+ *   numeric   fills A_pos[B_rows + 1], A_idx[nnz], A_val[nnz] (device arrays);
+ *   host_begin / host_finish  the same for HOST arrays (uploads, multiplies, downloads; finish releases the plan).
+ * DGB_ERR_UNSUPPORTED if a row of A has more than 4096 distinct columns or A more than 2^31 - 1 entries. */
+typedef struct dgb_spgemm dgb_spgemm;
+DGB_API int dgb_csr_spgemm_symbolic(dgb_spgemm** plan, int B_rows, int B_cols, int C_cols, const int* B_pos, const int* B_idx,
+                                    const int* C_pos, const int* C_idx, long long* nnz, dgb_stream_t s);
+DGB_API int dgb_csr_spgemm_numeric(dgb_spgemm* plan, const int* B_pos, const int* B_idx, const double* B_val, const int* C_pos,
+                                   const int* C_idx, const double* C_val, int* A_pos, int* A_idx, double* A_val, dgb_stream_t s);
+DGB_API int dgb_csr_spgemm_destroy(dgb_spgemm* plan);
+DGB_API int dgb_csr_spgemm_host_begin(dgb_spgemm** plan, int B_rows, int B_cols, int C_cols, const int* B_pos, const int* B_idx,
+                                      const double* B_val, const int* C_pos, const int* C_idx, const double* C_val, long long* nnz);
+DGB_API int dgb_csr_spgemm_host_finish(dgb_spgemm* plan, int* A_pos, int* A_idx, double* A_val);
+
 /* The pieces of dg::MPIDistMat::symv (inc/dg/backend/mpi_matrix.h:478-523) a row-distributed CSR matrix needs besides
  * dgb_csr_spmv for its inner part and dgb_comm_gather for the exchange (feltor_b200/dist_csr.py puts them together):
  *   dgb_gather_indexed        out[i] = x[idx[i]]: packs the values other ranks asked for (MPIGather, mpi_gather.h:454-705)

@@ -261,6 +261,39 @@ ORC_API void orc_csr_stencil(int kind, int num_rows, const int* pos, const int* 
     }
     free(scratch);
 }
+/* dg::detail::spgemm_cpu_kernel, inc/dg/backend/sparsematrix_cpu.h:19-95: A = B C.  Pass 1 (A_idx == NULL) fills A_pos only and
+ * returns the number of entries; pass 2 fills A_idx (sorted per row) and A_val.  The workspace update `w[j] += b*c` is an FMA in
+ * the reference's build (gcc -mfma contracts it; pinned on the live reference in tests/test_spgemm.py). */
+static int orc_cmp_int(const void* a, const void* b) { int x = *(const int*)a, y = *(const int*)b; return x < y ? -1 : x > y; }
+ORC_API long long orc_spgemm(int B_rows, int C_cols, const int* B_pos, const int* B_idx, const double* B_val, const int* C_pos,
+                             const int* C_idx, const double* C_val, int* A_pos, int* A_idx, double* A_val) {
+    char* seen = (char*)calloc(C_cols > 0 ? C_cols : 1, 1);
+    double* w = (double*)calloc(C_cols > 0 ? C_cols : 1, sizeof(double));
+    int* wlist = (int*)malloc(sizeof(int) * (C_cols > 0 ? C_cols : 1));
+    long long run = 0;
+    for (int i = 0; i < B_rows; i++) {
+        int m = 0;
+        for (int pB = B_pos[i]; pB < B_pos[i + 1]; pB++) {
+            int k = B_idx[pB];
+            for (int pC = C_pos[k]; pC < C_pos[k + 1]; pC++) {
+                int j = C_idx[pC];
+                if (!seen[j]) { seen[j] = 1; wlist[m++] = j; }
+                if (A_idx) w[j] = fma(B_val[pB], C_val[pC], w[j]);
+            }
+        }
+        qsort(wlist, m, sizeof(int), orc_cmp_int);
+        if (!A_idx) A_pos[i] = (int)run;
+        for (int q = 0; q < m; q++) {
+            int j = wlist[q];
+            if (A_idx) { A_idx[run + q] = j; A_val[run + q] = w[j]; w[j] = 0; }
+            seen[j] = 0;
+        }
+        run += m;
+    }
+    if (!A_idx) A_pos[B_rows] = (int)run;
+    free(seen); free(w); free(wlist);
+    return run;
+}
 /* EmbeddedPairSum subroutines.h:179-204: y = b0*y + sum b_i k_i ; yt likewise.  k = array of pointers */
 ORC_API void orc_embedded_pair_sum(int n, double* y, double* yt, double b0, double bt0, int nk, const double* b,
                                    const double* bt, const double* const* k) {

@@ -219,3 +219,17 @@ class Elliptic2d:
     def pcg_solve(self, x, b, P, W, eps, nrmb_correction=1.0, test_frequency=1, max_iter=None, residuals=None):
         return lib().orc_pcg_solve_elliptic2d(C.byref(self.s), dp(x), dp(b), dp(P), dp(W), d(eps), d(nrmb_correction),
                                               test_frequency, max_iter or self.size, dp(self.work), dp(residuals))
+
+
+def spgemm(B_rows, C_cols, B, Cm):
+    """dg::detail::spgemm_cpu_kernel (sparsematrix_cpu.h:19-95): B, Cm = (pos, idx, val) -> (pos, idx, val) of B Cm"""
+    L = lib()
+    L.orc_spgemm.restype = C.c_longlong
+    bp, bi, bv = (np.ascontiguousarray(B[0], dtype=np.int32), np.ascontiguousarray(B[1], dtype=np.int32), np.ascontiguousarray(B[2], dtype=np.float64))
+    cp, ci, cv = (np.ascontiguousarray(Cm[0], dtype=np.int32), np.ascontiguousarray(Cm[1], dtype=np.int32), np.ascontiguousarray(Cm[2], dtype=np.float64))
+    pos = np.zeros(B_rows + 1, dtype=np.int32)
+    nnz = L.orc_spgemm(B_rows, C_cols, ip(bp), ip(bi), dp(bv), ip(cp), ip(ci), dp(cv), ip(pos), None, None)
+    idx, val = np.zeros(max(nnz, 1), dtype=np.int32), np.zeros(max(nnz, 1))
+    L.orc_spgemm(B_rows, C_cols, ip(bp), ip(bi), dp(bv), ip(cp), ip(ci), dp(cv), ip(pos), ip(idx), dp(val))
+    return pos, idx[:nnz], val[:nnz]
+

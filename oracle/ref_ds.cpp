@@ -94,6 +94,20 @@ extern "C" void ref_csr_stencil(int kind, int num_rows, int num_cols, const int*
     for (int i = 0; i < num_rows; i++) y[i] = vy[i];
 }
 
+// dg::SparseMatrix::operator* = dg::detail::spgemm_cpu_kernel (inc/dg/backend/sparsematrix.h:549-566, sparsematrix_cpu.h:19-95).
+// Returns the number of entries; pass A_idx == NULL to learn it first (A_pos is filled either way).
+extern "C" long long ref_spgemm(int B_rows, int B_cols, int C_cols, const int* B_pos, const int* B_idx, const double* B_val, const int* C_pos,
+                                const int* C_idx, const double* C_val, int* A_pos, int* A_idx, double* A_val) {
+    thrust::host_vector<int> bp(B_pos, B_pos + B_rows + 1), bi(B_idx, B_idx + B_pos[B_rows]), cp(C_pos, C_pos + B_cols + 1), ci(C_idx, C_idx + C_pos[B_cols]);
+    Vec bv(B_val, B_val + B_pos[B_rows]), cv(C_val, C_val + C_pos[B_cols]);
+    dg::IHMatrix B(B_rows, B_cols, bp, bi, bv), Cm(B_cols, C_cols, cp, ci, cv);
+    dg::IHMatrix A = B * Cm;
+    for (int i = 0; i <= B_rows; i++) A_pos[i] = A.row_offsets()[i];
+    if (A_idx)
+        for (size_t k = 0; k < A.values().size(); k++) { A_idx[k] = A.column_indices()[k]; A_val[k] = A.values()[k]; }
+    return (long long)A.values().size();
+}
+
 // dg::create::limiter_stencil on a 1-d grid / along `direction` (0 x, 1 y) of a 2-d grid (inc/dg/topology/stencil.h:199-256)
 extern "C" int ref_limiter_stencil(int ndim, const double* x0, const double* x1, int n, const int* N, const int* bc, int direction, int bound,
                                    int* pos, int* idx, double* val) {

@@ -10,7 +10,7 @@ import pytest
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "tests", "golden"))
 sys.path.insert(0, os.path.join(ROOT, "oracle"))
-import orc
+from oracle import orc
 from util import same_bits
 
 GOLD = np.load(os.path.join(ROOT, "tests", "golden", "limiter_golden.npz"))
