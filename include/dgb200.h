@@ -289,7 +289,7 @@ DGB_API int dgb_csr_spmv_planes(int num_rows, int num_cols, const int* row_offse
 /* A = B C for CSR matrices ON THE DEVICE, bit-identical to the reference's host kernel dg::detail::spgemm_cpu_kernel
  * (inc/dg/backend/sparsematrix_cpu.h:19-95, called by SparseMatrix::operator*, sparsematrix.h:549-566): rows of A sorted by
  * column, duplicates and unsorted input allowed, every entry accumulated as w = fma(b, c, w) in the serial loop's candidate order.
- * The reference has no device version; dg::geo::Fieldaligned spends seconds to minutes in it (fieldaligned.h:549-735).
+ * The reference has no device version; dg::geo::Fieldaligned calls it three times per construction (fieldaligned.h:645-658).
  *   symbolic  counts the distinct columns of every row, returns the plan and the number of entries of A (synchronises);
  *   numeric   fills A_pos[B_rows + 1], A_idx[nnz], A_val[nnz] (device arrays);
  *   host_begin / host_finish  the same for HOST arrays (uploads, multiplies, downloads; finish releases the plan).

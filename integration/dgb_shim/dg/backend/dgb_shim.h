@@ -53,6 +53,14 @@ inline int& fusion_flag()
     return f;
 }
 
+// SparseMatrix::operator* of host matrices goes to the device from this many stored entries (both operands) on; smaller
+// products stay on the host (DGB_SHIM_SPGEMM_MIN overrides)
+inline size_t spgemm_threshold()
+{
+    static size_t t = [](){ const char* e = std::getenv( "DGB_SHIM_SPGEMM_MIN"); return e ? (size_t)std::atoll( e) : (size_t)200000; }();
+    return t;
+}
+
 // persistent-style launch geometry for the generic templates: enough CTAs to fill the machine, never more than needed
 inline unsigned generic_grid( size_t size, unsigned threads = 256)
 {

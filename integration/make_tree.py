@@ -11,6 +11,9 @@ What it does -- this is the complete change a Feltor maintainer would make to in
   3. applies two small edits to files that stay the reference's:
        backend/sparseblockmat.h   EllSparseBlockMat gets a launch-plan cache member (as SparseMatrix has CSRCache_gpu,
                                   sparsematrix.h:620-628); set_default_range / set_right_size / set_left_size drop it
+       backend/sparsematrix.h     SparseMatrix::operator* of two host matrices (the reference has no device spgemm) sends
+                                  large products to dgb_csr_spgemm_host_* (bit-identical, seconds -> milliseconds in
+                                  dg::geo::Fieldaligned's constructor)
        backend/blas2_stencil.h    the CUDA section (stencil_kernel + doParallelFor_dispatch( CudaTag,...)) is replaced
                                   by #include "dgb_parallel_for.cuh"
 Applications (src/toefl/toefl.h, ...) and every other header compile UNCHANGED:
@@ -196,6 +199,34 @@ def main():
     s = (s[:beg] + "#if THRUST_DEVICE_SYSTEM==THRUST_DEVICE_SYSTEM_CUDA\n" + ns_close +
          '#include "dgb_parallel_for.cuh" // libdgb200 binding: doParallelFor_dispatch( CudaTag, ...)\n' + ns_open + s[end:])
     open(st, "w").write(s)
+    # 3c. SparseMatrix::operator* of host matrices (the reference has no device spgemm): large products run on the device,
+    #     bit-identical to detail::spgemm_cpu_kernel (feltor_b200/csrc/spgemm.cu); dg::geo::Fieldaligned's setup is the customer
+    sm = os.path.join(a.out, "dg", "backend", "sparsematrix.h")
+    edit(sm, '#include "blas2_stencil.h"', '#include "blas2_stencil.h"\n#include "dgb_shim.h" // libdgb200 binding: device spgemm for host matrices')
+    edit(sm, "        Vector<Index> row_offsets, cols;\n        Vector<Value> vals;\n\n        detail::spgemm_cpu_kernel(",
+         "        Vector<Index> row_offsets, cols;\n        Vector<Value> vals;\n\n"
+         "        if constexpr( std::is_same_v<Index, int> && std::is_same_v<Value, double>)\n"
+         "        {   // libdgb200 binding: large products on the device\n"
+         "            if( dgb::shim::fusion_flag() && lhs.m_vals.size() + rhs.m_vals.size() >= dgb::shim::spgemm_threshold())\n"
+         "            {\n"
+         "                dgb_spgemm* plan = nullptr;\n"
+         "                long long nnz = 0;\n"
+         "                const int code = dgb_csr_spgemm_host_begin( &plan, (int)lhs.m_num_rows, (int)lhs.m_num_cols, (int)rhs.m_num_cols,\n"
+         "                    thrust::raw_pointer_cast( lhs.m_row_offsets.data()), thrust::raw_pointer_cast( lhs.m_cols.data()), thrust::raw_pointer_cast( lhs.m_vals.data()),\n"
+         "                    thrust::raw_pointer_cast( rhs.m_row_offsets.data()), thrust::raw_pointer_cast( rhs.m_cols.data()), thrust::raw_pointer_cast( rhs.m_vals.data()), &nnz);\n"
+         "                if( code == 0)\n"
+         "                {\n"
+         "                    row_offsets.resize( lhs.m_num_rows + 1); cols.resize( nnz); vals.resize( nnz);\n"
+         "                    dgb::shim::check( dgb_csr_spgemm_host_finish( plan, thrust::raw_pointer_cast( row_offsets.data()),\n"
+         "                        thrust::raw_pointer_cast( cols.data()), thrust::raw_pointer_cast( vals.data())), \"dg::SparseMatrix::operator*\");\n"
+         "                    dgb::shim::note_library();\n"
+         "                    return SparseMatrix( lhs.m_num_rows, rhs.m_num_cols, row_offsets, cols, vals);\n"
+         "                }\n"
+         "                if( code != DGB_ERR_UNSUPPORTED) dgb::shim::check( code, \"dg::SparseMatrix::operator*\");\n"
+         "                // a row with more distinct columns than the device kernel holds: the host kernel below\n"
+         "            }\n"
+         "        }\n"
+         "        detail::spgemm_cpu_kernel(")
     if not a.no_fusion:
         fusion_hooks(a.out)
     print("make_tree.py: wrote", a.out)
