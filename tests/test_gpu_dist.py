@@ -229,3 +229,84 @@ def test_dist_csr_self_exchange(G):
     for _ in range(3):
         m.symv(G.make(x), y)
     assert same_bits(G.get(y), G.get(want))
+
+
+def _emulated_dist_ell(G, m, size, row_part, col_part, left, right, alpha, beta, xs, ys):
+    """run DistEll.symv step by step for `size` ranks in this process (the exchange between them is a copy)"""
+    from feltor_b200.dist_ell import DistEll, DistEllPlan
+    plans = [DistEllPlan(r, size, m, row_part[r][0], row_part[r][1], col_part, left, right) for r in range(size)]
+    mats = []
+    for r in range(size):
+        comm_r = type("EmulatedRank", (), {"rank": r, "size": size, "h": None})()
+        mats.append(DistEll(comm_r, m, row_part[r][0], row_part[r][1], col_part, left, right, asked=[plans[p].requests[r] for p in range(size)]))
+    for r in range(size):
+        mats[r].pack(xs[r])
+    for r in range(size):
+        ro = 0
+        for p in range(size):
+            ch = mats[p].plan.chunk
+            so, cnt = int(mats[p].plan.send_blocks[:r].sum()) * ch, int(mats[p].plan.send_blocks[r]) * ch
+            assert cnt == int(mats[r].plan.recv_blocks[p]) * ch
+            mats[r].recv_buf[ro:ro + cnt].copy_(mats[p].send_buf[so:so + cnt])
+            ro += cnt
+    for r in range(size):
+        mats[r].apply_inner(alpha, xs[r], beta, ys[r])
+        mats[r].apply_outer(alpha, ys[r])
+    return mats
+
+
+@pytest.mark.parametrize("coord,size,bc,direction,n,N", [(0, 3, 1, 0, 3, [24, 10]), (0, 4, 0, 2, 3, [37, 6]), (1, 3, 0, 1, 3, [9, 31]), (1, 2, 4, 2, 2, [8, 12]),
+                                                         (0, 5, 2, "jump", 4, [25, 3]), (1, 8, 0, "jump", 3, [5, 16])])
+def test_dist_ell_equals_global(G, coord, size, bc, direction, n, N):
+    """dg::MPISparseBlockMat::symv (feltor_b200/dist_ell.py: inner Ell + outer Coo from make_mpi_sparseblockmat's row split, packed
+    block columns, exchange, mpi_matrix.h:183-330) for derivatives / jumps distributed along THEIR OWN axis -- x- and y-
+    decompositions, periodic wrap across the first and last rank, uneven partitions -- equals dgb_ell_symv of the global matrix
+    on the global vector bit for bit"""
+    from feltor_b200 import topology as T
+    from feltor_b200.dist import partition
+    bcs = [bc, bc]
+    g = T.Grid([0, 0], [1., 2.], n, N, bcs)
+    m = T.jump(coord, g, bc) if direction == "jump" else T.derivative(coord, g, bc, direction)
+    r = rng(coord * 10 + size)
+    x, y0 = r.uniform(-1, 1, g.size), r.uniform(-1, 1, g.size)
+    nx, ny = n * N[0], n * N[1]
+    part = partition(N[coord], size)
+    if coord == 0:
+        left, right = ny, 1
+        cut = lambda v, o, c: np.ascontiguousarray(v.reshape(ny, nx)[:, o * n:(o + c) * n]).reshape(-1)
+    else:
+        left, right = 1, nx
+        cut = lambda v, o, c: np.ascontiguousarray(v.reshape(ny, nx)[o * n:(o + c) * n]).reshape(-1)
+    for alpha, beta in ((1., 0.), (-0.7, 0.4)):
+        want = G.make(y0)
+        m.symv(alpha, G.make(x), beta, want)
+        want = G.get(want)
+        xs = [G.make(cut(x, o, c)) for o, c in part]
+        ys = [G.make(cut(y0, o, c) if beta != 0. else np.full(c * n * (ny if coord == 0 else nx), np.nan)) for o, c in part]
+        mats = _emulated_dist_ell(G, m, size, part, part, left, right, alpha, beta, xs, ys)
+        for (o, c), yl in zip(part, ys):
+            assert same_bits(G.get(yl), cut(want, o, c)), (alpha, beta, o)
+        assert sum(mt.plan.coo_rows.size for mt in mats) > 0
+
+
+def test_dist_ell_projection(G):
+    """a rectangular block matrix (fast projection: half as many block rows as columns) with different row and column
+    distributions"""
+    from feltor_b200 import topology as T
+    from feltor_b200.dist import partition
+    n, N = 3, [12, 16]
+    g = T.Grid([0, 0], [1., 2.], n, N, [1, 0])
+    m = T.fast_projection(1, g, 1, 2)           # along y: 8 block rows, 16 block columns, right = n Nx
+    r = rng(2)
+    x = r.uniform(-1, 1, g.size)
+    nx = n * N[0]
+    want = G.make(np.full(m.total_rows, np.nan))
+    m.symv(1., G.make(x), 0., want)
+    want = G.get(want)
+    size = 3
+    row_part, col_part = partition(N[1] // 2, size), [(0, 5), (5, 4), (9, 7)]      # rows and columns cut at unrelated places
+    xs = [G.make(x.reshape(-1, nx)[o * n:(o + c) * n].reshape(-1).copy()) for o, c in col_part]
+    ys = [G.make(np.full(c * n * nx, np.nan)) for _, c in row_part]
+    _emulated_dist_ell(G, m, size, row_part, col_part, 1, nx, 1., 0., xs, ys)
+    for (o, c), yl in zip(row_part, ys):
+        assert same_bits(G.get(yl), want.reshape(-1, nx)[o * n:(o + c) * n].reshape(-1))

@@ -149,6 +149,30 @@ for band in (None, 60):
     same_csr = np.array_equal(hvec(yl).view(np.int64), hvec(cy)[r0:r0 + nrl].view(np.int64))
     print(f"rank {rank}/{size} DistCsr band={band}: {same_csr} (outer rows {M.plan.scatter.size}, buffer {M.plan.buffer_size}, sends {M.plan.send_idx.size})", flush=True)
     ok = ok and same_csr
+# block matrices distributed along their own axis (dg::MPISparseBlockMat, feltor_b200/dist_ell.py): an x-decomposition of dx and
+# a y-decomposition of the jump matrix, periodic across the ranks, against the global product
+from feltor_b200.dist_ell import DistEll  # noqa: E402
+for coord, what in ((0, "dx centered"), (1, "jump y")):
+    ge = T.Grid([0, 0], [1., 2.], 3, [16 * size + 3, 12 * size + 1], [T.PER, T.PER])
+    me = T.derivative(0, ge, T.PER, T.CENTERED) if coord == 0 else T.jump(1, ge, T.PER)
+    re_ = np.random.default_rng(8)
+    xe, ye0 = re_.uniform(-1, 1, ge.size), re_.uniform(-1, 1, ge.size)
+    nxe, nye = 3 * ge.N[0], 3 * ge.N[1]
+    ywant = dvec(ye0)
+    me.symv(-0.6, dvec(xe), 0.3, ywant)
+    parte = partition(ge.N[coord], size)
+    o_, c_ = parte[rank]
+    if coord == 0:
+        cut = lambda v: np.ascontiguousarray(v.reshape(nye, nxe)[:, o_ * 3:(o_ + c_) * 3]).reshape(-1)
+        De = DistEll(comm, me, o_, c_, parte, nye, 1)
+    else:
+        cut = lambda v: np.ascontiguousarray(v.reshape(nye, nxe)[o_ * 3:(o_ + c_) * 3]).reshape(-1)
+        De = DistEll(comm, me, o_, c_, parte, 1, nxe)
+    yl, xl = dvec(cut(ye0)), dvec(cut(xe))
+    De.symv(-0.6, xl, 0.3, yl)
+    same_ell = np.array_equal(hvec(yl).view(np.int64), cut(hvec(ywant)).view(np.int64))
+    print(f"rank {rank}/{size} DistEll {what}: {same_ell} (outer entries {De.plan.coo_rows.size}, chunks {De.plan.num_chunks})", flush=True)
+    ok = ok and same_ell
 t = torch.tensor([1 if ok else 0], device="cuda")
 dist.all_reduce(t, op=dist.ReduceOp.MIN)
 if rank == 0:
