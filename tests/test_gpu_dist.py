@@ -310,3 +310,23 @@ def test_dist_ell_projection(G):
     _emulated_dist_ell(G, m, size, row_part, col_part, 1, nx, 1., 0., xs, ys)
     for (o, c), yl in zip(row_part, ys):
         assert same_bits(G.get(yl), want.reshape(-1, nx)[o * n:(o + c) * n].reshape(-1))
+
+
+@pytest.mark.timeout(600)
+def test_dist_check_on_all_visible_gpus(G):
+    """tools/dist_check.py under torch.distributed.run on every visible GPU (needs >= 2): slab Elliptic / PCG / exact dot / toefl /
+    DS on z-slabs / distributed CSR and block matrices, each rank's part bitwise equal to the single-GPU result, with the real
+    NCCL / peer-memory exchanges instead of the size-1 communicator and the emulated ranks of the tests above"""
+    import os
+    import subprocess
+    import sys
+    import torch
+    ngpu = torch.cuda.device_count()
+    if ngpu < 2:
+        pytest.skip("one visible GPU: the N > 1 exchanges are covered by tools/dist_check.py runs (profiles/dist_check_r02_n*.log)")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    n = 2 if ngpu < 4 else 4
+    port = 29600 + os.getpid() % 300
+    p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "tools", "dist_check.py")], capture_output=True, text=True, timeout=580)
+    assert p.returncode == 0 and "DIST_CHECK PASS" in p.stdout, p.stdout[-3000:] + p.stderr[-2000:]
