@@ -192,3 +192,49 @@ def test_dist_csr_requests_world2_gloo():
     for p in procs:
         p.join(timeout=30)
     assert sorted(res) == [(0, True), (1, True)]
+
+
+@pytest.mark.parametrize("size,periodic", [(1, True), (3, True), (4, False)])
+def test_dist_ell_plan(size, periodic):
+    """dg::make_mpi_sparseblockmat host logic (feltor_b200/dist_ell.py, mpi_matrix.h:242-330) on a three-block stencil matrix: a
+    block row is in the outer (Coo) matrix iff it touches another rank, the inner matrix keeps it empty, every row lists its
+    blocks in slot order with the right global column, and the requests of all ranks match the sends"""
+    import sys
+    sys.path.insert(0, ROOT)
+    from feltor_b200.dist import partition
+    from feltor_b200.dist_ell import DistEllPlan
+    N, n, bpl = 13, 2, 3
+
+    class M:
+        pass
+    m = M()
+    m.num_rows = m.num_cols = N
+    m.bpl, m.n = bpl, n
+    cols = np.array([[i - 1, i, i + 1] for i in range(N)])
+    cols = cols % N if periodic else np.where((cols < 0) | (cols >= N), -1, cols)
+    m.cols_idx = cols.reshape(-1).astype(np.int32)
+    m.data_idx = np.tile(np.arange(bpl), N).astype(np.int32)
+    m.data = np.arange(bpl * n * n, dtype=np.float64)
+    part = partition(N, size)
+    plans = [DistEllPlan(r, size, m, part[r][0], part[r][1], part, 4, 5) for r in range(size)]
+    offs = np.array([o for o, _ in part])
+    for r, p in enumerate(plans):
+        o, c = part[r]
+        recv_pid = np.repeat(np.arange(size), p.recv_blocks)
+        chunk_global = offs[recv_pid] + (np.concatenate(p.requests) if p.num_chunks else np.zeros(0, dtype=np.int64))
+        inner = p.inner_cols.reshape(c, bpl)
+        for i in range(c):
+            g = cols[o + i]
+            remote = np.any((g >= 0) & ((g < o) | (g >= o + c)))
+            mine = np.nonzero(p.coo_rows == i)[0]
+            if remote:
+                assert np.all(inner[i] == -1)
+                assert np.array_equal(chunk_global[p.coo_cols[mine]], g[g >= 0])          # slot order kept
+                assert np.array_equal(p.coo_didx[mine], m.data_idx.reshape(N, bpl)[o + i][g >= 0])
+            else:
+                assert mine.size == 0
+                assert np.array_equal(np.where(inner[i] >= 0, inner[i] + o, -1), g)
+        p.set_sends([plans[q].requests[r] for q in range(size)])
+        assert p.send_idx.size == int(p.send_blocks.sum()) * p.chunk and p.chunk == n * 4 * 5
+    if size == 1:
+        assert plans[0].num_chunks == 0 and plans[0].coo_rows.size == 0
