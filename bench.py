@@ -428,6 +428,12 @@ def main():
                           "mean_pcg_iterations_per_solve": t_out["mean_pcg_iterations_per_solve(stage0,1,2)"]}
         except Exception as e:
             toefl_dist = {"failed": repr(e)}
+        try:  # the multistep stepper config 3 names: one right-hand side per step
+            torch.cuda.empty_cache()
+            m_out, _ = toefl_bench.run(cells, 12, 4, 0.5, comm=comm, stepper="multistep")
+            toefl_dist["multistep"] = {"value": m_out["steps_per_s"], "unit": "steps/s", "config": m_out["workload"], "steps": m_out["steps"]}
+        except Exception as e:
+            toefl_dist["multistep"] = {"failed": repr(e)}
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -507,6 +513,13 @@ def main():
                             "mean_pcg_iterations_per_solve": t_out["mean_pcg_iterations_per_solve(stage0,1,2)"]}
         except Exception as e:
             out["toefl"] = {"failed": repr(e)}
+        try:  # the multistep stepper config 3 names (dg::ExplicitMultistep TVB-3-3: one right-hand side per step)
+            m_out, _ = toefl_bench.run(cells, 20, 5, 0.5, stepper="multistep")
+            out["toefl"]["multistep"] = {"metric": "toefl_steps_per_second", "value": m_out["steps_per_s"], "unit": "steps/s", "config": m_out["workload"],
+                                         "steps": m_out["steps"], "kernel_launches_per_step": m_out["kernel_launches"] / m_out["steps"],
+                                         "mean_pcg_iterations_per_solve": m_out["mean_pcg_iterations_per_solve(stage0,1,2)"]}
+        except Exception as e:
+            out["toefl"]["multistep"] = {"failed": repr(e)}
     if not args.no_cpu_baseline and world == 1:
         try:
             from oracle import refwrap as R

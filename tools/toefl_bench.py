@@ -3,7 +3,7 @@
 nested MultigridCG2d (3 stages) for the two Helmholtz and the polarisation solve, fixed-step Bogacki-Shampine-4-2-3 (the
 tableau the shipped toefl.cpp uses; FSAL: 3 right-hand sides per step).  Prints steps/s and RHS/s on one GPU.
 `python bench.py --workload toefl` runs this and times the unmodified reference (OpenMP) beside it.
-  python tools/toefl_bench.py [--cells 1024] [--steps 6] [--warmup 2] [--dt 0.5]"""
+  python tools/toefl_bench.py [--cells 1024] [--steps 6] [--warmup 2] [--dt 0.5] [--stepper erk|multistep] [--tableau NAME]"""
 import argparse
 import json
 import os
@@ -25,9 +25,12 @@ def params(N):
             "model": {"type": "global", "boussinesq": False, "curvature": 0.00015, "tau": 1, "nu": 1e-6}}
 
 
-def run(cells=1024, steps=6, warmup=2, dt=0.5, comm=None):
+def run(cells=1024, steps=6, warmup=2, dt=0.5, comm=None, stepper="erk", tableau=None):
     """returns (result dict, initial state as two numpy arrays); comm: feltor_b200.dist.Comm -> the grid is cut into y-slabs
-    (one per rank, feltor_b200/dist_toefl.py) and the time is the maximum over the ranks"""
+    (one per rank, feltor_b200/dist_toefl.py) and the time is the maximum over the ranks.
+    stepper "erk": fixed-step dg::ERKStep (default tableau Bogacki-Shampine-4-2-3, 3 right-hand sides per step);
+    stepper "multistep": dg::ExplicitMultistep (default tableau TVB-3-3, ONE right-hand side per step; its first two steps are
+    Shu-Osher start-up steps, so warmup must be >= 2) -- the stepper BASELINE.json's config 3 names"""
     N = cells
     if comm is not None and comm.size > 1:
         from feltor_b200.dist_toefl import DistExplicit
@@ -39,13 +42,24 @@ def run(cells=1024, steps=6, warmup=2, dt=0.5, comm=None):
     y_init = [hvec(u0[0]).copy(), hvec(u0[1]).copy()]
     u1 = [torch.zeros_like(u0[0]), torch.zeros_like(u0[0])]
     delta = [torch.zeros_like(u0[0]), torch.zeros_like(u0[0])]
-    erk = TF.ERKStep("Bogacki-Shampine-4-2-3", u0)
+    multistep = stepper == "multistep"
+    tableau = tableau or ("TVB-3-3" if multistep else "Bogacki-Shampine-4-2-3")
     state = {"t": 0., "u0": u0, "u1": u1}
     its = {"gammaN": [], "pol": [], "gammaPhi": []}
+    if multistep:
+        if warmup < 2:
+            raise ValueError("the multistep record needs warmup >= 2 (Shu-Osher start-up steps)")
+        ms = TF.ExplicitMultistep(tableau, u0)
+        ms.init(ex, 0., u0, dt)
+    else:
+        erk = TF.ERKStep(tableau, u0)
 
     def step():
-        state["t"] = erk.step(ex, state["t"], state["u0"], state["u1"], dt, delta)
-        state["u0"], state["u1"] = state["u1"], state["u0"]
+        if multistep:
+            state["t"] = ms.step(ex, state["t"], state["u0"])
+        else:
+            state["t"] = erk.step(ex, state["t"], state["u0"], state["u1"], dt, delta)
+            state["u0"], state["u1"] = state["u1"], state["u0"]
         for k in its:
             its[k].append(ex.numbers[k])
 
@@ -75,7 +89,7 @@ def run(cells=1024, steps=6, warmup=2, dt=0.5, comm=None):
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
         sec = tmax.item()
     calls = ex.ncalls - calls0
-    out = {"workload": "toefl global n=3 %dx%d, 3-stage MultigridCG2d, Bogacki-Shampine-4-2-3 fixed dt=%g" % (N, N, dt),
+    out = {"workload": "toefl global n=3 %dx%d, 3-stage MultigridCG2d, %s %s fixed dt=%g" % (N, N, "dg::ExplicitMultistep" if multistep else "dg::ERKStep", tableau, dt),
            "steps_per_s": steps / sec, "rhs_per_s": calls / sec, "ms_per_step": sec / steps * 1e3, "steps": steps,
            "rhs_calls": calls, "kernel_launches": int(fb.lib().raw["dgb_launch_count"]() - launches0),
            "mean_pcg_iterations_per_solve(stage0,1,2)": {k: [float(np.mean([v[s] for v in vals])) for s in range(3)] for k, vals in its.items()},
@@ -91,5 +105,7 @@ if __name__ == "__main__":
     ap.add_argument("--steps", type=int, default=6)
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--dt", type=float, default=0.5)
+    ap.add_argument("--stepper", default="erk", choices=["erk", "multistep"])
+    ap.add_argument("--tableau", default=None)
     a = ap.parse_args()
-    print(json.dumps(run(a.cells, a.steps, a.warmup, a.dt)[0]), flush=True)
+    print(json.dumps(run(a.cells, a.steps, a.warmup, a.dt, stepper=a.stepper, tableau=a.tableau)[0]), flush=True)
