@@ -369,12 +369,15 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
     sa::Fpe fpe;
     int bad = 0;
     if (DOT) {
-        if (A.pcg->done) return;  // solver already converged: the remaining launches of the batch are no-ops
         sa::block_init<1>(dsm);
         fpe.clear();
     }
     if (tid == 0) mbar_init(bar, 1);
     __syncthreads();
+    pdl_wait();  // programmatic dependent launch (common.cuh): nothing of the predecessor is touched above this line
+    if (DOT) {
+        if (A.pcg->done) return;  // solver already converged: the remaining launches of the batch are no-ops
+    }
     unsigned phase = 0;
     // rows/columns of cells that are interior rows of every matrix (host-computed intersection)
     for (int gtile = blockIdx.x; gtile < A.ntiles * A.nplanes; gtile += gridDim.x) {
@@ -408,6 +411,7 @@ elliptic2d_fused_kernel(const __grid_constant__ FusedArgs A, const __grid_consta
         if (fast) compute_tile<N, DIRK, DOT, true>(A, C, xs, ss, txs, tys, cx0, cy0, tid, fpe, bad, dsm, poff);
         else compute_tile<N, DIRK, DOT, false>(A, C, xs, ss, txs, tys, cx0, cy0, tid, fpe, bad, dsm, poff);
     }
+    pdl_trigger();  // the tiles are done: the dependent kernel's launch and prologue may overlap the exact-dot tail
     if (DOT) {
         fpe.flush_warp(dsm);
         fused_dot_finish(sa::block_finish<1>(dsm, bad, A.slot, 0), A.pcg, A.slot.result, A.p2p, A.epoch);
@@ -460,7 +464,10 @@ static int launch(Elliptic2dPlan& p, double alpha, const double* x, double beta,
     fill<N, 3>(C.jx, p.jumpx); fill<N, 3>(C.jy, p.jumpy);
     int per_sm = std::max(1, std::min(FUSED_MIN_CTAS, (int)(220 * 1024 / (TL::BYTES + 1024))));
     int grid = (int)std::min<long long>((long long)A.ntiles * nplanes, (long long)per_sm * sm_count());
-    elliptic2d_fused_kernel<N, DIRK, DOT><<<grid, FUSED_THREADS, TL::BYTES, st>>>(A, C, mx, ms);
+    if (DOT && fd->pdl)
+        DGB_CUDA(launch_pdl(elliptic2d_fused_kernel<N, DIRK, DOT>, dim3(grid), dim3(FUSED_THREADS), TL::BYTES, st, A, C, mx, ms));
+    else
+        elliptic2d_fused_kernel<N, DIRK, DOT><<<grid, FUSED_THREADS, TL::BYTES, st>>>(A, C, mx, ms);
     DGB_LAUNCHED();
     return 0;
 }

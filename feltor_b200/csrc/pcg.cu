@@ -97,9 +97,10 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, const double* ap, doub
     // zout: where z = P r goes -- the ap buffer itself (classic three-kernel iteration) or the z buffer of the folded
     // iteration, whose bottom / top rows are ALSO stored into the neighbours' ghost rows (rem_lo / rem_up, peer memory)
     __shared__ long long smem[2 * sa::BINS];  // one accumulator per dot and block: [0] rr (slot 1), [1] zr (slot 2)
+    sa::block_init<2>(smem);  // programmatic dependent launch (common.cuh): nothing of the predecessor is touched before pdl_wait()
+    pdl_wait();
     if (st->done) return;
     const double alpha = st->alpha, malpha = -alpha;
-    sa::block_init<2>(smem);
     long long* my_rr = smem;
     long long* my_zr = smem + sa::BINS;
     sa::Fpe frr, fzr, frr1, fzr1;  // two independent expansions per dot: the add cascades interleave in the FP64 pipe
@@ -166,6 +167,7 @@ pcg_update_kernel(size_t n, const double* __restrict__ p, const double* ap, doub
         if (!isfinite(b0)) { bad = 1; b0 = 0.; }
         fzr.add(b0, my_zr);
     }
+    pdl_trigger();  // the streaming part is done: the next kernel's launch and prologue may overlap the exact-dot tail
     // both dots leave together: one fence / ticket sequence
     fzr.merge(fzr1, my_zr);
     if (CHECK) {
@@ -439,6 +441,16 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
     const bool p2p_dots = dist && pview.enabled && in_kernel;
     FusedDot fd{W, s.slot, s.st, pview, 0ull};
     if (!p2p_dots) fd.p2p.enabled = 0;
+    // programmatic dependent launches between the two kernels of the iteration (single GPU, walker kernel): opt-out DGB_PDL=0
+    static int pdl_env = -1;
+    if (pdl_env < 0) { const char* ev = getenv("DGB_PDL"); pdl_env = ev ? atoi(ev) : 3; }  // bit 0: K2 launches, bit 1: K1 launches
+    const bool pdl_ok = !dist && !s.profile;
+    fd.pdl = (pdl_ok && (pdl_env & 2)) ? 1 : 0;
+    // K2 as a dependent launch pays off on the latency-bound stages (+4-5 % at <= 256^2 cells) and costs 5-9 % behind the walker
+    // kernel on large grids (measured, profiles/pdl_r02.md; cause not established): size gate, DGB_PDL_K2_MAX overrides
+    static long long k2_max = -1;
+    if (k2_max < 0) { const char* ev = getenv("DGB_PDL_K2_MAX"); k2_max = ev ? atoll(ev) : 1200000ll; }
+    const bool pdl_k2 = pdl_ok && (pdl_env & 1) && (long long)n <= k2_max;
     static int k2_elems = -1;  // experiment knob: elements per thread that size K2's grid
     if (k2_elems < 0) { const char* ev = getenv("DGB_PCG_K2_ELEMS"); k2_elems = ev ? atoi(ev) : 2; if (k2_elems < 2) k2_elems = 2; }
     const unsigned g2 = grid_for(n, k2_elems);
@@ -484,7 +496,12 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
             P2pView k2v = pview;
             k2v.enabled = p2p_dots ? 1 : 0;
             const unsigned long long k2e = p2p_dots ? comm_p2p_next_epoch(comm, check ? 1 : 2, check ? 2 : 1) : 0ull;
-            if (k2_variant == 0) {
+            if (k2_variant == 0 && pdl_k2) {
+                double* zo = fold ? s.z : s.ap;
+                double *zl = z_by_peer ? zrem_lo : nullptr, *zu = z_by_peer ? zrem_up : nullptr;
+                if (check) DGB_CUDA(launch_pdl(pcg_update_kernel<true, true, 2, false>, dim3(g2), dim3(PCG_THREADS), 0, st, n, pcur, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e, zo, zl, zu, gh));
+                else DGB_CUDA(launch_pdl(pcg_update_kernel<false, true, 2, false>, dim3(g2), dim3(PCG_THREADS), 0, st, n, pcur, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e, zo, zl, zu, gh));
+            } else if (k2_variant == 0) {
                 if (check) DGB_K2(true, true, 2)<<<g2, PCG_THREADS, 0, st>>>(n, pcur, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e, fold ? s.z : s.ap, z_by_peer ? zrem_lo : nullptr, z_by_peer ? zrem_up : nullptr, gh);
                 else DGB_K2(false, true, 2)<<<g2, PCG_THREADS, 0, st>>>(n, pcur, s.ap, x, s.r, P, W, s.st, s.slot, i, k2v, k2e, fold ? s.z : s.ap, z_by_peer ? zrem_lo : nullptr, z_by_peer ? zrem_up : nullptr, gh);
             } else if (k2_variant == 1) {

@@ -22,6 +22,7 @@ struct FusedDot {
     // multi-GPU with peer memory: the finishing block of the kernel exchanges the record itself (comm.cuh) and runs the hook
     P2pView p2p;
     unsigned long long epoch;
+    int pdl = 0;  // launch with programmatic stream serialization (common.cuh); single-GPU solves only
 };
 
 // normalise + round a summed record in place (status = number of ranks that met NaN/Inf)
