@@ -220,6 +220,8 @@ __global__ void __launch_bounds__(64) pcg_scalar_kernel(PcgState* st, dgb_dot_re
 __global__ void __launch_bounds__(PCG_THREADS, 4)
 pcg_direction_kernel(size_t n, const double* __restrict__ z, double* __restrict__ p, const PcgState* st, double* rem_lo,
                      double* rem_up, size_t gcnt) {
+    pdl_wait();     // programmatic dependent launch (common.cuh); no prologue worth overlapping, but the lighter kernel boundary counts
+    pdl_trigger();  // the successor (K1) still waits for this grid to complete before it reads p
     if (st->done) return;
     constexpr int U = 4;
     const double beta = st->beta;
@@ -523,7 +525,8 @@ int pcg_solve_impl(Pcg& s, Comm* comm, Elliptic2dPlan& A, double* x, const doubl
                 else if (z_by_peer) { if ((e = comm_p2p_neighbour_barrier(comm, nb_lower, nb_upper, st))) return e; }
                 else if ((e = halo(s.z))) return e;
             } else {
-                pcg_direction_kernel<<<g3, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st, rem_lo, rem_up, gh);
+                if (pdl_k2) DGB_CUDA(launch_pdl(pcg_direction_kernel, dim3(g3), dim3(PCG_THREADS), 0, st, n, (const double*)s.ap, s.p, s.st, rem_lo, rem_up, gh));
+                else pcg_direction_kernel<<<g3, PCG_THREADS, 0, st>>>(n, s.ap, s.p, s.st, rem_lo, rem_up, gh);
                 DGB_LAUNCHED();
                 if (p2p_halo) { if ((e = comm_p2p_neighbour_barrier(comm, nb_lower, nb_upper, st))) return e; }
                 else if ((e = halo(s.p))) return e;
