@@ -188,33 +188,36 @@ static void analyse(MultiMat& M, bool projection) {
     M.fused = projection ? 1 : 2;
     M.Nxc = Nxc; M.Nyc = Nyc;
 }
+// kind 1: factor-2 projection, 2: factor-2 interpolation; X / Y: the x- and y-matrix (their first two block slots name the blocks)
 template <int N>
-static int half_launch(const MultiMat& M, double alpha, double beta, const double* x, double* y, cudaStream_t st) {
+static int half_launch(const EllDev& X, const EllDev& Y, int kind, int Nxc, int Nyc, double alpha, double beta, const double* x, double* y,
+                       cudaStream_t st) {
     HalfCoef<N> C;
-    const bool projection = M.fused == 1;
     for (int d = 0; d < 2; d++)
         for (int k = 0; k < N; k++)
             for (int q = 0; q < N; q++) {
-                C.x[d][k][q] = M.mx.h_data[((size_t)M.mx.h_didx[d] * N + k) * N + q];
-                C.y[d][k][q] = M.my.h_data[((size_t)M.my.h_didx[d] * N + k) * N + q];
+                C.x[d][k][q] = X.h_data[((size_t)X.h_didx[d] * N + k) * N + q];
+                C.y[d][k][q] = Y.h_data[((size_t)Y.h_didx[d] * N + k) * N + q];
             }
-    const long long ncells = (long long)M.Nxc * M.Nyc;
+    const long long ncells = (long long)Nxc * Nyc;
     long long want = (ncells + 127) / 128, cap = (long long)sm_count() * 16;
     const unsigned grid = (unsigned)std::max(1ll, std::min(want, cap));
-    if (projection) project_half_kernel<N><<<grid, 128, 0, st>>>(C, M.Nxc, M.Nyc, alpha, beta, x, y);
-    else interpolate_double_kernel<N><<<grid, 128, 0, st>>>(C, M.Nxc, M.Nyc, alpha, beta, x, y);
+    if (kind == 1) project_half_kernel<N><<<grid, 128, 0, st>>>(C, Nxc, Nyc, alpha, beta, x, y);
+    else interpolate_double_kernel<N><<<grid, 128, 0, st>>>(C, Nxc, Nyc, alpha, beta, x, y);
     DGB_LAUNCHED();
     return 0;
 }
+static int half_dispatch(const EllDev& X, const EllDev& Y, int kind, int Nxc, int Nyc, double alpha, double beta, const double* x, double* y,
+                         cudaStream_t st) {
+    switch (X.n) {
+        case 2: return half_launch<2>(X, Y, kind, Nxc, Nyc, alpha, beta, x, y, st);
+        case 3: return half_launch<3>(X, Y, kind, Nxc, Nyc, alpha, beta, x, y, st);
+        default: return half_launch<4>(X, Y, kind, Nxc, Nyc, alpha, beta, x, y, st);
+    }
+}
 static int g_multimat_two_pass = 0;  // A/B switch of the tests (dgb_multigrid2d_set_two_pass)
 static int multimat_symv(const MultiMat& M, double alpha, const double* x, double beta, double* y, cudaStream_t st) {
-    if (M.fused && !g_multimat_two_pass && x != y) {
-        switch (M.mx.n) {
-            case 2: return half_launch<2>(M, alpha, beta, x, y, st);
-            case 3: return half_launch<3>(M, alpha, beta, x, y, st);
-            default: return half_launch<4>(M, alpha, beta, x, y, st);
-        }
-    }
+    if (M.fused && !g_multimat_two_pass && x != y) return half_dispatch(M.mx, M.my, M.fused, M.Nxc, M.Nyc, alpha, beta, x, y, st);
     int e;
     if ((e = ell_symv(M.mx, 1., x, 0., M.temp, st, false))) return e;
     return ell_symv(M.my, alpha, M.temp, beta, y, st, false);
@@ -296,16 +299,7 @@ int dgb_multimatrix2_symv(const dgb_ell* hx, const dgb_ell* hy, int kind, double
         const bool projection = kind == 1;
         const int Nxc = projection ? X.num_rows : X.num_cols, Nyc = projection ? Y.num_rows : Y.num_cols;
         if (X.n != Y.n || X.n < 2 || X.n > 4 || X.bpl != (projection ? 2 : 1) || Y.bpl != X.bpl) { set_error("dgb_multimatrix2_symv: kind does not match the matrices"); return DGB_ERR_INVALID; }
-        MultiMat M;
-        M.fused = kind; M.Nxc = Nxc; M.Nyc = Nyc;
-        // coefficient blocks only (no ownership): half_launch reads h_data / h_didx / n
-        M.mx.n = X.n; M.mx.h_data = X.h_data; M.mx.h_didx.assign(X.h_didx.begin(), X.h_didx.begin() + 2);
-        M.my.n = Y.n; M.my.h_data = Y.h_data; M.my.h_didx.assign(Y.h_didx.begin(), Y.h_didx.begin() + 2);
-        switch (X.n) {
-            case 2: return half_launch<2>(M, alpha, beta, x, y, st);
-            case 3: return half_launch<3>(M, alpha, beta, x, y, st);
-            default: return half_launch<4>(M, alpha, beta, x, y, st);
-        }
+        return half_dispatch(X, Y, kind, Nxc, Nyc, alpha, beta, x, y, st);
     }
     if (!temp) { set_error("dgb_multimatrix2_symv: the two-pass path needs the temporary"); return DGB_ERR_INVALID; }
     int e;

@@ -174,6 +174,14 @@ static int spg_launch(int num_rows, const int* rows, const int* Bpos, const int*
     return 0;
 }
 
+// scratch of one call: freed on every return path (DGB_CUDA returns early on errors)
+template <class T>
+struct DevBuf {
+    T* p = nullptr;
+    ~DevBuf() { cudaFree(p); }
+    cudaError_t alloc(size_t count) { return cudaMalloc(&p, (count ? count : 1) * sizeof(T)); }
+};
+
 struct Spgemm {
     int rows = 0;
     long long nnz = 0;
@@ -196,10 +204,11 @@ static void spg_free(Spgemm* s) {
 // pass 1: distinct columns per row -> row offsets (scan on the host)
 static int spg_symbolic(Spgemm* s, int B_rows, const int* Bpos, const int* Bidx, const int* Cpos, const int* Cidx, cudaStream_t st) {
     s->rows = B_rows;
-    int *counts = nullptr, *ocount = nullptr;
-    DGB_CUDA(cudaMalloc(&counts, ((size_t)B_rows + 1) * sizeof(int)));
+    DevBuf<int> counts_buf, ocount_buf;
+    DGB_CUDA(counts_buf.alloc((size_t)B_rows + 1));
     DGB_CUDA(cudaMalloc(&s->big_rows, ((size_t)B_rows + 1) * sizeof(int)));
-    DGB_CUDA(cudaMalloc(&ocount, 2 * sizeof(int)));
+    DGB_CUDA(ocount_buf.alloc(2));
+    int *counts = counts_buf.p, *ocount = ocount_buf.p;
     DGB_CUDA(cudaMemsetAsync(ocount, 0, 2 * sizeof(int), st));
     int e = spg_launch<SPG_H_FAST, SPG_W_FAST, false>(B_rows, nullptr, Bpos, Bidx, nullptr, Cpos, Cidx, nullptr, counts, s->big_rows, ocount,
                                                       nullptr, nullptr, nullptr, st);
@@ -233,20 +242,20 @@ static int spg_symbolic(Spgemm* s, int B_rows, const int* Bpos, const int* Bidx,
             DGB_CUDA(cudaStreamSynchronize(st));
         }
     }
-    cudaFree(counts); cudaFree(ocount);
     return e;
 }
 
 static int spg_numeric(Spgemm* s, const int* Bpos, const int* Bidx, const double* Bval, const int* Cpos, const int* Cidx, const double* Cval,
                        int* Aidx, double* Aval, cudaStream_t st) {
-    int* ocount = nullptr;
-    DGB_CUDA(cudaMalloc(&ocount, sizeof(int)));
+    DevBuf<int> ocount_buf;
+    DGB_CUDA(ocount_buf.alloc(1));
+    int* ocount = ocount_buf.p;
     DGB_CUDA(cudaMemsetAsync(ocount, 0, sizeof(int), st));
     // the fast kernel skips the rows it cannot hold (they overflow again); the large variant fills them in
     int e = spg_launch<SPG_H_FAST, SPG_W_FAST, true>(s->rows, nullptr, Bpos, Bidx, Bval, Cpos, Cidx, Cval, nullptr, nullptr, ocount, s->pos, Aidx, Aval, st);
     if (!e && s->big)
         e = spg_launch<SPG_H_BIG, SPG_W_BIG, true>(s->big, s->big_rows, Bpos, Bidx, Bval, Cpos, Cidx, Cval, nullptr, nullptr, ocount, s->pos, Aidx, Aval, st);
-    cudaFree(ocount);
+    if (!e) DGB_CUDA(cudaStreamSynchronize(st));  // the scratch counter must outlive the kernels that bump it
     return e;
 }
 
