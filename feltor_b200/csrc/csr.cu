@@ -65,6 +65,17 @@ csr_scatter_add_kernel(int num_rows, const int* __restrict__ pos, const int* __r
     y[dst] = __dadd_rn(y[dst], t);
 }
 
+// the allreduce mode of MPIDistMat (mpi_matrix.h:438-441,487-490: every rank applies its column block of the matrix, the
+// partial results are summed over the ranks): y[i] = ((part_0[i] + part_1[i]) + part_2[i]) + ... in RANK ORDER on every rank,
+// so all ranks hold the same bits whatever the arrival order (MPI_Allreduce of doubles gives no such guarantee).
+__global__ void __launch_bounds__(256) sum_ranks_kernel(int nranks, size_t m, const double* __restrict__ parts, double* __restrict__ y) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < m; i += (size_t)gridDim.x * blockDim.x) {
+        double t = __ldg(parts + i);
+        for (int r = 1; r < nranks; r++) t = __dadd_rn(t, __ldg(parts + (size_t)r * m + i));
+        y[i] = t;
+    }
+}
+
 static int csr_launch(int num_rows, int num_cols, const int* pos, const int* idx, const double* val, double alpha,
                       const double* x, double beta, double* y, int nplanes, int shift, cudaStream_t st) {
     if (num_rows < 0 || num_cols < 0 || nplanes < 0) { set_error("dgb_csr_spmv: negative size"); return DGB_ERR_INVALID; }
@@ -108,6 +119,14 @@ int dgb_csr_spmv_scatter_add(int num_rows, const int* pos, const int* idx, const
     if (num_rows == 0) return 0;
     if (num_rows < 0 || !pos || !idx || !val || !buffer || !scatter || !y) { set_error("dgb_csr_spmv_scatter_add: invalid argument"); return DGB_ERR_INVALID; }
     csr_scatter_add_kernel<<<(num_rows + 127) / 128, 128, 0, as_stream(s)>>>(num_rows, pos, idx, val, buffer, scatter, y);
+    DGB_LAUNCHED();
+    return 0;
+}
+int dgb_sum_ranks(int nranks, size_t m, const double* parts, double* y, dgb_stream_t s) {
+    if (m == 0) return 0;
+    if (nranks < 1 || !parts || !y) { set_error("dgb_sum_ranks: invalid argument"); return DGB_ERR_INVALID; }
+    size_t want = (m + 255) / 256, cap = (size_t)sm_count() * 16;
+    sum_ranks_kernel<<<(unsigned)(want < cap ? want : cap), 256, 0, as_stream(s)>>>(nranks, m, parts, y);
     DGB_LAUNCHED();
     return 0;
 }

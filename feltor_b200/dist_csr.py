@@ -158,3 +158,46 @@ class DistCsr:
         self.apply_inner(x, y)
         torch.cuda.current_stream().wait_event(self._arrived)
         self.apply_outer(y)
+
+
+class DistCsrAllreduce:
+    """dg::MPIDistMat in allreduce mode (mpi_matrix.h:438-441,487-490), the form dg::Average takes when the averaged axis is
+    distributed: every rank holds the COLUMN block of the matrix that belongs to its part of the vector (local column indices,
+    all rows), applies it, and the partial results are summed over the ranks.  The sum runs in rank order on every rank
+    (dgb_comm_gather of the partial vectors + dgb_sum_ranks), so all ranks end up with identical bits; it differs from the
+    single-GPU product only by the rounding of that regrouping (the reference's MPI_Allreduce differs the same way)."""
+
+    def __init__(self, comm, num_rows, local_cols, pos, idx, val):
+        import torch
+        from ._dev import dvec
+        self.comm, self.num_rows, self.local_cols = comm, int(num_rows), int(local_cols)
+        self.mat = tuple(dvec(np.ascontiguousarray(a, dtype=t)) for a, t in ((pos, np.int32), (idx, np.int32), (val, np.float64)))
+        self.partial = torch.empty(max(1, self.num_rows), dtype=torch.float64, device="cuda")
+        self.send = torch.empty(max(1, self.num_rows * comm.size), dtype=torch.float64, device="cuda")
+        self.parts = torch.empty(max(1, self.num_rows * comm.size), dtype=torch.float64, device="cuda")
+        self._cnt = (C.c_int * comm.size)(*([self.num_rows] * comm.size))
+
+    def apply_local(self, x):
+        from ._lib import lib
+        from ._dev import ptr, stream
+        lib().csr_spmv(self.num_rows, self.local_cols, *[ptr(a) for a in self.mat], C.c_double(1.), ptr(x), C.c_double(0.), ptr(self.partial), stream())
+
+    def reduce(self, y):
+        from ._lib import lib
+        from ._dev import ptr, stream
+        lib().sum_ranks(self.comm.size, self.num_rows, ptr(self.parts), ptr(y), stream())
+
+    def symv(self, x, y):
+        """y = M x with x distributed over the ranks and y replicated on all of them"""
+        from ._lib import lib
+        from ._dev import ptr, stream
+        self.apply_local(x)
+        if self.comm.size == 1:
+            y.copy_(self.partial[:self.num_rows])
+            return
+        m = self.num_rows
+        for r in range(self.comm.size):        # the same partial vector goes to every rank
+            self.send[r * m:(r + 1) * m].copy_(self.partial[:m])
+        lib().comm_gather(self.comm.h, ptr(self.send), self._cnt, ptr(self.parts), self._cnt, stream())
+        self.reduce(y)
+

@@ -312,6 +312,10 @@ DGB_API int dgb_csr_spgemm_host_finish(dgb_spgemm* plan, int* A_pos, int* A_idx,
 DGB_API int dgb_gather_indexed(size_t n, const int* idx, const double* x, double* out, dgb_stream_t s);
 DGB_API int dgb_csr_spmv_scatter_add(int num_rows, const int* row_offsets, const int* cols, const double* vals, const double* buffer,
                                      const int* scatter, double* y, dgb_stream_t s);
+/* allreduce mode of MPIDistMat (mpi_matrix.h:438-441,487-490; dg::Average over a distributed axis): parts = nranks vectors of m
+ * doubles, rank-major (what dgb_comm_gather delivers when every rank sends its partial result to every rank);
+ * y[i] = (..(parts[0][i] + parts[1][i]) + ..) + parts[nranks-1][i] -- rank order, hence the same bits on every rank */
+DGB_API int dgb_sum_ranks(int nranks, size_t m, const double* parts, double* y, dgb_stream_t s);
 
 /* dg::blas2::stencil(f, M, x, y) / parallel_for (blas2.h:413-454, blas2_stencil.h:13-70) for the library's CSR stencil
  * functors (topology/filter.h:174-266): the matrix only encodes the neighbourhood of each row (create::window_stencil).

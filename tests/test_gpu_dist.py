@@ -330,3 +330,48 @@ def test_dist_check_on_all_visible_gpus(G):
     p = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(n), "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(root, "tools", "dist_check.py")], capture_output=True, text=True, timeout=580)
     assert p.returncode == 0 and "DIST_CHECK PASS" in p.stdout, p.stdout[-3000:] + p.stderr[-2000:]
+
+
+@pytest.mark.parametrize("size", [1, 3, 8])
+def test_dist_csr_allreduce_mode(G, size):
+    """MPIDistMat in allreduce mode (dg::Average over a distributed axis, feltor_b200/dist_csr.py::DistCsrAllreduce): column blocks
+    of an averaging matrix on `size` emulated ranks, partial results summed in rank order by dgb_sum_ranks -- bitwise the
+    rank-ordered sum of the single-rank partial products, every rank the same bits, 1e-14 from the undistributed product"""
+    import ctypes as C
+    from feltor_b200._lib import lib
+    from feltor_b200._dev import dvec, ptr, stream
+    from feltor_b200.dist import partition
+    from feltor_b200.dist_csr import DistCsrAllreduce
+    r = rng(size)
+    nx, ny = 90, 64                                   # average over y: rows = nx, every row sums ny weighted entries
+    w = r.uniform(0.5, 1.5, ny)
+    pos = (np.arange(nx + 1) * ny).astype(np.int32)
+    idx = (np.arange(ny)[None, :] * nx + np.arange(nx)[:, None]).reshape(-1).astype(np.int32)
+    val = np.tile(w, nx)
+    x = r.uniform(-1, 1, nx * ny)
+    keep = [dvec(pos), dvec(idx), dvec(val), G.make(x)]
+    full = G.make(np.full(nx, np.nan))
+    lib().csr_spmv(nx, nx * ny, *[ptr(a) for a in keep[:3]], C.c_double(1.), ptr(keep[3]), C.c_double(0.), ptr(full), stream())
+    part = partition(ny, size)                        # ranks own blocks of y rows = contiguous pieces of the vector
+    mats, partials = [], []
+    for rank, (o, c) in enumerate(part):
+        lp = (np.arange(nx + 1) * c).astype(np.int32)
+        li = (np.arange(c)[None, :] * nx + np.arange(nx)[:, None]).reshape(-1).astype(np.int32)
+        lv = np.tile(w[o:o + c], nx)
+        comm_r = type("EmulatedRank", (), {"rank": rank, "size": size, "h": None})()
+        m = DistCsrAllreduce(comm_r, nx, c * nx, lp, li, lv)
+        m.apply_local(G.make(x[o * nx:(o + c) * nx]))
+        mats.append(m)
+        partials.append(G.get(m.partial)[:nx])
+    want = partials[0].copy()
+    for p_ in partials[1:]:
+        want = want + p_                               # rank order, one rounding per addition
+    for m in mats:
+        for rank in range(size):
+            m.parts[rank * nx:(rank + 1) * nx].copy_(mats[rank].partial[:nx])       # the exchange, emulated
+        y = G.make(np.full(nx, np.nan))
+        m.reduce(y)
+        assert same_bits(G.get(y), want)
+    assert np.max(np.abs(want - G.get(full))) <= 1e-14 * np.max(np.abs(G.get(full))) * ny
+    if size == 1:
+        assert same_bits(want, G.get(full))

@@ -149,6 +149,24 @@ for band in (None, 60):
     same_csr = np.array_equal(hvec(yl).view(np.int64), hvec(cy)[r0:r0 + nrl].view(np.int64))
     print(f"rank {rank}/{size} DistCsr band={band}: {same_csr} (outer rows {M.plan.scatter.size}, buffer {M.plan.buffer_size}, sends {M.plan.send_idx.size})", flush=True)
     ok = ok and same_csr
+# allreduce mode of MPIDistMat (dg::Average over a distributed axis): column blocks, rank-ordered sum, same bits on every rank
+from feltor_b200.dist_csr import DistCsrAllreduce  # noqa: E402
+nxa, nya = 120, 16 * size
+ra = np.random.default_rng(31)
+wa, xa = ra.uniform(0.5, 1.5, nya), ra.uniform(-1, 1, nxa * nya)
+oa, ca = partition(nya, size)[rank]
+lpa = (np.arange(nxa + 1) * ca).astype(np.int32)
+lia = (np.arange(ca)[None, :] * nxa + np.arange(nxa)[:, None]).reshape(-1).astype(np.int32)
+Ma = DistCsrAllreduce(comm, nxa, ca * nxa, lpa, lia, np.tile(wa[oa:oa + ca], nxa))
+ya = torch.full((nxa,), float("nan"), dtype=torch.float64, device="cuda")
+Ma.symv(dvec(xa[oa * nxa:(oa + ca) * nxa].copy()), ya)
+exact = (xa.reshape(nya, nxa) * wa[:, None]).sum(axis=0)
+everyone = [torch.empty_like(ya) for _ in range(size)]
+dist.all_gather(everyone, ya)
+same_avg = all(torch.equal(everyone[0].view(torch.int64), e.view(torch.int64)) for e in everyone) and \
+    float(np.max(np.abs(hvec(ya) - exact))) <= 1e-13 * float(np.max(np.abs(exact)))
+print(f"rank {rank}/{size} DistCsrAllreduce (average over the distributed axis): {same_avg}", flush=True)
+ok = ok and same_avg
 # block matrices distributed along their own axis (dg::MPISparseBlockMat, feltor_b200/dist_ell.py): an x-decomposition of dx and
 # a y-decomposition of the jump matrix, periodic across the ranks, against the global product
 from feltor_b200.dist_ell import DistEll  # noqa: E402
